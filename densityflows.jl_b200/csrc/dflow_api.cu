@@ -1,0 +1,734 @@
+// C ABI of libdflow.so (include/dflow.h): handle construction, validation, launches, host-buffer pipelines.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "dflow_internal.h"
+
+namespace dflow {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define CKA(call)                                                                         \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DFLOW_E_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+static int round_hp(int w) {
+  if (w <= 16) return 16;
+  if (w <= 32) return 32;
+  if (w <= 64) return 64;
+  return -1;
+}
+
+static int round_out(int a) {  // padded width of the last Dense: 4, 8, 16, 32, 64
+  int p = 4;
+  while (p < a) p <<= 1;
+  return p;
+}
+
+// Fill one DevNet from its descriptor; returns 0 or an error code.
+static int fill_net(const dflow_net_desc& nd, int expect_in, int expect_out, DevNet& net, int& P, int& hidden_max,
+                    const char* what, int elem) {
+  memset(&net, 0, sizeof(net));
+  if (nd.depth < 1 || nd.depth > MAX_DENSE) {
+    set_error("element %d %s: depth %d outside [1,%d]", elem, what, nd.depth, MAX_DENSE);
+    return nd.depth > MAX_DENSE ? DFLOW_E_UNSUPPORTED : DFLOW_E_INVALID_ARG;
+  }
+  if (!nd.widths || !nd.acts) {
+    set_error("element %d %s: widths/acts missing", elem, what);
+    return DFLOW_E_INVALID_ARG;
+  }
+  net.depth = nd.depth;
+  net.has_bias = nd.has_bias ? 1 : 0;
+  for (int j = 0; j <= nd.depth; ++j) {
+    net.w[j] = nd.widths[j];
+    if (net.w[j] < 1) {
+      set_error("element %d %s: width[%d]=%d", elem, what, j, net.w[j]);
+      return DFLOW_E_INVALID_ARG;
+    }
+  }
+  if (net.w[0] != expect_in || net.w[nd.depth] != expect_out) {
+    // CouplingLayer: input_dim = length(axis_nn), output_dim = length(axis_af) (src/Layers.jl:126-127)
+    set_error("element %d %s: net maps %d->%d but the axes need %d->%d", elem, what, net.w[0], net.w[nd.depth],
+              expect_in, expect_out);
+    return DFLOW_E_INVALID_ARG;
+  }
+  for (int j = 0; j < nd.depth; ++j) {
+    net.act[j] = nd.acts[j];
+    if (net.act[j] < DFLOW_ACT_IDENTITY || net.act[j] > DFLOW_ACT_SIGMOID) {
+      set_error("element %d %s: unsupported activation code %d", elem, what, net.act[j]);
+      return DFLOW_E_UNSUPPORTED;
+    }
+    if (j < nd.depth - 1) hidden_max = std::max(hidden_max, net.w[j + 1]);
+    net.p_w[j] = P;
+    P += net.w[j] * net.w[j + 1];
+    if (net.has_bias) {
+      net.p_b[j] = P;
+      P += net.w[j + 1];
+    } else {
+      net.p_b[j] = -1;
+    }
+  }
+  return DFLOW_OK;
+}
+
+static void layout_net(DevNet& net, int hp, int& off) {
+  for (int j = 0; j < net.depth; ++j) {
+    net.op[j] = (j < net.depth - 1) ? hp : round_out(net.w[j + 1]);
+    net.s_w[j] = off;
+    off += net.w[j] * net.op[j];
+    net.s_b[j] = off;
+    off += net.op[j];
+  }
+}
+
+}  // namespace dflow
+
+using namespace dflow;
+
+extern "C" {
+
+struct HostPipe;
+static void pipe_free(HostPipe* p);
+
+int dflow_version(void) { return DFLOW_VERSION; }
+const char* dflow_last_error(void) { return g_err; }
+
+int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
+  if (!desc || !out) {
+    set_error("null argument");
+    return DFLOW_E_INVALID_ARG;
+  }
+  *out = nullptr;
+  const int d = desc->d, n = desc->n, L = desc->n_elems;
+  if (d < 1 || n < 0 || L < 1 || !desc->elems) {
+    set_error("bad chain shape d=%d n=%d n_elems=%d", d, n, L);
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (d > DMAX || n > NMAX || L > LMAX) {
+    set_error("chain shape d=%d n=%d n_elems=%d exceeds the narrow path limits (%d,%d,%d)", d, n, L, DMAX, NMAX, LMAX);
+    return DFLOW_E_UNSUPPORTED;
+  }
+  std::vector<unsigned char> img(sizeof(DevChainHdr) + sizeof(DevElem) * (size_t)L, 0);
+  DevChain* C = reinterpret_cast<DevChain*>(img.data());
+  DevChainHdr& H = C->h;
+  H.d = d;
+  H.n = n;
+  H.L = L;
+  H.logpdf_c0 = -((float)d * 1.8378770664093453f) / 2.0f;  // -(d*log2π)/2 in Float32
+  int P = 0, hidden_max = 1, amax4 = 4, max_depth = 1;
+  for (int ei = 0; ei < L; ++ei) {
+    const dflow_elem_desc& ed = desc->elems[ei];
+    DevElem& E = C->e[ei];
+    E.kind = ed.kind;
+    if (ed.kind == DFLOW_ELEM_NORM) {
+      if (!ed.x_min || !ed.x_max) {
+        set_error("element %d: NormalizationLayer needs x_min/x_max", ei);
+        return DFLOW_E_INVALID_ARG;
+      }
+      if (!(ed.beta > ed.alpha)) {  // src/norm/Normalization.jl:55
+        set_error("element %d: bounds of the normalisation need beta > alpha", ei);
+        return DFLOW_E_INVALID_ARG;
+      }
+      continue;
+    }
+    if (ed.kind != DFLOW_ELEM_RNVP && ed.kind != DFLOW_ELEM_NICE) {
+      set_error("element %d: unknown kind %d", ei, ed.kind);
+      return DFLOW_E_INVALID_ARG;
+    }
+    const int a = ed.n_af;
+    if (a < 1 || a > d || !ed.axis_af) {
+      set_error("element %d: bad axis_af length %d", ei, a);
+      return DFLOW_E_INVALID_ARG;
+    }
+    bool seen[DMAX] = {false};
+    for (int j = 0; j < a; ++j) {
+      const int k = ed.axis_af[j];
+      if (k < 0 || k >= d) {  // src/Axes.jl:85
+        set_error("element %d: the mask cannot contain values higher than the dimension (axis_af[%d]=%d)", ei, j, k);
+        return DFLOW_E_INVALID_ARG;
+      }
+      if (seen[k]) {
+        set_error("element %d: duplicate index %d in axis_af", ei, k);
+        return DFLOW_E_INVALID_ARG;
+      }
+      seen[k] = true;
+      E.af[j] = (unsigned char)k;
+    }
+    // axis_id = findall(x -> !(x in mask), 1:d) (ascending), src/Axes.jl:88
+    int nid = 0;
+    for (int k = 0; k < d; ++k)
+      if (!seen[k]) E.id[nid++] = (unsigned char)k;
+    E.a = a;
+    E.nid = nid;
+    E.nin = n + nid;  // length(axis_nn), src/Axes.jl:98
+    if (E.nin < 1) {
+      set_error("element %d: conditioner has no inputs (n=0 and every dimension transformed)", ei);
+      return DFLOW_E_UNSUPPORTED;
+    }
+    int rc;
+    if (ed.kind == DFLOW_ELEM_RNVP) {
+      rc = fill_net(ed.s_net, E.nin, a, E.s, P, hidden_max, "s_net", ei);
+      if (rc) return rc;
+      max_depth = std::max(max_depth, E.s.depth);
+    }
+    rc = fill_net(ed.t_net, E.nin, a, E.t, P, hidden_max, "t_net", ei);
+    if (rc) return rc;
+    max_depth = std::max(max_depth, E.t.depth);
+    amax4 = std::max(amax4, round_out(a));
+  }
+  const int hp = round_hp(hidden_max);
+  if (hp < 0) {
+    set_error("hidden width %d > %d: the wide (tcgen05) conditioner path is not built yet", hidden_max, HP_MAX);
+    return DFLOW_E_UNSUPPORTED;
+  }
+  H.hp = hp;
+  H.P = P;
+  H.amax4 = amax4;
+  H.max_depth = max_depth;
+  // staged image layout
+  int total = 0, smax = 4;
+  for (int ei = 0; ei < L; ++ei) {
+    DevElem& E = C->e[ei];
+    E.stage_off = total;
+    int off = 0;
+    if (E.kind == DFLOW_ELEM_NORM) {
+      off = 2 * d + 4;
+    } else {
+      if (E.kind == DFLOW_ELEM_RNVP) layout_net(E.s, hp, off);
+      layout_net(E.t, hp, off);
+    }
+    off = (off + 3) & ~3;
+    E.stage_len = off;
+    total += off;
+    smax = std::max(smax, off);
+  }
+  H.stage_total = total;
+  H.stage_max = smax;
+
+  dflow_chain* c = new (std::nothrow) dflow_chain();
+  if (!c) {
+    set_error("out of host memory");
+    return DFLOW_E_NOMEM;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&c->device) != cudaSuccess || cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return DFLOW_E_CUDA;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  // keep the whole staged image in shared memory when it leaves room for >= 2 CTAs of columns
+  H.resident = (total * 4 <= 96 * 1024) ? 1 : 0;
+  c->chain_bytes = (int)((img.size() + 15) & ~(size_t)15);
+  img.resize(c->chain_bytes, 0);
+  c->host_chain = img;
+  if (desc->theta_min && desc->theta_max) dflow_chain_set_theta_range(c, desc->theta_min, desc->theta_max);
+
+  cudaError_t e1 = cudaMalloc(&c->d_chain, c->chain_bytes);
+  cudaError_t e2 = cudaMalloc(&c->d_staged, std::max(total, 4) * sizeof(float));
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("cudaMalloc failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    dflow_chain_destroy(c);
+    return DFLOW_E_NOMEM;
+  }
+  // norm blocks of the staged image are static: [x_min | x_max | alpha beta ldj_const 0]
+  std::vector<float> st(std::max(total, 4), 0.0f);
+  for (int ei = 0; ei < L; ++ei) {
+    const dflow_elem_desc& ed = desc->elems[ei];
+    const DevElem& E = c->hc()->e[ei];
+    if (E.kind != DFLOW_ELEM_NORM) continue;
+    float* b = st.data() + E.stage_off;
+    const float delta = ed.beta - ed.alpha;
+    float csum = 0.0f;  // sum(log.(x_diff ./ δ)) in Float32, src/norm/Normalization.jl:73
+    for (int k = 0; k < d; ++k) {
+      b[k] = ed.x_min[k];
+      b[d + k] = ed.x_max[k];
+      csum += logf((ed.x_max[k] - ed.x_min[k]) / delta);
+    }
+    b[2 * d] = ed.alpha;
+    b[2 * d + 1] = ed.beta;
+    b[2 * d + 2] = csum;
+  }
+  if (cudaMemcpy(c->d_staged, st.data(), st.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(c->d_chain, c->host_chain.data(), c->chain_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    dflow_chain_destroy(c);
+    return DFLOW_E_CUDA;
+  }
+  *out = c;
+  return DFLOW_OK;
+}
+
+int dflow_chain_destroy(dflow_chain* c) {
+  if (!c) return DFLOW_OK;
+  if (c->d_chain) cudaFree(c->d_chain);
+  if (c->d_staged) cudaFree(c->d_staged);
+  if (c->pipe) pipe_free((HostPipe*)c->pipe);
+  delete c;
+  return DFLOW_OK;
+}
+
+int64_t dflow_param_count(const dflow_chain* c) { return c ? c->hc()->h.P : DFLOW_E_INVALID_ARG; }
+
+int dflow_chain_axes(const dflow_chain* c, int32_t elem, int32_t* axis_id, int32_t* n_id, int32_t* axis_nn,
+                     int32_t* n_nn) {
+  if (!c || elem < 0 || elem >= c->hc()->h.L) {
+    set_error("bad element index");
+    return DFLOW_E_INVALID_ARG;
+  }
+  const DevElem& E = c->hc()->e[elem];
+  if (E.kind == DFLOW_ELEM_NORM) {
+    set_error("element %d is not a coupling layer", elem);
+    return DFLOW_E_INVALID_ARG;
+  }
+  const int n = c->hc()->h.n;
+  if (n_id) *n_id = E.nid;
+  if (n_nn) *n_nn = E.nin;
+  if (axis_id)
+    for (int k = 0; k < E.nid; ++k) axis_id[k] = E.id[k];
+  if (axis_nn) {  // vcat(1:n, axis_id .+ n), src/Axes.jl:98 (0-based here)
+    for (int k = 0; k < n; ++k) axis_nn[k] = k;
+    for (int k = 0; k < E.nid; ++k) axis_nn[n + k] = E.id[k] + n;
+  }
+  return DFLOW_OK;
+}
+
+int dflow_param_offset(const dflow_chain* c, int32_t elem, int32_t net, int32_t dense, int64_t* w_off, int64_t* b_off) {
+  if (!c || elem < 0 || elem >= c->hc()->h.L) {
+    set_error("bad element index");
+    return DFLOW_E_INVALID_ARG;
+  }
+  const DevElem& E = c->hc()->e[elem];
+  if (E.kind == DFLOW_ELEM_NORM || (net != 0 && net != 1) || (net == 0 && E.kind != DFLOW_ELEM_RNVP)) {
+    set_error("element %d has no net %d", elem, net);
+    return DFLOW_E_INVALID_ARG;
+  }
+  const DevNet& N = net == 0 ? E.s : E.t;
+  if (dense < 0 || dense >= N.depth) {
+    set_error("bad dense index %d", dense);
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (w_off) *w_off = N.p_w[dense];
+  if (b_off) *b_off = N.p_b[dense];
+  return DFLOW_OK;
+}
+
+int dflow_chain_set_theta_range(dflow_chain* c, const float* tmin, const float* tmax) {
+  if (!c || !tmin || !tmax) {
+    set_error("null argument");
+    return DFLOW_E_INVALID_ARG;
+  }
+  DevChainHdr& H = c->hc()->h;
+  for (int k = 0; k < H.n; ++k) {
+    H.theta_min[k] = tmin[k];
+    H.theta_rng[k] = tmax[k] - tmin[k];
+    H.theta_inv[k] = H.theta_rng[k] == 0.0f ? 0.0f : 1.0f / H.theta_rng[k];
+  }
+  H.has_theta_range = 1;
+  if (c->d_chain) CKA(cudaMemcpy(c->d_chain, c->host_chain.data(), sizeof(DevChainHdr), cudaMemcpyHostToDevice));
+  return DFLOW_OK;
+}
+
+static int check_common(dflow_chain* c, const float* W, const float* theta, const float* theta_const, int64_t B,
+                        int32_t flags) {
+  if (!c) {
+    set_error("null chain");
+    return DFLOW_E_INVALID_ARG;
+  }
+  const DevChainHdr& H = c->hc()->h;
+  if (B < 0) {
+    set_error("negative batch");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (H.P > 0 && !W) {
+    set_error("null parameter buffer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (H.n > 0 && B > 0 && !theta && !theta_const) {
+    set_error("chain has %d conditions but no θ was given", H.n);
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (theta && theta_const) {
+    set_error("pass either theta or theta_const, not both");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if ((flags & DFLOW_THETA_NORMALIZE) && !H.has_theta_range) {
+    set_error("DFLOW_THETA_NORMALIZE needs θ_min/θ_max on the chain");
+    return DFLOW_E_INVALID_ARG;
+  }
+  return DFLOW_OK;
+}
+
+static int run_fwd(dflow_chain* c, const float* W, FwdArgs& a, void* stream) {
+  if (a.B == 0) return DFLOW_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_prepack(c, W, st);
+  if (rc) return rc;
+  return launch_fwd(c, a, st);
+}
+
+int dflow_normalize(dflow_chain* c, const float* W, const float* x, const float* theta, int64_t B, int32_t flags,
+                    float* z_out, float* ldj_out, void* stream) {
+  int rc = check_common(c, W, theta, nullptr, B, flags);
+  if (rc) return rc;
+  if (B > 0 && (!x || !z_out || !ldj_out)) {
+    set_error("null data pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  FwdArgs a{};
+  a.x_in = x;
+  a.theta = theta;
+  a.x_out = z_out;
+  a.aux_out = ldj_out;
+  a.B = B;
+  a.mode = MODE_NORMALIZE;
+  a.flags = flags;
+  return run_fwd(c, W, a, stream);
+}
+
+int dflow_logpdf(dflow_chain* c, const float* W, const float* x, const float* theta, int64_t B, const int32_t* idx,
+                 int32_t flags, float* logp_out, void* stream) {
+  int rc = check_common(c, W, theta, nullptr, B, flags);
+  if (rc) return rc;
+  if (B > 0 && (!x || !logp_out)) {
+    set_error("null data pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  FwdArgs a{};
+  a.x_in = x;
+  a.theta = theta;
+  a.idx = idx;
+  a.aux_out = logp_out;
+  a.B = B;
+  a.mode = MODE_LOGPDF;
+  a.flags = flags;
+  return run_fwd(c, W, a, stream);
+}
+
+int dflow_logpdf_sum(dflow_chain* c, const float* W, const float* x, const float* theta, int64_t B, const int32_t* idx,
+                     int32_t flags, float* loss_out, void* stream) {
+  int rc = check_common(c, W, theta, nullptr, B, flags);
+  if (rc) return rc;
+  if (B > 0 && (!x || !loss_out)) {
+    set_error("null data pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  FwdArgs a{};
+  a.x_in = x;
+  a.theta = theta;
+  a.idx = idx;
+  a.aux_out = loss_out;
+  a.B = B;
+  a.mode = MODE_LOGPDF_SUM;
+  a.flags = flags;
+  return run_fwd(c, W, a, stream);
+}
+
+int dflow_sample_inplace(dflow_chain* c, const float* W, float* z, const float* theta, const float* theta_const,
+                         int64_t B, int32_t flags, void* stream) {
+  int rc = check_common(c, W, theta, theta_const, B, flags);
+  if (rc) return rc;
+  if (B > 0 && !z) {
+    set_error("null data pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  FwdArgs a{};
+  a.x_in = z;
+  a.theta = theta;
+  a.theta_const = theta_const;
+  a.x_out = z;
+  a.B = B;
+  a.mode = MODE_SAMPLE;
+  a.flags = flags;
+  return run_fwd(c, W, a, stream);
+}
+
+int dflow_forward_ldj(dflow_chain* c, const float* W, const float* z, const float* theta, int64_t B, int32_t flags,
+                      float* x_out, float* ldj_out, void* stream) {
+  int rc = check_common(c, W, theta, nullptr, B, flags);
+  if (rc) return rc;
+  if (B > 0 && (!z || !x_out || !ldj_out)) {
+    set_error("null data pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  FwdArgs a{};
+  a.x_in = z;
+  a.theta = theta;
+  a.x_out = x_out;
+  a.aux_out = ldj_out;
+  a.B = B;
+  a.mode = MODE_FORWARD_LDJ;
+  a.flags = flags;
+  return run_fwd(c, W, a, stream);
+}
+
+int dflow_sample_rng(dflow_chain* c, const float* W, uint64_t seed, uint32_t offset, uint64_t first_sample,
+                     const float* theta, const float* theta_const, int64_t B, int32_t flags, float* x_out,
+                     void* stream) {
+  int rc = check_common(c, W, theta, theta_const, B, flags);
+  if (rc) return rc;
+  if (B > 0 && !x_out) {
+    set_error("null data pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  FwdArgs a{};
+  a.theta = theta;
+  a.theta_const = theta_const;
+  a.x_out = x_out;
+  a.B = B;
+  a.mode = MODE_SAMPLE_RNG;
+  a.flags = flags;
+  a.seed = seed;
+  a.rng_offset = offset;
+  a.first_sample = first_sample;
+  return run_fwd(c, W, a, stream);
+}
+
+size_t dflow_workspace_bytes(const dflow_chain* c, int64_t B) {
+  (void)c;
+  (void)B;
+  return 0;  // the narrow adjoint keeps all per-sample state on chip
+}
+
+int dflow_loss_grad(dflow_chain* c, const float* W, const float* x, const float* theta, int64_t B, const int32_t* idx,
+                    float inv_btot, int32_t flags, float* loss_out, float* grad_out, void* ws, size_t ws_bytes,
+                    void* stream) {
+  (void)ws;
+  (void)ws_bytes;
+  int rc = check_common(c, W, theta, nullptr, B, flags);
+  if (rc) return rc;
+  if (B > 0 && (!x || !loss_out || !grad_out)) {
+    set_error("null data pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (B == 0) return DFLOW_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_prepack(c, W, st);
+  if (rc) return rc;
+  GradArgs a{};
+  a.x_in = x;
+  a.theta = theta;
+  a.idx = idx;
+  a.loss_out = loss_out;
+  a.grad_out = grad_out;
+  a.B = B;
+  a.inv_btot = inv_btot;
+  a.flags = flags;
+  return launch_grad(c, a, st);
+}
+
+int dflow_adam_step(float* W, const float* g, float* m, float* v, int64_t P, float lr, float beta1, float beta2,
+                    float eps, int64_t t, void* stream) {
+  if (P < 0 || t < 1 || (P > 0 && (!W || !g || !m || !v))) {
+    set_error("bad Adam arguments");
+    return DFLOW_E_INVALID_ARG;
+  }
+  return launch_adam(W, g, m, v, P, lr, beta1, beta2, eps, t, (cudaStream_t)stream);
+}
+
+int dflow_minmax(const float* x, int32_t rows, int64_t B, float* min_out, float* max_out, void* stream) {
+  if (rows < 1 || rows > 256 || B < 0 || !min_out || !max_out || (B > 0 && !x)) {
+    set_error("bad minmax arguments");
+    return DFLOW_E_INVALID_ARG;
+  }
+  return launch_minmax(x, rows, B, min_out, max_out, (cudaStream_t)stream);
+}
+
+// ---- host-buffer pipelines: chunked H2D -> kernel -> D2H on two streams ---------------------------------------
+struct HostPipe {
+  cudaStream_t st[2] = {nullptr, nullptr};
+  float* dx[2] = {nullptr, nullptr};
+  float* dt[2] = {nullptr, nullptr};
+  float* dout[2] = {nullptr, nullptr};
+  int64_t chunk = 0;
+  int d = 0, n = 0;
+};
+
+static void pipe_free(HostPipe* p) {
+  if (!p) return;
+  for (int i = 0; i < 2; ++i) {
+    if (p->dx[i]) cudaFree(p->dx[i]);
+    if (p->dt[i]) cudaFree(p->dt[i]);
+    if (p->dout[i]) cudaFree(p->dout[i]);
+    if (p->st[i]) cudaStreamDestroy(p->st[i]);
+  }
+  delete p;
+}
+
+static int pipe_get(dflow_chain* c, int64_t chunk, HostPipe** out) {
+  const DevChainHdr& H = c->hc()->h;
+  HostPipe* p = (HostPipe*)c->pipe;
+  if (p && p->chunk >= chunk) {
+    *out = p;
+    return DFLOW_OK;
+  }
+  pipe_free(p);
+  c->pipe = nullptr;
+  p = new (std::nothrow) HostPipe();
+  if (!p) return DFLOW_E_NOMEM;
+  p->chunk = chunk;
+  p->d = H.d;
+  p->n = H.n;
+  const size_t outw = std::max(H.d, 1);
+  for (int i = 0; i < 2; ++i) {
+    if (cudaStreamCreateWithFlags(&p->st[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&p->dx[i], sizeof(float) * H.d * chunk) != cudaSuccess ||
+        cudaMalloc(&p->dt[i], sizeof(float) * std::max(H.n, 1) * chunk) != cudaSuccess ||
+        cudaMalloc(&p->dout[i], sizeof(float) * outw * chunk) != cudaSuccess) {
+      set_error("host pipeline allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      pipe_free(p);
+      return DFLOW_E_NOMEM;
+    }
+  }
+  c->pipe = p;
+  *out = p;
+  return DFLOW_OK;
+}
+
+int dflow_logpdf_host(dflow_chain* c, const float* W, const float* x_host, const float* theta_host, int64_t B,
+                      int32_t flags, float* logp_host, int64_t chunk) {
+  int rc = check_common(c, W, theta_host, nullptr, B, flags);
+  if (rc) return rc;
+  if (B == 0) return DFLOW_OK;
+  if (!x_host || !logp_host) {
+    set_error("null host pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  const DevChainHdr& H = c->hc()->h;
+  if (chunk <= 0) chunk = 1 << 22;
+  chunk = std::min<int64_t>(chunk, B);
+  HostPipe* p;
+  rc = pipe_get(c, chunk, &p);
+  if (rc) return rc;
+  // the staged image is shared by both streams: prepack once, make both streams wait for it
+  cudaEvent_t ev;
+  CKA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  rc = launch_prepack(c, W, p->st[0]);
+  if (rc) return rc;
+  CKA(cudaEventRecord(ev, p->st[0]));
+  CKA(cudaStreamWaitEvent(p->st[1], ev, 0));
+  int64_t done = 0;
+  int slot = 0;
+  while (done < B) {
+    const int64_t nb = std::min(chunk, B - done);
+    cudaStream_t st = p->st[slot];
+    CKA(cudaMemcpyAsync(p->dx[slot], x_host + done * H.d, sizeof(float) * H.d * nb, cudaMemcpyHostToDevice, st));
+    if (H.n > 0)
+      CKA(cudaMemcpyAsync(p->dt[slot], theta_host + done * H.n, sizeof(float) * H.n * nb, cudaMemcpyHostToDevice, st));
+    FwdArgs a{};
+    a.x_in = p->dx[slot];
+    a.theta = H.n > 0 ? p->dt[slot] : nullptr;
+    a.aux_out = p->dout[slot];
+    a.B = nb;
+    a.mode = MODE_LOGPDF;
+    a.flags = flags;
+    rc = launch_fwd(c, a, st);
+    if (rc) return rc;
+    CKA(cudaMemcpyAsync(logp_host + done, p->dout[slot], sizeof(float) * nb, cudaMemcpyDeviceToHost, st));
+    done += nb;
+    slot ^= 1;
+  }
+  CKA(cudaStreamSynchronize(p->st[0]));
+  CKA(cudaStreamSynchronize(p->st[1]));
+  cudaEventDestroy(ev);
+  return DFLOW_OK;
+}
+
+int dflow_sample_host(dflow_chain* c, const float* W, uint64_t seed, const float* theta_const_host, int64_t B,
+                      int32_t flags, float* x_host, int64_t chunk) {
+  if (!c) {
+    set_error("null chain");
+    return DFLOW_E_INVALID_ARG;
+  }
+  const DevChainHdr& H = c->hc()->h;
+  if (B < 0 || (B > 0 && !x_host) || (H.n > 0 && !theta_const_host) || (H.P > 0 && !W)) {
+    set_error("bad sample_host arguments");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if ((flags & DFLOW_THETA_NORMALIZE) && !H.has_theta_range) {
+    set_error("DFLOW_THETA_NORMALIZE needs θ_min/θ_max on the chain");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (B == 0) return DFLOW_OK;
+  if (chunk <= 0) chunk = 1 << 22;
+  chunk = std::min<int64_t>(chunk, B);
+  HostPipe* p;
+  int rc = pipe_get(c, chunk, &p);
+  if (rc) return rc;
+  if (H.n > 0) {
+    CKA(cudaMemcpyAsync(p->dt[0], theta_const_host, sizeof(float) * H.n, cudaMemcpyHostToDevice, p->st[0]));
+  }
+  cudaEvent_t ev;
+  CKA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  rc = launch_prepack(c, W, p->st[0]);
+  if (rc) return rc;
+  CKA(cudaEventRecord(ev, p->st[0]));
+  CKA(cudaStreamWaitEvent(p->st[1], ev, 0));
+  int64_t done = 0;
+  int slot = 0;
+  while (done < B) {
+    const int64_t nb = std::min(chunk, B - done);
+    cudaStream_t st = p->st[slot];
+    FwdArgs a{};
+    a.theta_const = H.n > 0 ? p->dt[0] : nullptr;
+    a.x_out = p->dout[slot];
+    a.B = nb;
+    a.mode = MODE_SAMPLE_RNG;
+    a.flags = flags;
+    a.seed = seed;
+    a.first_sample = (unsigned long long)done;
+    rc = launch_fwd(c, a, st);
+    if (rc) return rc;
+    CKA(cudaMemcpyAsync(x_host + done * H.d, p->dout[slot], sizeof(float) * H.d * nb, cudaMemcpyDeviceToHost, st));
+    done += nb;
+    slot ^= 1;
+  }
+  CKA(cudaStreamSynchronize(p->st[0]));
+  CKA(cudaStreamSynchronize(p->st[1]));
+  cudaEventDestroy(ev);
+  return DFLOW_OK;
+}
+
+int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
+  if (!c || !key) {
+    set_error("null argument");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (!strcmp(key, "fwd_spt"))
+    c->fwd_spt = value;
+  else if (!strcmp(key, "fwd_threads"))
+    c->fwd_threads = value;
+  else if (!strcmp(key, "grad_threads"))
+    c->grad_threads = value;
+  else if (!strcmp(key, "ctas_per_sm"))
+    c->ctas_per_sm = value;
+  else {
+    set_error("unknown tuning key %s", key);
+    return DFLOW_E_INVALID_ARG;
+  }
+  return DFLOW_OK;
+}
+
+int64_t dflow_launch_count(const dflow_chain* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

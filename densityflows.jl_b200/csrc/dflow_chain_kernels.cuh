@@ -1,0 +1,736 @@
+// Narrow-conditioner (hidden <= 64) fused coupling-chain kernels for sm_100a (templates).
+//
+// One thread owns S samples.  The whole FlowChain (all coupling layers + NormalizationLayer + Gaussian base term)
+// runs inside one kernel, so x / z never round-trip HBM between layers (reference: one (d,B) allocation per
+// element, src/Chains.jl:149-197).  Conditioner weights live in shared memory in a padded [in][out4] image
+// (broadcast LDS.128 -> 4 FFMA per sample), per-sample state lives in bank-conflict-free shared-memory columns
+// col[unit * CS + slot], and the FFMA accumulators live in registers.
+//
+// Reference math: src/affine/RNVP.jl:77-96 (normalising), :99-147 (adjoint), :168-205 (sampling);
+// src/affine/NICE.jl:63-170; src/norm/Normalization.jl:64-103; src/Flows.jl:272-281,352-359; src/Data.jl:213-218.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "dflow_internal.h"
+
+namespace dflow {
+
+// ------------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float act_apply(int code, float v) {
+  switch (code) {
+    case DFLOW_ACT_RELU: return fmaxf(v, 0.0f);
+    case DFLOW_ACT_TANH: return tanhf(v);
+    case DFLOW_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    default: return v;
+  }
+}
+
+// derivative w.r.t. the pre-activation, expressed through the OUTPUT y; relu'(0) = 0 (NNlib convention)
+__device__ __forceinline__ float act_grad(int code, float y) {
+  switch (code) {
+    case DFLOW_ACT_RELU: return y > 0.0f ? 1.0f : 0.0f;
+    case DFLOW_ACT_TANH: return 1.0f - y * y;
+    case DFLOW_ACT_SIGMOID: return y * (1.0f - y);
+    default: return 1.0f;
+  }
+}
+
+// Selects the shared-memory column holding input row k of a Dense: for the first Dense the rows are
+// vcat(θ, x)[axis_nn] = θ_0..θ_{n-1}, x[axis_id[0]], ... (src/affine/RNVP.jl:157); otherwise the hidden column.
+struct InSel {
+  const float* th;
+  const float* xs;
+  const float* hc;
+  const unsigned char* id;
+  int n;
+  int CS;
+  bool first;
+  __device__ __forceinline__ const float* operator()(int k) const {
+    if (!first) return hc + k * CS;
+    return k < n ? th + k * CS : xs + (int)id[k - n] * CS;
+  }
+};
+
+// acc[o][s] += W[k][o] * in_k[s] for one input row k (NG broadcast LDS.128 -> NG*4*S FFMA)
+template <int NG, int S>
+__device__ __forceinline__ void dense_row(const float* src, const float* __restrict__ wrow, int slot0, int NT,
+                                          float (&acc)[NG * 4][S]) {
+  float v[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) v[s] = src[slot0 + s * NT];
+  const float4* wr = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const float4 w = wr[g];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      acc[4 * g + 0][s] = fmaf(w.x, v[s], acc[4 * g + 0][s]);
+      acc[4 * g + 1][s] = fmaf(w.y, v[s], acc[4 * g + 1][s]);
+      acc[4 * g + 2][s] = fmaf(w.z, v[s], acc[4 * g + 2][s]);
+      acc[4 * g + 3][s] = fmaf(w.w, v[s], acc[4 * g + 3][s]);
+    }
+  }
+}
+
+// Outputs [o0, o0 + NG*4) of a Dense: acc = bias + sum_k W[k][o] * in_k, activation, store to outcol rows o0...
+// W is staged as [K][ld] (ld = padded output width), so a chunk of the outputs is a column slice.
+template <int NG, int S>
+__device__ __forceinline__ void dense_to_col(const InSel& in, int K, const float* __restrict__ Wst, int ld,
+                                             const float* __restrict__ bst, int act, float* outcol, int CS, int slot0,
+                                             int NT) {
+  float acc[NG * 4][S];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const float4 b = *reinterpret_cast<const float4*>(bst + 4 * g);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      acc[4 * g + 0][s] = b.x;
+      acc[4 * g + 1][s] = b.y;
+      acc[4 * g + 2][s] = b.z;
+      acc[4 * g + 3][s] = b.w;
+    }
+  }
+  if (in.first) {
+    const int n = in.n;
+    for (int k = 0; k < n; ++k) dense_row<NG, S>(in.th + k * in.CS, Wst + k * ld, slot0, NT, acc);
+    for (int k = n; k < K; ++k) dense_row<NG, S>(in.xs + (int)in.id[k - n] * in.CS, Wst + k * ld, slot0, NT, acc);
+  } else {
+    const float* src = in.hc;
+    const float* wr = Wst;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+      dense_row<NG, S>(src, wr, slot0, NT, acc);
+      src += in.CS;
+      wr += ld;
+    }
+  }
+  if (act == DFLOW_ACT_RELU) {
+#pragma unroll
+    for (int o = 0; o < NG * 4; ++o)
+#pragma unroll
+      for (int s = 0; s < S; ++s) outcol[o * CS + slot0 + s * NT] = fmaxf(acc[o][s], 0.0f);
+  } else if (act == DFLOW_ACT_IDENTITY) {
+#pragma unroll
+    for (int o = 0; o < NG * 4; ++o)
+#pragma unroll
+      for (int s = 0; s < S; ++s) outcol[o * CS + slot0 + s * NT] = acc[o][s];
+  } else {
+#pragma unroll
+    for (int o = 0; o < NG * 4; ++o)
+#pragma unroll
+      for (int s = 0; s < S; ++s) outcol[o * CS + slot0 + s * NT] = act_apply(act, acc[o][s]);
+  }
+}
+
+// Evaluate one conditioner (Flux.Chain of Dense, src/Layers.jl:33-50).  Hidden activations go to
+// hc + j*hstride (hstride = 0: one reused column block; HP*CS: kept for the adjoint), the final output to outcol.
+// The last Dense (padded width op in {4,8,16,32,64}) is produced in chunks of <= 16 outputs so that the
+// accumulator tile never exceeds the hidden tile.
+template <int HP, int S>
+__device__ __forceinline__ void run_net(const DevNet& net, const float* __restrict__ wblk, InSel in, float* hc,
+                                        int hstride, float* outcol, int CS, int slot0, int NT) {
+  const int D = net.depth;
+  for (int j = 0; j < D; ++j) {
+    in.first = (j == 0);
+    in.hc = hc + (j > 0 ? (j - 1) * hstride : 0);
+    const int K = net.w[j];
+    const float* Wst = wblk + net.s_w[j];
+    const float* bst = wblk + net.s_b[j];
+    const int act = net.act[j];
+    if (j < D - 1) {
+      dense_to_col<HP / 4, S>(in, K, Wst, HP, bst, act, hc + j * hstride, CS, slot0, NT);
+    } else {
+      const int op = net.op[j];
+      if (op == 4) {
+        dense_to_col<1, S>(in, K, Wst, 4, bst, act, outcol, CS, slot0, NT);
+      } else if (op == 8) {
+        dense_to_col<2, S>(in, K, Wst, 8, bst, act, outcol, CS, slot0, NT);
+      } else {
+        for (int o0 = 0; o0 < op; o0 += 16)
+          dense_to_col<4, S>(in, K, Wst + o0, op, bst + o0, act, outcol + o0 * CS, CS, slot0, NT);
+      }
+    }
+  }
+}
+
+// cooperative float4 copy global -> shared (len4 = number of float4)
+__device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ src, int len4, int tid, int nt) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  for (int i = tid; i < len4; i += nt) d4[i] = __ldg(s4 + i);
+}
+
+// Apply one element in the normalising (`backward`, x -> z) or sampling direction to the S samples of this
+// thread.  ldj is accumulated with the reference's signs.
+template <int HP, int S>
+__device__ __forceinline__ void elem_apply(const DevChainHdr& H, const DevElem& E, const float* __restrict__ wblk,
+                                           bool sampling, float* xs, float* th, float* hc, int hstride, float* sb,
+                                           float* tb, int CS, int slot0, int NT, float (&ldj)[S]) {
+  if (E.kind == DFLOW_ELEM_NORM) {
+    // src/norm/Normalization.jl:64-103
+    const int d = H.d;
+    const float alpha = wblk[2 * d], beta = wblk[2 * d + 1], c = wblk[2 * d + 2];
+    for (int k = 0; k < d; ++k) {
+      const float xmin = wblk[k], xmax = wblk[d + k];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float* p = xs + k * CS + slot0 + s * NT;
+        const float v = *p;
+        if (!sampling)
+          *p = (beta * (v - xmin) + alpha * (xmax - v)) / (xmax - xmin);
+        else
+          *p = ((xmax - xmin) * v - alpha * xmax + beta * xmin) / (beta - alpha);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) ldj[s] += sampling ? c : -c;
+    return;
+  }
+  InSel in{th, xs, hc, E.id, H.n, CS, true};
+  const bool rnvp = (E.kind == DFLOW_ELEM_RNVP);
+  for (int ni = rnvp ? 0 : 1; ni < 2; ++ni)
+    run_net<HP, S>(ni == 0 ? E.s : E.t, wblk, in, hc, hstride, ni == 0 ? sb : tb, CS, slot0, NT);
+  float lsum[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) lsum[s] = 0.0f;
+  for (int j = 0; j < E.a; ++j) {
+    const int k = E.af[j];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int sl = slot0 + s * NT;
+      const float sv = rnvp ? sb[j * CS + sl] : 0.0f;
+      const float tv = tb[j * CS + sl];
+      float* p = xs + k * CS + sl;
+      if (!sampling)
+        *p = (*p - tv) * expf(-sv);  // RNVP.jl:92
+      else
+        *p = *p * expf(sv) + tv;  // RNVP.jl:184
+      lsum[s] += sv;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s) ldj[s] += sampling ? lsum[s] : -lsum[s];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (spec: oracle/philox.py)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
+                                              unsigned int k0, unsigned int k1, unsigned int (&r)[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  r[0] = c0;
+  r[1] = c1;
+  r[2] = c2;
+  r[3] = c3;
+}
+
+__device__ __forceinline__ void box_muller(unsigned int a, unsigned int b, float& z0, float& z1) {
+  const float u0 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
+  const float u1 = ((float)(b >> 8) + 0.5f) * 5.9604644775390625e-08f;
+  const float rad = sqrtf(-2.0f * logf(u0));
+  float sn, cs;
+  sincospif(2.0f * u1, &sn, &cs);
+  z0 = rad * cs;
+  z1 = rad * sn;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// shared-memory carve-up (identical arithmetic on host and device)
+// ------------------------------------------------------------------------------------------------------------
+struct SmemPlan {
+  int chain_f;  // floats reserved for the DevChain copy
+  int w_f;      // floats for weights
+  int cs;       // column stride (floats)
+  int cols_f;   // floats for columns
+  int grad_f;   // floats for the shared gradient accumulator (grad kernel)
+  __host__ __device__ size_t bytes() const { return 4ull * ((size_t)chain_f + w_f + cols_f + grad_f); }
+};
+
+__host__ __device__ inline SmemPlan plan_fwd(const DevChainHdr& h, int chain_bytes, int nts) {
+  SmemPlan p;
+  p.chain_f = ((chain_bytes + 15) / 16) * 4;
+  p.w_f = h.resident ? h.stage_total : h.stage_max;
+  p.cs = nts;
+  const int rows = h.d + h.n + h.hp + 2 * h.amax4;
+  p.cols_f = rows * p.cs;
+  p.grad_f = 0;
+  return p;
+}
+
+__host__ __device__ inline SmemPlan plan_grad(const DevChainHdr& h, int chain_bytes, int nt, int smem_grad) {
+  SmemPlan p;
+  p.chain_f = ((chain_bytes + 15) / 16) * 4;
+  p.w_f = h.resident ? h.stage_total : h.stage_max;
+  p.cs = nt + 4;
+  const int hd = h.max_depth > 1 ? h.max_depth - 1 : 1;
+  const int rows = 2 * h.d + h.n + hd * h.hp + h.hp + 4 * h.amax4;
+  p.cols_f = rows * p.cs;
+  p.grad_f = smem_grad ? ((h.P + 3) / 4) * 4 : 0;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1 / K2: fused chain, normalising or sampling direction
+// ------------------------------------------------------------------------------------------------------------
+template <int HP, int S>
+__global__ void __launch_bounds__(256) chain_fwd_kernel(const FwdArgs a) {
+  extern __shared__ float4 smem4[];
+  float* smem = reinterpret_cast<float*>(smem4);
+  const int tid = threadIdx.x, NT = blockDim.x, NTS = NT * S;
+
+  // DevChain -> shared
+  copy_f4(smem, reinterpret_cast<const float*>(a.chain), (a.chain_bytes + 15) / 16, tid, NT);
+  __syncthreads();
+  const DevChain* C = reinterpret_cast<const DevChain*>(smem);
+  const DevChainHdr& H = C->h;
+  const SmemPlan P = plan_fwd(H, a.chain_bytes, NTS);
+  float* wsm = smem + P.chain_f;
+  float* cols = wsm + P.w_f;
+  const int CS = P.cs;
+  float* xs = cols;
+  float* th = xs + H.d * CS;
+  float* hc = th + H.n * CS;
+  float* sb = hc + H.hp * CS;
+  float* tb = sb + H.amax4 * CS;
+
+  if (H.resident) {
+    copy_f4(wsm, a.staged, H.stage_total / 4, tid, NT);
+    __syncthreads();
+  }
+
+  const int d = H.d, n = H.n, L = H.L;
+  const bool sampling = (a.mode >= MODE_SAMPLE);
+  const long long ntiles = (a.B + NTS - 1) / NTS;
+  float lsum_thread = 0.0f, nonfinite = 0.0f;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long base = tile * NTS;
+    // ---- load ----
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int sl = tid + s * NT;
+      const long long gi = base + sl;
+      const bool valid = gi < a.B;
+      const long long src = (valid && a.idx) ? (long long)a.idx[gi] : gi;
+      if (a.mode == MODE_SAMPLE_RNG) {
+        const unsigned long long ctr = a.first_sample + (unsigned long long)gi;
+        for (int g = 0; g < (d + 3) / 4; ++g) {
+          unsigned int r[4];
+          philox4x32_10((unsigned int)ctr, (unsigned int)(ctr >> 32), (unsigned int)g, a.rng_offset,
+                        (unsigned int)a.seed, (unsigned int)(a.seed >> 32), r);
+          float z[4];
+          box_muller(r[0], r[1], z[0], z[1]);
+          box_muller(r[2], r[3], z[2], z[3]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * g + q < d) xs[(4 * g + q) * CS + sl] = z[q];
+        }
+      } else {
+        const float* xp = a.x_in + src * d;
+        for (int k = 0; k < d; ++k) xs[k * CS + sl] = valid ? __ldg(xp + k) : 0.0f;
+      }
+      for (int k = 0; k < n; ++k) {
+        float v = 0.0f;
+        if (a.theta_const)
+          v = __ldg(a.theta_const + k);
+        else if (valid && a.theta)
+          v = __ldg(a.theta + src * n + k);
+        if (a.flags & DFLOW_THETA_NORMALIZE) {
+          // normalize_input, src/Data.jl:213-218
+          v = (H.theta_rng[k] == 0.0f) ? 0.0f : (v - H.theta_min[k]) / H.theta_rng[k];
+        }
+        th[k * CS + sl] = v;
+      }
+    }
+    float ldj[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) ldj[s] = 0.0f;
+
+    // ---- chain ----
+    for (int step = 0; step < L; ++step) {
+      const int ei = sampling ? step : (L - 1 - step);  // src/Chains.jl:155-161 vs :174-180
+      const DevElem& E = C->e[ei];
+      const float* wblk;
+      if (H.resident) {
+        wblk = wsm + E.stage_off;
+      } else {
+        __syncthreads();
+        copy_f4(wsm, a.staged + E.stage_off, E.stage_len / 4, tid, NT);
+        __syncthreads();
+        wblk = wsm;
+      }
+      elem_apply<HP, S>(H, E, wblk, sampling, xs, th, hc, 0, sb, tb, CS, tid, NT, ldj);
+    }
+
+    // ---- store ----
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int sl = tid + s * NT;
+      const long long gi = base + sl;
+      if (gi >= a.B) continue;
+      if (a.mode == MODE_LOGPDF || a.mode == MODE_LOGPDF_SUM) {
+        float q = 0.0f;
+        for (int k = 0; k < d; ++k) {
+          const float v = xs[k * CS + sl];
+          q = fmaf(v, v, q);
+        }
+        const float lp = H.logpdf_c0 - 0.5f * q + ldj[s];  // src/Flows.jl:279
+        if (a.mode == MODE_LOGPDF)
+          a.aux_out[gi] = lp;
+        else {
+          if (isfinite(lp))
+            lsum_thread += lp;
+          else
+            nonfinite += 1.0f;
+        }
+      } else {
+        float* op = a.x_out + gi * d;
+        for (int k = 0; k < d; ++k) op[k] = xs[k * CS + sl];
+        if (a.mode == MODE_NORMALIZE || a.mode == MODE_FORWARD_LDJ) a.aux_out[gi] = ldj[s];
+      }
+    }
+  }
+
+  if (a.mode == MODE_LOGPDF_SUM) {
+    // block reduce -> one atomic per CTA
+    __syncthreads();
+    float v0 = lsum_thread, v1 = nonfinite;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+    }
+    float* red = cols;  // reuse
+    if ((tid & 31) == 0) {
+      red[(tid >> 5) * 2] = v0;
+      red[(tid >> 5) * 2 + 1] = v1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float t0 = 0.0f, t1 = 0.0f;
+      for (int w = 0; w < (NT + 31) / 32; ++w) {
+        t0 += red[2 * w];
+        t1 += red[2 * w + 1];
+      }
+      atomicAdd(a.aux_out, t0);
+      if (t1 != 0.0f) atomicAdd(a.aux_out + 1, t1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3: adjoint.  Forward normalising sweep, then a chain-order reverse sweep that RECOMPUTES each layer's
+// activations from its output (u_id = z_id, u_af = z_af*exp(s)+t), back-propagates through both conditioners and
+// accumulates the weight gradients warp-cooperatively (lane owns entries, loops over the warp's 32 samples).
+// ------------------------------------------------------------------------------------------------------------
+
+// dW[o][k] += sum_samples delta[o][s] * in_k[s] ; db[o] += sum_samples delta[o][s]
+__device__ __forceinline__ void dw_phase(const float* __restrict__ dcol, const InSel& in, int O, int K, int has_bias,
+                                         int p_w, int p_b, float* __restrict__ gsm, float* __restrict__ ggl, int CS,
+                                         int wbase, int lane) {
+  const int E = O * (K + (has_bias ? 1 : 0));
+  int o = lane % O, k = lane / O;
+  for (int e = lane; e < E; e += 32) {
+    const float4* dp = reinterpret_cast<const float4*>(dcol + o * CS + wbase);
+    float acc0 = 0.0f, acc1 = 0.0f;
+    int gi;
+    if (k < K) {
+      const float4* hp = reinterpret_cast<const float4*>(in(k) + wbase);
+#pragma unroll
+      for (int q = 0; q < 8; q += 2) {
+        const float4 x0 = dp[q], y0 = hp[q], x1 = dp[q + 1], y1 = hp[q + 1];
+        acc0 = fmaf(x0.x, y0.x, acc0);
+        acc0 = fmaf(x0.y, y0.y, acc0);
+        acc0 = fmaf(x0.z, y0.z, acc0);
+        acc0 = fmaf(x0.w, y0.w, acc0);
+        acc1 = fmaf(x1.x, y1.x, acc1);
+        acc1 = fmaf(x1.y, y1.y, acc1);
+        acc1 = fmaf(x1.z, y1.z, acc1);
+        acc1 = fmaf(x1.w, y1.w, acc1);
+      }
+      gi = p_w + o + O * k;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; q += 2) {
+        const float4 x0 = dp[q], x1 = dp[q + 1];
+        acc0 += (x0.x + x0.y) + (x0.z + x0.w);
+        acc1 += (x1.x + x1.y) + (x1.z + x1.w);
+      }
+      gi = p_b + o;
+    }
+    if (gsm)
+      atomicAdd(gsm + gi, acc0 + acc1);
+    else
+      atomicAdd(ggl + gi, acc0 + acc1);
+    o += 32;
+    while (o >= O) {
+      o -= O;
+      ++k;
+    }
+  }
+}
+
+// g_in[k] = sum_o W[k][o] * delta[o] for k in [k0, K); `first` selects what happens to the result:
+// hidden: dlc[k] = g_in[k] * act'(hprev[k]);  first Dense: gx[axis_id[k-n]] += g_in[k].
+template <int NG>
+__device__ __forceinline__ void dense_T(const float* dcol, int CS, int sl, const float* __restrict__ Wst, int k0,
+                                        int K, bool first, float* dlc, const float* hprev, int actp, float* gx,
+                                        const unsigned char* id, int n) {
+  float dl[NG * 4];
+#pragma unroll
+  for (int o = 0; o < NG * 4; ++o) dl[o] = dcol[o * CS + sl];
+  for (int k = k0; k < K; ++k) {
+    const float4* wr = reinterpret_cast<const float4*>(Wst + k * (NG * 4));
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float4 w = wr[g];
+      a0 = fmaf(w.x, dl[4 * g + 0], a0);
+      a1 = fmaf(w.y, dl[4 * g + 1], a1);
+      a2 = fmaf(w.z, dl[4 * g + 2], a2);
+      a3 = fmaf(w.w, dl[4 * g + 3], a3);
+    }
+    const float v = (a0 + a1) + (a2 + a3);
+    if (first)
+      gx[(int)id[k - n] * CS + sl] += v;
+    else
+      dlc[k * CS + sl] = v * act_grad(actp, hprev[k * CS + sl]);
+  }
+}
+
+// Back-propagate through one conditioner.  gb holds the output cotangent (padded rows zero); hidden activations
+// are in hc + j*hstride; dlc is the delta column; input cotangent rows >= n are accumulated into gx[axis_id].
+template <int HP>
+__device__ __forceinline__ void net_backward(const DevChainHdr& H, const DevElem& E, const DevNet& net,
+                                             const float* __restrict__ wblk, float* xs, float* gx, float* th,
+                                             float* hc, int hstride, float* dlc, float* gb, const float* outvals,
+                                             float* gsm, float* ggl, int CS, int sl, int wbase, int lane) {
+  const int D = net.depth;
+  // delta of the last Dense: gout * act'(out)
+  {
+    const int actL = net.act[D - 1];
+    if (actL != DFLOW_ACT_IDENTITY) {
+      const int O = net.w[D];
+      for (int o = 0; o < O; ++o) gb[o * CS + sl] *= act_grad(actL, outvals[o * CS + sl]);
+    }
+  }
+  for (int j = D - 1; j >= 0; --j) {
+    const float* dcol = (j == D - 1) ? gb : dlc;
+    InSel in{th, xs, hc + (j > 0 ? (j - 1) * hstride : 0), E.id, H.n, CS, j == 0};
+    const int O = net.w[j + 1], K = net.w[j];
+    __syncwarp();
+    dw_phase(dcol, in, O, K, net.has_bias, net.p_w[j], net.p_b[j], gsm, ggl, CS, wbase, lane);
+    __syncwarp();
+    const float* Wst = wblk + net.s_w[j];
+    const bool first = (j == 0);
+    const float* hprev = hc + (j > 0 ? (j - 1) * hstride : 0);
+    const int actp = j > 0 ? net.act[j - 1] : 0;
+    const int k0 = first ? H.n : 0;  // θ rows (k < n) of the first Dense are discarded
+    // note: dcol may alias dlc (hidden layers): dense_T loads all of delta into registers before its first store
+    switch (net.op[j] >> 2) {
+      case 1: dense_T<1>(dcol, CS, sl, Wst, k0, K, first, dlc, hprev, actp, gx, E.id, H.n); break;
+      case 2: dense_T<2>(dcol, CS, sl, Wst, k0, K, first, dlc, hprev, actp, gx, E.id, H.n); break;
+      case 4: dense_T<4>(dcol, CS, sl, Wst, k0, K, first, dlc, hprev, actp, gx, E.id, H.n); break;
+      case 8: dense_T<8>(dcol, CS, sl, Wst, k0, K, first, dlc, hprev, actp, gx, E.id, H.n); break;
+      default: dense_T<16>(dcol, CS, sl, Wst, k0, K, first, dlc, hprev, actp, gx, E.id, H.n); break;
+    }
+    if (!first)
+      for (int k = K; k < HP; ++k) dlc[k * CS + sl] = 0.0f;  // padded units carry no gradient
+  }
+}
+
+template <int HP>
+__global__ void __launch_bounds__(256) chain_grad_kernel(const GradArgs a) {
+  extern __shared__ float4 smem4[];
+  float* smem = reinterpret_cast<float*>(smem4);
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, wbase = tid & ~31;
+  copy_f4(smem, reinterpret_cast<const float*>(a.chain), (a.chain_bytes + 15) / 16, tid, NT);
+  __syncthreads();
+  const DevChain* C = reinterpret_cast<const DevChain*>(smem);
+  const DevChainHdr& H = C->h;
+  const SmemPlan P = plan_grad(H, a.chain_bytes, NT, a.smem_grad);
+  float* wsm = smem + P.chain_f;
+  float* cols = wsm + P.w_f;
+  float* gsm = cols + P.cols_f;
+  const int CS = P.cs;
+  const int d = H.d, n = H.n, L = H.L;
+  const int hd = H.max_depth > 1 ? H.max_depth - 1 : 1;
+  const int hstride = H.hp * CS;
+  float* xs = cols;
+  float* gx = xs + d * CS;
+  float* th = gx + d * CS;
+  float* hc = th + n * CS;
+  float* dlc = hc + hd * hstride;
+  float* ob = dlc + H.hp * CS;    // s values
+  float* tb = ob + H.amax4 * CS;  // t values
+  float* eb = tb + H.amax4 * CS;  // exp(-s)
+  float* gb = eb + H.amax4 * CS;  // output cotangent
+
+  if (H.resident) copy_f4(wsm, a.staged, H.stage_total / 4, tid, NT);
+  if (a.smem_grad)
+    for (int i = tid; i < P.grad_f; i += NT) gsm[i] = 0.0f;
+  __syncthreads();
+  float* gacc = a.smem_grad ? gsm : nullptr;
+
+  const long long ntiles = (a.B + NT - 1) / NT;
+  float lsum_thread = 0.0f, nonfinite = 0.0f;
+  const int sl = tid;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long gi = tile * NT + tid;
+    const bool valid = gi < a.B;
+    const long long src = (valid && a.idx) ? (long long)a.idx[gi] : gi;
+    {
+      const float* xp = a.x_in + src * d;
+      for (int k = 0; k < d; ++k) xs[k * CS + sl] = valid ? __ldg(xp + k) : 0.0f;
+      for (int k = 0; k < n; ++k) {
+        float v = (valid && a.theta) ? __ldg(a.theta + src * n + k) : 0.0f;
+        if (a.flags & DFLOW_THETA_NORMALIZE) v = (H.theta_rng[k] == 0.0f) ? 0.0f : (v - H.theta_min[k]) / H.theta_rng[k];
+        th[k * CS + sl] = v;
+      }
+    }
+    // ---- forward (normalising) sweep: last element first ----
+    float ldj[1] = {0.0f};
+    for (int step = 0; step < L; ++step) {
+      const DevElem& E = C->e[L - 1 - step];
+      const float* wblk;
+      if (H.resident) {
+        wblk = wsm + E.stage_off;
+      } else {
+        __syncthreads();
+        copy_f4(wsm, a.staged + E.stage_off, E.stage_len / 4, tid, NT);
+        __syncthreads();
+        wblk = wsm;
+      }
+      elem_apply<HP, 1>(H, E, wblk, false, xs, th, hc, 0, ob, tb, CS, sl, NT, ldj);
+    }
+    // ---- loss and seeds: z̄ = z * inv_btot, j̄ = -inv_btot (src/Flows.jl:352-359) ----
+    float q = 0.0f;
+    for (int k = 0; k < d; ++k) {
+      const float v = xs[k * CS + sl];
+      q = fmaf(v, v, q);
+    }
+    const float lp = H.logpdf_c0 - 0.5f * q + ldj[0];
+    if (valid) {
+      if (isfinite(lp))
+        lsum_thread += lp;
+      else
+        nonfinite += 1.0f;
+    }
+    const float ib = valid ? a.inv_btot : 0.0f;
+    for (int k = 0; k < d; ++k) gx[k * CS + sl] = xs[k * CS + sl] * ib;
+    const float jb = -ib;
+
+    // ---- reverse sweep in chain order ----
+    for (int ei = 0; ei < L; ++ei) {
+      const DevElem& E = C->e[ei];
+      const float* wblk;
+      if (H.resident) {
+        wblk = wsm + E.stage_off;
+      } else {
+        __syncthreads();
+        copy_f4(wsm, a.staged + E.stage_off, E.stage_len / 4, tid, NT);
+        __syncthreads();
+        wblk = wsm;
+      }
+      if (E.kind == DFLOW_ELEM_NORM) {
+        const float alpha = wblk[2 * d], beta = wblk[2 * d + 1];
+        for (int k = 0; k < d; ++k) {
+          const float xmin = wblk[k], xmax = wblk[d + k];
+          gx[k * CS + sl] *= (beta - alpha) / (xmax - xmin);
+          const float v = xs[k * CS + sl];
+          xs[k * CS + sl] = ((xmax - xmin) * v - alpha * xmax + beta * xmin) / (beta - alpha);
+        }
+        continue;
+      }
+      const bool rnvp = (E.kind == DFLOW_ELEM_RNVP);
+      InSel in{th, xs, hc, E.id, n, CS, true};
+      const int a4 = H.amax4;
+      if (!rnvp)
+        for (int j = 0; j < a4; ++j) eb[j * CS + sl] = 1.0f;
+      for (int ni = rnvp ? 0 : 1; ni < 2; ++ni) {
+        const DevNet& net = ni == 0 ? E.s : E.t;
+        float* outc = ni == 0 ? ob : tb;
+        run_net<HP, 1>(net, wblk, in, hc, hstride, outc, CS, sl, NT);  // recompute, keep hidden activations
+        for (int j = 0; j < a4; ++j) {
+          float gout = 0.0f;
+          if (j < E.a) {
+            const int k = E.af[j];
+            if (ni == 0) {
+              const float em = expf(-ob[j * CS + sl]);
+              eb[j * CS + sl] = em;
+              gout = -gx[k * CS + sl] * xs[k * CS + sl] - jb;  // s̄, RNVP.jl:134 with z_af = (u_af - t) exp(-s)
+            } else {
+              gout = -gx[k * CS + sl] * eb[j * CS + sl];  // t̄, RNVP.jl:135
+            }
+          } else if (ni == 0) {
+            eb[j * CS + sl] = 1.0f;
+          }
+          gb[j * CS + sl] = gout;
+        }
+        net_backward<HP>(H, E, net, wblk, xs, gx, th, hc, hstride, dlc, gb, outc, gacc, a.grad_out, CS, sl, wbase,
+                         lane);
+      }
+      // reconstruct the layer input and finish ū (RNVP.jl:137-139)
+      for (int j = 0; j < E.a; ++j) {
+        const int k = E.af[j];
+        const float sv = rnvp ? ob[j * CS + sl] : 0.0f;
+        xs[k * CS + sl] = xs[k * CS + sl] * expf(sv) + tb[j * CS + sl];
+        gx[k * CS + sl] *= eb[j * CS + sl];
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- flush ----
+  __syncthreads();
+  if (a.smem_grad)
+    for (int i = tid; i < H.P; i += NT) {
+      const float v = gsm[i];
+      if (v != 0.0f) atomicAdd(a.grad_out + i, v);
+    }
+  float v0 = lsum_thread, v1 = nonfinite;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+  }
+  float* red = cols;
+  if (lane == 0) {
+    red[(tid >> 5) * 2] = v0;
+    red[(tid >> 5) * 2 + 1] = v1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float t0 = 0.0f, t1 = 0.0f;
+    for (int w = 0; w < (NT + 31) / 32; ++w) {
+      t0 += red[2 * w];
+      t1 += red[2 * w + 1];
+    }
+    atomicAdd(a.loss_out, t0);
+    if (t1 != 0.0f) atomicAdd(a.loss_out + 1, t1);
+  }
+}
+
+// per-instantiation launch shims (defined in the inst_*.cu units)
+template <int HP, int S>
+cudaError_t launch_fwd_inst(const FwdArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st);
+template <int HP>
+cudaError_t launch_grad_inst(const GradArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st);
+
+}  // namespace dflow

@@ -1,0 +1,141 @@
+// Internal structures shared by the host API (dflow_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dflow.h"
+
+namespace dflow {
+
+constexpr int DMAX = 64;       // data dimensions handled by the narrow (CUDA-core) path
+constexpr int NMAX = 32;       // conditions
+constexpr int MAX_DENSE = 6;   // Dense layers per conditioner
+constexpr int LMAX = 64;       // leaf elements per chain
+constexpr int HP_MAX = 64;     // widest hidden layer of the narrow path
+
+// One conditioner MLP.  Widths are the true Flux widths; `op` is the padded row stride of the staged image.
+struct DevNet {
+  int depth;
+  int has_bias;
+  int w[MAX_DENSE + 1];
+  int act[MAX_DENSE];
+  int op[MAX_DENSE];   // padded output width of dense j in the staged image (multiple of 4)
+  int p_w[MAX_DENSE];  // offsets into the packed parameter / gradient buffer
+  int p_b[MAX_DENSE];  // -1 when no bias
+  int s_w[MAX_DENSE];  // offsets (floats) into the element's staged block: W as [in][op]
+  int s_b[MAX_DENSE];  // offsets (floats) of the padded bias [op] (zeros when no bias)
+};
+
+struct DevElem {
+  int kind;
+  int a;          // |axis_af|
+  int nid;        // |axis_id| = d - a
+  int nin;        // conditioner input width = n + nid
+  int stage_off;  // offset (floats, multiple of 4) of this element's block in the staged image
+  int stage_len;  // floats, multiple of 4
+  unsigned char af[DMAX];  // 0-based, caller order (src/Axes.jl:91)
+  unsigned char id[DMAX];  // 0-based ascending complement (src/Axes.jl:88)
+  DevNet s, t;
+  // NORM elements keep [x_min(d) | x_max(d) | alpha, beta, ldj_const, 0] in their staged block.
+};
+
+struct DevChainHdr {
+  int d, n, L;
+  int hp;            // padded hidden width template (8/16/32/64)
+  int P;             // parameter count
+  int stage_total;   // floats
+  int stage_max;     // largest element block (floats)
+  int resident;      // 1: whole staged image kept in shared memory
+  int amax4;         // max padded output width
+  int max_depth;
+  int has_theta_range;
+  float logpdf_c0;   // -(d*log(2pi))/2
+  float theta_min[NMAX];
+  float theta_inv[NMAX];  // 1/(max-min), 0 for a zero range (src/Data.jl:213-218)
+  float theta_rng[NMAX];  // max - min
+};
+
+struct DevChain {
+  DevChainHdr h;
+  DevElem e[1];  // L entries
+};
+
+enum FwdMode {
+  MODE_NORMALIZE = 0,   // x -> z, ldj
+  MODE_LOGPDF = 1,      // x -> logp
+  MODE_LOGPDF_SUM = 2,  // x -> sum logp (+ non-finite count)
+  MODE_SAMPLE = 3,      // z -> x (in place or out of place), no ldj
+  MODE_FORWARD_LDJ = 4, // z -> x, ldj
+  MODE_SAMPLE_RNG = 5   // philox -> x
+};
+
+struct FwdArgs {
+  const DevChain* chain;   // device
+  const float* staged;     // device, padded weight image
+  const float* x_in;
+  const float* theta;       // (n,B) or null
+  const float* theta_const; // n floats or null
+  const int32_t* idx;
+  float* x_out;
+  float* aux_out;  // ldj / logp / loss[2]
+  long long B;
+  int mode;
+  int flags;
+  int chain_bytes;
+  unsigned long long seed;
+  unsigned int rng_offset;
+  unsigned long long first_sample;
+};
+
+struct GradArgs {
+  const DevChain* chain;
+  const float* staged;
+  const float* x_in;
+  const float* theta;
+  const int32_t* idx;
+  float* loss_out;  // [2]
+  float* grad_out;  // [P] (or copies in ws)
+  long long B;
+  float inv_btot;
+  int flags;
+  int chain_bytes;
+  int smem_grad;  // 1: accumulate the whole gradient in shared memory, flush once per CTA
+};
+
+struct PrepackArgs {
+  const DevChain* chain;
+  const float* W;
+  float* staged;
+};
+
+}  // namespace dflow
+
+struct dflow_chain {
+  int device = 0;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  std::vector<unsigned char> host_chain;  // DevChain image
+  dflow::DevChain* d_chain = nullptr;
+  float* d_staged = nullptr;
+  int chain_bytes = 0;
+  // tuning
+  int fwd_spt = 0, fwd_threads = 0, grad_threads = 0, ctas_per_sm = 0;
+  long long launches = 0;
+  // host pipeline scratch (dflow_*_host)
+  void* pipe = nullptr;
+  const dflow::DevChain* hc() const { return reinterpret_cast<const dflow::DevChain*>(host_chain.data()); }
+  dflow::DevChain* hc() { return reinterpret_cast<dflow::DevChain*>(host_chain.data()); }
+};
+
+namespace dflow {
+void set_error(const char* fmt, ...);
+int launch_prepack(dflow_chain* c, const float* W, cudaStream_t st);
+int launch_fwd(dflow_chain* c, FwdArgs& a, cudaStream_t st);
+int launch_grad(dflow_chain* c, GradArgs& a, cudaStream_t st);
+int launch_adam(float* W, const float* g, float* m, float* v, long long P, float lr, float b1, float b2, float eps,
+                long long t, cudaStream_t st);
+int launch_minmax(const float* x, int rows, long long B, float* mn, float* mx, cudaStream_t st);
+}  // namespace dflow

@@ -1,0 +1,265 @@
+// Launchers and small kernels (prepack, Adam, min/max) of the narrow path; the chain kernels themselves are
+// instantiated one (HP, S) pair per translation unit (dflow_inst.cu) so that they build in parallel.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+
+#include "dflow_chain_kernels.cuh"
+
+namespace dflow {
+
+// ------------------------------------------------------------------------------------------------------------
+// prepack: packed Flux parameters -> padded staged image ([in][out4] per Dense, zero padded)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void prepack_kernel(const PrepackArgs a) {
+  const DevChain* C = a.chain;
+  const DevElem& E = C->e[blockIdx.x];
+  if (E.kind == DFLOW_ELEM_NORM) return;
+  float* blk = a.staged + E.stage_off;
+  for (int ni = 0; ni < 2; ++ni) {
+    const DevNet& net = ni == 0 ? E.s : E.t;
+    for (int j = 0; j < net.depth; ++j) {
+      const int K = net.w[j], O = net.w[j + 1], op = net.op[j];
+      for (int i = threadIdx.x; i < K * op; i += blockDim.x) {
+        const int k = i / op, o = i - k * op;
+        blk[net.s_w[j] + i] = (o < O) ? a.W[net.p_w[j] + o + O * k] : 0.0f;
+      }
+      for (int o = threadIdx.x; o < op; o += blockDim.x)
+        blk[net.s_b[j] + o] = (net.has_bias && o < O) ? a.W[net.p_b[j] + o] : 0.0f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4: Optimisers.Adam (call site src/Flows.jl:415)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ W, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long P, float lr, float b1, float b2, float eps, float c1,
+                            float c2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * (gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    W[i] -= mi / c1 / (sqrtf(vi / c2) + eps) * lr;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: per-row min / max
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+  if (v >= 0.0f)
+    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+  if (v >= 0.0f)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void minmax_init_kernel(float* mn, float* mx, int rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) {
+    mn[i] = INFINITY;
+    mx[i] = -INFINITY;
+  }
+}
+
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x, int rows, long long B, float* mn,
+                                                     float* mx) {
+  extern __shared__ float4 smem4[];
+  float* smin = reinterpret_cast<float*>(smem4);
+  float* smax = smin + rows * 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  // one warp per strip of samples; lane keeps per-row running values in shared memory [row][lane] of warp 0's
+  // layout, reduced at the end.  Elements are read flat (coalesced).
+  for (int i = tid; i < rows * 32; i += blockDim.x) {
+    smin[i] = INFINITY;
+    smax[i] = -INFINITY;
+  }
+  __syncthreads();
+  const long long total = B * rows;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long e = blockIdx.x * (long long)blockDim.x + tid;
+  int row = (int)(e % rows);
+  const int rstep = (int)(stride % rows);
+  (void)warp;
+  (void)nw;
+  for (; e < total; e += stride) {
+    const float v = __ldg(x + e) + 0.0f;  // -0.0 -> +0.0 (keeps the integer-ordered atomics exact)
+    // shared atomics keep this simple; the kernel is a set-up time reduction, HBM-bound
+    atomic_min_f(&smin[row * 32 + lane], v);
+    atomic_max_f(&smax[row * 32 + lane], v);
+    row += rstep;
+    if (row >= rows) row -= rows;
+  }
+  __syncthreads();
+  for (int r = tid; r < rows; r += blockDim.x) {
+    float a = INFINITY, b = -INFINITY;
+    for (int l = 0; l < 32; ++l) {
+      a = fminf(a, smin[r * 32 + l]);
+      b = fmaxf(b, smax[r * 32 + l]);
+    }
+    atomic_min_f(mn + r, a);
+    atomic_max_f(mx + r, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------------------
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DFLOW_E_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+int launch_prepack(dflow_chain* c, const float* W, cudaStream_t st) {
+  PrepackArgs pa{c->d_chain, W, c->d_staged};
+  prepack_kernel<<<c->hc()->h.L, 256, 0, st>>>(pa);
+  CK(cudaGetLastError());
+  c->launches++;
+  return DFLOW_OK;
+}
+
+template <int HP, int S>
+static int launch_fwd_t(dflow_chain* c, FwdArgs& a, cudaStream_t st, int nt) {
+  const DevChainHdr& h = c->hc()->h;
+  SmemPlan p = plan_fwd(h, c->chain_bytes, nt * S);
+  while (p.bytes() > (size_t)c->max_smem_optin && nt > 32) {
+    nt >>= 1;
+    p = plan_fwd(h, c->chain_bytes, nt * S);
+  }
+  if (p.bytes() > (size_t)c->max_smem_optin) {
+    set_error("chain needs %zu bytes of shared memory (> %d)", p.bytes(), c->max_smem_optin);
+    return DFLOW_E_UNSUPPORTED;
+  }
+  const long long ntiles = (a.B + (long long)nt * S - 1) / ((long long)nt * S);
+  int per_sm = c->ctas_per_sm;
+  if (per_sm <= 0) {
+    per_sm = (int)((size_t)c->max_smem_optin / (p.bytes() + 1024));
+    const int by_threads = 2048 / nt;
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+  }
+  long long grid = (long long)c->sm_count * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  CK((launch_fwd_inst<HP, S>(a, (unsigned)grid, nt, p.bytes(), st)));
+  c->launches++;
+  return DFLOW_OK;
+}
+
+int launch_fwd(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
+  const DevChainHdr& h = c->hc()->h;
+  a.chain = c->d_chain;
+  a.staged = c->d_staged;
+  a.chain_bytes = c->chain_bytes;
+  int spt = c->fwd_spt;
+  int nt = c->fwd_threads > 0 ? c->fwd_threads : (h.hp >= 64 ? 128 : 256);
+  if (nt > 256) nt = 256;
+  nt = (nt + 31) & ~31;
+  if (spt <= 0) spt = (h.hp >= 64) ? 1 : 2;
+  switch (h.hp) {
+    case 16:
+      if (spt >= 4) return launch_fwd_t<16, 4>(c, a, st, nt);
+      if (spt == 2) return launch_fwd_t<16, 2>(c, a, st, nt);
+      return launch_fwd_t<16, 1>(c, a, st, nt);
+    case 32:
+      if (spt >= 2) return launch_fwd_t<32, 2>(c, a, st, nt);
+      return launch_fwd_t<32, 1>(c, a, st, nt);
+    case 64:
+      return launch_fwd_t<64, 1>(c, a, st, nt);
+  }
+  set_error("hidden width template %d not built", h.hp);
+  return DFLOW_E_UNSUPPORTED;
+}
+
+template <int HP>
+static int launch_grad_t(dflow_chain* c, GradArgs& a, cudaStream_t st, int nt) {
+  const DevChainHdr& h = c->hc()->h;
+  a.smem_grad = (h.P * 4 <= 64 * 1024) ? 1 : 0;
+  SmemPlan p = plan_grad(h, c->chain_bytes, nt, a.smem_grad);
+  while (p.bytes() > (size_t)c->max_smem_optin && nt > 32) {
+    nt >>= 1;
+    p = plan_grad(h, c->chain_bytes, nt, a.smem_grad);
+  }
+  if (p.bytes() > (size_t)c->max_smem_optin) {
+    set_error("adjoint needs %zu bytes of shared memory (> %d)", p.bytes(), c->max_smem_optin);
+    return DFLOW_E_UNSUPPORTED;
+  }
+  const long long ntiles = (a.B + nt - 1) / nt;
+  int per_sm = c->ctas_per_sm;
+  if (per_sm <= 0) {
+    per_sm = (int)((size_t)c->max_smem_optin / (p.bytes() + 1024));
+    const int by_threads = 2048 / nt;
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+  }
+  long long grid = (long long)c->sm_count * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  CK(launch_grad_inst<HP>(a, (unsigned)grid, nt, p.bytes(), st));
+  c->launches++;
+  return DFLOW_OK;
+}
+
+int launch_grad(dflow_chain* c, GradArgs& a, cudaStream_t st) {
+  const DevChainHdr& h = c->hc()->h;
+  a.chain = c->d_chain;
+  a.staged = c->d_staged;
+  a.chain_bytes = c->chain_bytes;
+  int nt = c->grad_threads > 0 ? c->grad_threads : (h.hp >= 64 ? 128 : 256);
+  if (nt > 256) nt = 256;
+  nt = (nt + 31) & ~31;
+  switch (h.hp) {
+    case 16: return launch_grad_t<16>(c, a, st, nt);
+    case 32: return launch_grad_t<32>(c, a, st, nt);
+    case 64: return launch_grad_t<64>(c, a, st, nt);
+  }
+  set_error("hidden width template %d not built", h.hp);
+  return DFLOW_E_UNSUPPORTED;
+}
+
+int launch_adam(float* W, const float* g, float* m, float* v, long long P, float lr, float b1, float b2, float eps,
+                long long t, cudaStream_t st) {
+  if (P <= 0) return DFLOW_OK;
+  // bias corrections in Float32 like Optimisers.jl (βt is a Float32 running product)
+  float b1t = 1.0f, b2t = 1.0f;
+  for (long long i = 0; i < t; ++i) {
+    b1t *= b1;
+    b2t *= b2;
+  }
+  const float c1 = 1.0f - b1t, c2 = 1.0f - b2t;
+  long long blocks = (P + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(W, g, m, v, P, lr, b1, b2, eps, c1, c2);
+  CK(cudaGetLastError());
+  return DFLOW_OK;
+}
+
+int launch_minmax(const float* x, int rows, long long B, float* mn, float* mx, cudaStream_t st) {
+  minmax_init_kernel<<<(rows + 127) / 128, 128, 0, st>>>(mn, mx, rows);
+  CK(cudaGetLastError());
+  if (B <= 0) return DFLOW_OK;
+  const long long total = B * rows;
+  long long blocks = (total + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = (size_t)rows * 32 * 2 * sizeof(float);
+  minmax_kernel<<<(unsigned)blocks, 256, smem, st>>>(x, rows, B, mn, mx);
+  CK(cudaGetLastError());
+  return DFLOW_OK;
+}
+
+}  // namespace dflow

@@ -1,0 +1,306 @@
+"""Flow / train! / sample / logpdf -- mirror of src/Flows.jl, running on libdflow.so.
+
+`train_` (= `train!`) keeps the dataset resident on the GPU, gathers each minibatch inside the adjoint kernel
+through an index vector, runs the Adam update as a kernel and -- when torch.distributed is initialised (one process
+per GPU) -- shards every minibatch across ranks and all-reduces the packed gradient (+ loss) with NCCL.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .arrays import jl_empty, n_samples, to_jl
+from .data import DataArrays, MetaData, maximum_θ, minimum_θ, number_conditions, number_dimensions
+from .model import FlowChain, PackedChain, _gen
+
+# ------------------------------------------------------------------------------------------------------------
+# Optimisers.jl mirror (only what train! uses: Optimisers.setup(Optimisers.Adam(η), flow.model))
+# ------------------------------------------------------------------------------------------------------------
+
+
+class Adam:
+    """Optimisers.Adam(η=1f-3, β=(0.9, 0.999), ϵ=1e-8)."""
+
+    def __init__(self, η: float = 1e-3, β: Tuple[float, float] = (0.9, 0.999), ϵ: float = 1e-8):
+        self.eta, self.beta, self.epsilon = float(η), (float(β[0]), float(β[1])), float(ϵ)
+
+
+class OptimiserState:
+    """What Optimisers.setup returns for a FlowChain: first/second moment buffers in the packed layout + step."""
+
+    def __init__(self, rule: Adam, model: FlowChain):
+        self.rule, self.model = rule, model
+        self.m: Optional[torch.Tensor] = None
+        self.v: Optional[torch.Tensor] = None
+        self.t = 0
+
+    def _ensure(self, pc: PackedChain):
+        if self.m is None or self.m.device != pc.device or self.m.numel() != max(pc.P, 1):
+            self.m = torch.zeros(max(pc.P, 1), device=pc.device, dtype=torch.float32)
+            self.v = torch.zeros_like(self.m)
+
+
+def setup(rule: Adam, model: FlowChain) -> OptimiserState:
+    """Optimisers.setup(rule, flow.model) (test/runtests.jl:113)."""
+    return OptimiserState(rule, model)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Flow
+# ------------------------------------------------------------------------------------------------------------
+
+
+class Flow:
+    """Flow([base,] model, data), src/Flows.jl:37-122.  The base distribution is MvNormal(0, I_d)
+    (src/Flows.jl:114); other bases are not on the fused path."""
+
+    def __init__(self, model: FlowChain, data: DataArrays, train_loss: Optional[List[float]] = None,
+                 valid_loss: Optional[List[float]] = None, base: Optional[str] = None):
+        if base not in (None, "MvNormal"):
+            raise NotImplementedError("only the default MvNormal(0, I) base distribution is fused")
+        if not isinstance(model, FlowChain):
+            raise TypeError("model must be a FlowChain")
+        self.model = model
+        self.base = "MvNormal"
+        d, n = number_dimensions(data), number_conditions(data)
+        self.metadata = MetaData("", d, n, minimum_θ(data), maximum_θ(data))
+        self.train_loss: List[float] = [] if train_loss is None else train_loss
+        self.valid_loss: List[float] = [] if valid_loss is None else valid_loss
+        self.device = data.x.device
+        self._packed: Optional[PackedChain] = None
+
+    d = property(lambda self: self.metadata.d)
+    n = property(lambda self: self.metadata.n)
+
+    def packed(self) -> PackedChain:
+        if self._packed is None:
+            pc = PackedChain(self.model._leaves(), self.device if self.device.type == "cuda" else None,
+                             self.metadata.θ_min if self.n > 0 else None, self.metadata.θ_max if self.n > 0 else None)
+            if (pc.d, pc.n) != (self.d, self.n):
+                raise ValueError(f"model is built for (d,n)=({pc.d},{pc.n}) but the data has ({self.d},{self.n})")
+            self._packed = pc
+            self.model._packed = pc
+        self._packed.refresh()
+        return self._packed
+
+    def __call__(self, z, θ=None):  # @auto_functor Flow
+        from .model import forward
+
+        return forward(self, z, θ)
+
+    def summarize(self) -> str:
+        return "- model --------------------\n" + self.model.summarize() + "\n- base distribution --------\nMvNormal"
+
+
+def training_loss(flow: Flow) -> List[float]:
+    return flow.train_loss
+
+
+def validation_loss(flow: Flow) -> List[float]:
+    return flow.valid_loss
+
+
+def predict(flow: Flow, z, θ=None):
+    """predict(flow, z, θ) = forward(flow, z, θ)[1] (src/Flows.jl:126)."""
+    from .model import forward
+
+    return forward(flow, z, θ)[0]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# sample -- src/Flows.jl:157-192
+# ------------------------------------------------------------------------------------------------------------
+
+
+def _dims_tuple(dims) -> Tuple[int, ...]:
+    return (int(dims),) if isinstance(dims, (int, np.integer)) else tuple(int(v) for v in dims)
+
+
+def sample(*args):
+    """sample([rng,] flow, dims[, θ]).
+
+    dims: Integer or tuple.  θ: array of size (n, dims...) (one condition per point) or an n-tuple (same condition
+    for every point, src/Flows.jl:174-185).  The base draw r ~ N(0, I) happens inside the kernel (Philox4x32-10,
+    counter = sample index), replacing rand(rng, flow.base, prod(dims)) + forward!; `rng` may be an int seed or a
+    torch.Generator (a seed is drawn from it)."""
+    args = list(args)
+    rng = None
+    if not isinstance(args[0], Flow):
+        rng = args.pop(0)
+    flow, dims = args[0], _dims_tuple(args[1])
+    θ = args[2] if len(args) > 2 else None
+    pc = flow.packed()
+    if isinstance(rng, (int, np.integer)):
+        seed_ = int(rng)
+    else:
+        seed_ = int(torch.randint(0, 2**62, (1,), generator=rng or _gen()).item())
+    B = int(np.prod(dims)) if dims else 1
+    out = jl_empty((flow.d,) + dims, pc.device)
+    flags = L.THETA_NORMALIZE if flow.n > 0 else 0
+    if isinstance(θ, tuple):
+        if len(θ) != flow.n:
+            raise ValueError(f"θ must be an NTuple of length n={flow.n}")
+        θc = torch.tensor([float(v) for v in θ], device=pc.device, dtype=torch.float32) if flow.n > 0 else None
+        pc.sample_rng(B, seed_, None, θc, flags, out=out)
+    else:
+        if θ is None:
+            if flow.n != 0:
+                raise ValueError("dimensions θ must match (n, dims...) with n number of trained parameters")
+        else:
+            θ = to_jl(θ, pc.device)
+            # @assert K == M+1, src/Flows.jl:165
+            assert θ.dim() == len(dims) + 1 and tuple(θ.shape[1:]) == dims and int(θ.shape[0]) == flow.n, \
+                "dimensions θ must match (n, dims...) with n number of trained parameters"
+        pc.sample_rng(B, seed_, θ if flow.n > 0 else None, None, flags, out=out)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# logpdf / pdf -- src/Flows.jl:272-349
+# ------------------------------------------------------------------------------------------------------------
+
+
+def _θ_broadcast(flow: Flow, θ: tuple, tail: Tuple[int, ...], device) -> Optional[torch.Tensor]:
+    if flow.n == 0:
+        return None
+    col = torch.tensor([float(v) for v in θ], device=device, dtype=torch.float32)
+    B = int(np.prod(tail)) if tail else 1
+    return to_jl(col.reshape(-1, 1).expand(flow.n, B).reshape((flow.n,) + tuple(tail)), device)
+
+
+def logpdf(flow: Flow, x, θ=None):
+    """logpdf(flow, x[, θ]): x of size (d, dims...) with θ an array (n, dims...) or an n-tuple, or x a tuple of d
+    vectors -> values on the tensor-product grid (src/Flows.jl:272-331)."""
+    pc = flow.packed()
+    flags = L.THETA_NORMALIZE if flow.n > 0 else 0
+    if isinstance(x, (tuple, list)) and not isinstance(x, torch.Tensor):
+        if len(x) != flow.d:
+            raise ValueError(f"grid logpdf needs {flow.d} coordinate vectors")
+        vs = [torch.as_tensor(np.asarray(v, np.float32) if not isinstance(v, torch.Tensor) else v, dtype=torch.float32,
+                              device=pc.device).reshape(-1) for v in x]
+        lens = tuple(int(v.numel()) for v in vs)
+        # Iterators.product(x...): first vector varies fastest == Julia column-major grid (src/Flows.jl:301)
+        grids = torch.meshgrid(*vs, indexing="ij")
+        y = jl_empty((flow.d,) + lens, pc.device)
+        for k, g in enumerate(grids):
+            y[k] = g
+        θa = _θ_broadcast(flow, tuple(θ) if θ is not None else (), lens, pc.device)
+        return pc.logpdf(y, θa, flags)
+    x = to_jl(x, pc.device)
+    if isinstance(θ, tuple):
+        θ = _θ_broadcast(flow, θ, tuple(x.shape[1:]), pc.device)
+    return pc.logpdf(x, θ, flags)
+
+
+def pdf(flow: Flow, x, θ=None):
+    """pdf = exp.(logpdf) (src/Flows.jl:345-349)."""
+    return torch.exp(logpdf(flow, x, θ))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# train! -- src/Flows.jl:380-445
+# ------------------------------------------------------------------------------------------------------------
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+
+
+class TrainStep:
+    """One data-parallel minibatch step on resident data: adjoint kernel on this rank's slice of the index list
+    (seed 1/B_global), NCCL all-reduce(sum) of [grad | Σlogp | #nonfinite], Adam kernel on every replica."""
+
+    def __init__(self, pc: PackedChain, state: OptimiserState):
+        self.pc, self.state = pc, state
+        state._ensure(pc)
+        self.buf = torch.zeros(max(pc.P, 1) + 2, device=pc.device, dtype=torch.float32)  # grad | loss2
+        self.grad = self.buf[: max(pc.P, 1)]
+        self.loss2 = self.buf[max(pc.P, 1):]
+
+    def __call__(self, x, θ, idx: Optional[torch.Tensor], B_global: int, flags: int = 0) -> None:
+        pc, st = self.pc, self.state
+        self.buf.zero_()
+        nb = n_samples(x) if idx is None else int(idx.numel())
+        if nb > 0:
+            pc.loss_grad(x, θ, self.grad, self.loss2, 1.0 / B_global, flags, idx)
+        d = _dist()
+        if d is not None:
+            d.all_reduce(self.buf)
+        st.t += 1
+        r = st.rule
+        pc.adam_step(self.grad, st.m, st.v, st.t, r.eta, r.beta, r.epsilon)
+
+
+def _full_loss(pc: PackedChain, x, θ, idx: torch.Tensor, n_global: int, flags: int, tmp: torch.Tensor) -> float:
+    """loss = -mean(logpdf(base, z) + ldj) over a whole partition (src/Flows.jl:419-430), sharded over ranks."""
+    tmp.zero_()
+    if idx.numel() > 0:
+        pc.logpdf_sum(x, θ, tmp, flags, idx)
+    d = _dist()
+    if d is not None:
+        d.all_reduce(tmp)
+    s, bad = tmp.tolist()
+    return float("nan") if bad > 0 else -s / max(n_global, 1)
+
+
+def train_(flow: Flow, data: DataArrays, optimiser_state: OptimiserState, epochs: int = 100, batchsize: int = 64,
+           shuffle: bool = True, verbose: bool = True, debug: bool = False, rng: Optional[torch.Generator] = None):
+    """train!(flow, data, state; epochs=100, batchsize=64, shuffle=true, verbose=true, debug=false),
+    src/Flows.jl:380-445.  Per epoch: reshuffled minibatches (partial last batch kept, like Flux.DataLoader),
+    gradient + Adam per batch, then the full-set training and validation losses are pushed to the flow."""
+    pc = flow.packed()
+    flags = L.THETA_NORMALIZE if flow.n > 0 else 0  # θ is normalised in-kernel (src/Data.jl:189-199)
+    x = to_jl(data.x, pc.device)
+    θ = to_jl(data.θ, pc.device) if flow.n > 0 else None
+    if x.dim() != 2:
+        raise NotImplementedError("train! partitions along dim 2; only (d, N) arrays are supported (src/Data.jl:167)")
+    tr = data.partition.training.to(pc.device)
+    va = data.partition.validation.to(pc.device)
+    step = TrainStep(pc, optimiser_state)
+    d = _dist()
+    rank, world = (d.get_rank(), d.get_world_size()) if d is not None else (0, 1)
+    n_tr, n_va = int(tr.numel()), int(va.numel())
+    gen = rng or _gen()
+    tmp = torch.zeros(2, device=pc.device, dtype=torch.float32)
+
+    def shard(v: torch.Tensor) -> torch.Tensor:
+        if world == 1:
+            return v
+        per = (v.numel() + world - 1) // world
+        return v[rank * per: min((rank + 1) * per, v.numel())]
+
+    for _ in range(epochs):
+        if shuffle:
+            # every rank draws the same permutation (same generator state) -> global shuffle, per-rank slices
+            perm = torch.randperm(n_tr, generator=gen).to(pc.device)
+            order = tr[perm]
+        else:
+            order = tr
+        for b0 in range(0, n_tr, batchsize):
+            batch = order[b0: b0 + batchsize]
+            step(x, θ, shard(batch), int(batch.numel()), flags)
+            if debug:
+                s, bad = step.loss2.tolist()
+                if bad > 0 or not math.isfinite(s):
+                    raise ValueError(f"non-finite minibatch loss (Σlogp={s}, non-finite samples={bad})")  # Flows.jl:405-409
+        train_loss = _full_loss(pc, x, θ, shard(tr), n_tr, flags, tmp)
+        flow.train_loss.append(train_loss)
+        if debug and not math.isfinite(train_loss):
+            print(f"Problem with train loss {train_loss}")
+            return pc.normalize(x.index_select(1, tr.long()), None if θ is None else θ.index_select(1, tr.long()), flags)
+        valid_loss = _full_loss(pc, x, θ, shard(va), n_va, flags, tmp)
+        flow.valid_loss.append(valid_loss)
+        if debug and not math.isfinite(valid_loss):
+            print(f"Problem with valid loss {valid_loss}")
+            return pc.normalize(x.index_select(1, va.long()), None if θ is None else θ.index_select(1, va.long()), flags)
+        if verbose and rank == 0:
+            print(f"epoch: {len(flow.train_loss)} | train_loss = {train_loss}, valid_loss = {valid_loss}")
+    if debug:
+        return None, None
+    return None

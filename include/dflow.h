@@ -1,0 +1,164 @@
+/* dflow.h -- C ABI of libdflow.so: B200 (sm_100a) kernels for the DensityFlows.jl coupling-chain hot path.
+ *
+ * The reference (pure Julia, /root/reference) has no FFI: its extension point is the FlowElement method
+ * protocol `backward / forward / forward!(elem, array, θ) -> (array, ln_det_jac)` (src/Chains.jl:33-72,
+ * docs/src/documentation.md:170-197).  This header is the boundary a Julia `ccall` layer binds
+ * (julia/DensityFlowsB200.jl); every entry point cites the reference function it replaces.
+ *
+ * Conventions
+ *  - All arrays are Float32, Julia column-major `(rows, B)` => sample-contiguous: element (k,b) at ptr[k + rows*b].
+ *  - Index vectors are int32, 0-based (Julia side subtracts 1).
+ *  - Data / weight / gradient / workspace buffers are DEVICE pointers owned by the caller unless the name ends
+ *    in `_host`.  The library owns only the opaque handles.  Compute calls are asynchronous on `stream`
+ *    (a cudaStream_t passed as void*); one stream at a time per chain handle.
+ *  - Every function returns 0 on success or a negative DFLOW_E_* code; the message is in dflow_last_error()
+ *    (thread-local).  Nothing throws or aborts across the ABI.  There is no CPU fallback.
+ *  - Packed parameter buffer (length dflow_param_count): chain order; per coupling layer s_net then t_net
+ *    (Flux.@layer trainable=(s_net,t_net), src/affine/RNVP.jl:51); per Dense `vec(weight)` (Flux (out,in)
+ *    column-major: W[o + out*i]) then `bias`.  Gradients use the identical layout.
+ */
+#ifndef DFLOW_H
+#define DFLOW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFLOW_VERSION 100 /* 0.1.0 */
+
+enum {
+  DFLOW_OK = 0,
+  DFLOW_E_INVALID_ARG = -1,
+  DFLOW_E_UNSUPPORTED = -2,
+  DFLOW_E_CUDA = -3,
+  DFLOW_E_NCCL = -4,
+  DFLOW_E_NOMEM = -5
+};
+
+/* element kinds: RNVPCouplingLayer (src/affine/RNVP.jl:41), NICECouplingLayer (src/affine/NICE.jl),
+ * NormalizationLayer (src/norm/Normalization.jl:30).  CouplingBlock / nested FlowChain are flattened by the host
+ * into chain order (block -> layer_1, layer_2; src/Blocks.jl:127-161). */
+enum { DFLOW_ELEM_RNVP = 0, DFLOW_ELEM_NICE = 1, DFLOW_ELEM_NORM = 2 };
+
+/* Dense activations (Flux.relu default, src/Layers.jl:37) */
+enum { DFLOW_ACT_IDENTITY = 0, DFLOW_ACT_RELU = 1, DFLOW_ACT_TANH = 2, DFLOW_ACT_SIGMOID = 3 };
+
+/* per-call flags */
+enum {
+  DFLOW_THETA_NORMALIZE = 1 /* apply normalize_input(θ, θ_min, θ_max) (src/Data.jl:213-218, src/Macros.jl:104-112) */
+};
+
+/* A conditioner MLP = Flux.Chain of Dense (src/Layers.jl:33-50). */
+typedef struct dflow_net_desc {
+  int32_t depth;         /* number of Dense layers (n_sublayers + 1); 0 = net absent */
+  const int32_t* widths; /* depth+1 entries: in, ..., out */
+  const int32_t* acts;   /* depth entries, DFLOW_ACT_* */
+  int32_t has_bias;
+} dflow_net_desc;
+
+typedef struct dflow_elem_desc {
+  int32_t kind;           /* DFLOW_ELEM_* */
+  int32_t n_af;           /* |axis_af| (coupling layers) */
+  const int32_t* axis_af; /* 0-based transformed dims in CALLER ORDER (src/Axes.jl:91); axis_id / axis_nn are derived */
+  dflow_net_desc s_net;   /* RNVP only */
+  dflow_net_desc t_net;   /* RNVP and NICE */
+  const float* x_min;     /* NORM only: host pointers, d entries (src/norm/Normalization.jl:51-57) */
+  const float* x_max;
+  float alpha, beta;
+} dflow_elem_desc;
+
+typedef struct dflow_chain_desc {
+  int32_t d;       /* data dimensions */
+  int32_t n;       /* conditions */
+  int32_t n_elems; /* leaf elements in chain order */
+  const dflow_elem_desc* elems;
+  const float* theta_min; /* host, n entries, or NULL (MetaData, src/Data.jl:75-86) */
+  const float* theta_max;
+} dflow_chain_desc;
+
+typedef struct dflow_chain dflow_chain; /* opaque */
+
+int dflow_version(void);
+const char* dflow_last_error(void);
+
+/* Build a chain handle on the CURRENT CUDA device (replaces constructing FlowChain / CouplingLayer / CouplingAxes:
+ * src/Chains.jl:99-101, src/Layers.jl:113-136, src/Axes.jl:79-102). */
+int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out);
+int dflow_chain_destroy(dflow_chain* chain);
+/* number of trainable Float32 parameters (= sum(length, Flux.trainables(chain))) */
+int64_t dflow_param_count(const dflow_chain* chain);
+/* Derived integer index vectors of coupling element `elem` (0-based): axis_id (ascending complement,
+ * src/Axes.jl:88) and axis_nn (rows of vcat(θ,x), src/Axes.jl:98).  Buffers must hold d and n+d ints. */
+int dflow_chain_axes(const dflow_chain* chain, int32_t elem, int32_t* axis_id, int32_t* n_id, int32_t* axis_nn,
+                     int32_t* n_nn);
+/* offset of Dense `dense` of net `net` (0 = s_net, 1 = t_net) of element `elem` inside the packed buffer;
+ * *b_off = -1 if the Dense has no bias. */
+int dflow_param_offset(const dflow_chain* chain, int32_t elem, int32_t net, int32_t dense, int64_t* w_off,
+                       int64_t* b_off);
+/* replace θ_min / θ_max (host pointers, n entries each) */
+int dflow_chain_set_theta_range(dflow_chain* chain, const float* theta_min, const float* theta_max);
+
+/* ---- normalising direction: backward(chain, x, θ) -> (z, ln_det_jac)  (src/Chains.jl:149-164) -------------- */
+int dflow_normalize(dflow_chain* chain, const float* W, const float* x, const float* theta, int64_t B, int32_t flags,
+                    float* z_out, float* ldj_out, void* stream);
+/* logpdf(flow, x, θ) = logpdf(MvNormal(0,I), z) + ln_det_jac (src/Flows.jl:272-281).  idx (device int32[B], may be
+ * NULL) gathers sample b from column idx[b] of x and θ (selectdim views of src/Data.jl:185-187 / DataLoader batches). */
+int dflow_logpdf(dflow_chain* chain, const float* W, const float* x, const float* theta, int64_t B, const int32_t* idx,
+                 int32_t flags, float* logp_out, void* stream);
+/* Σ_b logpdf_b accumulated into loss_out[0] (device float[2], caller zeroes it); loss_out[1] counts non-finite
+ * samples.  loss = -loss_out[0]/B (src/Flows.jl:352-359; epoch-end passes src/Flows.jl:419-430). */
+int dflow_logpdf_sum(dflow_chain* chain, const float* W, const float* x, const float* theta, int64_t B,
+                     const int32_t* idx, int32_t flags, float* loss_out, void* stream);
+
+/* ---- sampling direction -------------------------------------------------------------------------------- */
+/* forward!(chain, z, θ): in place, no ln_det_jac (src/Chains.jl:187-197).  Exactly one of theta (n x B) /
+ * theta_const (device, n floats, same θ for every sample: the NTuple method src/Flows.jl:174-185) may be non-NULL
+ * when n > 0. */
+int dflow_sample_inplace(dflow_chain* chain, const float* W, float* z_inout, const float* theta,
+                         const float* theta_const, int64_t B, int32_t flags, void* stream);
+/* forward(chain, z, θ) -> (x, ln_det_jac) (src/Chains.jl:167-183) */
+int dflow_forward_ldj(dflow_chain* chain, const float* W, const float* z, const float* theta, int64_t B, int32_t flags,
+                      float* x_out, float* ldj_out, void* stream);
+/* sample(flow, B, θ) with the base draw done in-kernel (Philox4x32-10 + Box-Muller, spec in oracle/philox.py);
+ * replaces rand(rng, base, B) + forward! (src/Flows.jl:157-192).  Sample b uses counter first_sample + b. */
+int dflow_sample_rng(dflow_chain* chain, const float* W, uint64_t seed, uint32_t offset, uint64_t first_sample,
+                     const float* theta, const float* theta_const, int64_t B, int32_t flags, float* x_out,
+                     void* stream);
+
+/* ---- adjoint: gradient of loss = -inv_btot * Σ_b logpdf_b w.r.t. the packed parameters ------------------- */
+/* Replaces Flux.gradient through backward(::FlowChain) + loss (src/Flows.jl:400-413) incl. the rrule of
+ * src/affine/RNVP.jl:99-147 and the Dense pullbacks.  grad_out (P floats) is ACCUMULATED INTO (caller zeroes it);
+ * loss_out[0] += Σ logpdf_b, loss_out[1] += #non-finite.  inv_btot = 1/B for a single device, 1/B_global for a
+ * data-parallel shard (the all-reduce is then a pure sum).  ws / ws_bytes: workspace from dflow_workspace_bytes. */
+size_t dflow_workspace_bytes(const dflow_chain* chain, int64_t B);
+int dflow_loss_grad(dflow_chain* chain, const float* W, const float* x, const float* theta, int64_t B,
+                    const int32_t* idx, float inv_btot, int32_t flags, float* loss_out, float* grad_out, void* ws,
+                    size_t ws_bytes, void* stream);
+
+/* ---- Optimisers.Adam update (call site src/Flows.jl:415), in place on packed buffers; t = step count >= 1 ---- */
+int dflow_adam_step(float* W, const float* g, float* m, float* v, int64_t P, float lr, float beta1, float beta2,
+                    float eps, int64_t t, void* stream);
+
+/* ---- per-row min / max over B samples (NormalizationLayer ctor src/norm/Normalization.jl:52-53; minimum_θ /
+ * maximum_θ src/Data.jl:182-183).  min_out / max_out: device float[rows]. */
+int dflow_minmax(const float* x, int32_t rows, int64_t B, float* min_out, float* max_out, void* stream);
+
+/* ---- host-buffer entry points (pinned or pageable host memory; chunked H2D -> kernel -> D2H pipeline) -------- */
+int dflow_logpdf_host(dflow_chain* chain, const float* W, const float* x_host, const float* theta_host, int64_t B,
+                      int32_t flags, float* logp_host, int64_t chunk);
+int dflow_sample_host(dflow_chain* chain, const float* W, uint64_t seed, const float* theta_const_host, int64_t B,
+                      int32_t flags, float* x_host, int64_t chunk);
+
+/* ---- tuning / introspection ------------------------------------------------------------------------------ */
+/* keys: "fwd_spt" (samples per thread), "fwd_threads", "grad_threads", "ctas_per_sm"; value 0 = automatic */
+int dflow_set_tuning(dflow_chain* chain, const char* key, int32_t value);
+/* number of kernels the library has launched on behalf of this handle since creation */
+int64_t dflow_launch_count(const dflow_chain* chain);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFLOW_H */

@@ -1,0 +1,284 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical weights and inputs.
+
+Tolerances (BASELINE.json north_star): transforms / log-dets / log-densities rtol 1e-5 (+ atol 1e-5 on O(1)
+quantities, the reference's own `≈`/atol=2f-6 style), gradients rtol 1e-4 of the gradient's max-norm.
+"""
+import numpy as np
+import pytest
+import torch
+
+import densityflows.jl_b200 as df
+from oracle import dflow_oracle as O
+from oracle import philox as PH
+from tests.helpers import assert_close, chain_from_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-5
+DEV = "cuda:0"
+
+
+def _chains():
+    """name -> (oracle chain builder, d, n)"""
+    out = {}
+
+    def readme(n):
+        def mk(x):
+            return O.readme_chain(n, x)
+        return mk
+
+    out["readme_n2"] = (readme(2), 5, 2)
+    out["readme_n1"] = (readme(1), 5, 1)
+
+    def ref_chain_test(x):  # test/runtests.jl:66-95
+        rng = np.random.default_rng(3)
+        l1 = O.coupling_layer(O.coupling_axes(7, [1, 3, 5, 7], n=2), rng=rng, bias_scale=0.1)
+        l2 = O.coupling_layer(O.coupling_axes(7, [4, 2, 5, 1, 6], n=2), rng=rng, bias_scale=0.1)
+        blk = O.coupling_block(O.coupling_axes(7, [4, 2, 5, 1], n=2), rng=rng, bias_scale=0.1)
+        return O.concatenate((O.Chain([l1, l2]), O.Chain([blk, O.norm_layer_from_data(x)])))
+
+    out["ref_chain_d7"] = (ref_chain_test, 7, 2)
+
+    def hetero(x):  # different widths / depths / activations per net, NICE layer, no bias, norm in the middle
+        rng = np.random.default_rng(5)
+        l1 = O.coupling_layer(O.coupling_axes(6, [2, 5], n=0), hidden_dim_s=10, hidden_dim_t=24, n_sublayers_s=1,
+                              n_sublayers_t=3, act_s="tanh", act_t="sigmoid", rng=rng, bias_scale=0.2)
+        l2 = O.coupling_layer(O.coupling_axes(6, [1, 3, 4, 6], n=0), kind="nice", hidden_dim_t=12, rng=rng, bias_scale=0.2)
+        l3 = O.coupling_layer(O.coupling_axes(6, [6, 1, 2, 3, 4], n=0), hidden_dim_s=32, hidden_dim_t=8, bias=False, rng=rng)
+        return O.Chain([l1, O.norm_layer_from_data(x, -2.0, 3.0), l2, l3])
+
+    out["hetero_d6_n0"] = (hetero, 6, 0)
+
+    def c3small(x):
+        return O.block_chain(16, 4, 8, 64, x)
+
+    out["c3_d16_h64"] = (c3small, 16, 4)
+
+    def h32(x):
+        return O.block_chain(10, 3, 4, 32, x, s_out_scale=0.5)
+
+    out["blocks_d10_h32"] = (h32, 10, 3)
+    return out
+
+
+CHAINS = _chains()
+
+
+def _setup(name, B, seed=11):
+    mk, d, n = CHAINS[name]
+    x, th = O.synthetic_data(d, n, B, seed=seed)
+    ochain = mk(x)
+    chain = chain_from_oracle(ochain)
+    return ochain, chain, x, th
+
+
+@pytest.mark.parametrize("name", list(CHAINS))
+@pytest.mark.parametrize("B", [1, 33, 1000])
+def test_normalize_and_logpdf(name, B):
+    ochain, chain, x, th = _setup(name, B)
+    z, ldj = df.backward(chain, x, th if th.shape[0] else None)
+    zo, lo = O.chain_backward(ochain, x, th)
+    zo64, lo64 = O.chain_backward(ochain, x, th, np.float64)
+    # the f32 oracle itself sits this far from the f64 truth; the kernel must not be further than that + tolerance
+    slack = np.abs(zo - zo64).max() + np.abs(lo - lo64).max()
+    assert_close(df.to_numpy(z), zo64, RTOL, ATOL + slack, f"{name} z")
+    assert_close(df.to_numpy(ldj), lo64, RTOL, ATOL + slack, f"{name} ldj")
+    lp = chain.packed().logpdf(x, th if th.shape[0] else None)
+    lpo = O.mvnormal_logpdf(zo64, np.float64) + lo64
+    assert_close(df.to_numpy(lp), lpo, RTOL, 1e-4 + 10 * slack, f"{name} logpdf")
+
+
+@pytest.mark.parametrize("name", list(CHAINS))
+def test_sampling_direction(name):
+    ochain, chain, x, th = _setup(name, 777)
+    mk, d, n = CHAINS[name]
+    z = np.random.default_rng(2).standard_normal((d, 777)).astype(np.float32) * 0.7
+    tharg = th if n else None
+    xg, ldj = df.forward(chain, z, tharg)
+    xo, lo = O.chain_forward(ochain, z, th, np.float64)
+    scale = max(1.0, np.abs(xo).max())
+    assert_close(df.to_numpy(xg), xo, RTOL, ATOL * scale, f"{name} forward x")
+    assert_close(df.to_numpy(ldj), lo, RTOL, ATOL * 10, f"{name} forward ldj")
+    # forward! (in place, no ldj) gives the same x
+    zt = df.to_jl(z, DEV).clone()
+    zt = df.to_jl(zt)
+    df.forward_(chain, zt, tharg)
+    assert torch.equal(zt, xg)
+    # round trip + ldj antisymmetry (test/runtests.jl:89-93)
+    z2, ldj2 = df.backward(chain, xg, tharg)
+    assert_close(df.to_numpy(z2), z, 1e-4, 1e-4, f"{name} round trip")
+    assert_close(df.to_numpy(ldj2) + df.to_numpy(ldj), 0 * lo, 0, 1e-4, f"{name} ldj antisymmetry")
+
+
+@pytest.mark.parametrize("name", list(CHAINS))
+@pytest.mark.parametrize("B", [5, 300, 2049])
+def test_loss_grad(name, B):
+    ochain, chain, x, th = _setup(name, B, seed=21)
+    pc = chain.packed()
+    grad = torch.zeros(max(pc.P, 1), device=DEV)
+    loss2 = torch.zeros(2, device=DEV)
+    pc.loss_grad(x, th if th.shape[0] else None, grad, loss2)
+    lo, go, _, _ = O.chain_loss_and_grad(ochain, x, th, np.float64)
+    assert pc.P == go.size
+    assert loss2[1].item() == 0
+    assert abs(-loss2[0].item() / B - lo) <= 1e-5 * abs(lo) + 1e-4
+    g = grad.cpu().numpy()[: pc.P]
+    assert np.abs(g - go).max() <= 1e-4 * np.abs(go).max(), (np.abs(g - go).max(), np.abs(go).max())
+    # per-Dense check so that a small block cannot hide behind a large one
+    off = 0
+    for e in O.flatten(ochain):
+        for net in O._trainable_nets(e):
+            for dl in net:
+                k = dl.W.size + (dl.b.size if dl.b is not None else 0)
+                ref = go[off:off + k]
+                err = np.abs(g[off:off + k] - ref).max()
+                assert err <= 2e-4 * np.abs(ref).max() + 1e-7 * np.abs(go).max(), (name, off, err, np.abs(ref).max())
+                off += k
+
+
+def test_grad_idx_and_dp_seed():
+    """Gather through an index + data-parallel seed: two half batches with inv_btot = 1/B sum to the full gradient."""
+    ochain, chain, x, th = _setup("readme_n2", 512, seed=4)
+    pc = chain.packed()
+    xd, td = df.to_jl(x, DEV), df.to_jl(th, DEV)
+    perm = torch.randperm(512, generator=torch.Generator().manual_seed(1)).to(torch.int32).to(DEV)
+    full = torch.zeros(pc.P, device=DEV)
+    l_full = torch.zeros(2, device=DEV)
+    pc.loss_grad(xd, td, full, l_full)
+    acc = torch.zeros(pc.P, device=DEV)
+    l_acc = torch.zeros(2, device=DEV)
+    pc.loss_grad(xd, td, acc, l_acc, 1.0 / 512, 0, perm[:200].contiguous())
+    pc.loss_grad(xd, td, acc, l_acc, 1.0 / 512, 0, perm[200:].contiguous())
+    assert torch.allclose(acc, full, rtol=1e-4, atol=1e-6 * full.abs().max().item())
+    assert abs(l_acc[0].item() - l_full[0].item()) <= 1e-4 * abs(l_full[0].item())
+    # logpdf through the same index
+    lp = pc.logpdf(xd, td)
+    lpi = pc.logpdf(xd, td, 0, perm)
+    assert torch.equal(lp[perm.long()], lpi)
+
+
+def test_theta_normalize_flag():
+    """Flow-level calls normalise θ with (θ - θ_min)/(θ_max - θ_min), zero range -> 0 (src/Data.jl:213-218)."""
+    x, th = O.synthetic_data(5, 2, 300, seed=9)
+    th[1] = 0.75  # zero-range row
+    ochain = O.readme_chain(2, x)
+    chain = chain_from_oracle(ochain)
+    data = df.DataArrays(x, th, device=DEV)
+    flow = df.Flow(chain, data)
+    lp = df.logpdf(flow, x, th)
+    tmin, tmax = th.min(axis=1), th.max(axis=1)
+    np.testing.assert_array_equal(flow.metadata.θ_min, tmin)
+    np.testing.assert_array_equal(flow.metadata.θ_max, tmax)
+    lpo = O.logpdf(ochain, x, th, tmin, tmax, np.float64)
+    assert_close(df.to_numpy(lp), lpo, RTOL, 1e-4, "flow logpdf")
+    # tuple θ == broadcast array θ
+    lp_t = df.logpdf(flow, x, (0.3, 0.75))
+    th_b = np.tile(np.array([[0.3], [0.75]], np.float32), (1, 300))
+    assert torch.equal(lp_t, df.logpdf(flow, x, th_b))
+
+
+def test_adam_matches_optimisers_formula():
+    rng = np.random.default_rng(0)
+    P = 5000
+    w = rng.standard_normal(P).astype(np.float32)
+    m = np.zeros(P, np.float32)
+    v = np.zeros(P, np.float32)
+    wt, mt, vt = (torch.tensor(a, device=DEV) for a in (w, m, v))
+    import ctypes
+
+    lib = df._lib.lib()
+    for t in range(1, 6):
+        g = rng.standard_normal(P).astype(np.float32) * 0.1
+        gt = torch.tensor(g, device=DEV)
+        df._lib.check(lib.dflow_adam_step(wt.data_ptr(), gt.data_ptr(), mt.data_ptr(), vt.data_ptr(), P, 1e-3, 0.9,
+                                          0.999, 1e-8, t, torch.cuda.current_stream().cuda_stream))
+        w, m, v = O.adam_step(w, g, m, v, t)
+        np.testing.assert_allclose(wt.cpu().numpy(), w, rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(mt.cpu().numpy(), m, rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(vt.cpu().numpy(), v, rtol=2e-6, atol=1e-12)
+
+
+def test_minmax_rows():
+    rng = np.random.default_rng(1)
+    for rows, B in [(1, 1), (5, 1000), (7, 123457), (64, 4099)]:
+        a = (rng.standard_normal((rows, B)) * 3).astype(np.float32)
+        a[0, 0] = -0.0
+        mn, mx = df.minmax_rows(df.to_jl(a, DEV))
+        np.testing.assert_array_equal(mn, a.min(axis=1))
+        np.testing.assert_array_equal(mx, a.max(axis=1))
+    a = np.abs(rng.standard_normal((3, 100))).astype(np.float32) + 1  # all positive
+    mn, mx = df.minmax_rows(df.to_jl(a, DEV))
+    np.testing.assert_array_equal(mn, a.min(axis=1))
+    a = -a  # all negative
+    mn, mx = df.minmax_rows(df.to_jl(a, DEV))
+    np.testing.assert_array_equal(mx, a.max(axis=1))
+    np.testing.assert_array_equal(mn, a.min(axis=1))
+
+
+def test_sample_rng_matches_philox_spec():
+    ochain, chain, x, th = _setup("readme_n2", 64)
+    pc = chain.packed()
+    B, seed = 1000, 0x1234_5678_9ABC
+    thc = torch.tensor([0.3, -0.2], device=DEV)
+    xs = pc.sample_rng(B, seed, None, thc, first_sample=17)
+    z = PH.normal_samples(5, B, seed, 0, first_sample=17)
+    thb = np.tile(np.array([[0.3], [-0.2]], np.float32), (1, B))
+    xo, _ = O.chain_forward(ochain, z, thb, np.float64)
+    assert_close(df.to_numpy(xs), xo, 1e-5, 2e-5 * max(1.0, np.abs(xo).max()), "sample_rng")
+    # moments of the base draw itself (identity chain = NICE layer with zero weights is overkill; check z stats)
+    z_big = PH.normal_samples(5, 200000, 7)
+    assert abs(z_big.mean()) < 0.01 and abs(z_big.std() - 1) < 0.01
+
+
+def test_reference_flow_testset_shapes():
+    """test/runtests.jl:97-121 on synthetic fixture-shaped data: train! runs, sample(flow,(2,5,7),(-1,)) has size (5,2,5,7)."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((5, 1000)).astype(np.float32)
+    th = np.where(np.arange(1000) < 500, -1.0, 2.0).astype(np.float32)[None, :]
+    df.seed(0)
+    data = df.DataArrays(x, th, device=DEV)
+    chain = df.FlowChain(
+        df.CouplingLayer(data, [1, 2, 3], hidden_dim_s=16, hidden_dim_t=16),
+        df.CouplingLayer(data, [3, 4, 5], hidden_dim_s=16, hidden_dim_t=16),
+        df.CouplingLayer(data, [5, 1, 2], hidden_dim_s=16, hidden_dim_t=16),
+        df.NormalizationLayer(data.x, -1.0, 1.0),
+    )
+    flow = df.Flow(chain, data)
+    state = df.setup(df.Adam(1e-3), flow.model)
+    df.train_(flow, data, state, epochs=5, verbose=False)
+    assert len(flow.train_loss) == 5 and len(flow.valid_loss) == 5
+    assert all(np.isfinite(flow.train_loss)) and flow.train_loss[-1] < flow.train_loss[0]
+    x_new = df.sample(flow, (2, 5, 7), (-1.0,))
+    assert tuple(x_new.shape) == (5, 2, 5, 7)
+    assert torch.isfinite(x_new).all()
+
+
+def test_train_matches_oracle_trajectory():
+    """Three epochs of minibatch Adam with a pinned shuffle: loss histories and final weights follow the oracle."""
+    x, th = O.synthetic_data(5, 1, 400, seed=3)
+    ochain = O.readme_chain(1, x)
+    chain = chain_from_oracle(ochain)
+    data = df.DataArrays(x, th, device=DEV, rng=torch.Generator().manual_seed(5))
+    flow = df.Flow(chain, data)
+    state = df.setup(df.Adam(1e-3), flow.model)
+    gen = torch.Generator().manual_seed(77)
+    df.train_(flow, data, state, epochs=3, batchsize=64, verbose=False, rng=gen)
+    # replay on the oracle with the same partition and permutations
+    tr = data.partition.training.cpu().numpy()
+    va = data.partition.validation.cpu().numpy()
+    gen2 = torch.Generator().manual_seed(77)
+    perms = [torch.randperm(len(tr), generator=gen2).numpy() for _ in range(3)]
+    tmin, tmax = th.min(axis=1), th.max(axis=1)
+    thn = O.normalize_input(th, tmin, tmax)
+    tl, vl = O.train(ochain, x[:, tr], thn[:, tr], x[:, va], thn[:, va], epochs=3, batchsize=64, perms=perms,
+                     dtype=np.float64)
+    np.testing.assert_allclose(flow.train_loss, tl, rtol=2e-4)
+    np.testing.assert_allclose(flow.valid_loss, vl, rtol=2e-4)
+    w = flow.packed().W.cpu().numpy()
+    np.testing.assert_allclose(w, O.pack_params(ochain), rtol=0, atol=2e-4)
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+
+    g.smoke()
