@@ -26,6 +26,8 @@ class ElemDesc(C.Structure):
         ("kind", C.c_int32),
         ("n_af", C.c_int32),
         ("axis_af", c_i32p),
+        ("n_id", C.c_int32),
+        ("axis_id", c_i32p),
         ("s_net", NetDesc),
         ("t_net", NetDesc),
         ("x_min", c_f32p),

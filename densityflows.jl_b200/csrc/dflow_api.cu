@@ -173,10 +173,29 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
       seen[k] = true;
       E.af[j] = (unsigned char)k;
     }
-    // axis_id = findall(x -> !(x in mask), 1:d) (ascending), src/Axes.jl:88
     int nid = 0;
-    for (int k = 0; k < d; ++k)
-      if (!seen[k]) E.id[nid++] = (unsigned char)k;
+    if (ed.axis_id) {
+      // explicit order (reverse(axes) keeps the former axis_af order, src/Axes.jl:129-135)
+      nid = ed.n_id;
+      if (nid != d - a) {
+        set_error("element %d: axis_id has %d entries, expected %d", ei, nid, d - a);
+        return DFLOW_E_INVALID_ARG;
+      }
+      bool seen_id[DMAX] = {false};
+      for (int j = 0; j < nid; ++j) {
+        const int k = ed.axis_id[j];
+        if (k < 0 || k >= d || seen[k] || seen_id[k]) {
+          set_error("element %d: axis_id[%d]=%d is out of range, duplicated or also in axis_af", ei, j, k);
+          return DFLOW_E_INVALID_ARG;
+        }
+        seen_id[k] = true;
+        E.id[j] = (unsigned char)k;
+      }
+    } else {
+      // axis_id = findall(x -> !(x in mask), 1:d) (ascending), src/Axes.jl:88
+      for (int k = 0; k < d; ++k)
+        if (!seen[k]) E.id[nid++] = (unsigned char)k;
+    }
     E.a = a;
     E.nid = nid;
     E.nin = n + nid;  // length(axis_nn), src/Axes.jl:98
@@ -222,6 +241,16 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
     smax = std::max(smax, off);
   }
   H.stage_total = total;
+  // adjoint checkpoints: the layer inputs' transformed coordinates are saved in the forward sweep and restored
+  // bit-exactly in the reverse sweep (an inverse-map reconstruction drifts by ~1e-6 and flips ReLU kinks)
+  int ck = 0;
+  for (int ei = 0; ei < L; ++ei) {
+    DevElem& E = C->e[ei];
+    E.ck_off = ck;
+    E.ck_len = (E.kind == DFLOW_ELEM_NORM) ? (ei == L - 1 ? 0 : d) : E.a;
+    ck += E.ck_len;
+  }
+  H.ck_total = ck;
   H.stage_max = smax;
 
   dflow_chain* c = new (std::nothrow) dflow_chain();
@@ -505,20 +534,24 @@ int dflow_sample_rng(dflow_chain* c, const float* W, uint64_t seed, uint32_t off
 }
 
 size_t dflow_workspace_bytes(const dflow_chain* c, int64_t B) {
-  (void)c;
   (void)B;
-  return 0;  // the narrow adjoint keeps all per-sample state on chip
+  if (!c) return 0;
+  // one checkpoint slab per resident CTA (not per sample): grid <= sm_count * 4 CTAs of <= 256 threads
+  return (size_t)c->sm_count * 4 * 256 * (size_t)c->hc()->h.ck_total * sizeof(float) + 256;
 }
 
 int dflow_loss_grad(dflow_chain* c, const float* W, const float* x, const float* theta, int64_t B, const int32_t* idx,
                     float inv_btot, int32_t flags, float* loss_out, float* grad_out, void* ws, size_t ws_bytes,
                     void* stream) {
-  (void)ws;
-  (void)ws_bytes;
   int rc = check_common(c, W, theta, nullptr, B, flags);
   if (rc) return rc;
   if (B > 0 && (!x || !loss_out || !grad_out)) {
     set_error("null data pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (B > 0 && (!ws || ws_bytes < dflow_workspace_bytes(c, B))) {
+    set_error("workspace too small: need %zu bytes (dflow_workspace_bytes), got %zu", dflow_workspace_bytes(c, B),
+              ws_bytes);
     return DFLOW_E_INVALID_ARG;
   }
   if (B == 0) return DFLOW_OK;
@@ -531,6 +564,7 @@ int dflow_loss_grad(dflow_chain* c, const float* W, const float* x, const float*
   a.idx = idx;
   a.loss_out = loss_out;
   a.grad_out = grad_out;
+  a.ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   a.B = B;
   a.inv_btot = inv_btot;
   a.flags = flags;

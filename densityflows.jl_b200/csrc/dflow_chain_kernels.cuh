@@ -590,6 +590,7 @@ __global__ void __launch_bounds__(256) chain_grad_kernel(const GradArgs a) {
   const long long ntiles = (a.B + NT - 1) / NT;
   float lsum_thread = 0.0f, nonfinite = 0.0f;
   const int sl = tid;
+  float* ckb = a.ws + (size_t)blockIdx.x * H.ck_total * NT + tid;  // this thread's checkpoint column
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long gi = tile * NT + tid;
@@ -616,6 +617,14 @@ __global__ void __launch_bounds__(256) chain_grad_kernel(const GradArgs a) {
         copy_f4(wsm, a.staged + E.stage_off, E.stage_len / 4, tid, NT);
         __syncthreads();
         wblk = wsm;
+      }
+      // checkpoint the coordinates this element is about to change (restored bit-exactly in the reverse sweep)
+      if (E.ck_len > 0) {
+        float* ck = ckb + (size_t)E.ck_off * NT;
+        if (E.kind == DFLOW_ELEM_NORM)
+          for (int k = 0; k < d; ++k) ck[k * NT] = xs[k * CS + sl];
+        else
+          for (int j = 0; j < E.a; ++j) ck[j * NT] = xs[(int)E.af[j] * CS + sl];
       }
       elem_apply<HP, 1>(H, E, wblk, false, xs, th, hc, 0, ob, tb, CS, sl, NT, ldj);
     }
@@ -653,8 +662,7 @@ __global__ void __launch_bounds__(256) chain_grad_kernel(const GradArgs a) {
         for (int k = 0; k < d; ++k) {
           const float xmin = wblk[k], xmax = wblk[d + k];
           gx[k * CS + sl] *= (beta - alpha) / (xmax - xmin);
-          const float v = xs[k * CS + sl];
-          xs[k * CS + sl] = ((xmax - xmin) * v - alpha * xmax + beta * xmin) / (beta - alpha);
+          if (E.ck_len > 0) xs[k * CS + sl] = ckb[(size_t)(E.ck_off + k) * NT];
         }
         continue;
       }
@@ -686,11 +694,10 @@ __global__ void __launch_bounds__(256) chain_grad_kernel(const GradArgs a) {
         net_backward<HP>(H, E, net, wblk, xs, gx, th, hc, hstride, dlc, gb, outc, gacc, a.grad_out, CS, sl, wbase,
                          lane);
       }
-      // reconstruct the layer input and finish ū (RNVP.jl:137-139)
+      // restore the layer input from its checkpoint and finish ū (RNVP.jl:137-139)
       for (int j = 0; j < E.a; ++j) {
         const int k = E.af[j];
-        const float sv = rnvp ? ob[j * CS + sl] : 0.0f;
-        xs[k * CS + sl] = xs[k * CS + sl] * expf(sv) + tb[j * CS + sl];
+        xs[k * CS + sl] = ckb[(size_t)(E.ck_off + j) * NT];
         gx[k * CS + sl] *= eb[j * CS + sl];
       }
     }

@@ -36,6 +36,8 @@ struct DevElem {
   int nin;        // conditioner input width = n + nid
   int stage_off;  // offset (floats, multiple of 4) of this element's block in the staged image
   int stage_len;  // floats, multiple of 4
+  int ck_off;     // adjoint checkpoint offset (floats per sample) of this element's transformed coordinates
+  int ck_len;     // a (coupling) or d (normalisation); 0 when nothing has to be restored
   unsigned char af[DMAX];  // 0-based, caller order (src/Axes.jl:91)
   unsigned char id[DMAX];  // 0-based ascending complement (src/Axes.jl:88)
   DevNet s, t;
@@ -51,6 +53,7 @@ struct DevChainHdr {
   int resident;      // 1: whole staged image kept in shared memory
   int amax4;         // max padded output width
   int max_depth;
+  int ck_total;      // checkpoint floats per sample (adjoint workspace)
   int has_theta_range;
   float logpdf_c0;   // -(d*log(2pi))/2
   float theta_min[NMAX];
@@ -97,7 +100,8 @@ struct GradArgs {
   const float* theta;
   const int32_t* idx;
   float* loss_out;  // [2]
-  float* grad_out;  // [P] (or copies in ws)
+  float* grad_out;  // [P]
+  float* ws;        // checkpoint workspace: grid * ck_total * blockDim floats
   long long B;
   float inv_btot;
   int flags;

@@ -37,12 +37,16 @@ __global__ void adam_kernel(float* __restrict__ W, const float* __restrict__ g, 
                             float* __restrict__ v, long long P, float lr, float b1, float b2, float eps, float c1,
                             float c2) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+    // explicit round-to-nearest ops (no FMA contraction): bit-identical to the un-fused Float32 broadcast of
+    // Optimisers.jl  mt = β1*mt + (1-β1)*dx ; vt = β2*vt + (1-β2)*dx^2 ; dx' = mt/(1-β1^t)/(sqrt(vt/(1-β2^t))+ϵ)*η
     const float gi = g[i];
-    const float mi = b1 * m[i] + (1.0f - b1) * gi;
-    const float vi = b2 * v[i] + (1.0f - b2) * (gi * gi);
+    const float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(1.0f - b1, gi));
+    const float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(1.0f - b2, __fmul_rn(gi, gi)));
     m[i] = mi;
     v[i] = vi;
-    W[i] -= mi / c1 / (sqrtf(vi / c2) + eps) * lr;
+    const float den = __fadd_rn(__fsqrt_rn(__fdiv_rn(vi, c2)), eps);
+    const float stepv = __fmul_rn(__fdiv_rn(__fdiv_rn(mi, c1), den), lr);
+    W[i] = __fsub_rn(W[i], stepv);
   }
 }
 

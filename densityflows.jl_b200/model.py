@@ -456,6 +456,14 @@ class ChainDescriptor:
             self._keep.append(arr)
             ed.n_af = len(af0)
             ed.axis_af = C.cast(arr, L.c_i32p)
+            id0 = [k - 1 for k in e.axes.axis_id]
+            if len(id0) != self.d - len(af0) or set(id0) & set(af0):
+                raise L.DflowInvalidArg(L.E_INVALID_ARG, "axis_id and axis_af must partition 1:d")
+            if id0:
+                arr_id = (C.c_int32 * len(id0))(*id0)
+                self._keep.append(arr_id)
+                ed.n_id = len(id0)
+                ed.axis_id = C.cast(arr_id, L.c_i32p)
             if isinstance(e, RNVPCouplingLayer):
                 self._fill_net(ed.s_net, e.s_net)
             self._fill_net(ed.t_net, e.t_net)
@@ -507,6 +515,7 @@ class PackedChain:
         self.P = int(L.lib().dflow_param_count(self.handle))
         self.has_theta_range = theta_min is not None
         self.W = torch.zeros(max(self.P, 1), device=self.device, dtype=torch.float32)
+        self._ws: Optional[torch.Tensor] = None  # adjoint workspace (dflow_workspace_bytes)
         self._bind_views()
 
     def _bind_views(self) -> None:
@@ -666,10 +675,13 @@ class PackedChain:
         x, θ = self._prep(x, θ)
         B = n_samples(x) if idx is None else int(idx.numel())
         ib = (1.0 / B) if inv_btot is None else float(inv_btot)
+        need = int(L.lib().dflow_workspace_bytes(self.handle, B))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
         with torch.cuda.device(self.device):
             L.check(L.lib().dflow_loss_grad(self.handle, self.W.data_ptr(), self._ptr(x), self._ptr(θ), B,
                                             None if idx is None else idx.data_ptr(), ib, flags, loss2.data_ptr(),
-                                            grad.data_ptr(), None, 0, self._stream()))
+                                            grad.data_ptr(), self._ws.data_ptr(), self._ws.numel(), self._stream()))
         return B
 
     def adam_step(self, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, t: int, lr=1e-3, β=(0.9, 0.999),

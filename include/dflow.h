@@ -62,7 +62,11 @@ typedef struct dflow_net_desc {
 typedef struct dflow_elem_desc {
   int32_t kind;           /* DFLOW_ELEM_* */
   int32_t n_af;           /* |axis_af| (coupling layers) */
-  const int32_t* axis_af; /* 0-based transformed dims in CALLER ORDER (src/Axes.jl:91); axis_id / axis_nn are derived */
+  const int32_t* axis_af; /* 0-based transformed dims in CALLER ORDER (src/Axes.jl:91) */
+  int32_t n_id;           /* |axis_id|; 0 with axis_id == NULL => derive the ascending complement (src/Axes.jl:88) */
+  const int32_t* axis_id; /* 0-based identity dims IN ORDER: they are the conditioner's x inputs (axis_nn = [0..n-1,
+                             axis_id + n], src/Axes.jl:98).  reverse(axes) (src/Axes.jl:129-135) makes this the
+                             un-sorted former axis_af, so it cannot always be derived. */
   dflow_net_desc s_net;   /* RNVP only */
   dflow_net_desc t_net;   /* RNVP and NICE */
   const float* x_min;     /* NORM only: host pointers, d entries (src/norm/Normalization.jl:51-57) */
@@ -133,6 +137,8 @@ int dflow_sample_rng(dflow_chain* chain, const float* W, uint64_t seed, uint32_t
  * src/affine/RNVP.jl:99-147 and the Dense pullbacks.  grad_out (P floats) is ACCUMULATED INTO (caller zeroes it);
  * loss_out[0] += Σ logpdf_b, loss_out[1] += #non-finite.  inv_btot = 1/B for a single device, 1/B_global for a
  * data-parallel shard (the all-reduce is then a pure sum).  ws / ws_bytes: workspace from dflow_workspace_bytes. */
+/* The workspace holds the per-CTA checkpoints of each layer's transformed coordinates (Σ_l a_l floats per resident
+ * sample slot, independent of B), so that the reverse sweep recomputes activations from bit-identical inputs. */
 size_t dflow_workspace_bytes(const dflow_chain* chain, int64_t B);
 int dflow_loss_grad(dflow_chain* chain, const float* W, const float* x, const float* theta, int64_t B,
                     const int32_t* idx, float inv_btot, int32_t flags, float* loss_out, float* grad_out, void* ws,

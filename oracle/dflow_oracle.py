@@ -303,7 +303,7 @@ def _nn_input(axes: Axes, x: np.ndarray, theta: np.ndarray) -> np.ndarray:
 
 
 def _flat2(a: np.ndarray) -> Tuple[np.ndarray, Tuple[int, ...]]:
-    return a.reshape(a.shape[0], -1), a.shape[1:]
+    return a.reshape(a.shape[0], int(np.prod(a.shape[1:], dtype=np.int64))), a.shape[1:]
 
 
 def rnvp_backward(layer: RNVPLayer, x: np.ndarray, theta: np.ndarray, dtype=np.float32):
@@ -700,8 +700,11 @@ def adam_step(w, g, m, v, t: int, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, dtype=np.
     one = dtype(1)
     m = b1 * m + (one - b1) * g
     v = b2 * v + (one - b2) * (g * g)
-    b1t = dtype(float(b1) ** t)
-    b2t = dtype(float(b2) ** t)
+    # Optimisers keeps βt as a running product in the parameter eltype: state βt .* β after every step
+    b1t, b2t = dtype(1), dtype(1)
+    for _ in range(t):
+        b1t = dtype(b1t * b1)
+        b2t = dtype(b2t * b2)
     step = m / (one - b1t) / (np.sqrt(v / (one - b2t)) + eps) * lr
     return w - step, m, v
 

@@ -36,7 +36,9 @@ def run(name, d, n, mk, B, Bg, tunes):
     for tune in tunes:
         if "fwd_spt" in tune and tune["fwd_spt"] not in (0, 1): pass
         pc.tune(**tune)
-        f = lambda: df._lib.check(lib.dflow_loss_grad(pc.handle, pc.W.data_ptr(), xp, tp, Bg, None, 1.0 / Bg, 0, l2.data_ptr(), grad.data_ptr(), None, 0, st))
+        wsb = int(lib.dflow_workspace_bytes(pc.handle, Bg))
+        ws = torch.empty(wsb, device="cuda:0", dtype=torch.uint8)
+        f = lambda: df._lib.check(lib.dflow_loss_grad(pc.handle, pc.W.data_ptr(), xp, tp, Bg, None, 1.0 / Bg, 0, l2.data_ptr(), grad.data_ptr(), ws.data_ptr(), wsb, st))
         med, mn = timeit(f, iters=3, warm=1)
         print(json.dumps({"cfg": name, "op": "loss_grad", "B": Bg, "tune": tune, "ms": med, "ms_min": mn, "samples_per_s": Bg / med * 1e3}), flush=True)
     thc = torch.zeros(max(n, 1), device="cuda:0")

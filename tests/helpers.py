@@ -14,7 +14,7 @@ def _net_from_oracle(net):
 
 
 def _axes_from_oracle(a):
-    return df.CouplingAxes(a.d, list(a.axis_af), n=a.n)
+    return df.CouplingAxes(None, _raw=(a.d, a.n, list(a.axis_id), list(a.axis_af), list(a.axis_nn)))
 
 
 def elem_from_oracle(e):
