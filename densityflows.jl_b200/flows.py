@@ -212,6 +212,22 @@ def _dist():
     return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
 
 
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of an n-element index list owned by `rank` (SURVEY.md §8e partitioning)."""
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def allreduce_sum_(buf: torch.Tensor) -> torch.Tensor:
+    """In-place all-reduce(sum) of the packed [grad | Σlogp | #non-finite] buffer (NCCL on GPUs, gloo in CPU tests);
+    a no-op for a single process."""
+    d = _dist()
+    if d is not None:
+        d.all_reduce(buf)
+    return buf
+
+
 class TrainStep:
     """One data-parallel minibatch step on resident data: adjoint kernel on this rank's slice of the index list
     (seed 1/B_global), NCCL all-reduce(sum) of [grad | Σlogp | #nonfinite], Adam kernel on every replica."""
@@ -229,9 +245,7 @@ class TrainStep:
         nb = n_samples(x) if idx is None else int(idx.numel())
         if nb > 0:
             pc.loss_grad(x, θ, self.grad, self.loss2, 1.0 / B_global, flags, idx)
-        d = _dist()
-        if d is not None:
-            d.all_reduce(self.buf)
+        allreduce_sum_(self.buf)
         st.t += 1
         r = st.rule
         pc.adam_step(self.grad, st.m, st.v, st.t, r.eta, r.beta, r.epsilon)
@@ -242,9 +256,7 @@ def _full_loss(pc: PackedChain, x, θ, idx: torch.Tensor, n_global: int, flags: 
     tmp.zero_()
     if idx.numel() > 0:
         pc.logpdf_sum(x, θ, tmp, flags, idx)
-    d = _dist()
-    if d is not None:
-        d.all_reduce(tmp)
+    allreduce_sum_(tmp)
     s, bad = tmp.tolist()
     return float("nan") if bad > 0 else -s / max(n_global, 1)
 
@@ -272,8 +284,8 @@ def train_(flow: Flow, data: DataArrays, optimiser_state: OptimiserState, epochs
     def shard(v: torch.Tensor) -> torch.Tensor:
         if world == 1:
             return v
-        per = (v.numel() + world - 1) // world
-        return v[rank * per: min((rank + 1) * per, v.numel())]
+        lo, hi = shard_range(int(v.numel()), rank, world)
+        return v[lo:hi]
 
     for _ in range(epochs):
         if shuffle:
