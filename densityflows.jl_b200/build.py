@@ -20,7 +20,9 @@ LIB = os.path.join(LIBDIR, "libdflow.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
-FWD_INST = [(16, 1), (16, 2), (16, 4), (32, 1), (32, 2), (64, 1)]
+# (HP, samples per thread, register-resident activations)
+FWD_INST = [(16, 1, 0), (16, 2, 0), (16, 4, 0), (16, 2, 1), (16, 4, 1), (32, 1, 0), (32, 2, 0), (32, 4, 0), (32, 2, 1),
+            (64, 1, 0), (64, 2, 0)]
 GRAD_INST = [16, 32, 64]
 
 
@@ -33,8 +35,9 @@ def _nvcc() -> str:
 
 def _units():
     units = [("dflow_api.o", "dflow_api.cu", []), ("dflow_kernels.o", "dflow_kernels.cu", [])]
-    for hp, s in FWD_INST:
-        units.append((f"inst_fwd_{hp}_{s}.o", "dflow_inst.cu", ["-DDFLOW_INST_FWD", f"-DDFLOW_HP={hp}", f"-DDFLOW_S={s}"]))
+    for hp, s, reg in FWD_INST:
+        units.append((f"inst_fwd_{hp}_{s}_{reg}.o", "dflow_inst.cu",
+                      ["-DDFLOW_INST_FWD", f"-DDFLOW_HP={hp}", f"-DDFLOW_S={s}", f"-DDFLOW_REG={reg}"]))
     for hp in GRAD_INST:
         units.append((f"inst_grad_{hp}.o", "dflow_inst.cu", ["-DDFLOW_INST_GRAD", f"-DDFLOW_HP={hp}"]))
     extra = os.path.join(CSRC, "dflow_wide.cu")

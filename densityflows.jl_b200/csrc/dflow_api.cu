@@ -94,7 +94,7 @@ static void layout_net(DevNet& net, int hp, int& off) {
   for (int j = 0; j < net.depth; ++j) {
     net.op[j] = (j < net.depth - 1) ? hp : round_out(net.w[j + 1]);
     net.s_w[j] = off;
-    off += net.w[j] * net.op[j];
+    off += (j == 0 ? net.w[j] : hp) * net.op[j];  // hidden Dense rows are zero-padded to hp (unrolled kernels)
     net.s_b[j] = off;
     off += net.op[j];
   }
@@ -135,6 +135,7 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
   H.L = L;
   H.logpdf_c0 = -((float)d * 1.8378770664093453f) / 2.0f;  // -(d*log2π)/2 in Float32
   int P = 0, hidden_max = 1, amax4 = 4, max_depth = 1;
+  bool relu_only = true;
   for (int ei = 0; ei < L; ++ei) {
     const dflow_elem_desc& ed = desc->elems[ei];
     DevElem& E = C->e[ei];
@@ -223,6 +224,16 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
   H.P = P;
   H.amax4 = amax4;
   H.max_depth = max_depth;
+  for (int ei = 0; ei < L; ++ei) {
+    const DevElem& E = C->e[ei];
+    if (E.kind == DFLOW_ELEM_NORM) continue;
+    for (int ni = (E.kind == DFLOW_ELEM_RNVP ? 0 : 1); ni < 2; ++ni) {
+      const DevNet& net = ni == 0 ? E.s : E.t;
+      for (int j = 0; j + 1 < net.depth; ++j)
+        if (net.act[j] != DFLOW_ACT_RELU && net.act[j] != DFLOW_ACT_IDENTITY) relu_only = false;
+    }
+  }
+  H.relu_only = relu_only ? 1 : 0;
   // staged image layout
   int total = 0, smax = 4;
   for (int ei = 0; ei < L; ++ei) {

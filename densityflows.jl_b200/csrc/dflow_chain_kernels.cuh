@@ -55,13 +55,40 @@ struct InSel {
   }
 };
 
+// The S samples of a thread sit next to each other in every column (slot = tid*S + s), so a thread moves its S
+// values of one unit with a single 32/64/128-bit shared-memory access (conflict-free: consecutive lanes touch
+// consecutive S*4-byte chunks) and the address arithmetic is one add per unit instead of one LEA per sample.
+template <int S>
+__device__ __forceinline__ void ld_samples(const float* p, float (&v)[S]) {
+  if constexpr (S == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (S == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+#pragma unroll
+    for (int s = 0; s < S; ++s) v[s] = p[s];
+  }
+}
+template <int S>
+__device__ __forceinline__ void st_samples(float* p, const float (&v)[S]) {
+  if constexpr (S == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (S == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  } else {
+#pragma unroll
+    for (int s = 0; s < S; ++s) p[s] = v[s];
+  }
+}
+
 // acc[o][s] += W[k][o] * in_k[s] for one input row k (NG broadcast LDS.128 -> NG*4*S FFMA)
 template <int NG, int S>
 __device__ __forceinline__ void dense_row(const float* src, const float* __restrict__ wrow, int slot0, int NT,
                                           float (&acc)[NG * 4][S]) {
   float v[S];
-#pragma unroll
-  for (int s = 0; s < S; ++s) v[s] = src[slot0 + s * NT];
+  ld_samples<S>(src + slot0 * S, v);
   const float4* wr = reinterpret_cast<const float4*>(wrow);
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
@@ -83,26 +110,34 @@ __device__ __forceinline__ void dense_to_col(const InSel& in, int K, const float
                                              const float* __restrict__ bst, int act, float* outcol, int CS, int slot0,
                                              int NT) {
   float acc[NG * 4][S];
+  // row 0 is peeled so that the bias enters as the FFMA addend (no per-sample register copies of the bias)
+  {
+    const float* src0 = in.first ? (in.n > 0 ? in.th : in.xs + (int)in.id[0] * in.CS) : in.hc;
+    float v[S];
+    ld_samples<S>(src0 + slot0 * S, v);
 #pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    const float4 b = *reinterpret_cast<const float4*>(bst + 4 * g);
+    for (int g = 0; g < NG; ++g) {
+      const float4 b = *reinterpret_cast<const float4*>(bst + 4 * g);
+      const float4 w = *reinterpret_cast<const float4*>(Wst + 4 * g);
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      acc[4 * g + 0][s] = b.x;
-      acc[4 * g + 1][s] = b.y;
-      acc[4 * g + 2][s] = b.z;
-      acc[4 * g + 3][s] = b.w;
+      for (int s = 0; s < S; ++s) {
+        acc[4 * g + 0][s] = fmaf(w.x, v[s], b.x);
+        acc[4 * g + 1][s] = fmaf(w.y, v[s], b.y);
+        acc[4 * g + 2][s] = fmaf(w.z, v[s], b.z);
+        acc[4 * g + 3][s] = fmaf(w.w, v[s], b.w);
+      }
     }
   }
   if (in.first) {
     const int n = in.n;
-    for (int k = 0; k < n; ++k) dense_row<NG, S>(in.th + k * in.CS, Wst + k * ld, slot0, NT, acc);
-    for (int k = n; k < K; ++k) dense_row<NG, S>(in.xs + (int)in.id[k - n] * in.CS, Wst + k * ld, slot0, NT, acc);
+    for (int k = 1; k < n; ++k) dense_row<NG, S>(in.th + k * in.CS, Wst + k * ld, slot0, NT, acc);
+    for (int k = (n > 1 ? n : 1); k < K; ++k)
+      dense_row<NG, S>(in.xs + (int)in.id[k - n] * in.CS, Wst + k * ld, slot0, NT, acc);
   } else {
-    const float* src = in.hc;
-    const float* wr = Wst;
+    const float* src = in.hc + in.CS;
+    const float* wr = Wst + ld;
 #pragma unroll 2
-    for (int k = 0; k < K; ++k) {
+    for (int k = 1; k < K; ++k) {
       dense_row<NG, S>(src, wr, slot0, NT, acc);
       src += in.CS;
       wr += ld;
@@ -110,19 +145,25 @@ __device__ __forceinline__ void dense_to_col(const InSel& in, int K, const float
   }
   if (act == DFLOW_ACT_RELU) {
 #pragma unroll
-    for (int o = 0; o < NG * 4; ++o)
+    for (int o = 0; o < NG * 4; ++o) {
 #pragma unroll
-      for (int s = 0; s < S; ++s) outcol[o * CS + slot0 + s * NT] = fmaxf(acc[o][s], 0.0f);
-  } else if (act == DFLOW_ACT_IDENTITY) {
-#pragma unroll
-    for (int o = 0; o < NG * 4; ++o)
-#pragma unroll
-      for (int s = 0; s < S; ++s) outcol[o * CS + slot0 + s * NT] = acc[o][s];
+      for (int s = 0; s < S; ++s) acc[o][s] = fmaxf(acc[o][s], 0.0f);
+      st_samples<S>(outcol + o * CS + slot0 * S, acc[o]);
+    }
   } else {
 #pragma unroll
-    for (int o = 0; o < NG * 4; ++o)
-#pragma unroll
-      for (int s = 0; s < S; ++s) outcol[o * CS + slot0 + s * NT] = act_apply(act, acc[o][s]);
+    for (int o = 0; o < NG * 4; ++o) st_samples<S>(outcol + o * CS + slot0 * S, acc[o]);
+    if (act != DFLOW_ACT_IDENTITY) {
+      // tanh / sigmoid: applied in a ROLLED loop over the stored column (keeps the transcendental code out of the
+      // unrolled tile; an unrolled copy per element blew the kernel up to 270 KB of SASS and thrashed the I-cache)
+#pragma unroll 1
+      for (int o = 0; o < NG * 4; ++o)
+#pragma unroll 1
+        for (int s = 0; s < S; ++s) {
+          float* p = outcol + o * CS + slot0 * S + s;
+          *p = act_apply(act, *p);
+        }
+    }
   }
 }
 
@@ -157,6 +198,144 @@ __device__ __forceinline__ void run_net(const DevNet& net, const float* __restri
   }
 }
 
+// ---- register-resident variant (hidden <= 32) ---------------------------------------------------------------
+// Measured on B200 (scripts/ubench.cu): a broadcast LDS.128 costs 2 clk/SM and 3-register FFMA issues at
+// ~115-128 /clk/SM, so every staged weight has to feed >= 4 FFMA per thread or the kernel is shared-memory bound.
+// Here the hidden activations of the S samples stay in REGISTERS between the Dense layers (fully unrolled over the
+// padded width HP, zero-padded weight rows), so the only shared-memory traffic of a hidden Dense is HP*HP/4
+// broadcast LDS.128 for HP*HP*S FFMA.
+template <int HP, int S>
+__device__ __forceinline__ void act_regs(float (&h)[HP][S], int act) {
+  if (act == DFLOW_ACT_RELU) {
+#pragma unroll
+    for (int o = 0; o < HP; ++o)
+#pragma unroll
+      for (int s = 0; s < S; ++s) h[o][s] = fmaxf(h[o][s], 0.0f);
+  }
+  // tanh / sigmoid chains never reach the register-resident kernels (DevChainHdr::relu_only, launch_fwd)
+}
+
+template <int HP, int S>
+__device__ __forceinline__ void bias_regs(float (&h)[HP][S], const float* __restrict__ bst) {
+#pragma unroll
+  for (int g = 0; g < HP / 4; ++g) {
+    const float4 b = *reinterpret_cast<const float4*>(bst + 4 * g);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      h[4 * g + 0][s] = b.x;
+      h[4 * g + 1][s] = b.y;
+      h[4 * g + 2][s] = b.z;
+      h[4 * g + 3][s] = b.w;
+    }
+  }
+}
+
+// out[NG*4 outputs starting at o0] of the LAST Dense from register-resident inputs; stored to outcol rows o0...
+template <int HP, int S, int NG>
+__device__ __forceinline__ void last_dense_regs(const float (&h)[HP][S], const float* __restrict__ Wst, int ld,
+                                                const float* __restrict__ bst, int act, float* outcol, int CS,
+                                                int slot0, int NT) {
+  float acc[NG * 4][S];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const float4 b = *reinterpret_cast<const float4*>(bst + 4 * g);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      acc[4 * g + 0][s] = b.x;
+      acc[4 * g + 1][s] = b.y;
+      acc[4 * g + 2][s] = b.z;
+      acc[4 * g + 3][s] = b.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < HP; ++k) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const float4 w = *reinterpret_cast<const float4*>(Wst + k * ld + 4 * g);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        acc[4 * g + 0][s] = fmaf(w.x, h[k][s], acc[4 * g + 0][s]);
+        acc[4 * g + 1][s] = fmaf(w.y, h[k][s], acc[4 * g + 1][s]);
+        acc[4 * g + 2][s] = fmaf(w.z, h[k][s], acc[4 * g + 2][s]);
+        acc[4 * g + 3][s] = fmaf(w.w, h[k][s], acc[4 * g + 3][s]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < NG * 4; ++o) st_samples<S>(outcol + o * CS + slot0 * S, acc[o]);
+  if (act != DFLOW_ACT_IDENTITY) {
+#pragma unroll 1
+    for (int o = 0; o < NG * 4; ++o)
+#pragma unroll 1
+      for (int s = 0; s < S; ++s) {
+        float* p = outcol + o * CS + slot0 * S + s;
+        *p = act_apply(act, *p);
+      }
+  }
+}
+
+template <int HP, int S>
+__device__ __forceinline__ void run_net_reg(const DevNet& net, const float* __restrict__ wblk, const InSel& in,
+                                            float* outcol, int CS, int slot0, int NT) {
+  const int D = net.depth;
+  if (D == 1) {  // a single Dense straight from the inputs: use the column form
+    InSel in0 = in;
+    in0.first = true;
+    const int op = net.op[0];
+    for (int o0 = 0; o0 < op; o0 += 4)
+      dense_to_col<1, S>(in0, net.w[0], wblk + net.s_w[0] + o0, op, wblk + net.s_b[0] + o0, net.act[0],
+                         outcol + o0 * CS, CS, slot0, NT);
+    return;
+  }
+  float h[HP][S];
+  // first Dense: inputs are the gathered θ / x columns (runtime width), outputs in registers
+  bias_regs<HP, S>(h, wblk + net.s_b[0]);
+  {
+    const float* W0 = wblk + net.s_w[0];
+    const int n = in.n, K = net.w[0];
+    for (int k = 0; k < n; ++k) dense_row<HP / 4, S>(in.th + k * CS, W0 + k * HP, slot0, NT, h);
+    for (int k = n; k < K; ++k) dense_row<HP / 4, S>(in.xs + (int)in.id[k - n] * CS, W0 + k * HP, slot0, NT, h);
+  }
+  act_regs<HP, S>(h, net.act[0]);
+  // hidden Dense layers: registers -> registers, fully unrolled (weight rows are zero-padded to HP)
+  for (int j = 1; j < D - 1; ++j) {
+    float o[HP][S];
+    bias_regs<HP, S>(o, wblk + net.s_b[j]);
+    const float* Wj = wblk + net.s_w[j];
+#pragma unroll
+    for (int k = 0; k < HP; ++k) {
+#pragma unroll
+      for (int g = 0; g < HP / 4; ++g) {
+        const float4 w = *reinterpret_cast<const float4*>(Wj + k * HP + 4 * g);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          o[4 * g + 0][s] = fmaf(w.x, h[k][s], o[4 * g + 0][s]);
+          o[4 * g + 1][s] = fmaf(w.y, h[k][s], o[4 * g + 1][s]);
+          o[4 * g + 2][s] = fmaf(w.z, h[k][s], o[4 * g + 2][s]);
+          o[4 * g + 3][s] = fmaf(w.w, h[k][s], o[4 * g + 3][s]);
+        }
+      }
+    }
+    act_regs<HP, S>(o, net.act[j]);
+#pragma unroll
+    for (int k = 0; k < HP; ++k)
+#pragma unroll
+      for (int s = 0; s < S; ++s) h[k][s] = o[k][s];
+  }
+  // last Dense: padded width op in {4, 8, 16, 32, 64}, groups of <= 8 outputs at a time
+  {
+    const int jl = D - 1, op = net.op[jl], act = net.act[jl];
+    const float* Wl = wblk + net.s_w[jl];
+    const float* bl = wblk + net.s_b[jl];
+    if (op == 4) {
+      last_dense_regs<HP, S, 1>(h, Wl, 4, bl, act, outcol, CS, slot0, NT);
+    } else {
+      for (int o0 = 0; o0 < op; o0 += 8)
+        last_dense_regs<HP, S, 2>(h, Wl + o0, op, bl + o0, act, outcol + o0 * CS, CS, slot0, NT);
+    }
+  }
+}
+
 // cooperative float4 copy global -> shared (len4 = number of float4)
 __device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ src, int len4, int tid, int nt) {
   float4* d4 = reinterpret_cast<float4*>(dst);
@@ -166,7 +345,7 @@ __device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ sr
 
 // Apply one element in the normalising (`backward`, x -> z) or sampling direction to the S samples of this
 // thread.  ldj is accumulated with the reference's signs.
-template <int HP, int S>
+template <int HP, int S, bool REG = false>
 __device__ __forceinline__ void elem_apply(const DevChainHdr& H, const DevElem& E, const float* __restrict__ wblk,
                                            bool sampling, float* xs, float* th, float* hc, int hstride, float* sb,
                                            float* tb, int CS, int slot0, int NT, float (&ldj)[S]) {
@@ -178,7 +357,7 @@ __device__ __forceinline__ void elem_apply(const DevChainHdr& H, const DevElem& 
       const float xmin = wblk[k], xmax = wblk[d + k];
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        float* p = xs + k * CS + slot0 + s * NT;
+        float* p = xs + k * CS + slot0 * S + s;
         const float v = *p;
         if (!sampling)
           *p = (beta * (v - xmin) + alpha * (xmax - v)) / (xmax - xmin);
@@ -192,25 +371,35 @@ __device__ __forceinline__ void elem_apply(const DevChainHdr& H, const DevElem& 
   }
   InSel in{th, xs, hc, E.id, H.n, CS, true};
   const bool rnvp = (E.kind == DFLOW_ELEM_RNVP);
-  for (int ni = rnvp ? 0 : 1; ni < 2; ++ni)
-    run_net<HP, S>(ni == 0 ? E.s : E.t, wblk, in, hc, hstride, ni == 0 ? sb : tb, CS, slot0, NT);
+  for (int ni = rnvp ? 0 : 1; ni < 2; ++ni) {
+    if constexpr (REG)
+      run_net_reg<HP, S>(ni == 0 ? E.s : E.t, wblk, in, ni == 0 ? sb : tb, CS, slot0, NT);
+    else
+      run_net<HP, S>(ni == 0 ? E.s : E.t, wblk, in, hc, hstride, ni == 0 ? sb : tb, CS, slot0, NT);
+  }
   float lsum[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) lsum[s] = 0.0f;
   for (int j = 0; j < E.a; ++j) {
     const int k = E.af[j];
+    float sv[S], tv[S], xv[S];
+    if (rnvp) {
+      ld_samples<S>(sb + j * CS + slot0 * S, sv);
+    } else {
+#pragma unroll
+      for (int s = 0; s < S; ++s) sv[s] = 0.0f;
+    }
+    ld_samples<S>(tb + j * CS + slot0 * S, tv);
+    ld_samples<S>(xs + k * CS + slot0 * S, xv);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const int sl = slot0 + s * NT;
-      const float sv = rnvp ? sb[j * CS + sl] : 0.0f;
-      const float tv = tb[j * CS + sl];
-      float* p = xs + k * CS + sl;
       if (!sampling)
-        *p = (*p - tv) * expf(-sv);  // RNVP.jl:92
+        xv[s] = (xv[s] - tv[s]) * expf(-sv[s]);  // RNVP.jl:92
       else
-        *p = *p * expf(sv) + tv;  // RNVP.jl:184
-      lsum[s] += sv;
+        xv[s] = xv[s] * expf(sv[s]) + tv[s];  // RNVP.jl:184
+      lsum[s] += sv[s];
     }
+    st_samples<S>(xs + k * CS + slot0 * S, xv);
   }
 #pragma unroll
   for (int s = 0; s < S; ++s) ldj[s] += sampling ? lsum[s] : -lsum[s];
@@ -261,12 +450,12 @@ struct SmemPlan {
   __host__ __device__ size_t bytes() const { return 4ull * ((size_t)chain_f + w_f + cols_f + grad_f); }
 };
 
-__host__ __device__ inline SmemPlan plan_fwd(const DevChainHdr& h, int chain_bytes, int nts) {
+__host__ __device__ inline SmemPlan plan_fwd(const DevChainHdr& h, int chain_bytes, int nts, bool reg = false) {
   SmemPlan p;
   p.chain_f = ((chain_bytes + 15) / 16) * 4;
   p.w_f = h.resident ? h.stage_total : h.stage_max;
   p.cs = nts;
-  const int rows = h.d + h.n + h.hp + 2 * h.amax4;
+  const int rows = h.d + h.n + (reg ? 0 : h.hp) + 2 * h.amax4;  // REG keeps hidden activations in registers
   p.cols_f = rows * p.cs;
   p.grad_f = 0;
   return p;
@@ -287,8 +476,20 @@ __host__ __device__ inline SmemPlan plan_grad(const DevChainHdr& h, int chain_by
 // ------------------------------------------------------------------------------------------------------------
 // K1 / K2: fused chain, normalising or sampling direction
 // ------------------------------------------------------------------------------------------------------------
-template <int HP, int S>
-__global__ void __launch_bounds__(256) chain_fwd_kernel(const FwdArgs a) {
+// max threads per CTA of an instantiation (host clamps blockDim to this): big accumulator tiles get 128 threads
+// and up to 255 registers, the others 256 threads x 2 CTAs (<= 128 registers)
+template <int HP, int S, bool REG>
+constexpr int fwd_max_threads() {
+  return (REG || HP * S >= 64) ? 128 : 256;
+}
+template <int HP, int S, bool REG>
+constexpr int fwd_min_ctas() {
+  return (REG || HP * S > 64) ? 2 : (HP * S == 64 ? 3 : 2);  // 255 / 168 / 128 registers
+}
+
+template <int HP, int S, bool REG>
+__global__ void __launch_bounds__((fwd_max_threads<HP, S, REG>()), (fwd_min_ctas<HP, S, REG>()))
+    chain_fwd_kernel(const FwdArgs a) {
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
   const int tid = threadIdx.x, NT = blockDim.x, NTS = NT * S;
@@ -298,14 +499,14 @@ __global__ void __launch_bounds__(256) chain_fwd_kernel(const FwdArgs a) {
   __syncthreads();
   const DevChain* C = reinterpret_cast<const DevChain*>(smem);
   const DevChainHdr& H = C->h;
-  const SmemPlan P = plan_fwd(H, a.chain_bytes, NTS);
+  const SmemPlan P = plan_fwd(H, a.chain_bytes, NTS, REG);
   float* wsm = smem + P.chain_f;
   float* cols = wsm + P.w_f;
   const int CS = P.cs;
   float* xs = cols;
   float* th = xs + H.d * CS;
   float* hc = th + H.n * CS;
-  float* sb = hc + H.hp * CS;
+  float* sb = hc + (REG ? 0 : H.hp) * CS;
   float* tb = sb + H.amax4 * CS;
 
   if (H.resident) {
@@ -315,15 +516,55 @@ __global__ void __launch_bounds__(256) chain_fwd_kernel(const FwdArgs a) {
 
   const int d = H.d, n = H.n, L = H.L;
   const bool sampling = (a.mode >= MODE_SAMPLE);
+  // 128-bit global access needs 16-byte aligned array bases (cudaMalloc / CuArray / torch give >= 256)
+  const bool io_aligned = ((reinterpret_cast<uintptr_t>(a.x_in) | reinterpret_cast<uintptr_t>(a.theta) |
+                            reinterpret_cast<uintptr_t>(a.x_out) | reinterpret_cast<uintptr_t>(a.aux_out)) & 15) == 0;
   const long long ntiles = (a.B + NTS - 1) / NTS;
   float lsum_thread = 0.0f, nonfinite = 0.0f;
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long base = tile * NTS;
     // ---- load ----
+    // fast path (S == 4, full tile, no gather): the thread's 4 consecutive samples are 4*d contiguous floats =
+    // d aligned float4 -> coalesced 128-bit global loads, transposed into the columns on the fly
+    const bool vec_io = (S == 4) && a.idx == nullptr && (base + NTS <= a.B) && io_aligned;
+    if (vec_io && a.mode != MODE_SAMPLE_RNG) {
+      const float4* xp4 = reinterpret_cast<const float4*>(a.x_in + (base + (long long)tid * S) * d);
+      int s = 0, k = 0;
+      for (int c = 0; c < d; ++c) {
+        const float4 t = __ldg(xp4 + c);
+        const float e[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          xs[k * CS + tid * S + s] = e[q];
+          if (++k == d) {
+            k = 0;
+            ++s;
+          }
+        }
+      }
+    }
+    if (vec_io && a.theta != nullptr && n > 0) {
+      const float4* tp4 = reinterpret_cast<const float4*>(a.theta + (base + (long long)tid * S) * n);
+      int s = 0, k = 0;
+      for (int c = 0; c < n; ++c) {
+        const float4 t = __ldg(tp4 + c);
+        const float e[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v = e[q];
+          if (a.flags & DFLOW_THETA_NORMALIZE) v = (H.theta_rng[k] == 0.0f) ? 0.0f : (v - H.theta_min[k]) / H.theta_rng[k];
+          th[k * CS + tid * S + s] = v;
+          if (++k == n) {
+            k = 0;
+            ++s;
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const int sl = tid + s * NT;
+      const int sl = tid * S + s;
       const long long gi = base + sl;
       const bool valid = gi < a.B;
       const long long src = (valid && a.idx) ? (long long)a.idx[gi] : gi;
@@ -340,10 +581,11 @@ __global__ void __launch_bounds__(256) chain_fwd_kernel(const FwdArgs a) {
           for (int q = 0; q < 4; ++q)
             if (4 * g + q < d) xs[(4 * g + q) * CS + sl] = z[q];
         }
-      } else {
+      } else if (!vec_io) {
         const float* xp = a.x_in + src * d;
         for (int k = 0; k < d; ++k) xs[k * CS + sl] = valid ? __ldg(xp + k) : 0.0f;
       }
+      if (vec_io && a.theta != nullptr) continue;  // θ already loaded by the vector path
       for (int k = 0; k < n; ++k) {
         float v = 0.0f;
         if (a.theta_const)
@@ -374,15 +616,17 @@ __global__ void __launch_bounds__(256) chain_fwd_kernel(const FwdArgs a) {
         __syncthreads();
         wblk = wsm;
       }
-      elem_apply<HP, S>(H, E, wblk, sampling, xs, th, hc, 0, sb, tb, CS, tid, NT, ldj);
+      elem_apply<HP, S, REG>(H, E, wblk, sampling, xs, th, hc, 0, sb, tb, CS, tid, NT, ldj);
     }
 
     // ---- store ----
+    const bool vec_out = (S == 4) && (base + NTS <= a.B) && io_aligned;
+    float aux[S];  // per-sample scalar result: logp or ldj
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const int sl = tid + s * NT;
+      const int sl = tid * S + s;
       const long long gi = base + sl;
-      if (gi >= a.B) continue;
+      aux[s] = ldj[s];
       if (a.mode == MODE_LOGPDF || a.mode == MODE_LOGPDF_SUM) {
         float q = 0.0f;
         for (int k = 0; k < d; ++k) {
@@ -390,19 +634,40 @@ __global__ void __launch_bounds__(256) chain_fwd_kernel(const FwdArgs a) {
           q = fmaf(v, v, q);
         }
         const float lp = H.logpdf_c0 - 0.5f * q + ldj[s];  // src/Flows.jl:279
-        if (a.mode == MODE_LOGPDF)
-          a.aux_out[gi] = lp;
-        else {
+        aux[s] = lp;
+        if (a.mode == MODE_LOGPDF_SUM && gi < a.B) {
           if (isfinite(lp))
             lsum_thread += lp;
           else
             nonfinite += 1.0f;
         }
-      } else {
+      } else if (!vec_out && gi < a.B) {
         float* op = a.x_out + gi * d;
         for (int k = 0; k < d; ++k) op[k] = xs[k * CS + sl];
-        if (a.mode == MODE_NORMALIZE || a.mode == MODE_FORWARD_LDJ) a.aux_out[gi] = ldj[s];
       }
+      if (!vec_out && gi < a.B && a.mode != MODE_LOGPDF_SUM && a.mode != MODE_SAMPLE && a.mode != MODE_SAMPLE_RNG)
+        a.aux_out[gi] = aux[s];
+    }
+    if (vec_out) {
+      if (a.mode != MODE_LOGPDF && a.mode != MODE_LOGPDF_SUM) {
+        // 4 consecutive samples = d float4 of contiguous output
+        float4* op4 = reinterpret_cast<float4*>(a.x_out + (base + (long long)tid * S) * d);
+        int s = 0, k = 0;
+        for (int c = 0; c < d; ++c) {
+          float e[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            e[q] = xs[k * CS + tid * S + s];
+            if (++k == d) {
+              k = 0;
+              ++s;
+            }
+          }
+          op4[c] = make_float4(e[0], e[1], e[2], e[3]);
+        }
+      }
+      if (a.mode != MODE_LOGPDF_SUM && a.mode != MODE_SAMPLE && a.mode != MODE_SAMPLE_RNG)
+        *reinterpret_cast<float4*>(a.aux_out + base + (long long)tid * S) = make_float4(aux[0], aux[1 % S], aux[2 % S], aux[3 % S]);
     }
   }
 
@@ -735,7 +1000,7 @@ __global__ void __launch_bounds__(256) chain_grad_kernel(const GradArgs a) {
 }
 
 // per-instantiation launch shims (defined in the inst_*.cu units)
-template <int HP, int S>
+template <int HP, int S, bool REG>
 cudaError_t launch_fwd_inst(const FwdArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st);
 template <int HP>
 cudaError_t launch_grad_inst(const GradArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st);

@@ -54,6 +54,7 @@ struct DevChainHdr {
   int amax4;         // max padded output width
   int max_depth;
   int ck_total;      // checkpoint floats per sample (adjoint workspace)
+  int relu_only;     // 1: every hidden activation is relu / identity (register-resident kernels apply)
   int has_theta_range;
   float logpdf_c0;   // -(d*log(2pi))/2
   float theta_min[NMAX];

@@ -20,9 +20,10 @@ __global__ void prepack_kernel(const PrepackArgs a) {
     const DevNet& net = ni == 0 ? E.s : E.t;
     for (int j = 0; j < net.depth; ++j) {
       const int K = net.w[j], O = net.w[j + 1], op = net.op[j];
-      for (int i = threadIdx.x; i < K * op; i += blockDim.x) {
+      const int Kp = (j == 0) ? K : C->h.hp;  // rows of hidden Dense layers are zero-padded to hp
+      for (int i = threadIdx.x; i < Kp * op; i += blockDim.x) {
         const int k = i / op, o = i - k * op;
-        blk[net.s_w[j] + i] = (o < O) ? a.W[net.p_w[j] + o + O * k] : 0.0f;
+        blk[net.s_w[j] + i] = (o < O && k < K) ? a.W[net.p_w[j] + o + O * k] : 0.0f;
       }
       for (int o = threadIdx.x; o < op; o += blockDim.x)
         blk[net.s_b[j] + o] = (net.has_bias && o < O) ? a.W[net.p_b[j] + o] : 0.0f;
@@ -134,13 +135,14 @@ int launch_prepack(dflow_chain* c, const float* W, cudaStream_t st) {
   return DFLOW_OK;
 }
 
-template <int HP, int S>
+template <int HP, int S, bool REG>
 static int launch_fwd_t(dflow_chain* c, FwdArgs& a, cudaStream_t st, int nt) {
   const DevChainHdr& h = c->hc()->h;
-  SmemPlan p = plan_fwd(h, c->chain_bytes, nt * S);
+  if (nt > fwd_max_threads<HP, S, REG>()) nt = fwd_max_threads<HP, S, REG>();
+  SmemPlan p = plan_fwd(h, c->chain_bytes, nt * S, REG);
   while (p.bytes() > (size_t)c->max_smem_optin && nt > 32) {
     nt >>= 1;
-    p = plan_fwd(h, c->chain_bytes, nt * S);
+    p = plan_fwd(h, c->chain_bytes, nt * S, REG);
   }
   if (p.bytes() > (size_t)c->max_smem_optin) {
     set_error("chain needs %zu bytes of shared memory (> %d)", p.bytes(), c->max_smem_optin);
@@ -150,7 +152,7 @@ static int launch_fwd_t(dflow_chain* c, FwdArgs& a, cudaStream_t st, int nt) {
   int per_sm = c->ctas_per_sm;
   if (per_sm <= 0) {
     per_sm = (int)((size_t)c->max_smem_optin / (p.bytes() + 1024));
-    const int by_threads = 2048 / nt;
+    const int by_threads = (REG ? 512 : 2048) / nt;
     if (per_sm > by_threads) per_sm = by_threads;
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
@@ -158,31 +160,39 @@ static int launch_fwd_t(dflow_chain* c, FwdArgs& a, cudaStream_t st, int nt) {
   long long grid = (long long)c->sm_count * per_sm;
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
-  CK((launch_fwd_inst<HP, S>(a, (unsigned)grid, nt, p.bytes(), st)));
+  CK((launch_fwd_inst<HP, S, REG>(a, (unsigned)grid, nt, p.bytes(), st)));
   c->launches++;
   return DFLOW_OK;
 }
 
+// Kernel selection (fwd_spt tuning: 0 = automatic; negative = force the shared-memory-column variant with |spt|)
 int launch_fwd(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
   const DevChainHdr& h = c->hc()->h;
   a.chain = c->d_chain;
   a.staged = c->d_staged;
   a.chain_bytes = c->chain_bytes;
   int spt = c->fwd_spt;
+  if (!h.relu_only && spt < 0) spt = -spt;  // tanh / sigmoid: shared-memory-column kernels only
   int nt = c->fwd_threads > 0 ? c->fwd_threads : (h.hp >= 64 ? 128 : 256);
   if (nt > 256) nt = 256;
   nt = (nt + 31) & ~31;
-  if (spt <= 0) spt = (h.hp >= 64) ? 1 : 2;
+  // spt > 0: shared-memory-column kernels with spt samples per thread; spt < 0: register-resident kernels with
+  // |spt| samples per thread (relu chains only); 0: automatic
   switch (h.hp) {
     case 16:
-      if (spt >= 4) return launch_fwd_t<16, 4>(c, a, st, nt);
-      if (spt == 2) return launch_fwd_t<16, 2>(c, a, st, nt);
-      return launch_fwd_t<16, 1>(c, a, st, nt);
+      if (spt == 0 || spt == 4) return launch_fwd_t<16, 4, false>(c, a, st, nt);
+      if (spt == 2) return launch_fwd_t<16, 2, false>(c, a, st, nt);
+      if (spt == -4) return launch_fwd_t<16, 4, true>(c, a, st, nt);
+      if (spt == -2) return launch_fwd_t<16, 2, true>(c, a, st, nt);
+      return launch_fwd_t<16, 1, false>(c, a, st, nt);
     case 32:
-      if (spt >= 2) return launch_fwd_t<32, 2>(c, a, st, nt);
-      return launch_fwd_t<32, 1>(c, a, st, nt);
+      if (spt == 0 || spt == 4) return launch_fwd_t<32, 4, false>(c, a, st, nt);
+      if (spt == 2) return launch_fwd_t<32, 2, false>(c, a, st, nt);
+      if (spt == -2) return launch_fwd_t<32, 2, true>(c, a, st, nt);
+      return launch_fwd_t<32, 1, false>(c, a, st, nt);
     case 64:
-      return launch_fwd_t<64, 1>(c, a, st, nt);
+      if (spt == 0 || spt == 2) return launch_fwd_t<64, 2, false>(c, a, st, nt);
+      return launch_fwd_t<64, 1, false>(c, a, st, nt);
   }
   set_error("hidden width template %d not built", h.hp);
   return DFLOW_E_UNSUPPORTED;

@@ -51,7 +51,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "c2"
     if which in ("c2", "all"):
         tunes = [dict(fwd_spt=s, fwd_threads=t, grad_threads=gt, ctas_per_sm=c) for s, t, gt, c in
-                 [(2, 256, 256, 0), (1, 256, 128, 0), (4, 128, 256, 2), (4, 256, 256, 1), (2, 128, 128, 4), (2, 256, 256, 2), (1, 128, 256, 4)]]
+                 [(4, 128, 256, 0), (4, 128, 256, 2), (4, 128, 256, 3), (4, 256, 256, 1), (4, 256, 256, 2), (4, 64, 256, 4), (4, 64, 256, 6), (2, 256, 256, 2), (-2, 128, 256, 3)]]
         run("C2", 5, 2, lambda x: O.readme_chain(2, x), 1 << 25, 1 << 23, tunes)
     if which in ("c3", "all"):
         tunes = [dict(fwd_spt=1, fwd_threads=t, grad_threads=gt, ctas_per_sm=c) for t, gt, c in [(128, 128, 0), (256, 64, 0), (64, 128, 2)]]
