@@ -277,7 +277,8 @@ def run_ours(args):
     tp_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp_file):
         try:
-            traffic = json.load(open(tp_file)).get("chain_fwd_kernel_bytes_per_launch")
+            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, scaled per launch
+            traffic = float(json.load(open(tp_file))["chain_fwd_kernel_bytes_per_sample"]) * B
         except Exception:
             traffic = None
     tfl = FLOP_PER_SAMPLE_FWD * B / (ms * 1e-3) / 1e12
