@@ -24,6 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 FWD_INST = [(16, 1, 0), (16, 2, 0), (16, 4, 0), (16, 2, 1), (16, 4, 1), (32, 1, 0), (32, 2, 0), (32, 4, 0), (32, 2, 1),
             (64, 1, 0), (64, 2, 0)]
 GRAD_INST = [16, 32, 64]
+GRAD2_INST = [(16, 1), (16, 2), (16, 4), (32, 1), (32, 2), (64, 1), (64, 2)]
 
 
 def _nvcc() -> str:
@@ -40,6 +41,8 @@ def _units():
                       ["-DDFLOW_INST_FWD", f"-DDFLOW_HP={hp}", f"-DDFLOW_S={s}", f"-DDFLOW_REG={reg}"]))
     for hp in GRAD_INST:
         units.append((f"inst_grad_{hp}.o", "dflow_inst.cu", ["-DDFLOW_INST_GRAD", f"-DDFLOW_HP={hp}"]))
+    for hp, s in GRAD2_INST:
+        units.append((f"inst_grad2_{hp}_{s}.o", "dflow_inst.cu", ["-DDFLOW_INST_GRAD2", f"-DDFLOW_HP={hp}", f"-DDFLOW_S={s}"]))
     extra = os.path.join(CSRC, "dflow_wide.cu")
     if os.path.exists(extra):
         units.append(("dflow_wide.o", "dflow_wide.cu", []))

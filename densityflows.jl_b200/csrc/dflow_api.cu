@@ -548,7 +548,7 @@ size_t dflow_workspace_bytes(const dflow_chain* c, int64_t B) {
   (void)B;
   if (!c) return 0;
   // one checkpoint slab per resident CTA (not per sample): grid <= sm_count * 4 CTAs of <= 256 threads
-  return (size_t)c->sm_count * 4 * 256 * (size_t)c->hc()->h.ck_total * sizeof(float) + 256;
+  return (size_t)c->sm_count * 4 * 512 * (size_t)c->hc()->h.ck_total * sizeof(float) + 256;
 }
 
 int dflow_loss_grad(dflow_chain* c, const float* W, const float* x, const float* theta, int64_t B, const int32_t* idx,
@@ -765,6 +765,8 @@ int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
     c->fwd_threads = value;
   else if (!strcmp(key, "grad_threads"))
     c->grad_threads = value;
+  else if (!strcmp(key, "grad_spt"))
+    c->grad_spt = value;
   else if (!strcmp(key, "ctas_per_sm"))
     c->ctas_per_sm = value;
   else {

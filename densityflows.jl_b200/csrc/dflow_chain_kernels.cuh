@@ -487,12 +487,14 @@ constexpr int fwd_min_ctas() {
   return (REG || HP * S > 64) ? 2 : (HP * S == 64 ? 3 : 2);  // 255 / 168 / 128 registers
 }
 
-template <int HP, int S, bool REG>
-__global__ void __launch_bounds__((fwd_max_threads<HP, S, REG>()), (fwd_min_ctas<HP, S, REG>()))
-    chain_fwd_kernel(const FwdArgs a) {
+// FIXED: blockDim.x equals fwd_max_threads, so the column stride CS = NT*S is a compile-time constant and every
+// column address `unit*CS + slot` of an unrolled loop folds into an immediate offset (the runtime-stride build spent
+// ~15 % of its instructions on LEA/IMAD/IADD3 address arithmetic; profiles/r01_ncu_fwd_summary.md).
+template <int HP, int S, bool REG, bool FIXED>
+__device__ __forceinline__ void chain_fwd_body(const FwdArgs& a) {
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
-  const int tid = threadIdx.x, NT = blockDim.x, NTS = NT * S;
+  const int tid = threadIdx.x, NT = FIXED ? fwd_max_threads<HP, S, REG>() : (int)blockDim.x, NTS = NT * S;
 
   // DevChain -> shared
   copy_f4(smem, reinterpret_cast<const float*>(a.chain), (a.chain_bytes + 15) / 16, tid, NT);
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__((fwd_max_threads<HP, S, REG>()), (fwd_min_ctas
   const SmemPlan P = plan_fwd(H, a.chain_bytes, NTS, REG);
   float* wsm = smem + P.chain_f;
   float* cols = wsm + P.w_f;
-  const int CS = P.cs;
+  const int CS = FIXED ? NTS : P.cs;
   float* xs = cols;
   float* th = xs + H.d * CS;
   float* hc = th + H.n * CS;
@@ -696,6 +698,15 @@ __global__ void __launch_bounds__((fwd_max_threads<HP, S, REG>()), (fwd_min_ctas
       if (t1 != 0.0f) atomicAdd(a.aux_out + 1, t1);
     }
   }
+}
+
+template <int HP, int S, bool REG>
+__global__ void __launch_bounds__((fwd_max_threads<HP, S, REG>()), (fwd_min_ctas<HP, S, REG>()))
+    chain_fwd_kernel(const FwdArgs a) {
+  if (blockDim.x == fwd_max_threads<HP, S, REG>())
+    chain_fwd_body<HP, S, REG, true>(a);
+  else
+    chain_fwd_body<HP, S, REG, false>(a);
 }
 
 // ------------------------------------------------------------------------------------------------------------

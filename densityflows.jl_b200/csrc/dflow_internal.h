@@ -127,7 +127,7 @@ struct dflow_chain {
   float* d_staged = nullptr;
   int chain_bytes = 0;
   // tuning
-  int fwd_spt = 0, fwd_threads = 0, grad_threads = 0, ctas_per_sm = 0;
+  int fwd_spt = 0, fwd_threads = 0, grad_threads = 0, grad_spt = 0, ctas_per_sm = 0;
   long long launches = 0;
   // host pipeline scratch (dflow_*_host)
   void* pipe = nullptr;

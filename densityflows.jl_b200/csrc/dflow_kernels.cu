@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "dflow_chain_kernels.cuh"
+#include "dflow_grad_kernel.cuh"
 
 namespace dflow {
 
@@ -173,7 +174,7 @@ int launch_fwd(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
   a.chain_bytes = c->chain_bytes;
   int spt = c->fwd_spt;
   if (!h.relu_only && spt < 0) spt = -spt;  // tanh / sigmoid: shared-memory-column kernels only
-  int nt = c->fwd_threads > 0 ? c->fwd_threads : (h.hp >= 64 ? 128 : 256);
+  int nt = c->fwd_threads > 0 ? c->fwd_threads : 256;  // clamped to the instantiation's fixed block size
   if (nt > 256) nt = 256;
   nt = (nt + 31) & ~31;
   // spt > 0: shared-memory-column kernels with spt samples per thread; spt < 0: register-resident kernels with
@@ -228,11 +229,58 @@ static int launch_grad_t(dflow_chain* c, GradArgs& a, cudaStream_t st, int nt) {
   return DFLOW_OK;
 }
 
+template <int HP, int S>
+static int launch_grad2_t(dflow_chain* c, GradArgs& a, cudaStream_t st, int nt) {
+  const DevChainHdr& h = c->hc()->h;
+  if (nt > grad2_max_threads<HP, S>()) nt = grad2_max_threads<HP, S>();
+  a.smem_grad = (h.P * 4 <= 64 * 1024) ? 1 : 0;
+  SmemPlan p = plan_grad2(h, c->chain_bytes, nt * S, a.smem_grad);
+  while (p.bytes() > (size_t)c->max_smem_optin && nt > 32) {
+    nt >>= 1;
+    p = plan_grad2(h, c->chain_bytes, nt * S, a.smem_grad);
+  }
+  if (p.bytes() > (size_t)c->max_smem_optin) {
+    set_error("adjoint needs %zu bytes of shared memory (> %d)", p.bytes(), c->max_smem_optin);
+    return DFLOW_E_UNSUPPORTED;
+  }
+  const long long ntiles = (a.B + (long long)nt * S - 1) / ((long long)nt * S);
+  int per_sm = c->ctas_per_sm;
+  if (per_sm <= 0) {
+    per_sm = (int)((size_t)c->max_smem_optin / (p.bytes() + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+  }
+  long long grid = (long long)c->sm_count * per_sm;
+  if (grid > (long long)c->sm_count * 4) grid = (long long)c->sm_count * 4;  // workspace is sized for <= 4 CTAs/SM
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  CK((launch_grad2_inst<HP, S>(a, (unsigned)grid, nt, p.bytes(), st)));
+  c->launches++;
+  return DFLOW_OK;
+}
+
 int launch_grad(dflow_chain* c, GradArgs& a, cudaStream_t st) {
   const DevChainHdr& h = c->hc()->h;
   a.chain = c->d_chain;
   a.staged = c->d_staged;
   a.chain_bytes = c->chain_bytes;
+  if (c->grad_spt >= 0) {  // v2 adjoint (register-tiled dW); grad_spt < 0 selects the first-generation kernel
+    int nt2 = c->grad_threads > 0 ? c->grad_threads : 256;  // clamped to the instantiation's fixed block size
+    nt2 = (nt2 + 31) & ~31;
+    const int s = c->grad_spt;
+    switch (h.hp) {
+      case 16:
+        if (s == 1) return launch_grad2_t<16, 1>(c, a, st, nt2);
+        if (s == 4) return launch_grad2_t<16, 4>(c, a, st, nt2);
+        return launch_grad2_t<16, 2>(c, a, st, nt2);
+      case 32:
+        if (s == 1) return launch_grad2_t<32, 1>(c, a, st, nt2);
+        return launch_grad2_t<32, 2>(c, a, st, nt2);
+      case 64:
+        if (s == 2) return launch_grad2_t<64, 2>(c, a, st, nt2);
+        return launch_grad2_t<64, 1>(c, a, st, nt2);
+    }
+  }
   int nt = c->grad_threads > 0 ? c->grad_threads : (h.hp >= 64 ? 128 : 256);
   if (nt > 256) nt = 256;
   nt = (nt + 31) & ~31;

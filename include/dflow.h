@@ -159,7 +159,8 @@ int dflow_sample_host(dflow_chain* chain, const float* W, uint64_t seed, const f
                       int32_t flags, float* x_host, int64_t chunk);
 
 /* ---- tuning / introspection ------------------------------------------------------------------------------ */
-/* keys: "fwd_spt" (samples per thread), "fwd_threads", "grad_threads", "ctas_per_sm"; value 0 = automatic */
+/* keys: "fwd_spt", "grad_spt" (samples per thread; negative selects the alternative kernel generation),
+ * "fwd_threads", "grad_threads", "ctas_per_sm"; value 0 = automatic */
 int dflow_set_tuning(dflow_chain* chain, const char* key, int32_t value);
 /* number of kernels the library has launched on behalf of this handle since creation */
 int64_t dflow_launch_count(const dflow_chain* chain);

@@ -33,8 +33,10 @@ def run(name, d, n, mk, B, Bg, tunes):
         f = lambda: df._lib.check(lib.dflow_logpdf(pc.handle, pc.W.data_ptr(), xp, tp, B, None, 0, out.data_ptr(), st))
         med, mn = timeit(f)
         print(json.dumps({"cfg": name, "op": "logpdf", "B": B, "tune": tune, "ms": med, "ms_min": mn, "samples_per_s": B / med * 1e3}), flush=True)
-    for tune in tunes:
-        if "fwd_spt" in tune and tune["fwd_spt"] not in (0, 1): pass
+    gtunes = [dict(grad_spt=s, grad_threads=t, ctas_per_sm=c) for s, t, c in
+              ([(2, 0, 0), (2, 0, 1), (2, 0, 2), (2, 128, 2), (1, 0, 0), (1, 0, 2), (4, 0, 1), (4, 0, 2), (-1, 256, 0)]
+               if name == "C2" else [(1, 0, 0), (1, 0, 2), (1, 64, 2), (2, 0, 0), (2, 0, 1), (-1, 128, 0)])]
+    for tune in gtunes:
         pc.tune(**tune)
         wsb = int(lib.dflow_workspace_bytes(pc.handle, Bg))
         ws = torch.empty(wsb, device="cuda:0", dtype=torch.uint8)
@@ -51,7 +53,7 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "c2"
     if which in ("c2", "all"):
         tunes = [dict(fwd_spt=s, fwd_threads=t, grad_threads=gt, ctas_per_sm=c) for s, t, gt, c in
-                 [(4, 128, 256, 0), (4, 128, 256, 2), (4, 128, 256, 3), (4, 256, 256, 1), (4, 256, 256, 2), (4, 64, 256, 4), (4, 64, 256, 6), (2, 256, 256, 2), (-2, 128, 256, 3)]]
+                 [(4, 0, 0, 0), (4, 0, 0, 2), (4, 0, 0, 3), (4, 64, 0, 4), (2, 0, 0, 0), (2, 0, 0, 2), (2, 128, 0, 4), (-2, 0, 0, 3)]]
         run("C2", 5, 2, lambda x: O.readme_chain(2, x), 1 << 25, 1 << 23, tunes)
     if which in ("c3", "all"):
         tunes = [dict(fwd_spt=1, fwd_threads=t, grad_threads=gt, ctas_per_sm=c) for t, gt, c in [(128, 128, 0), (256, 64, 0), (64, 128, 2)]]
