@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "dflow_internal.h"
+#include "dflow_wide.h"
 
 namespace dflow {
 
@@ -103,6 +104,143 @@ static void layout_net(DevNet& net, int hp, int& off) {
 }  // namespace dflow
 
 using namespace dflow;
+
+// Lay out the wide weight image (dflow_wide.cu) for a chain whose conditioners are wider than 64.
+static int build_wide_plan(dflow_chain* c) {
+  const DevChain* C = c->hc();
+  const DevChainHdr& H = C->h;
+  WidePlan* wp = new (std::nothrow) WidePlan();
+  if (!wp) return DFLOW_E_NOMEM;
+  c->wide = wp;
+  long long off = 0;
+  for (int ei = 0; ei < H.L; ++ei) {
+    const DevElem& E = C->e[ei];
+    WideLayer Ld;
+    memset(&Ld, 0, sizeof(Ld));
+    if (E.kind == DFLOW_ELEM_NORM) {
+      Ld.is_coupling = 0;
+      Ld.norm_off = E.stage_off;
+      wp->layers.push_back(Ld);
+      continue;
+    }
+    Ld.is_coupling = 1;
+    Ld.has_s = (E.kind == DFLOW_ELEM_RNVP) ? 1 : 0;
+    Ld.h = E.t.w[1];
+    Ld.nin = E.nin;
+    Ld.kinp = (E.nin + 7) & ~7;
+    Ld.a = E.a;
+    Ld.a16 = (E.a + 15) & ~15;
+    memcpy(Ld.af, E.af, sizeof(Ld.af));
+    memcpy(Ld.id, E.id, sizeof(Ld.id));
+    const int h = Ld.h, NH = h < 256 ? h : 256, passes = h / NH, nch = h / 32;
+    for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
+      const DevNet& net = ni == 0 ? E.s : E.t;
+      WideNet& N = Ld.net[ni];
+      for (int j = 0; j < 3; ++j) {
+        N.p_w[j] = net.p_w[j];
+        N.p_b[j] = net.p_b[j];
+      }
+      N.img_off = off;
+      int o = 0;
+      N.b1 = o; o += h;
+      N.b2 = o; o += h;
+      N.b3 = o; o += Ld.a16;
+      o = (o + 3) & ~3;
+      N.w1 = o; o += nch * 2 * 32 * Ld.kinp;
+      N.w2 = o; o += passes * nch * 2 * NH * 32;
+      N.w3 = o; o += nch * 2 * Ld.a16 * 32;
+      off += (o + 3) & ~3;
+    }
+    if (wide_layer_smem_bytes(Ld) > (size_t)c->max_smem_optin) {
+      set_error("element %d: wide layer needs %zu bytes of shared memory", ei, wide_layer_smem_bytes(Ld));
+      return DFLOW_E_UNSUPPORTED;
+    }
+    wp->layers.push_back(Ld);
+  }
+  wp->img_floats = (size_t)std::max<long long>(off, 4);
+  if (cudaMalloc(&wp->d_img, wp->img_floats * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&wp->d_layers, wp->layers.size() * sizeof(WideLayer)) != cudaSuccess) {
+    set_error("cudaMalloc failed for the wide weight image (%zu floats)", wp->img_floats);
+    return DFLOW_E_NOMEM;
+  }
+  if (cudaMemcpy(wp->d_layers, wp->layers.data(), wp->layers.size() * sizeof(WideLayer), cudaMemcpyHostToDevice) !=
+      cudaSuccess) {
+    set_error("cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return DFLOW_E_CUDA;
+  }
+  return DFLOW_OK;
+}
+
+// grow-only device scratch of the wide path (working copies for logpdf / gathers)
+static int wide_scratch(dflow_chain* c, size_t floats, float** out) {
+  WidePlan* wp = c->wide;
+  if (wp->scratch_floats < floats) {
+    if (wp->d_scratch) cudaFree(wp->d_scratch);
+    wp->d_scratch = nullptr;
+    wp->scratch_floats = 0;
+    if (cudaMalloc(&wp->d_scratch, floats * sizeof(float)) != cudaSuccess) {
+      set_error("cudaMalloc failed for %zu floats of wide-path scratch", floats);
+      return DFLOW_E_NOMEM;
+    }
+    wp->scratch_floats = floats;
+  }
+  *out = wp->d_scratch;
+  return DFLOW_OK;
+}
+
+// Wide-path implementation of the forward-type entry points.  Working buffer layout in scratch:
+// [x copy (d*B)] [ldj (B)] [θ gather (n*B)]
+static int wide_fwd(dflow_chain* c, const float* W, FwdArgs& a, void* stream) {
+  if (a.B == 0) return DFLOW_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevChainHdr& H = c->hc()->h;
+  const long long B = a.B;
+  const int d = H.d, n = H.n;
+  int rc = wide_prepack(c, W, st);
+  if (rc) return rc;
+  const bool sampling = a.mode >= MODE_SAMPLE;
+  const bool need_copy = (a.mode == MODE_LOGPDF || a.mode == MODE_LOGPDF_SUM);
+  const bool want_ldj = !(a.mode == MODE_SAMPLE || a.mode == MODE_SAMPLE_RNG);
+  float* scratch = nullptr;
+  const size_t need = (need_copy ? (size_t)d * B : 0) + (size_t)B + (a.idx ? (size_t)n * B : 0) + 16;
+  rc = wide_scratch(c, need, &scratch);
+  if (rc) return rc;
+  float* xw = need_copy ? scratch : a.x_out;
+  float* ldj = scratch + (need_copy ? (size_t)d * B : 0);
+  float* thg = ldj + B;
+  const float* theta = a.theta;
+  // input -> working buffer
+  if (a.mode == MODE_SAMPLE_RNG) {
+    rc = wide_philox(c, xw, B, a.seed, a.rng_offset, a.first_sample, st);
+    if (rc) return rc;
+  } else if (a.idx) {
+    rc = wide_gather(c, a.x_in, a.idx, B, d, xw, st);
+    if (rc) return rc;
+    if (theta && n > 0) {
+      rc = wide_gather(c, theta, a.idx, B, n, thg, st);
+      if (rc) return rc;
+      theta = thg;
+    }
+  } else if (xw != a.x_in) {
+    if (cudaMemcpyAsync(xw, a.x_in, sizeof(float) * d * B, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return DFLOW_E_CUDA;
+    }
+  }
+  float* ldj_dst = nullptr;
+  if (want_ldj) {
+    ldj_dst = (a.mode == MODE_NORMALIZE || a.mode == MODE_FORWARD_LDJ) ? a.aux_out : ldj;
+    if (cudaMemsetAsync(ldj_dst, 0, sizeof(float) * B, st) != cudaSuccess) {
+      set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return DFLOW_E_CUDA;
+    }
+  }
+  rc = wide_run_chain(c, xw, theta, a.theta_const, ldj_dst, B, sampling ? 1 : 0, a.flags, st);
+  if (rc) return rc;
+  if (a.mode == MODE_LOGPDF) return wide_logpdf(c, xw, ldj, B, a.aux_out, nullptr, st);
+  if (a.mode == MODE_LOGPDF_SUM) return wide_logpdf(c, xw, ldj, B, nullptr, a.aux_out, st);
+  return DFLOW_OK;
+}
 
 extern "C" {
 
@@ -215,10 +353,27 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
     max_depth = std::max(max_depth, E.t.depth);
     amax4 = std::max(amax4, round_out(a));
   }
-  const int hp = round_hp(hidden_max);
-  if (hp < 0) {
-    set_error("hidden width %d > %d: the wide (tcgen05) conditioner path is not built yet", hidden_max, HP_MAX);
-    return DFLOW_E_UNSUPPORTED;
+  int hp = round_hp(hidden_max);
+  const bool wide = hp < 0;  // hidden > 64: tcgen05 path (dflow_wide.cu)
+  if (wide) {
+    // the wide kernels cover the reference's default conditioner only: Dense(in,h,relu), Dense(h,h,relu), Dense(h,a)
+    for (int ei = 0; ei < L; ++ei) {
+      const DevElem& E = C->e[ei];
+      if (E.kind == DFLOW_ELEM_NORM) continue;
+      for (int ni = (E.kind == DFLOW_ELEM_RNVP ? 0 : 1); ni < 2; ++ni) {
+        const DevNet& net = ni == 0 ? E.s : E.t;
+        const int h = net.w[1];
+        const bool ok = net.depth == 3 && net.has_bias && net.w[2] == h && net.act[0] == DFLOW_ACT_RELU &&
+                        net.act[1] == DFLOW_ACT_RELU && net.act[2] == DFLOW_ACT_IDENTITY && h % 32 == 0 && h >= 32 &&
+                        (h <= 256 || h == 512) && E.nin <= 64 && E.a <= 32 && h == E.t.w[1];
+        if (!ok) {
+          set_error("element %d: wide conditioners (hidden > 64) must be Dense(in,h,relu)->Dense(h,h,relu)->Dense(h,a) with "
+                    "bias, h a multiple of 32 up to 256 or 512, <= 64 inputs and <= 32 outputs", ei);
+          return DFLOW_E_UNSUPPORTED;
+        }
+      }
+    }
+    hp = 64;  // narrow-path fields stay consistent but are not used
   }
   H.hp = hp;
   H.P = P;
@@ -242,7 +397,7 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
     int off = 0;
     if (E.kind == DFLOW_ELEM_NORM) {
       off = 2 * d + 4;
-    } else {
+    } else if (!wide) {
       if (E.kind == DFLOW_ELEM_RNVP) layout_net(E.s, hp, off);
       layout_net(E.t, hp, off);
     }
@@ -315,6 +470,13 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
     dflow_chain_destroy(c);
     return DFLOW_E_CUDA;
   }
+  if (wide) {
+    int rc = build_wide_plan(c);
+    if (rc) {
+      dflow_chain_destroy(c);
+      return rc;
+    }
+  }
   *out = c;
   return DFLOW_OK;
 }
@@ -323,6 +485,12 @@ int dflow_chain_destroy(dflow_chain* c) {
   if (!c) return DFLOW_OK;
   if (c->d_chain) cudaFree(c->d_chain);
   if (c->d_staged) cudaFree(c->d_staged);
+  if (c->wide) {
+    if (c->wide->d_layers) cudaFree(c->wide->d_layers);
+    if (c->wide->d_img) cudaFree(c->wide->d_img);
+    if (c->wide->d_scratch) cudaFree(c->wide->d_scratch);
+    delete c->wide;
+  }
   if (c->pipe) pipe_free((HostPipe*)c->pipe);
   delete c;
   return DFLOW_OK;
@@ -421,6 +589,7 @@ static int check_common(dflow_chain* c, const float* W, const float* theta, cons
 
 static int run_fwd(dflow_chain* c, const float* W, FwdArgs& a, void* stream) {
   if (a.B == 0) return DFLOW_OK;
+  if (c->wide) return wide_fwd(c, W, a, stream);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_prepack(c, W, st);
   if (rc) return rc;
@@ -566,6 +735,10 @@ int dflow_loss_grad(dflow_chain* c, const float* W, const float* x, const float*
     return DFLOW_E_INVALID_ARG;
   }
   if (B == 0) return DFLOW_OK;
+  if (c->wide) {
+    set_error("the adjoint of wide conditioners (hidden > 64) is not built yet (tcgen05 backward: round 2)");
+    return DFLOW_E_UNSUPPORTED;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_prepack(c, W, st);
   if (rc) return rc;
@@ -668,7 +841,7 @@ int dflow_logpdf_host(dflow_chain* c, const float* W, const float* x_host, const
   // the staged image is shared by both streams: prepack once, make both streams wait for it
   cudaEvent_t ev;
   CKA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  rc = launch_prepack(c, W, p->st[0]);
+  rc = c->wide ? DFLOW_OK : launch_prepack(c, W, p->st[0]);  // the wide path prepacks inside wide_fwd
   if (rc) return rc;
   CKA(cudaEventRecord(ev, p->st[0]));
   CKA(cudaStreamWaitEvent(p->st[1], ev, 0));
@@ -687,11 +860,11 @@ int dflow_logpdf_host(dflow_chain* c, const float* W, const float* x_host, const
     a.B = nb;
     a.mode = MODE_LOGPDF;
     a.flags = flags;
-    rc = launch_fwd(c, a, st);
+    rc = c->wide ? wide_fwd(c, W, a, st) : launch_fwd(c, a, st);
     if (rc) return rc;
     CKA(cudaMemcpyAsync(logp_host + done, p->dout[slot], sizeof(float) * nb, cudaMemcpyDeviceToHost, st));
     done += nb;
-    slot ^= 1;
+    if (!c->wide) slot ^= 1;  // the wide path owns one scratch buffer: keep it on a single stream
   }
   CKA(cudaStreamSynchronize(p->st[0]));
   CKA(cudaStreamSynchronize(p->st[1]));
@@ -725,7 +898,7 @@ int dflow_sample_host(dflow_chain* c, const float* W, uint64_t seed, const float
   }
   cudaEvent_t ev;
   CKA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  rc = launch_prepack(c, W, p->st[0]);
+  rc = c->wide ? DFLOW_OK : launch_prepack(c, W, p->st[0]);  // the wide path prepacks inside wide_fwd
   if (rc) return rc;
   CKA(cudaEventRecord(ev, p->st[0]));
   CKA(cudaStreamWaitEvent(p->st[1], ev, 0));
@@ -742,11 +915,11 @@ int dflow_sample_host(dflow_chain* c, const float* W, uint64_t seed, const float
     a.flags = flags;
     a.seed = seed;
     a.first_sample = (unsigned long long)done;
-    rc = launch_fwd(c, a, st);
+    rc = c->wide ? wide_fwd(c, W, a, st) : launch_fwd(c, a, st);
     if (rc) return rc;
     CKA(cudaMemcpyAsync(x_host + done * H.d, p->dout[slot], sizeof(float) * H.d * nb, cudaMemcpyDeviceToHost, st));
     done += nb;
-    slot ^= 1;
+    if (!c->wide) slot ^= 1;  // the wide path owns one scratch buffer: keep it on a single stream
   }
   CKA(cudaStreamSynchronize(p->st[0]));
   CKA(cudaStreamSynchronize(p->st[1]));

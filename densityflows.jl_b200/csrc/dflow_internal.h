@@ -110,6 +110,8 @@ struct GradArgs {
   int smem_grad;  // 1: accumulate the whole gradient in shared memory, flush once per CTA
 };
 
+struct WidePlan;
+
 struct PrepackArgs {
   const DevChain* chain;
   const float* W;
@@ -131,6 +133,8 @@ struct dflow_chain {
   long long launches = 0;
   // host pipeline scratch (dflow_*_host)
   void* pipe = nullptr;
+  // wide-conditioner (tcgen05) plan; non-null when some hidden width exceeds the narrow path's 64
+  dflow::WidePlan* wide = nullptr;
   const dflow::DevChain* hc() const { return reinterpret_cast<const dflow::DevChain*>(host_chain.data()); }
   dflow::DevChain* hc() { return reinterpret_cast<dflow::DevChain*>(host_chain.data()); }
 };
