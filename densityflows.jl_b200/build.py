@@ -46,6 +46,8 @@ def _units():
     extra = os.path.join(CSRC, "dflow_wide.cu")
     if os.path.exists(extra):
         units.append(("dflow_wide.o", "dflow_wide.cu", []))
+    if os.path.exists(os.path.join(CSRC, "dflow_tc.cu")):
+        units.append(("dflow_tc.o", "dflow_tc.cu", []))
     return units
 
 

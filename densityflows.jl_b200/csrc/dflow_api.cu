@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "dflow_internal.h"
+#include "dflow_tc.h"
 #include "dflow_wide.h"
 
 namespace dflow {
@@ -196,7 +197,7 @@ static int wide_fwd(dflow_chain* c, const float* W, FwdArgs& a, void* stream) {
   const DevChainHdr& H = c->hc()->h;
   const long long B = a.B;
   const int d = H.d, n = H.n;
-  int rc = wide_prepack(c, W, st);
+  int rc = c->wide_gen >= 2 ? tc_prepack(c, W, false, st) : wide_prepack(c, W, st);
   if (rc) return rc;
   const bool sampling = a.mode >= MODE_SAMPLE;
   const bool need_copy = (a.mode == MODE_LOGPDF || a.mode == MODE_LOGPDF_SUM);
@@ -235,7 +236,8 @@ static int wide_fwd(dflow_chain* c, const float* W, FwdArgs& a, void* stream) {
       return DFLOW_E_CUDA;
     }
   }
-  rc = wide_run_chain(c, xw, theta, a.theta_const, ldj_dst, B, sampling ? 1 : 0, a.flags, st);
+  rc = c->wide_gen >= 2 ? tc_run_chain(c, xw, theta, a.theta_const, ldj_dst, B, sampling ? 1 : 0, a.flags, st)
+                        : wide_run_chain(c, xw, theta, a.theta_const, ldj_dst, B, sampling ? 1 : 0, a.flags, st);
   if (rc) return rc;
   if (a.mode == MODE_LOGPDF) return wide_logpdf(c, xw, ldj, B, a.aux_out, nullptr, st);
   if (a.mode == MODE_LOGPDF_SUM) return wide_logpdf(c, xw, ldj, B, nullptr, a.aux_out, st);
@@ -354,27 +356,32 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
     amax4 = std::max(amax4, round_out(a));
   }
   int hp = round_hp(hidden_max);
-  const bool wide = hp < 0;  // hidden > 64: tcgen05 path (dflow_wide.cu)
-  if (wide) {
-    // the wide kernels cover the reference's default conditioner only: Dense(in,h,relu), Dense(h,h,relu), Dense(h,a)
-    for (int ei = 0; ei < L; ++ei) {
-      const DevElem& E = C->e[ei];
-      if (E.kind == DFLOW_ELEM_NORM) continue;
-      for (int ni = (E.kind == DFLOW_ELEM_RNVP ? 0 : 1); ni < 2; ++ni) {
-        const DevNet& net = ni == 0 ? E.s : E.t;
-        const int h = net.w[1];
-        const bool ok = net.depth == 3 && net.has_bias && net.w[2] == h && net.act[0] == DFLOW_ACT_RELU &&
-                        net.act[1] == DFLOW_ACT_RELU && net.act[2] == DFLOW_ACT_IDENTITY && h % 32 == 0 && h >= 32 &&
-                        (h <= 256 || h == 512) && E.nin <= 64 && E.a <= 32 && h == E.t.w[1];
-        if (!ok) {
+  const bool wide = hp < 0;  // hidden > 64: tcgen05 path (dflow_tc.cu / dflow_wide.cu)
+  // the tensor-core kernels cover the reference's default conditioner only: Dense(in,h,relu), Dense(h,h,relu), Dense(h,a)
+  bool tc_eligible = true;
+  int has_coupling = 0;
+  for (int ei = 0; ei < L; ++ei) {
+    const DevElem& E = C->e[ei];
+    if (E.kind == DFLOW_ELEM_NORM) continue;
+    has_coupling = 1;
+    for (int ni = (E.kind == DFLOW_ELEM_RNVP ? 0 : 1); ni < 2; ++ni) {
+      const DevNet& net = ni == 0 ? E.s : E.t;
+      const int h = net.w[1];
+      const bool ok = net.depth == 3 && net.has_bias && net.w[2] == h && net.act[0] == DFLOW_ACT_RELU &&
+                      net.act[1] == DFLOW_ACT_RELU && net.act[2] == DFLOW_ACT_IDENTITY && h % 32 == 0 && h >= 32 &&
+                      (h <= 256 || h == 512) && E.nin <= 64 && E.a <= 32 && h == E.t.w[1];
+      if (!ok) {
+        tc_eligible = false;
+        if (wide) {
           set_error("element %d: wide conditioners (hidden > 64) must be Dense(in,h,relu)->Dense(h,h,relu)->Dense(h,a) with "
                     "bias, h a multiple of 32 up to 256 or 512, <= 64 inputs and <= 32 outputs", ei);
           return DFLOW_E_UNSUPPORTED;
         }
       }
     }
-    hp = 64;  // narrow-path fields stay consistent but are not used
   }
+  if (!has_coupling) tc_eligible = false;
+  if (wide) hp = 64;  // narrow-path fields stay consistent but are not used
   H.hp = hp;
   H.P = P;
   H.amax4 = amax4;
@@ -470,11 +477,23 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
     dflow_chain_destroy(c);
     return DFLOW_E_CUDA;
   }
-  if (wide) {
+  c->must_wide = wide ? 1 : 0;
+  if (tc_eligible) {
     int rc = build_wide_plan(c);
-    if (rc) {
+    if (!rc) rc = tc_build_plan(c);
+    if (rc && wide) {
       dflow_chain_destroy(c);
       return rc;
+    }
+    if (rc) {  // a narrow chain simply stays on the CUDA-core path
+      tc_free_plan(c);
+      if (c->wide) {
+        if (c->wide->d_layers) cudaFree(c->wide->d_layers);
+        if (c->wide->d_img) cudaFree(c->wide->d_img);
+        if (c->wide->d_scratch) cudaFree(c->wide->d_scratch);
+        delete c->wide;
+        c->wide = nullptr;
+      }
     }
   }
   *out = c;
@@ -485,6 +504,7 @@ int dflow_chain_destroy(dflow_chain* c) {
   if (!c) return DFLOW_OK;
   if (c->d_chain) cudaFree(c->d_chain);
   if (c->d_staged) cudaFree(c->d_staged);
+  tc_free_plan(c);
   if (c->wide) {
     if (c->wide->d_layers) cudaFree(c->wide->d_layers);
     if (c->wide->d_img) cudaFree(c->wide->d_img);
@@ -589,7 +609,7 @@ static int check_common(dflow_chain* c, const float* W, const float* theta, cons
 
 static int run_fwd(dflow_chain* c, const float* W, FwdArgs& a, void* stream) {
   if (a.B == 0) return DFLOW_OK;
-  if (c->wide) return wide_fwd(c, W, a, stream);
+  if (c->use_tc()) return wide_fwd(c, W, a, stream);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_prepack(c, W, st);
   if (rc) return rc;
@@ -714,8 +734,8 @@ int dflow_sample_rng(dflow_chain* c, const float* W, uint64_t seed, uint32_t off
 }
 
 size_t dflow_workspace_bytes(const dflow_chain* c, int64_t B) {
-  (void)B;
   if (!c) return 0;
+  if (c->use_tc()) return tc_workspace_bytes(c, B);
   // one checkpoint slab per resident CTA (not per sample): grid <= sm_count * 4 CTAs of <= 256 threads
   return (size_t)c->sm_count * 4 * 512 * (size_t)c->hc()->h.ck_total * sizeof(float) + 256;
 }
@@ -735,11 +755,8 @@ int dflow_loss_grad(dflow_chain* c, const float* W, const float* x, const float*
     return DFLOW_E_INVALID_ARG;
   }
   if (B == 0) return DFLOW_OK;
-  if (c->wide) {
-    set_error("the adjoint of wide conditioners (hidden > 64) is not built yet (tcgen05 backward: round 2)");
-    return DFLOW_E_UNSUPPORTED;
-  }
   cudaStream_t st = (cudaStream_t)stream;
+  if (c->use_tc()) return tc_loss_grad(c, W, x, theta, B, idx, inv_btot, flags, loss_out, grad_out, ws, ws_bytes, st);
   rc = launch_prepack(c, W, st);
   if (rc) return rc;
   GradArgs a{};
@@ -841,7 +858,7 @@ int dflow_logpdf_host(dflow_chain* c, const float* W, const float* x_host, const
   // the staged image is shared by both streams: prepack once, make both streams wait for it
   cudaEvent_t ev;
   CKA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  rc = c->wide ? DFLOW_OK : launch_prepack(c, W, p->st[0]);  // the wide path prepacks inside wide_fwd
+  rc = c->use_tc() ? DFLOW_OK : launch_prepack(c, W, p->st[0]);  // the wide path prepacks inside wide_fwd
   if (rc) return rc;
   CKA(cudaEventRecord(ev, p->st[0]));
   CKA(cudaStreamWaitEvent(p->st[1], ev, 0));
@@ -860,11 +877,11 @@ int dflow_logpdf_host(dflow_chain* c, const float* W, const float* x_host, const
     a.B = nb;
     a.mode = MODE_LOGPDF;
     a.flags = flags;
-    rc = c->wide ? wide_fwd(c, W, a, st) : launch_fwd(c, a, st);
+    rc = c->use_tc() ? wide_fwd(c, W, a, st) : launch_fwd(c, a, st);
     if (rc) return rc;
     CKA(cudaMemcpyAsync(logp_host + done, p->dout[slot], sizeof(float) * nb, cudaMemcpyDeviceToHost, st));
     done += nb;
-    if (!c->wide) slot ^= 1;  // the wide path owns one scratch buffer: keep it on a single stream
+    if (!c->use_tc()) slot ^= 1;  // the wide path owns one scratch buffer: keep it on a single stream
   }
   CKA(cudaStreamSynchronize(p->st[0]));
   CKA(cudaStreamSynchronize(p->st[1]));
@@ -898,7 +915,7 @@ int dflow_sample_host(dflow_chain* c, const float* W, uint64_t seed, const float
   }
   cudaEvent_t ev;
   CKA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  rc = c->wide ? DFLOW_OK : launch_prepack(c, W, p->st[0]);  // the wide path prepacks inside wide_fwd
+  rc = c->use_tc() ? DFLOW_OK : launch_prepack(c, W, p->st[0]);  // the wide path prepacks inside wide_fwd
   if (rc) return rc;
   CKA(cudaEventRecord(ev, p->st[0]));
   CKA(cudaStreamWaitEvent(p->st[1], ev, 0));
@@ -915,11 +932,11 @@ int dflow_sample_host(dflow_chain* c, const float* W, uint64_t seed, const float
     a.flags = flags;
     a.seed = seed;
     a.first_sample = (unsigned long long)done;
-    rc = c->wide ? wide_fwd(c, W, a, st) : launch_fwd(c, a, st);
+    rc = c->use_tc() ? wide_fwd(c, W, a, st) : launch_fwd(c, a, st);
     if (rc) return rc;
     CKA(cudaMemcpyAsync(x_host + done * H.d, p->dout[slot], sizeof(float) * H.d * nb, cudaMemcpyDeviceToHost, st));
     done += nb;
-    if (!c->wide) slot ^= 1;  // the wide path owns one scratch buffer: keep it on a single stream
+    if (!c->use_tc()) slot ^= 1;  // the wide path owns one scratch buffer: keep it on a single stream
   }
   CKA(cudaStreamSynchronize(p->st[0]));
   CKA(cudaStreamSynchronize(p->st[1]));
@@ -942,6 +959,22 @@ int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
     c->grad_spt = value;
   else if (!strcmp(key, "ctas_per_sm"))
     c->ctas_per_sm = value;
+  else if (!strcmp(key, "tc_debug"))
+    c->tc_debug = value;
+  else if (!strcmp(key, "wide_gen"))
+    c->wide_gen = value == 1 ? 1 : 2;
+  else if (!strcmp(key, "tc_mode")) {
+    if (value > 0 && !(c->wide && c->tcp)) {
+      set_error("tc_mode: this chain is not eligible for the tensor-core path (needs Dense(in,h,relu)->Dense(h,h,relu)->"
+                "Dense(h,a) conditioners with bias, h a multiple of 32)");
+      return DFLOW_E_UNSUPPORTED;
+    }
+    if (value < 0 && c->must_wide) {
+      set_error("tc_mode: hidden widths above 64 only run on the tensor-core path");
+      return DFLOW_E_UNSUPPORTED;
+    }
+    c->tc_mode = value;
+  }
   else {
     set_error("unknown tuning key %s", key);
     return DFLOW_E_INVALID_ARG;

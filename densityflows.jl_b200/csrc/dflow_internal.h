@@ -111,6 +111,7 @@ struct GradArgs {
 };
 
 struct WidePlan;
+struct TcPlan;
 
 struct PrepackArgs {
   const DevChain* chain;
@@ -135,6 +136,13 @@ struct dflow_chain {
   void* pipe = nullptr;
   // wide-conditioner (tcgen05) plan; non-null when some hidden width exceeds the narrow path's 64
   dflow::WidePlan* wide = nullptr;
+  // generation-2 tensor-core plan (dflow_tc.cu): warp-specialised forward + adjoint; built for every eligible chain
+  dflow::TcPlan* tcp = nullptr;
+  int wide_gen = 2;    // 1: dflow_wide.cu kernels, 2: dflow_tc.cu kernels
+  int must_wide = 0;   // some hidden width > 64: the CUDA-core kernels cannot run this chain
+  int tc_debug = 0;    // timing experiments (dflow_tc.cu)
+  int tc_mode = 0;     // 0: automatic (tensor cores iff must_wide), 1: force tensor cores, -1: force CUDA cores
+  bool use_tc() const { return wide && tcp && (must_wide || tc_mode > 0); }
   const dflow::DevChain* hc() const { return reinterpret_cast<const dflow::DevChain*>(host_chain.data()); }
   dflow::DevChain* hc() { return reinterpret_cast<dflow::DevChain*>(host_chain.data()); }
 };

@@ -1,0 +1,1318 @@
+// Tensor-core path, generation 2 (sm_100a): warp-specialised tcgen05 / TMEM pipeline for conditioners with
+// hidden width >= 64, forward (both directions) and adjoint.
+//
+// One launch per (coupling layer, conditioner).  CTA = 6 warps:
+//   warps 0-3  epilogue: thread t <-> sample row t of the 128-sample tile <-> TMEM lane t
+//   warp  4    producer: streams pre-split weight stage blocks global -> shared with cp.async.bulk (TMA engine),
+//              completion on mbarriers; nets that fit stay resident in shared memory for the life of the CTA
+//   warp  5    MMA issuer (one lane): tcgen05.mma kind::tf32, accumulators in TMEM
+//
+// Float32 parity on a TF32 tensor core: every operand is split into hi = cvt.rna.tf32(x), lo = x - hi and each
+// product is issued as lo*hi + hi*lo + hi*hi (the dropped lo*lo term is ~2^-22 relative).
+//
+// Pipeline per 128-sample tile and conditioner (chunks of WKC = 16 hidden units):
+//   D1[c&1] (128 x 16)   = A1 (128 x K0) * M1_c^T             TMEM cols [0,16) / [32,48), double buffered
+//   epilogue 1           : tcgen05.ld, bias + relu (or relu mask), split -> A2[q&1] in shared memory
+//   D2 (128 x NH)       += A2 (128 x 16) * M2_c^T             TMEM cols [128, 128+NH)
+//   epilogue 2 (per 16)  : tcgen05.ld, bias + relu (or mask), split -> A2[q&1]
+//   D3 (128 x N3)       += A2 * M3_cc^T                       TMEM cols [64, 64+N3)
+// While the tensor pipe runs D2 of chunk c the epilogue warps already process D1 of chunk c+1.
+// The adjoint's input-gradient chain  delta3 -> (.W3) mask2 -> (.W2) mask1 -> (.W1)  is the same pipeline on
+// the transposed matrices (dflow_tc.h).  Weight gradients are K = samples GEMMs in tc_dw_kernel.
+//
+// Reference math: src/affine/RNVP.jl:77-96 (normalising), :99-147 (adjoint), :150-205 (gather, sampling);
+// src/affine/NICE.jl:63-170; src/norm/Normalization.jl:64-103; src/Flows.jl:272-281,352-359.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "dflow_tc.cuh"
+#include "dflow_tc.h"
+
+namespace dflow {
+
+using namespace tc;
+
+constexpr int WKC = TC_WKC;
+constexpr int NSMAX = TC_NSMAX;
+
+enum { TC_FWD = 0, TC_FWD_STORE = 1, TC_BWD = 2 };
+
+// TMEM column map of the net kernel
+constexpr uint32_t TM_D1 = 0;    // two buffers, 32 columns apart
+constexpr uint32_t TM_D3 = 64;   // <= 64 columns
+constexpr uint32_t TM_D2 = 128;  // <= 256 columns
+
+// barrier slots (uint64 each) behind the ring
+enum {
+  BAR_W_FULL = 0,
+  BAR_W_EMPTY = NSMAX,
+  BAR_D1_FULL = 2 * NSMAX,
+  BAR_D1_EMPTY = 2 * NSMAX + 2,
+  BAR_A2_FULL = 2 * NSMAX + 4,
+  BAR_A2_EMPTY = 2 * NSMAX + 6,
+  BAR_D2_FULL = 2 * NSMAX + 8,
+  BAR_D2_EMPTY,
+  BAR_D3_FULL,
+  BAR_D3_EMPTY,
+  BAR_A1_FULL,
+  BAR_A1_EMPTY,
+  BAR_TMEM_SLOT,
+  BAR_COUNT
+};
+
+struct TcArgs {
+  TcNetImg im;
+  const float* img;
+  long long B;
+  int net_id, has_s, d, n, a, a16, nin;
+  int sampling, flags;
+  int resident, NS, tmem_cols;
+  int debug;  // timing experiments only: bit 0 = weights loaded once per CTA (wrong results when streamed)
+  unsigned char af[DMAX], id[DMAX];
+  float theta_min[NMAX], theta_rng[NMAX];
+  const float* x_in;
+  float* x_out;
+  const float* theta;
+  const float* theta_const;
+  float* ldj;
+  float* sbuf;  // [tiles][a16][128] s values of this layer
+  // training buffers, all [tiles][rows][128]
+  float* inbuf;
+  float* h1buf;
+  float* h2buf;
+  uint32_t* m1buf;
+  uint32_t* m2buf;
+  float* d1buf;
+  float* d2buf;
+  float* d3buf;
+  float* zbar;        // (d, B) cotangent of the layer output, updated in place to the cotangent of its input
+  const float* zout;  // (d, B) layer output (normalising direction)
+  float inv_btot;
+  float* grad;
+  int p_b3;
+};
+
+// ---- prepack: packed Flux parameters -> stage blocks (hi/lo split, core layout) ---------------------------------
+__global__ void tc_prepack_kernel(const TcPackJob* jobs, const float* __restrict__ W, float* __restrict__ img) {
+  const TcPackJob& J = jobs[blockIdx.x];
+  const TcNetImg& im = J.im;
+  float* base = img + im.off;
+  const int H = im.H, K0p = im.K0p, N3p = im.N3p, NH = im.NH, nch = im.nch;
+  const int part = blockIdx.y, nparts = gridDim.y;
+  const int t0 = part * blockDim.x + threadIdx.x, ts = nparts * blockDim.x;
+  // biases
+  for (int i = t0; i < H; i += ts) {
+    base[im.bias_off + i] = J.pb1 >= 0 ? W[J.pb1 + i] : 0.0f;
+    base[im.bias_off + H + i] = J.pb2 >= 0 ? W[J.pb2 + i] : 0.0f;
+  }
+  for (int i = t0; i < N3p; i += ts) base[im.bias_off + 2 * H + i] = (J.pb3 >= 0 && i < J.nb3) ? W[J.pb3 + i] : 0.0f;
+  // M1 [H x K0p]: chunk c = rows c*WKC.., replicated in every pass
+  for (int i = t0; i < H * K0p; i += ts) {
+    const int u = i / K0p, k = i - u * K0p;
+    const float w = k < J.vk1 ? W[J.base1 + u * J.sn1 + k * J.sk1] : 0.0f;
+    const float hi = to_tf32(w);
+    const int c = u / WKC, r = u - c * WKC;
+    for (int p = 0; p < im.passes; ++p) {
+      float* blk = base + im.s1_off + (size_t)(p * nch + c) * im.s1_floats;
+      blk[core_idx(r, k, K0p)] = hi;
+      blk[WKC * K0p + core_idx(r, k, K0p)] = w - hi;
+    }
+  }
+  // M2 [H x H]: (pass p, chunk c) holds rows p*NH.. (n index), columns c*WKC.. (k index)
+  for (int i = t0; i < H * H; i += ts) {
+    const int nn = i / H, k = i - nn * H;
+    const float w = W[J.base2 + nn * J.sn2 + k * J.sk2];
+    const float hi = to_tf32(w);
+    const int p = nn / NH, r = nn - p * NH, c = k / WKC, kk = k - c * WKC;
+    float* blk = base + im.s1_off + (size_t)(p * nch + c) * im.s1_floats + 2 * WKC * K0p;
+    blk[core_idx(r, kk, WKC)] = hi;
+    blk[NH * WKC + core_idx(r, kk, WKC)] = w - hi;
+  }
+  // M3 [N3p x H]: chunk gc holds columns gc*WKC..
+  for (int i = t0; i < N3p * H; i += ts) {
+    const int nn = i / H, k = i - nn * H;
+    const float w = nn < J.vn3 ? W[J.base3 + nn * J.sn3 + k * J.sk3] : 0.0f;
+    const float hi = to_tf32(w);
+    const int c = k / WKC, kk = k - c * WKC;
+    float* blk = base + im.s3_off + (size_t)c * im.s3_floats;
+    blk[core_idx(nn, kk, WKC)] = hi;
+    blk[N3p * WKC + core_idx(nn, kk, WKC)] = w - hi;
+  }
+}
+
+// ---- the net kernel ------------------------------------------------------------------------------------------
+// this thread's row of a 16-unit activation chunk as hi / lo operands (K-major core layout, Kc = 16)
+__device__ __forceinline__ void store_a2_row(float* a_hi, float* a_lo, int row, const float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 hi, lo;
+    hi.x = to_tf32(v[4 * q + 0]); lo.x = v[4 * q + 0] - hi.x;
+    hi.y = to_tf32(v[4 * q + 1]); lo.y = v[4 * q + 1] - hi.y;
+    hi.z = to_tf32(v[4 * q + 2]); lo.z = v[4 * q + 2] - hi.z;
+    hi.w = to_tf32(v[4 * q + 3]); lo.w = v[4 * q + 3] - hi.w;
+    const int idx = core_idx(row, 4 * q, WKC);
+    *reinterpret_cast<float4*>(a_hi + idx) = hi;
+    *reinterpret_cast<float4*>(a_lo + idx) = lo;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_constant__ TcArgs a) {
+  extern __shared__ float4 smem4[];
+  float* smem = reinterpret_cast<float*>(smem4);
+  const TcNetImg& im = a.im;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K0p = im.K0p, H = im.H, N3p = im.N3p, NH = im.NH, passes = im.passes, nch = im.nch,
+            nch_pass = im.nch_pass;
+  const int d = a.d, n = a.n;
+
+  float* A1h = smem;
+  float* A1l = A1h + 128 * K0p;
+  float* A2 = A1l + 128 * K0p;  // buffer b: hi at A2 + b * 2*128*WKC, lo 128*WKC further
+  float* biasS = A2 + 4 * 128 * WKC;
+  const int nbias = (2 * H + N3p + 3) & ~3;
+  float* ring = biasS + nbias;
+  const int ring_floats = a.resident ? (passes * nch * im.s1_floats + nch * im.s3_floats) : a.NS * im.s1_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + ring_floats);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_TMEM_SLOT);
+  const float* gimg = a.img + im.off;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSMAX; ++i) {
+      mbar_init(bars + BAR_W_FULL + i, 1);
+      mbar_init(bars + BAR_W_EMPTY + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bars + BAR_D1_FULL + i, 1);
+      mbar_init(bars + BAR_D1_EMPTY + i, 128);
+      mbar_init(bars + BAR_A2_FULL + i, 128);
+      mbar_init(bars + BAR_A2_EMPTY + i, 1);
+    }
+    mbar_init(bars + BAR_D2_FULL, 1);
+    mbar_init(bars + BAR_D2_EMPTY, 128);
+    mbar_init(bars + BAR_D3_FULL, 1);
+    mbar_init(bars + BAR_D3_EMPTY, 128);
+    mbar_init(bars + BAR_A1_FULL, 128);
+    mbar_init(bars + BAR_A1_EMPTY, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  for (int i = tid; i < nbias; i += TC_THREADS) biasS[i] = i < 2 * H + N3p ? __ldg(gimg + im.bias_off + i) : 0.0f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  const long long ntiles = (a.B + 127) / 128;
+
+  if (warp < 4) {
+    // =========================== epilogue warps ===========================
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    uint32_t q = 0, j1 = 0, npass = 0, tcount = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const long long gi = tile * 128 + tid;
+      const bool valid = gi < a.B;
+      mbar_wait(bars + BAR_A1_EMPTY, (tcount & 1) ^ 1);
+      // ---- A1: this sample's GEMM-1 input row ----
+      if constexpr (MODE == TC_BWD) {
+        // delta3 of this conditioner (src/affine/RNVP.jl:118-127): s: -zbar_af * z_af - jbar, t: -zbar_af * exp(-s)
+        for (int k0 = 0; k0 < K0p; k0 += 4) {
+          float v[4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int j = k0 + qq;
+            float val = 0.0f;
+            if (valid && j < a.a) {
+              const int k = a.af[j];
+              const float zb = a.zbar[gi * d + k];
+              if (a.net_id == 0) {
+                val = -zb * a.zout[gi * d + k] + a.inv_btot;
+              } else {
+                const float sv = a.has_s ? a.sbuf[((size_t)tile * a.a16 + j) * 128 + tid] : 0.0f;
+                val = -zb * expf(-sv);
+              }
+            }
+            v[qq] = val;
+            a.d3buf[((size_t)tile * K0p + j) * 128 + tid] = val;
+            // bias gradient of the last Dense: sum over the tile's samples
+            float r = val;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (lane == 0 && j < a.a && r != 0.0f) atomicAdd(a.grad + a.p_b3 + j, r);
+          }
+          float4 hi, lo;
+          hi.x = to_tf32(v[0]); lo.x = v[0] - hi.x;
+          hi.y = to_tf32(v[1]); lo.y = v[1] - hi.y;
+          hi.z = to_tf32(v[2]); lo.z = v[2] - hi.z;
+          hi.w = to_tf32(v[3]); lo.w = v[3] - hi.w;
+          const int idx = core_idx(tid, k0, K0p);
+          *reinterpret_cast<float4*>(A1h + idx) = hi;
+          *reinterpret_cast<float4*>(A1l + idx) = lo;
+        }
+      } else {
+        // conditioner input row [theta_0..theta_{n-1}, x[axis_id...], 0 pad] (src/affine/RNVP.jl:157)
+        if (a.x_out != a.x_in && a.net_id == 1 && valid)
+          for (int k = 0; k < d; ++k) a.x_out[gi * d + k] = a.x_in[gi * d + k];
+        for (int k0 = 0; k0 < K0p; k0 += 4) {
+          float v[4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int k = k0 + qq;
+            float val = 0.0f;
+            if (valid && k < a.nin) {
+              if (k < n) {
+                val = a.theta_const ? __ldg(a.theta_const + k) : __ldg(a.theta + gi * n + k);
+                if (a.flags & DFLOW_THETA_NORMALIZE)
+                  val = (a.theta_rng[k] == 0.0f) ? 0.0f : (val - a.theta_min[k]) / a.theta_rng[k];
+              } else {
+                val = a.x_in[gi * d + a.id[k - n]];
+              }
+            }
+            v[qq] = val;
+            if constexpr (MODE == TC_FWD_STORE)
+              if (a.net_id == 1) a.inbuf[((size_t)tile * K0p + k) * 128 + tid] = val;
+          }
+          float4 hi, lo;
+          hi.x = to_tf32(v[0]); lo.x = v[0] - hi.x;
+          hi.y = to_tf32(v[1]); lo.y = v[1] - hi.y;
+          hi.z = to_tf32(v[2]); lo.z = v[2] - hi.z;
+          hi.w = to_tf32(v[3]); lo.w = v[3] - hi.w;
+          const int idx = core_idx(tid, k0, K0p);
+          *reinterpret_cast<float4*>(A1h + idx) = hi;
+          *reinterpret_cast<float4*>(A1l + idx) = lo;
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(bars + BAR_A1_FULL);
+
+      uint32_t mword = 0;
+      for (int p = 0; p < passes; ++p) {
+        // ---- epilogue 1: hidden-1 chunks ----
+        for (int c = 0; c < nch; ++c) {
+          const uint32_t b = j1 & 1;
+          mbar_wait(bars + BAR_D1_FULL + b, (j1 >> 1) & 1);
+          tc_fence_after();
+          float v[16];
+          tmem_ld16(tbase + lane_off + TM_D1 + b * 32, v);
+          tc_fence_before();
+          mbar_arrive(bars + BAR_D1_EMPTY + b);
+          ++j1;
+          if constexpr (MODE == TC_BWD) {
+            if (!(c & 1)) mword = a.m2buf[((size_t)tile * (H >> 5) + (c >> 1)) * 128 + tid];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[j] = ((mword >> ((c & 1) * 16 + j)) & 1u) ? v[j] : 0.0f;
+              a.d2buf[((size_t)tile * H + c * WKC + j) * 128 + tid] = v[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + biasS[c * WKC + j], 0.0f);
+            if constexpr (MODE == TC_FWD_STORE) {
+              if (p == 0) {
+                if (!(c & 1)) mword = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  a.h1buf[((size_t)tile * H + c * WKC + j) * 128 + tid] = v[j];
+                  mword |= (v[j] > 0.0f ? 1u : 0u) << ((c & 1) * 16 + j);
+                }
+                if (c & 1) a.m1buf[((size_t)tile * (H >> 5) + (c >> 1)) * 128 + tid] = mword;
+              }
+            }
+          }
+          const uint32_t ab = q & 1;
+          mbar_wait(bars + BAR_A2_EMPTY + ab, ((q >> 1) & 1) ^ 1);
+          store_a2_row(A2 + ab * 2 * 128 * WKC, A2 + ab * 2 * 128 * WKC + 128 * WKC, tid, v);
+          fence_async_smem();
+          mbar_arrive(bars + BAR_A2_FULL + ab);
+          ++q;
+        }
+        // ---- epilogue 2: hidden-2 chunks of this pass ----
+        mbar_wait(bars + BAR_D2_FULL, npass & 1);
+        tc_fence_after();
+        for (int cc = 0; cc < nch_pass; ++cc) {
+          const int gc = p * nch_pass + cc;
+          float v[16];
+          tmem_ld16(tbase + lane_off + TM_D2 + cc * WKC, v);
+          if (cc == nch_pass - 1) {
+            tc_fence_before();
+            mbar_arrive(bars + BAR_D2_EMPTY);
+          }
+          if constexpr (MODE == TC_BWD) {
+            if (!(gc & 1)) mword = a.m1buf[((size_t)tile * (H >> 5) + (gc >> 1)) * 128 + tid];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[j] = ((mword >> ((gc & 1) * 16 + j)) & 1u) ? v[j] : 0.0f;
+              a.d1buf[((size_t)tile * H + gc * WKC + j) * 128 + tid] = v[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + biasS[H + gc * WKC + j], 0.0f);
+            if constexpr (MODE == TC_FWD_STORE) {
+              if (!(gc & 1)) mword = 0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                a.h2buf[((size_t)tile * H + gc * WKC + j) * 128 + tid] = v[j];
+                mword |= (v[j] > 0.0f ? 1u : 0u) << ((gc & 1) * 16 + j);
+              }
+              if (gc & 1) a.m2buf[((size_t)tile * (H >> 5) + (gc >> 1)) * 128 + tid] = mword;
+            }
+          }
+          const uint32_t ab = q & 1;
+          mbar_wait(bars + BAR_A2_EMPTY + ab, ((q >> 1) & 1) ^ 1);
+          store_a2_row(A2 + ab * 2 * 128 * WKC, A2 + ab * 2 * 128 * WKC + 128 * WKC, tid, v);
+          fence_async_smem();
+          mbar_arrive(bars + BAR_A2_FULL + ab);
+          ++q;
+        }
+        ++npass;
+      }
+      // ---- outputs of the conditioner ----
+      mbar_wait(bars + BAR_D3_FULL, tcount & 1);
+      tc_fence_after();
+      float lsum = 0.0f;
+      for (int o0 = 0; o0 < N3p; o0 += 16) {
+        float v[16];
+        tmem_ld16(tbase + lane_off + TM_D3 + o0, v);
+        if (o0 + 16 >= N3p) {
+          tc_fence_before();
+          mbar_arrive(bars + BAR_D3_EMPTY);
+        }
+        if constexpr (MODE == TC_BWD) {
+          // cotangent of the conditioner input: rows n.. go to the identity coordinates (theta rows are dropped)
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int k = o0 + j;
+              if (k >= n && k < a.nin) a.zbar[gi * d + a.id[k - n]] += v[j];
+            }
+          }
+        } else if (a.net_id == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a.sbuf[((size_t)tile * a.a16 + o0 + j) * 128 + tid] = v[j] + biasS[2 * H + o0 + j];
+        } else if (valid) {
+          // coupling transform (src/affine/RNVP.jl:92,184; NICE: s = 0)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int jj = o0 + j;
+            if (jj < a.a) {
+              const int k = a.af[jj];
+              const float tv = v[j] + biasS[2 * H + jj];
+              const float sv = a.has_s ? a.sbuf[((size_t)tile * a.a16 + jj) * 128 + tid] : 0.0f;
+              const float xv = a.x_in[gi * d + k];
+              a.x_out[gi * d + k] = a.sampling ? xv * expf(sv) + tv : (xv - tv) * expf(-sv);
+              lsum += sv;
+            }
+          }
+        }
+      }
+      if constexpr (MODE == TC_BWD) {
+        // cotangent of the transformed coordinates: ubar_af = zbar_af * exp(-s) (src/affine/RNVP.jl:134)
+        if (a.net_id == 1 && a.has_s && valid)
+          for (int j = 0; j < a.a; ++j) {
+            const float sv = a.sbuf[((size_t)tile * a.a16 + j) * 128 + tid];
+            a.zbar[gi * d + a.af[j]] *= expf(-sv);
+          }
+      } else {
+        if (a.net_id == 1 && a.ldj && valid) a.ldj[gi] += a.sampling ? lsum : -lsum;
+      }
+    }
+  } else if (warp == 4) {
+    // =========================== producer ===========================
+    if (lane == 0) {
+      uint32_t sq = 0;
+      const uint32_t s1b = (uint32_t)im.s1_floats * 4u, s3b = (uint32_t)im.s3_floats * 4u;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int p = 0; p < passes; ++p) {
+          for (int c = 0; c < nch; ++c, ++sq) {
+            float* dst;
+            uint32_t slot;
+            if (a.resident) {
+              slot = (uint32_t)c;
+              dst = ring + (size_t)c * im.s1_floats;
+            } else {
+              slot = sq % (uint32_t)a.NS;
+              dst = ring + (size_t)slot * im.s1_floats;
+              if ((a.debug & 1) && sq >= (uint32_t)a.NS) continue;
+              mbar_wait(bars + BAR_W_EMPTY + slot, ((sq / (uint32_t)a.NS) & 1) ^ 1);
+            }
+            mbar_expect_tx(bars + BAR_W_FULL + slot, s1b);
+            bulk_g2s(dst, gimg + im.s1_off + (size_t)(p * nch + c) * im.s1_floats, s1b, bars + BAR_W_FULL + slot);
+          }
+          for (int cc = 0; cc < nch_pass; ++cc, ++sq) {
+            const int gc = p * nch_pass + cc;
+            float* dst;
+            uint32_t slot;
+            if (a.resident) {
+              slot = (uint32_t)(nch + gc);
+              dst = ring + (size_t)nch * im.s1_floats + (size_t)gc * im.s3_floats;
+            } else {
+              slot = sq % (uint32_t)a.NS;
+              dst = ring + (size_t)slot * im.s1_floats;
+              if ((a.debug & 1) && sq >= (uint32_t)a.NS) continue;
+              mbar_wait(bars + BAR_W_EMPTY + slot, ((sq / (uint32_t)a.NS) & 1) ^ 1);
+            }
+            mbar_expect_tx(bars + BAR_W_FULL + slot, s3b);
+            bulk_g2s(dst, gimg + im.s3_off + (size_t)gc * im.s3_floats, s3b, bars + BAR_W_FULL + slot);
+          }
+        }
+        if (a.resident) break;  // loaded once, kept for every tile of this CTA
+      }
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    // The whole warp runs this loop uniformly (descriptors live in uniform registers); one elected lane issues.
+    const uint32_t hiK0 = desc_hi(K0p), hi16 = desc_hi(WKC);
+    const uint64_t dA1h = desc_at(hiK0, smem_u32(A1h)), dA1l = desc_at(hiK0, smem_u32(A1l));
+    const uint32_t a2_u32 = smem_u32(A2), ring_u32 = smem_u32(ring);
+    const uint32_t id1 = instr_desc_tf32(WKC), id2 = instr_desc_tf32(NH), id3 = instr_desc_tf32(N3p);
+    const int k1steps = K0p >> 3;
+    const uint32_t w1_bytes = (uint32_t)(WKC * K0p) * 4u, w2_bytes = (uint32_t)(NH * WKC) * 4u,
+                   w3_bytes = (uint32_t)(N3p * WKC) * 4u, a2_bytes = 128u * WKC * 4u;
+    const uint32_t s1_bytes = (uint32_t)im.s1_floats * 4u, s3_bytes = (uint32_t)im.s3_floats * 4u;
+    uint32_t q = 0, j1 = 0, sq = 0, npass = 0, tcount = 0;
+    bool first = true;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      mbar_wait(bars + BAR_A1_FULL, tcount & 1);
+      tc_fence_after();
+      for (int p = 0; p < passes; ++p) {
+        mbar_wait(bars + BAR_D2_EMPTY, (npass & 1) ^ 1);
+        tc_fence_after();
+        uint32_t prev_stage = 0, prev_slot = 0;
+        for (int c = 0; c <= nch; ++c) {
+          uint32_t stage = 0, slot = 0;
+          if (c < nch) {
+            if (a.resident) {
+              slot = (uint32_t)c;
+              stage = ring_u32 + (uint32_t)c * s1_bytes;
+              if (first) mbar_wait(bars + BAR_W_FULL + slot, 0);
+            } else {
+              slot = sq % (uint32_t)a.NS;
+              stage = ring_u32 + slot * s1_bytes;
+              if (!((a.debug & 1) && sq >= (uint32_t)a.NS)) mbar_wait(bars + BAR_W_FULL + slot, (sq / (uint32_t)a.NS) & 1);
+            }
+            ++sq;
+            const uint32_t b = j1 & 1;
+            mbar_wait(bars + BAR_D1_EMPTY + b, ((j1 >> 1) & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+              gemm3_desc(tbase + TM_D1 + b * 32, dA1h, dA1l, desc_at(hiK0, stage), desc_at(hiK0, stage + w1_bytes), k1steps,
+                         id1, 0u);
+              mma_commit(bars + BAR_D1_FULL + b);
+              if (c == nch - 1 && p == passes - 1) mma_commit(bars + BAR_A1_EMPTY);
+            }
+            __syncwarp();
+            ++j1;
+          }
+          if (c >= 1) {
+            // D2 += h1 chunk (c-1) * M2 chunk
+            const uint32_t ab = q & 1;
+            mbar_wait(bars + BAR_A2_FULL + ab, (q >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a2 = a2_u32 + ab * 2u * a2_bytes, w2 = prev_stage + 2u * w1_bytes;
+              gemm3_desc(tbase + TM_D2, desc_at(hi16, a2), desc_at(hi16, a2 + a2_bytes), desc_at(hi16, w2),
+                         desc_at(hi16, w2 + w2_bytes), WKC / 8, id2, c > 1 ? 1u : 0u);
+              mma_commit(bars + BAR_A2_EMPTY + ab);
+              if (!a.resident) mma_commit(bars + BAR_W_EMPTY + prev_slot);
+              if (c == nch) mma_commit(bars + BAR_D2_FULL);
+            }
+            __syncwarp();
+            ++q;
+          }
+          prev_stage = stage;
+          prev_slot = slot;
+        }
+        for (int cc = 0; cc < nch_pass; ++cc) {
+          const int gc = p * nch_pass + cc;
+          uint32_t stage, slot;
+          if (a.resident) {
+            slot = (uint32_t)(nch + gc);
+            stage = ring_u32 + (uint32_t)nch * s1_bytes + (uint32_t)gc * s3_bytes;
+            if (first) mbar_wait(bars + BAR_W_FULL + slot, 0);
+          } else {
+            slot = sq % (uint32_t)a.NS;
+            stage = ring_u32 + slot * s1_bytes;
+            if (!((a.debug & 1) && sq >= (uint32_t)a.NS)) mbar_wait(bars + BAR_W_FULL + slot, (sq / (uint32_t)a.NS) & 1);
+          }
+          ++sq;
+          const uint32_t ab = q & 1;
+          mbar_wait(bars + BAR_A2_FULL + ab, (q >> 1) & 1);
+          tc_fence_after();
+          if (gc == 0) {
+            mbar_wait(bars + BAR_D3_EMPTY, (tcount & 1) ^ 1);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            const uint32_t a2 = a2_u32 + ab * 2u * a2_bytes;
+            gemm3_desc(tbase + TM_D3, desc_at(hi16, a2), desc_at(hi16, a2 + a2_bytes), desc_at(hi16, stage),
+                       desc_at(hi16, stage + w3_bytes), WKC / 8, id3, gc > 0 ? 1u : 0u);
+            mma_commit(bars + BAR_A2_EMPTY + ab);
+            if (!a.resident) mma_commit(bars + BAR_W_EMPTY + slot);
+            if (gc == nch - 1) mma_commit(bars + BAR_D3_FULL);
+          }
+          __syncwarp();
+          ++q;
+        }
+        ++npass;
+      }
+      first = false;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tmem_dealloc(tbase, (uint32_t)a.tmem_cols);
+  }
+}
+
+// ---- weight gradients: K = samples GEMMs ------------------------------------------------------------------------
+// CTA = (conditioner, 128-row tile mt of the hidden units, a contiguous range of sample tiles).  Operands come from the
+// [tile][row][128] buffers written by the forward / input-gradient sweeps: four consecutive samples of one row are
+// one 16-byte core-matrix row of a K-major operand with K = samples.  Per stage of KS = 16 samples:
+//   dW2[mt] (128 x H)    += delta2[mt] * h1^T          db2 += delta2[mt] * 1
+//   dW1[mt] (128 x K0p)  += delta1[mt] * in^T          db1 += delta1[mt] * 1
+//   dW3^T[mt] (128 x a16) += h2[mt] * delta3^T
+// accumulated in TMEM over the CTA's whole sample range and flushed once with red.global.add.
+constexpr int DW_KS = TC_DW_KS;
+constexpr int DW_STAGE_THREADS = 256;
+constexpr int DW_THREADS = DW_STAGE_THREADS + 32;
+constexpr uint32_t DWT_W2 = 0, DWT_W1 = 256, DWT_W3 = 320, DWT_B2 = 384, DWT_B1 = 400;
+
+struct DwArgs {
+  int H, K0p, K0, a, a16, mtiles, units, ksplit;
+  long long ntiles;
+  const float* h1buf[2];
+  const float* h2buf[2];
+  const float* d1buf[2];
+  const float* d2buf[2];
+  const float* d3buf[2];
+  const float* inbuf;
+  int first_net;
+  int p_w[2][3], p_b[2][3];
+  float* grad;
+};
+
+__device__ __forceinline__ void dw_stage_rows(float* dst_hi, float* dst_lo, const float* __restrict__ src, int rows,
+                                              int rows_valid, int s0, int stid) {
+  // rows x 16 samples: group g = (row, quad of 4 samples); a warp covers 8 rows x 4 quads = 512 contiguous bytes
+  const int ngroups = rows * 4;
+  for (int g = stid; g < ngroups; g += DW_STAGE_THREADS) {
+    const int blk = g >> 5, l = g & 31;
+    const int row = blk * 8 + (l & 7), quad = l >> 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows_valid) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * 128 + s0 + quad * 4));
+    float4 hi, lo;
+    hi.x = to_tf32(v.x); lo.x = v.x - hi.x;
+    hi.y = to_tf32(v.y); lo.y = v.y - hi.y;
+    hi.z = to_tf32(v.z); lo.z = v.z - hi.z;
+    hi.w = to_tf32(v.w); lo.w = v.w - hi.w;
+    const int idx = core_idx(row, quad * 4, DW_KS);
+    *reinterpret_cast<float4*>(dst_hi + idx) = hi;
+    *reinterpret_cast<float4*>(dst_lo + idx) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_constant__ DwArgs a) {
+  extern __shared__ float4 smem4[];
+  float* smem = reinterpret_cast<float*>(smem4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = a.H, K0p = a.K0p, a16 = a.a16;
+  const int unit = blockIdx.x % a.units, ks = blockIdx.x / a.units;
+  const int net = a.first_net + unit / a.mtiles, mt = unit % a.mtiles;
+  const int rows_valid = min(128, H - mt * 128);
+  // per stage (floats): A operands 3 x [128 x KS] hi/lo, B operands [H | K0p | a16] x KS hi/lo
+  const int a_fl = 128 * DW_KS, stage_fl = 2 * (3 * a_fl + (H + K0p + a16) * DW_KS);
+  float* stage0 = smem;
+  float* ones = smem + 2 * stage_fl;  // [16 x KS] hi only: row 0 = 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + 16 * DW_KS);
+  uint64_t* full = bars;       // [2]
+  uint64_t* empty = bars + 2;  // [2]
+  uint64_t* done = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(full + i, DW_STAGE_THREADS);
+      mbar_init(empty + i, 1);
+    }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < 16 * DW_KS; i += DW_THREADS) ones[i] = 0.0f;
+  __syncthreads();
+  if (tid < DW_KS) ones[core_idx(0, tid, DW_KS)] = 1.0f;
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+
+  const long long per = (a.ntiles + a.ksplit - 1) / a.ksplit;
+  const long long t0 = ks * per, t1 = min(a.ntiles, t0 + per);
+  const long long nstages = (t1 > t0) ? (t1 - t0) * (128 / DW_KS) : 0;
+
+  if (warp < 8) {
+    const float* d2 = a.d2buf[net];
+    const float* d1 = a.d1buf[net];
+    const float* h2 = a.h2buf[net];
+    const float* h1 = a.h1buf[net];
+    const float* d3 = a.d3buf[net];
+    for (long long s = 0; s < nstages; ++s) {
+      const uint32_t slot = (uint32_t)(s & 1);
+      const long long tile = t0 + s / (128 / DW_KS);
+      const int s0 = (int)(s % (128 / DW_KS)) * DW_KS;
+      mbar_wait(empty + slot, (uint32_t)(((s >> 1) & 1) ^ 1));
+      float* st = stage0 + (size_t)slot * stage_fl;
+      float* A_d2 = st;
+      float* A_d1 = st + 2 * a_fl;
+      float* A_h2 = st + 4 * a_fl;
+      float* B_h1 = st + 6 * a_fl;
+      float* B_in = B_h1 + 2 * H * DW_KS;
+      float* B_d3 = B_in + 2 * K0p * DW_KS;
+      dw_stage_rows(A_d2, A_d2 + a_fl, d2 + ((size_t)tile * H + mt * 128) * 128, 128, rows_valid, s0, tid);
+      dw_stage_rows(A_d1, A_d1 + a_fl, d1 + ((size_t)tile * H + mt * 128) * 128, 128, rows_valid, s0, tid);
+      dw_stage_rows(A_h2, A_h2 + a_fl, h2 + ((size_t)tile * H + mt * 128) * 128, 128, rows_valid, s0, tid);
+      dw_stage_rows(B_h1, B_h1 + H * DW_KS, h1 + (size_t)tile * H * 128, H, H, s0, tid);
+      dw_stage_rows(B_in, B_in + K0p * DW_KS, a.inbuf + (size_t)tile * K0p * 128, K0p, K0p, s0, tid);
+      dw_stage_rows(B_d3, B_d3 + a16 * DW_KS, d3 + (size_t)tile * a16 * 128, a16, a16, s0, tid);
+      fence_async_smem();
+      mbar_arrive(full + slot);
+    }
+    // ---- flush: warps 0-3 own TMEM lanes 32w..32w+31 = hidden unit rows of this m-tile ----
+    if (warp < 4 && nstages > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+      const int o = mt * 128 + tid;  // hidden unit (row of delta2 / delta1 / h2)
+      const bool ok = tid < rows_valid;
+      float v[16];
+      for (int i0 = 0; i0 < H; i0 += 16) {  // dW2[o][i] at p_w2 + o + H * i
+        tmem_ld16(tbase + lane_off + DWT_W2 + i0, v);
+        if (ok)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(a.grad + a.p_w[net][1] + o + (size_t)H * (i0 + j), v[j]);
+      }
+      for (int k0 = 0; k0 < K0p; k0 += 16) {  // dW1[o][k] at p_w1 + o + H * k   (K0p may be 8 mod 16: guard)
+        tmem_ld16(tbase + lane_off + DWT_W1 + k0, v);
+        if (ok)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (k0 + j < a.K0) atomicAdd(a.grad + a.p_w[net][0] + o + (size_t)H * (k0 + j), v[j]);
+      }
+      for (int j0 = 0; j0 < a16; j0 += 16) {  // dW3[j][i=o] at p_w3 + j + a * o
+        tmem_ld16(tbase + lane_off + DWT_W3 + j0, v);
+        if (ok)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j0 + j < a.a) atomicAdd(a.grad + a.p_w[net][2] + (j0 + j) + (size_t)a.a * o, v[j]);
+      }
+      tmem_ld16(tbase + lane_off + DWT_B2, v);
+      if (ok) atomicAdd(a.grad + a.p_b[net][1] + o, v[0]);
+      tmem_ld16(tbase + lane_off + DWT_B1, v);
+      if (ok) atomicAdd(a.grad + a.p_b[net][0] + o, v[0]);
+    }
+  } else {
+    // MMA issuer: the warp runs the loop uniformly, one elected lane issues
+    const int K0n = (K0p + 15) & ~15;  // N of the dW1 GEMM (M = 128 needs N % 16 == 0); extra rows read B_d3 (finite)
+    const uint32_t hi = desc_hi(DW_KS);
+    const uint32_t idW2 = instr_desc_tf32(H), idW1 = instr_desc_tf32(K0n), idW3 = instr_desc_tf32(a16),
+                   idB = instr_desc_tf32(16);
+    const uint32_t st_u32 = smem_u32(stage0), ones_u32 = smem_u32(ones);
+    const uint32_t a_b = (uint32_t)a_fl * 4u;
+    const uint32_t oB_h1 = 6u * a_b, oB_in = oB_h1 + 2u * (uint32_t)(H * DW_KS) * 4u,
+                   oB_d3 = oB_in + 2u * (uint32_t)(K0p * DW_KS) * 4u;
+    const uint64_t dOnes = desc_at(hi, ones_u32);
+    for (long long s = 0; s < nstages; ++s) {
+      const uint32_t slot = (uint32_t)(s & 1);
+      mbar_wait(full + slot, (uint32_t)((s >> 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t st = st_u32 + slot * (uint32_t)stage_fl * 4u;
+        const uint32_t acc = s > 0 ? 1u : 0u;
+        const uint64_t dD2h = desc_at(hi, st), dD2l = desc_at(hi, st + a_b);
+        const uint64_t dD1h = desc_at(hi, st + 2u * a_b), dD1l = desc_at(hi, st + 3u * a_b);
+        const uint64_t dH2h = desc_at(hi, st + 4u * a_b), dH2l = desc_at(hi, st + 5u * a_b);
+        gemm3_desc(tbase + DWT_W2, dD2h, dD2l, desc_at(hi, st + oB_h1), desc_at(hi, st + oB_h1 + (uint32_t)(H * DW_KS) * 4u),
+                   DW_KS / 8, idW2, acc);
+        gemm3_desc(tbase + DWT_W1, dD1h, dD1l, desc_at(hi, st + oB_in), desc_at(hi, st + oB_in + (uint32_t)(K0p * DW_KS) * 4u),
+                   DW_KS / 8, idW1, acc);
+        gemm3_desc(tbase + DWT_W3, dH2h, dH2l, desc_at(hi, st + oB_d3), desc_at(hi, st + oB_d3 + (uint32_t)(a16 * DW_KS) * 4u),
+                   DW_KS / 8, idW3, acc);
+        // column sums: (lo + hi) * 1
+#pragma unroll
+        for (int k8 = 0; k8 < DW_KS / 8; ++k8) {
+          const uint64_t o = (uint64_t)(k8 * 16);
+          const uint32_t acc2 = (acc || k8 > 0) ? 1u : 0u;
+          mma_tf32(tbase + DWT_B2, dD2l + o, dOnes + o, idB, acc2);
+          mma_tf32(tbase + DWT_B2, dD2h + o, dOnes + o, idB, 1u);
+          mma_tf32(tbase + DWT_B1, dD1l + o, dOnes + o, idB, acc2);
+          mma_tf32(tbase + DWT_B1, dD1h + o, dOnes + o, idB, 1u);
+        }
+        mma_commit(empty + slot);
+        if (s == nstages - 1) mma_commit(done);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tmem_dealloc(tbase, 512);
+  }
+}
+
+// ---- small element-wise kernels ------------------------------------------------------------------------------
+__global__ void tc_norm_kernel(const float* x_in, float* x_out, float* ldj, long long B, int d,
+                               const float* __restrict__ blk, int sampling) {
+  // blk = [x_min(d) | x_max(d) | alpha, beta, ldj_const]   (src/norm/Normalization.jl:64-103)
+  const float alpha = blk[2 * d], beta = blk[2 * d + 1], c = blk[2 * d + 2];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * d; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % d);
+    const float xmin = blk[k], xmax = blk[d + k], v = x_in[i];
+    x_out[i] = sampling ? ((xmax - xmin) * v - alpha * xmax + beta * xmin) / (beta - alpha)
+                        : (beta * (v - xmin) + alpha * (xmax - v)) / (xmax - xmin);
+    if (k == 0 && ldj) ldj[i / d] += sampling ? c : -c;
+  }
+}
+
+// cotangent through a NormalizationLayer in the normalising direction: dz/dx = (beta - alpha) / (x_max - x_min)
+__global__ void tc_norm_bwd_kernel(float* zbar, long long B, int d, const float* __restrict__ blk) {
+  const float alpha = blk[2 * d], beta = blk[2 * d + 1];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * d; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % d);
+    zbar[i] *= (beta - alpha) / (blk[d + k] - blk[k]);
+  }
+}
+
+// loss terms and adjoint seeds: logp_b = c0 - 0.5 |z_b|^2 + ldj_b (src/Flows.jl:279); zbar = z * inv_btot
+__global__ void tc_seed_kernel(const float* __restrict__ z, const float* __restrict__ ldj, long long B, int d, float c0,
+                               float inv_btot, float* zbar, float* loss2) {
+  float ls = 0.0f, bad = 0.0f;
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    float qd = 0.0f;
+    for (int k = 0; k < d; ++k) {
+      const float v = z[b * d + k];
+      qd = fmaf(v, v, qd);
+      zbar[b * d + k] = v * inv_btot;
+    }
+    const float lp = c0 - 0.5f * qd + ldj[b];
+    if (isfinite(lp))
+      ls += lp;
+    else
+      bad += 1.0f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ls += __shfl_xor_sync(0xffffffffu, ls, o);
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(loss2, ls);
+    if (bad != 0.0f) atomicAdd(loss2 + 1, bad);
+  }
+}
+
+__global__ void tc_gather_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, long long first,
+                                 long long B, int rows, float* dst) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * rows; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / rows;
+    const long long col = idx ? (long long)idx[first + b] : first + b;
+    dst[i] = src[col * rows + (i - b * rows)];
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+#define CKT(call)                                                                          \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DFLOW_E_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+static void fill_img(TcNetImg& im, int K0, int H, int N3, long long& off, int k0_align = 8) {
+  im.off = off;
+  im.K0 = K0;
+  im.K0p = (K0 + k0_align - 1) & ~(k0_align - 1);
+  im.H = H;
+  im.N3 = N3;
+  im.N3p = (N3 + 15) & ~15;
+  im.NH = H < 256 ? H : 256;
+  im.passes = H / im.NH;
+  im.nch = H / WKC;
+  im.nch_pass = im.NH / WKC;
+  im.s1_floats = 2 * WKC * im.K0p + 2 * im.NH * WKC;
+  im.s3_floats = 2 * im.N3p * WKC;
+  int o = 0;
+  im.bias_off = o;
+  o += (2 * H + im.N3p + 3) & ~3;
+  im.s1_off = o;
+  o += im.passes * im.nch * im.s1_floats;
+  im.s3_off = o;
+  o += im.nch * im.s3_floats;
+  im.total = o;
+  off += o;
+}
+
+struct TcLaunchCfg {
+  size_t smem;
+  int resident, NS, tmem_cols, ctas_per_sm;
+};
+
+static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg& cfg) {
+  const size_t base = (size_t)(2 * 128 * im.K0p + 4 * 128 * WKC + ((2 * im.H + im.N3p + 3) & ~3)) * 4;
+  const size_t bar_bytes = (size_t)BAR_COUNT * 8 + 16;
+  const size_t cap = (size_t)c->max_smem_optin;
+  const size_t ring_res = (size_t)(im.passes * im.nch * im.s1_floats + im.nch * im.s3_floats) * 4;
+  const int T = im.passes * im.nch + im.nch;
+  cfg.tmem_cols = (TM_D2 + (uint32_t)im.NH) <= 256 ? 256 : 512;
+  if (im.passes == 1 && T <= NSMAX && base + ring_res + bar_bytes <= cap) {
+    cfg.resident = 1;
+    cfg.NS = T;
+    cfg.smem = base + ring_res + bar_bytes;
+  } else {
+    const size_t room = cap > base + bar_bytes ? cap - base - bar_bytes : 0;
+    int ns = (int)(room / ((size_t)im.s1_floats * 4));
+    if (ns > 6) ns = 6;
+    if (ns < 3) return false;
+    cfg.resident = 0;
+    cfg.NS = ns;
+    cfg.smem = base + (size_t)ns * im.s1_floats * 4 + bar_bytes;
+  }
+  // co-residency: limited by shared memory (228 KB per SM, 1 KB reserved per CTA) and by TMEM columns
+  const int by_tmem = 512 / cfg.tmem_cols;
+  int by_smem = (int)(233472 / (cfg.smem + 1024));
+  if (by_smem < 1) by_smem = 1;
+  if (by_smem > by_tmem) {
+    // pad the request so that no more CTAs than TMEM can serve become resident (they would spin in tcgen05.alloc)
+    const size_t want = 233472 / (size_t)(by_tmem + 1) + 1;
+    if (want > cfg.smem + 1024 && want - 1024 <= cap) cfg.smem = want - 1024;
+    by_smem = by_tmem;
+  }
+  cfg.ctas_per_sm = std::min(std::min(by_smem, by_tmem), 2);
+  return true;
+}
+
+int tc_build_plan(dflow_chain* c) {
+  const DevChain* C = c->hc();
+  const DevChainHdr& Hd = C->h;
+  TcPlan* tp = new (std::nothrow) TcPlan();
+  if (!tp) return DFLOW_E_NOMEM;
+  c->tcp = tp;
+  long long off = 0;
+  tp->train_ok = true;
+  for (int ei = 0; ei < Hd.L; ++ei) {
+    const DevElem& E = C->e[ei];
+    TcLayer Ld;
+    memset(&Ld, 0, sizeof(Ld));
+    if (E.kind == DFLOW_ELEM_NORM) {
+      Ld.is_coupling = 0;
+      Ld.norm_off = E.stage_off;
+      tp->layers.push_back(Ld);
+      continue;
+    }
+    Ld.is_coupling = 1;
+    Ld.has_s = (E.kind == DFLOW_ELEM_RNVP) ? 1 : 0;
+    Ld.h = E.t.w[1];
+    Ld.nin = E.nin;
+    Ld.a = E.a;
+    Ld.a16 = (E.a + 15) & ~15;
+    memcpy(Ld.af, E.af, sizeof(Ld.af));
+    memcpy(Ld.id, E.id, sizeof(Ld.id));
+    const int h = Ld.h, a = Ld.a;
+    if (h > 256) tp->train_ok = false;
+    tp->hmax = std::max(tp->hmax, h);
+    tp->a16max = std::max(tp->a16max, Ld.a16);
+    for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
+      const DevNet& net = ni == 0 ? E.s : E.t;
+      for (int j = 0; j < 3; ++j) {
+        Ld.p_w[ni][j] = net.p_w[j];
+        Ld.p_b[ni][j] = net.p_b[j];
+      }
+      // forward orientation: M1 = W1 (h x nin), M2 = W2, M3 = W3 (a x h); Flux (out,in) column-major W[o + out*i]
+      fill_img(Ld.fwd[ni], Ld.nin, h, a, off);
+      TcPackJob J;
+      memset(&J, 0, sizeof(J));
+      J.im = Ld.fwd[ni];
+      J.base1 = net.p_w[0]; J.sn1 = 1; J.sk1 = h; J.vk1 = Ld.nin;
+      J.base2 = net.p_w[1]; J.sn2 = 1; J.sk2 = h;
+      J.base3 = net.p_w[2]; J.sn3 = 1; J.sk3 = a; J.vn3 = a;
+      J.pb1 = net.p_b[0]; J.pb2 = net.p_b[1]; J.pb3 = net.p_b[2]; J.nb3 = a;
+      tp->jobs_fwd.push_back(J);
+      tp->k0pmax = std::max(tp->k0pmax, Ld.fwd[ni].K0p);
+      if (h <= 256) {
+        // adjoint orientation: M1[u][o] = W3[o][u], M2[i][o] = W2[o][i], M3[k][u] = W1[u][k]
+        fill_img(Ld.bwd[ni], a, h, Ld.nin, off, 16);  // K0p = a16: delta3 rows double as the dW3 operand
+        memset(&J, 0, sizeof(J));
+        J.im = Ld.bwd[ni];
+        J.base1 = net.p_w[2]; J.sn1 = a; J.sk1 = 1; J.vk1 = a;
+        J.base2 = net.p_w[1]; J.sn2 = h; J.sk2 = 1;
+        J.base3 = net.p_w[0]; J.sn3 = h; J.sk3 = 1; J.vn3 = Ld.nin;
+        J.pb1 = J.pb2 = J.pb3 = -1;
+        tp->jobs_bwd.push_back(J);
+      }
+    }
+    TcLaunchCfg cfg;
+    for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
+      if (!tc_launch_cfg(c, Ld.fwd[ni], cfg) || (h <= 256 && !tc_launch_cfg(c, Ld.bwd[ni], cfg))) {
+        set_error("element %d: conditioner does not fit the tensor-core pipeline's shared memory", ei);
+        return DFLOW_E_UNSUPPORTED;
+      }
+    }
+    tp->layers.push_back(Ld);
+  }
+  tp->img_floats = (size_t)std::max<long long>(off, 4);
+  if (cudaMalloc(&tp->d_img, tp->img_floats * sizeof(float)) != cudaSuccess) {
+    set_error("cudaMalloc failed for the tensor-core weight image (%zu floats)", tp->img_floats);
+    return DFLOW_E_NOMEM;
+  }
+  const size_t nf = tp->jobs_fwd.size(), nb = tp->jobs_bwd.size();
+  if (cudaMalloc(&tp->d_jobs_fwd, std::max<size_t>(nf, 1) * sizeof(TcPackJob)) != cudaSuccess ||
+      cudaMalloc(&tp->d_jobs_bwd, std::max<size_t>(nb, 1) * sizeof(TcPackJob)) != cudaSuccess) {
+    set_error("cudaMalloc failed for the prepack job table");
+    return DFLOW_E_NOMEM;
+  }
+  if ((nf && cudaMemcpy(tp->d_jobs_fwd, tp->jobs_fwd.data(), nf * sizeof(TcPackJob), cudaMemcpyHostToDevice) != cudaSuccess) ||
+      (nb && cudaMemcpy(tp->d_jobs_bwd, tp->jobs_bwd.data(), nb * sizeof(TcPackJob), cudaMemcpyHostToDevice) != cudaSuccess)) {
+    set_error("cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return DFLOW_E_CUDA;
+  }
+  return DFLOW_OK;
+}
+
+void tc_free_plan(dflow_chain* c) {
+  TcPlan* tp = c->tcp;
+  if (!tp) return;
+  if (tp->d_img) cudaFree(tp->d_img);
+  if (tp->d_jobs_fwd) cudaFree(tp->d_jobs_fwd);
+  if (tp->d_jobs_bwd) cudaFree(tp->d_jobs_bwd);
+  if (tp->d_sbuf) cudaFree(tp->d_sbuf);
+  delete tp;
+  c->tcp = nullptr;
+}
+
+int tc_prepack(dflow_chain* c, const float* W, bool with_bwd, cudaStream_t st) {
+  TcPlan* tp = c->tcp;
+  if (!tp->jobs_fwd.empty()) {
+    tc_prepack_kernel<<<dim3((unsigned)tp->jobs_fwd.size(), 8), 256, 0, st>>>(tp->d_jobs_fwd, W, tp->d_img);
+    CKT(cudaGetLastError());
+    c->launches++;
+  }
+  if (with_bwd && !tp->jobs_bwd.empty()) {
+    tc_prepack_kernel<<<dim3((unsigned)tp->jobs_bwd.size(), 8), 256, 0, st>>>(tp->d_jobs_bwd, W, tp->d_img);
+    CKT(cudaGetLastError());
+    c->launches++;
+  }
+  return DFLOW_OK;
+}
+
+static void fill_common(const dflow_chain* c, const TcLayer& Ld, TcArgs& a) {
+  const DevChainHdr& Hd = c->hc()->h;
+  a.img = c->tcp->d_img;
+  a.has_s = Ld.has_s;
+  a.d = Hd.d;
+  a.n = Hd.n;
+  a.a = Ld.a;
+  a.a16 = Ld.a16;
+  a.nin = Ld.nin;
+  memcpy(a.af, Ld.af, sizeof(a.af));
+  memcpy(a.id, Ld.id, sizeof(a.id));
+  for (int k = 0; k < NMAX; ++k) {
+    a.theta_min[k] = Hd.theta_min[k];
+    a.theta_rng[k] = Hd.theta_rng[k];
+  }
+}
+
+template <int MODE>
+static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st) {
+  TcLaunchCfg cfg;
+  if (!tc_launch_cfg(c, a.im, cfg)) {
+    set_error("conditioner does not fit the tensor-core pipeline's shared memory");
+    return DFLOW_E_UNSUPPORTED;
+  }
+  a.resident = cfg.resident;
+  a.NS = cfg.NS;
+  a.debug = c->tc_debug;
+  a.tmem_cols = cfg.tmem_cols;
+  CKT(cudaFuncSetAttribute(tc_net_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+  long long grid = (a.B + 127) / 128;
+  const long long cap = (long long)c->sm_count * cfg.ctas_per_sm;
+  if (grid > cap) grid = cap;
+  tc_net_kernel<MODE><<<(unsigned)grid, TC_THREADS, cfg.smem, st>>>(a);
+  CKT(cudaGetLastError());
+  c->launches++;
+  return DFLOW_OK;
+}
+
+static int grow_sbuf(TcPlan* tp, size_t floats) {
+  if (tp->sbuf_floats >= floats) return DFLOW_OK;
+  if (tp->d_sbuf) cudaFree(tp->d_sbuf);
+  tp->d_sbuf = nullptr;
+  tp->sbuf_floats = 0;
+  if (cudaMalloc(&tp->d_sbuf, floats * sizeof(float)) != cudaSuccess) {
+    set_error("cudaMalloc failed for %zu floats of conditioner-output scratch", floats);
+    return DFLOW_E_NOMEM;
+  }
+  tp->sbuf_floats = floats;
+  return DFLOW_OK;
+}
+
+static unsigned ew_blocks(long long work) {
+  long long blocks = (work + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// Runs the whole chain on `x` in place (x already holds the input), accumulating ldj.
+int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* theta_const, float* ldj, long long B,
+                 int sampling, int flags, cudaStream_t st) {
+  TcPlan* tp = c->tcp;
+  const DevChainHdr& Hd = c->hc()->h;
+  const int L = (int)tp->layers.size();
+  const long long Bp = ((B + 127) / 128) * 128;
+  int rc = grow_sbuf(tp, (size_t)tp->a16max * Bp + 16);
+  if (rc) return rc;
+  for (int step = 0; step < L; ++step) {
+    const int ei = sampling ? step : (L - 1 - step);  // src/Chains.jl:155-161 vs :174-180
+    const TcLayer& Ld = tp->layers[ei];
+    if (!Ld.is_coupling) {
+      tc_norm_kernel<<<ew_blocks(B * Hd.d), 256, 0, st>>>(x, x, ldj, B, Hd.d, c->d_staged + Ld.norm_off, sampling);
+      CKT(cudaGetLastError());
+      c->launches++;
+      continue;
+    }
+    for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
+      TcArgs a;
+      memset(&a, 0, sizeof(a));
+      fill_common(c, Ld, a);
+      a.im = Ld.fwd[ni];
+      a.net_id = ni;
+      a.B = B;
+      a.sampling = sampling;
+      a.flags = flags;
+      a.x_in = x;
+      a.x_out = x;
+      a.theta = theta;
+      a.theta_const = theta_const;
+      a.ldj = ldj;
+      a.sbuf = tp->d_sbuf;
+      rc = launch_net<TC_FWD>(c, a, st);
+      if (rc) return rc;
+    }
+  }
+  return DFLOW_OK;
+}
+
+// ---- training -------------------------------------------------------------------------------------------------
+static void train_layout(const dflow_chain* c, long long B, TcTrainLayout& T) {
+  const TcPlan* tp = c->tcp;
+  const DevChainHdr& Hd = c->hc()->h;
+  const long long L = (long long)tp->layers.size();
+  // per-sample floats of everything that scales with the macro-batch
+  const long long per = (L + 1) * Hd.d + 1 + Hd.d + Hd.n + L * tp->a16max + L * tp->k0pmax + L * 4 * tp->hmax +
+                        L * 4 * (tp->hmax / 32) + 4 * tp->hmax + 2 * tp->a16max;
+  long long MB = ((B + 127) / 128) * 128;
+  const long long budget = (long long)12 << 30;  // bytes
+  long long cap = budget / (per * 4);
+  cap = std::max<long long>(128, (cap / 128) * 128);
+  if (MB > cap) MB = cap;
+  T.MB = MB;
+  size_t o = 64;
+  auto take = [&](long long floats) {
+    size_t r = o;
+    o += (size_t)((floats + 63) & ~63LL);
+    return r;
+  };
+  T.traj = take((L + 1) * Hd.d * MB);
+  T.ldj = take(MB);
+  T.zbar = take(Hd.d * MB);
+  T.theta = take((long long)Hd.n * MB);
+  T.sbuf = take(L * tp->a16max * MB);
+  T.inbuf = take(L * tp->k0pmax * MB);
+  T.hbuf = take(L * 4 * tp->hmax * MB);
+  T.mbuf = take(L * 4 * (tp->hmax / 32) * MB);
+  T.dbuf = take(4LL * tp->hmax * MB);
+  T.d3buf = take(2LL * tp->a16max * MB);
+  T.total = o;
+}
+
+size_t tc_workspace_bytes(const dflow_chain* c, long long B) {
+  TcTrainLayout T;
+  train_layout(c, B, T);
+  return T.total * sizeof(float) + 256;
+}
+
+int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* theta, long long B, const int32_t* idx,
+                 float inv_btot, int flags, float* loss_out, float* grad_out, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+  TcPlan* tp = c->tcp;
+  const DevChainHdr& Hd = c->hc()->h;
+  if (!tp->train_ok) {
+    set_error("the adjoint of conditioners wider than 256 is not built (sampling / log-density only)");
+    return DFLOW_E_UNSUPPORTED;
+  }
+  (void)ws_bytes;
+  TcTrainLayout T;
+  train_layout(c, B, T);
+  float* wsf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  const int L = (int)tp->layers.size(), d = Hd.d, n = Hd.n, hmax = tp->hmax, a16m = tp->a16max, k0m = tp->k0pmax;
+  int rc = tc_prepack(c, W, true, st);
+  if (rc) return rc;
+  for (long long first = 0; first < B; first += T.MB) {
+    const long long mb = std::min<long long>(T.MB, B - first);
+    const long long ntiles = (mb + 127) / 128;
+    float* traj = wsf + T.traj;
+    float* ldj = wsf + T.ldj;
+    float* zbar = wsf + T.zbar;
+    float* thg = wsf + T.theta;
+    const size_t st_d = (size_t)d * T.MB;
+    auto slot = [&](int e) { return traj + (size_t)e * st_d; };
+    auto sbuf_of = [&](int e) { return wsf + T.sbuf + (size_t)e * a16m * T.MB; };
+    auto inbuf_of = [&](int e) { return wsf + T.inbuf + (size_t)e * k0m * T.MB; };
+    auto hbuf_of = [&](int e, int net, int which) {
+      return wsf + T.hbuf + ((size_t)(e * 2 + net) * 2 + which) * (size_t)hmax * T.MB;
+    };
+    auto mbuf_of = [&](int e, int net, int which) {
+      return reinterpret_cast<uint32_t*>(wsf + T.mbuf) + ((size_t)(e * 2 + net) * 2 + which) * (size_t)(hmax / 32) * T.MB;
+    };
+    auto dbuf_of = [&](int net, int which) { return wsf + T.dbuf + (size_t)(net * 2 + which) * (size_t)hmax * T.MB; };
+    auto d3buf_of = [&](int net) { return wsf + T.d3buf + (size_t)net * a16m * T.MB; };
+    // input slot L: gather (or copy) this macro-batch
+    tc_gather_kernel<<<ew_blocks(mb * d), 256, 0, st>>>(x, idx, first, mb, d, slot(L));
+    CKT(cudaGetLastError());
+    c->launches++;
+    const float* th = nullptr;
+    if (n > 0) {
+      if (idx) {
+        tc_gather_kernel<<<ew_blocks(mb * n), 256, 0, st>>>(theta, idx, first, mb, n, thg);
+        CKT(cudaGetLastError());
+        c->launches++;
+        th = thg;
+      } else {
+        th = theta + (size_t)first * n;
+      }
+    }
+    CKT(cudaMemsetAsync(ldj, 0, sizeof(float) * mb, st));
+    // ---- forward (normalising) sweep with stored activations: elements L-1 .. 0 ----
+    for (int ei = L - 1; ei >= 0; --ei) {
+      const TcLayer& Ld = tp->layers[ei];
+      if (!Ld.is_coupling) {
+        tc_norm_kernel<<<ew_blocks(mb * d), 256, 0, st>>>(slot(ei + 1), slot(ei), ldj, mb, d, c->d_staged + Ld.norm_off, 0);
+        CKT(cudaGetLastError());
+        c->launches++;
+        continue;
+      }
+      for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
+        TcArgs a;
+        memset(&a, 0, sizeof(a));
+        fill_common(c, Ld, a);
+        a.im = Ld.fwd[ni];
+        a.net_id = ni;
+        a.B = mb;
+        a.sampling = 0;
+        a.flags = flags;
+        a.x_in = slot(ei + 1);
+        a.x_out = slot(ei);
+        a.theta = th;
+        a.ldj = ldj;
+        a.sbuf = sbuf_of(ei);
+        a.inbuf = inbuf_of(ei);
+        a.h1buf = hbuf_of(ei, ni, 0);
+        a.h2buf = hbuf_of(ei, ni, 1);
+        a.m1buf = mbuf_of(ei, ni, 0);
+        a.m2buf = mbuf_of(ei, ni, 1);
+        rc = launch_net<TC_FWD_STORE>(c, a, st);
+        if (rc) return rc;
+      }
+    }
+    // ---- loss and seeds ----
+    tc_seed_kernel<<<ew_blocks(mb), 256, 0, st>>>(slot(0), ldj, mb, d, Hd.logpdf_c0, inv_btot, zbar, loss_out);
+    CKT(cudaGetLastError());
+    c->launches++;
+    // ---- reverse sweep in chain order ----
+    int last_coupling = -1;
+    for (int ei = 0; ei < L; ++ei)
+      if (tp->layers[ei].is_coupling) last_coupling = ei;
+    for (int ei = 0; ei <= last_coupling; ++ei) {
+      const TcLayer& Ld = tp->layers[ei];
+      if (!Ld.is_coupling) {
+        tc_norm_bwd_kernel<<<ew_blocks(mb * d), 256, 0, st>>>(zbar, mb, d, c->d_staged + Ld.norm_off);
+        CKT(cudaGetLastError());
+        c->launches++;
+        continue;
+      }
+      for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
+        TcArgs a;
+        memset(&a, 0, sizeof(a));
+        fill_common(c, Ld, a);
+        a.im = Ld.bwd[ni];
+        a.net_id = ni;
+        a.B = mb;
+        a.flags = flags;
+        a.sbuf = sbuf_of(ei);
+        a.m1buf = mbuf_of(ei, ni, 0);
+        a.m2buf = mbuf_of(ei, ni, 1);
+        a.d1buf = dbuf_of(ni, 0);
+        a.d2buf = dbuf_of(ni, 1);
+        a.d3buf = d3buf_of(ni);
+        a.zbar = zbar;
+        a.zout = slot(ei);
+        a.inv_btot = inv_btot;
+        a.grad = grad_out;
+        a.p_b3 = Ld.p_b[ni][2];
+        rc = launch_net<TC_BWD>(c, a, st);
+        if (rc) return rc;
+      }
+      // weight gradients of this layer
+      DwArgs w;
+      memset(&w, 0, sizeof(w));
+      w.H = Ld.h;
+      w.K0p = Ld.fwd[1].K0p;
+      w.K0 = Ld.nin;
+      w.a = Ld.a;
+      w.a16 = Ld.a16;
+      w.mtiles = (Ld.h + 127) / 128;
+      w.first_net = Ld.has_s ? 0 : 1;
+      w.units = (Ld.has_s ? 2 : 1) * w.mtiles;
+      w.ksplit = (int)std::max<long long>(1, std::min<long long>(ntiles, c->sm_count / w.units));
+      w.ntiles = ntiles;
+      for (int ni = 0; ni < 2; ++ni) {
+        w.h1buf[ni] = hbuf_of(ei, ni, 0);
+        w.h2buf[ni] = hbuf_of(ei, ni, 1);
+        w.d1buf[ni] = dbuf_of(ni, 0);
+        w.d2buf[ni] = dbuf_of(ni, 1);
+        w.d3buf[ni] = d3buf_of(ni);
+        for (int j = 0; j < 3; ++j) {
+          w.p_w[ni][j] = Ld.p_w[ni][j];
+          w.p_b[ni][j] = Ld.p_b[ni][j];
+        }
+      }
+      w.inbuf = inbuf_of(ei);
+      w.grad = grad_out;
+      const size_t stage_fl = 2 * (3 * 128 * DW_KS + (size_t)(w.H + w.K0p + w.a16) * DW_KS);
+      const size_t smem = (2 * stage_fl + 16 * DW_KS) * 4 + 64;
+      if (smem > (size_t)c->max_smem_optin) {
+        set_error("weight-gradient stage needs %zu bytes of shared memory", smem);
+        return DFLOW_E_UNSUPPORTED;
+      }
+      CKT(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_dw_kernel<<<(unsigned)(w.units * w.ksplit), DW_THREADS, smem, st>>>(w);
+      CKT(cudaGetLastError());
+      c->launches++;
+    }
+  }
+  return DFLOW_OK;
+}
+
+}  // namespace dflow

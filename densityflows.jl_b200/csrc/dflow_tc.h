@@ -1,0 +1,92 @@
+// Tensor-core (tcgen05) path, generation 2: plan structures shared by dflow_api.cu and dflow_tc.cu.
+//
+// A conditioner Dense(in,h,relu) -> Dense(h,h,relu) -> Dense(h,a) and its transposed (adjoint) chain
+// delta3 -> (.W3) mask -> (.W2) mask -> (.W1) are the same three-GEMM pipeline with different matrices and epilogues,
+// so both are described by one "net image": three matrices M1 [H x K0], M2 [H x H], M3 [N3 x H], pre-split into
+// TF32 hi/lo parts and laid out as a sequence of stage blocks in consumption order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "dflow_internal.h"
+
+namespace dflow {
+
+constexpr int TC_WKC = 16;     // hidden units per pipeline chunk (N of GEMM 1, K of GEMMs 2 and 3)
+constexpr int TC_NSMAX = 16;   // ring slots
+constexpr int TC_THREADS = 192;  // 4 epilogue warps + producer warp + MMA warp
+constexpr int TC_DW_KS = 16;   // samples per stage of the weight-gradient kernel
+
+struct TcNetImg {
+  long long off;  // floats, start of this image inside the plan's weight image
+  int K0, K0p;    // GEMM-1 depth, padded to a multiple of 8
+  int H;          // hidden width
+  int N3, N3p;    // GEMM-3 outputs, padded to a multiple of 16
+  int NH, passes, nch, nch_pass;
+  int s1_floats;  // stage-1 block: [M1 chunk hi | lo] (WKC x K0p each) + [M2 chunk hi | lo] (NH x WKC each)
+  int s3_floats;  // stage-3 block: [M3 chunk hi | lo] (N3p x WKC each)
+  int bias_off;   // [b1 (H) | b2 (H) | b3 (N3p)] (forward orientation; zeros otherwise)
+  int s1_off, s3_off;
+  int total;      // floats
+};
+
+struct TcPackJob {
+  TcNetImg im;
+  // element (n, k) of matrix j is W[base + n * sn + k * sk]; M1 valid for k < vk1, M3 valid for n < vn3
+  int base1, sn1, sk1, vk1;
+  int base2, sn2, sk2;
+  int base3, sn3, sk3, vn3;
+  int pb1, pb2, pb3, nb3;  // bias offsets in the packed buffer (-1: zeros), number of real b3 entries
+};
+
+struct TcLayer {
+  int is_coupling, has_s;
+  int h, nin, a, a16;
+  int norm_off;
+  unsigned char af[DMAX], id[DMAX];
+  int p_w[2][3], p_b[2][3];
+  TcNetImg fwd[2], bwd[2];
+};
+
+// per-layer training buffers (offsets in floats inside the caller's workspace)
+struct TcTrainLayout {
+  long long MB;        // macro-batch (samples, multiple of 128)
+  size_t traj;         // [L+1][d * MB]   states: slot e = output of element e (normalising direction), slot L = input
+  size_t ldj;          // [MB]
+  size_t zbar;         // [d * MB]
+  size_t theta;        // [n * MB] gathered theta (idx != null)
+  size_t sbuf;         // [L][a16max * MB]
+  size_t inbuf;        // [L][K0pmax * MB]
+  size_t hbuf;         // [L][2 nets][2][hmax * MB]   post-relu activations h1, h2
+  size_t mbuf;         // [L][2 nets][2][(hmax/32) * MB]  relu masks (uint32)
+  size_t dbuf;         // [2 nets][2][hmax * MB]      delta1, delta2 of the current layer
+  size_t d3buf;        // [2 nets][a16max * MB]
+  size_t total;        // floats
+};
+
+struct TcPlan {
+  std::vector<TcLayer> layers;  // chain order
+  std::vector<TcPackJob> jobs_fwd, jobs_bwd;
+  TcPackJob* d_jobs_fwd = nullptr;
+  TcPackJob* d_jobs_bwd = nullptr;
+  float* d_img = nullptr;
+  size_t img_floats = 0;
+  float* d_sbuf = nullptr;  // s values of the current layer (forward-type calls), grow-only
+  size_t sbuf_floats = 0;
+  int hmax = 0, a16max = 0, k0pmax = 0;
+  bool train_ok = false;  // adjoint supported (h <= 256)
+};
+
+int tc_build_plan(dflow_chain* c);
+void tc_free_plan(dflow_chain* c);
+int tc_prepack(dflow_chain* c, const float* W, bool with_bwd, cudaStream_t st);
+int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* theta_const, float* ldj, long long B,
+                 int sampling, int flags, cudaStream_t st);
+size_t tc_workspace_bytes(const dflow_chain* c, long long B);
+int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* theta, long long B, const int32_t* idx,
+                 float inv_btot, int flags, float* loss_out, float* grad_out, void* ws, size_t ws_bytes,
+                 cudaStream_t st);
+
+}  // namespace dflow
