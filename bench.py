@@ -9,7 +9,9 @@ A step is one log-density pass over B = 1e8 samples per GPU (x 2.0 GB + θ 0.8 G
 inputs >> the 126 MB L2, so no L2 flush is needed).  `value` = samples/s with inputs resident in HBM;
 `e2e` = the same through the host-buffer C-ABI call (pinned host -> device -> host, copies inside the timed
 region).  Also reported in `ops`: sample() (in-kernel Philox, fixed θ) and the train step (adjoint + gradient
-all-reduce + Adam) on C2 and on C3 (d=16, n=4, 8 layers, hidden 64, global batch 4 Mi sharded over the ranks).
+all-reduce + Adam) on C2 and on C3 (d=16, n=4, 8 layers, hidden 64, global batch 4 Mi sharded over the ranks; on the
+CUDA-core kernels and on the tensor-core kernels), and the wide configs on the tcgen05 path: C4 (hidden 256)
+log-density + train step, C5 (hidden 512) sampling.
 
 Under torchrun (N > 1) every rank owns one GPU and an equal shard (weak scaling for logpdf / sample: no
 communication; the train step all-reduces the packed gradient over NCCL).  Time = max over ranks of the
@@ -49,6 +51,16 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback"
+
+
+def tensor_peak_tf32():
+    """Dense TF32 peak in TFLOP/s: half of the measured cuBLAS bf16 burst figure (same tensor pipe, half rate);
+    falls back to half of the recipe's 1590 TFLOP/s."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["bf16_tflops"]) / 2.0
+    except Exception:
+        return 1590.0 / 2.0
 
 
 class ClockSampler:
@@ -271,6 +283,77 @@ def run_ours(args):
         ops["train_step_c3"] = {"samples_per_s": Bg / (ms3 * 1e-3), "ms_per_step": ms3, "global_batch": Bg,
                                 "scaling": "strong", "allreduce_bytes": 4 * (pc3.P + 2)}
 
+        # the same step with the conditioners on the tensor cores (tcgen05, 3xTF32): dflow_tc.cu
+        pc3.tune(tc_mode=1)
+        ts3b = TrainStep(pc3, df.setup(df.Adam(1e-3), c3))
+        ms3b = timed(step_c3_tc := (lambda: ts3b(x3, th3, None, Bg, flags)), 2, 1, dist)
+        ops["train_step_c3_tensor"] = {"samples_per_s": Bg / (ms3b * 1e-3), "ms_per_step": ms3b, "global_batch": Bg,
+                                       "scaling": "strong", "path": "tcgen05 3xTF32 (tc_mode=1)"}
+        del x3, th3, pc3, ts3, ts3b
+        torch.cuda.empty_cache()
+
+    # ---- wide conditioners on the tensor cores: C4 (h=256) log-density + train step, C5 (h=512) sampling ----
+    if not args.no_wide:
+        from oracle import dflow_oracle as O
+
+        tf32_peak = tensor_peak_tf32()
+
+        def wide_chain(d_, n_, L_, h_):
+            xs_, _ = O.synthetic_data(d_, n_, 8192, seed=1234)
+            return chain_from_oracle(O.block_chain(d_, n_, L_, h_, xs_))
+
+        # C4: d=32, n=8, 12 coupling layers, hidden 256 (+ NormalizationLayer); 256 Ki samples per GPU and step
+        c4 = wide_chain(32, 8, 12, 256)
+        B4 = 1 << 18
+        x4, th4 = device_inputs(32, 8, B4, dev, 7 + rank)
+        pc4 = df.PackedChain(c4._leaves(), dev, np.full(8, -1.0, np.float32), np.full(8, 2.0, np.float32))
+        out4 = torch.empty(B4, device=dev)
+        x4p, t4p = df.arrays.flat_view(x4).data_ptr(), df.arrays.flat_view(th4).data_ptr()
+
+        def step_c4_logpdf():
+            df._lib.check(lib.dflow_logpdf(pc4.handle, pc4.W.data_ptr(), x4p, t4p, B4, None, flags, out4.data_ptr(), st))
+
+        ms4 = timed(step_c4_logpdf, 3, 2, dist)
+        f4 = 3637248.0  # 2*MAC per sample, forward
+        ops["logpdf_c4"] = {"samples_per_s": world * B4 / (ms4 * 1e-3), "ms_per_step": ms4, "B_per_gpu": B4,
+                            "fp32_equiv_tflops_per_gpu": f4 * B4 / (ms4 * 1e-3) / 1e12,
+                            "tensor_tflops_3xtf32_per_gpu": 3 * f4 * B4 / (ms4 * 1e-3) / 1e12,
+                            "tensor_frac_of_measured_tf32": 3 * f4 * B4 / (ms4 * 1e-3) / 1e12 / tf32_peak,
+                            "tf32_peak_tflops": tf32_peak, "tf32_peak_source": "MEASURED_PEAKS.json bf16_tflops / 2"}
+        ts4 = TrainStep(pc4, df.setup(df.Adam(1e-3), c4))
+
+        def step_c4_train():
+            ts4(x4, th4, None, B4 * world, flags)
+
+        ms4t = timed(step_c4_train, 2, 1, dist)
+        ops["train_step_c4"] = {"samples_per_s": world * B4 / (ms4t * 1e-3), "ms_per_step": ms4t, "B_per_gpu": B4,
+                                "scaling": "weak", "allreduce_bytes": 4 * (pc4.P + 2),
+                                "tensor_tflops_3xtf32_per_gpu": 9 * f4 * B4 / (ms4t * 1e-3) / 1e12,
+                                "tensor_frac_of_measured_tf32": 9 * f4 * B4 / (ms4t * 1e-3) / 1e12 / tf32_peak}
+        del x4, th4, pc4, ts4, out4
+        torch.cuda.empty_cache()
+        # C5: d=64, n=16, 16 coupling layers, hidden 512; inverse sampling with a fixed condition, no communication
+        c5 = wide_chain(64, 16, 16, 512)
+        B5 = 1 << 18
+        pc5 = df.PackedChain(c5._leaves(), dev, np.full(16, -1.0, np.float32), np.full(16, 2.0, np.float32))
+        th5 = torch.full((16,), 0.5, device=dev)
+        x5 = df.jl_empty((64, B5), dev)
+        x5p = df.arrays.flat_view(x5).data_ptr()
+
+        def step_c5_sample():
+            df._lib.check(lib.dflow_sample_rng(pc5.handle, pc5.W.data_ptr(), 777, 0, rank * B5, None, th5.data_ptr(), B5,
+                                               flags, x5p, st))
+
+        ms5 = timed(step_c5_sample, 3, 2, dist)
+        f5 = 19398656.0
+        ops["sample_rng_c5"] = {"samples_per_s": world * B5 / (ms5 * 1e-3), "ms_per_step": ms5, "B_per_gpu": B5,
+                                "seconds_for_1e9_samples": 1e9 / (world * B5 / (ms5 * 1e-3)),
+                                "tensor_tflops_3xtf32_per_gpu": 3 * f5 * B5 / (ms5 * 1e-3) / 1e12,
+                                "tensor_frac_of_measured_tf32": 3 * f5 * B5 / (ms5 * 1e-3) / 1e12 / tf32_peak}
+        assert torch.isfinite(df.arrays.flat_view(x5)[:: max(1, 64 * B5 // 4096)]).all()
+        del x5, pc5
+        torch.cuda.empty_cache()
+
     hbm, how = peaks()
     achieved = BYTES_PER_SAMPLE_LOGPDF * B / (ms * 1e-3) / 1e9
     traffic = None
@@ -389,6 +472,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-c3", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-wide", action="store_true", help="skip the tensor-core configs C4 / C5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

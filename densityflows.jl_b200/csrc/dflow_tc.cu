@@ -43,20 +43,18 @@ constexpr int NSMAX = TC_NSMAX;
 
 enum { TC_FWD = 0, TC_FWD_STORE = 1, TC_BWD = 2 };
 
-// TMEM column map of the net kernel
-constexpr uint32_t TM_D1 = 0;    // two buffers, 32 columns apart
-constexpr uint32_t TM_D3 = 64;   // <= 64 columns
-constexpr uint32_t TM_D2 = 128;  // <= 256 columns
+// TMEM column map of the net kernel (per launch, TcArgs): D1 ring of NG groups x GW columns at 0, then D3 (<= 64
+// columns) and D2 (NH <= 256 columns)
 
 // barrier slots (uint64 each) behind the ring
 enum {
   BAR_W_FULL = 0,
   BAR_W_EMPTY = NSMAX,
-  BAR_D1_FULL = 2 * NSMAX,
-  BAR_D1_EMPTY = 2 * NSMAX + 2,
-  BAR_A2_FULL = 2 * NSMAX + 4,
-  BAR_A2_EMPTY = 2 * NSMAX + 6,
-  BAR_D2_FULL = 2 * NSMAX + 8,
+  BAR_D1_FULL = 2 * NSMAX,       // [4] D1 group buffers
+  BAR_D1_EMPTY = 2 * NSMAX + 4,  // [4]
+  BAR_A2_FULL = 2 * NSMAX + 8,   // [4] A2 ring
+  BAR_A2_EMPTY = 2 * NSMAX + 12, // [4]
+  BAR_D2_FULL = 2 * NSMAX + 16,
   BAR_D2_EMPTY,
   BAR_D3_FULL,
   BAR_D3_EMPTY,
@@ -73,6 +71,7 @@ struct TcArgs {
   int net_id, has_s, d, n, a, a16, nin;
   int sampling, flags;
   int resident, NS, tmem_cols;
+  int NG, NA, tm_d3, tm_d2;  // D1 group buffers, A2 ring depth, TMEM columns of D3 / D2
   int debug;  // timing experiments only: bit 0 = weights loaded once per CTA (wrong results when streamed)
   unsigned char af[DMAX], id[DMAX];
   float theta_min[NMAX], theta_rng[NMAX];
@@ -112,17 +111,15 @@ __global__ void tc_prepack_kernel(const TcPackJob* jobs, const float* __restrict
     base[im.bias_off + H + i] = J.pb2 >= 0 ? W[J.pb2 + i] : 0.0f;
   }
   for (int i = t0; i < N3p; i += ts) base[im.bias_off + 2 * H + i] = (J.pb3 >= 0 && i < J.nb3) ? W[J.pb3 + i] : 0.0f;
-  // M1 [H x K0p]: chunk c = rows c*WKC.., replicated in every pass
+  // M1 [H x K0p]: group g = rows g*GW..
   for (int i = t0; i < H * K0p; i += ts) {
     const int u = i / K0p, k = i - u * K0p;
     const float w = k < J.vk1 ? W[J.base1 + u * J.sn1 + k * J.sk1] : 0.0f;
     const float hi = to_tf32(w);
-    const int c = u / WKC, r = u - c * WKC;
-    for (int p = 0; p < im.passes; ++p) {
-      float* blk = base + im.s1_off + (size_t)(p * nch + c) * im.s1_floats;
-      blk[core_idx(r, k, K0p)] = hi;
-      blk[WKC * K0p + core_idx(r, k, K0p)] = w - hi;
-    }
+    const int g = u / im.GW, r = u - g * im.GW;
+    float* blk = base + im.g1_off + (size_t)g * im.g1_floats;
+    blk[core_idx(r, k, K0p)] = hi;
+    blk[im.GW * K0p + core_idx(r, k, K0p)] = w - hi;
   }
   // M2 [H x H]: (pass p, chunk c) holds rows p*NH.. (n index), columns c*WKC.. (k index)
   for (int i = t0; i < H * H; i += ts) {
@@ -130,7 +127,7 @@ __global__ void tc_prepack_kernel(const TcPackJob* jobs, const float* __restrict
     const float w = W[J.base2 + nn * J.sn2 + k * J.sk2];
     const float hi = to_tf32(w);
     const int p = nn / NH, r = nn - p * NH, c = k / WKC, kk = k - c * WKC;
-    float* blk = base + im.s1_off + (size_t)(p * nch + c) * im.s1_floats + 2 * WKC * K0p;
+    float* blk = base + im.s2_off + (size_t)(p * nch + c) * im.s2_floats;
     blk[core_idx(r, kk, WKC)] = hi;
     blk[NH * WKC + core_idx(r, kk, WKC)] = w - hi;
   }
@@ -162,6 +159,17 @@ __device__ __forceinline__ void store_a2_row(float* a_hi, float* a_lo, int row, 
   }
 }
 
+// ring cursor: slot index + phase parity, advanced without divisions
+struct Ring {
+  uint32_t slot, par, n;
+  __device__ __forceinline__ void next() {
+    if (++slot == n) {
+      slot = 0;
+      par ^= 1u;
+    }
+  }
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ float4 smem4[];
@@ -169,16 +177,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
   const TcNetImg& im = a.im;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K0p = im.K0p, H = im.H, N3p = im.N3p, NH = im.NH, passes = im.passes, nch = im.nch,
-            nch_pass = im.nch_pass;
-  const int d = a.d, n = a.n;
+            nch_pass = im.nch_pass, GW = im.GW, ng = im.ng, cpg = im.GW / WKC;
+  const int d = a.d, n = a.n, NG = a.NG, NA = a.NA;
+  const uint32_t TM_D1 = 0, TM_D3 = (uint32_t)a.tm_d3, TM_D2 = (uint32_t)a.tm_d2;
 
   float* A1h = smem;
   float* A1l = A1h + 128 * K0p;
-  float* A2 = A1l + 128 * K0p;  // buffer b: hi at A2 + b * 2*128*WKC, lo 128*WKC further
-  float* biasS = A2 + 4 * 128 * WKC;
+  float* A2 = A1l + 128 * K0p;  // ring slot s: hi at A2 + s * 2*128*WKC, lo 128*WKC further
+  float* biasS = A2 + NA * 2 * 128 * WKC;
   const int nbias = (2 * H + N3p + 3) & ~3;
   float* ring = biasS + nbias;
-  const int ring_floats = a.resident ? (passes * nch * im.s1_floats + nch * im.s3_floats) : a.NS * im.s1_floats;
+  const int ring_floats = a.resident ? im.blocks_floats : a.NS * im.slot_floats;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + ring_floats);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_TMEM_SLOT);
   const float* gimg = a.img + im.off;
@@ -188,7 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
       mbar_init(bars + BAR_W_FULL + i, 1);
       mbar_init(bars + BAR_W_EMPTY + i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(bars + BAR_D1_FULL + i, 1);
       mbar_init(bars + BAR_D1_EMPTY + i, 128);
       mbar_init(bars + BAR_A2_FULL + i, 128);
@@ -213,7 +222,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
   if (warp < 4) {
     // =========================== epilogue warps ===========================
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    uint32_t q = 0, j1 = 0, npass = 0, tcount = 0;
+    Ring rA2{0, 0, (uint32_t)NA}, rD1{0, 0, (uint32_t)NG};
+    uint32_t npass = 0, tcount = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const long long gi = tile * 128 + tid;
       const bool valid = gi < a.B;
@@ -292,44 +302,48 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
 
       uint32_t mword = 0;
       for (int p = 0; p < passes; ++p) {
-        // ---- epilogue 1: hidden-1 chunks ----
-        for (int c = 0; c < nch; ++c) {
-          const uint32_t b = j1 & 1;
-          mbar_wait(bars + BAR_D1_FULL + b, (j1 >> 1) & 1);
+        // ---- epilogue 1: hidden-1 units, one D1 group (GW columns) at a time ----
+        for (int g = 0; g < ng; ++g) {
+          mbar_wait(bars + BAR_D1_FULL + rD1.slot, rD1.par);
           tc_fence_after();
-          float v[16];
-          tmem_ld16(tbase + lane_off + TM_D1 + b * 32, v);
-          tc_fence_before();
-          mbar_arrive(bars + BAR_D1_EMPTY + b);
-          ++j1;
-          if constexpr (MODE == TC_BWD) {
-            if (!(c & 1)) mword = a.m2buf[((size_t)tile * (H >> 5) + (c >> 1)) * 128 + tid];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              v[j] = ((mword >> ((c & 1) * 16 + j)) & 1u) ? v[j] : 0.0f;
-              a.d2buf[((size_t)tile * H + c * WKC + j) * 128 + tid] = v[j];
+          for (int cg = 0; cg < cpg; ++cg) {
+            const int c = g * cpg + cg;
+            float v[16];
+            tmem_ld16(tbase + lane_off + TM_D1 + rD1.slot * (uint32_t)GW + (uint32_t)(cg * WKC), v);
+            if (cg == cpg - 1) {
+              tc_fence_before();
+              mbar_arrive(bars + BAR_D1_EMPTY + rD1.slot);
             }
-          } else {
+            if constexpr (MODE == TC_BWD) {
+              if (!(c & 1)) mword = a.m2buf[((size_t)tile * (H >> 5) + (c >> 1)) * 128 + tid];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + biasS[c * WKC + j], 0.0f);
-            if constexpr (MODE == TC_FWD_STORE) {
-              if (p == 0) {
-                if (!(c & 1)) mword = 0;
+              for (int j = 0; j < 16; ++j) {
+                v[j] = ((mword >> ((c & 1) * 16 + j)) & 1u) ? v[j] : 0.0f;
+                a.d2buf[((size_t)tile * H + c * WKC + j) * 128 + tid] = v[j];
+              }
+            } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  a.h1buf[((size_t)tile * H + c * WKC + j) * 128 + tid] = v[j];
-                  mword |= (v[j] > 0.0f ? 1u : 0u) << ((c & 1) * 16 + j);
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + biasS[c * WKC + j], 0.0f);
+              if constexpr (MODE == TC_FWD_STORE) {
+                if (p == 0) {
+                  if (!(c & 1)) mword = 0;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    a.h1buf[((size_t)tile * H + c * WKC + j) * 128 + tid] = v[j];
+                    mword |= (v[j] > 0.0f ? 1u : 0u) << ((c & 1) * 16 + j);
+                  }
+                  if (c & 1) a.m1buf[((size_t)tile * (H >> 5) + (c >> 1)) * 128 + tid] = mword;
                 }
-                if (c & 1) a.m1buf[((size_t)tile * (H >> 5) + (c >> 1)) * 128 + tid] = mword;
               }
             }
+            mbar_wait(bars + BAR_A2_EMPTY + rA2.slot, rA2.par ^ 1);
+            float* a2 = A2 + rA2.slot * 2 * 128 * WKC;
+            if (!(a.debug & 16)) store_a2_row(a2, a2 + 128 * WKC, tid, v);
+            fence_async_smem();
+            mbar_arrive(bars + BAR_A2_FULL + rA2.slot);
+            rA2.next();
           }
-          const uint32_t ab = q & 1;
-          mbar_wait(bars + BAR_A2_EMPTY + ab, ((q >> 1) & 1) ^ 1);
-          store_a2_row(A2 + ab * 2 * 128 * WKC, A2 + ab * 2 * 128 * WKC + 128 * WKC, tid, v);
-          fence_async_smem();
-          mbar_arrive(bars + BAR_A2_FULL + ab);
-          ++q;
+          rD1.next();
         }
         // ---- epilogue 2: hidden-2 chunks of this pass ----
         mbar_wait(bars + BAR_D2_FULL, npass & 1);
@@ -362,12 +376,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
               if (gc & 1) a.m2buf[((size_t)tile * (H >> 5) + (gc >> 1)) * 128 + tid] = mword;
             }
           }
-          const uint32_t ab = q & 1;
-          mbar_wait(bars + BAR_A2_EMPTY + ab, ((q >> 1) & 1) ^ 1);
-          store_a2_row(A2 + ab * 2 * 128 * WKC, A2 + ab * 2 * 128 * WKC + 128 * WKC, tid, v);
+          mbar_wait(bars + BAR_A2_EMPTY + rA2.slot, rA2.par ^ 1);
+          float* a2 = A2 + rA2.slot * 2 * 128 * WKC;
+          if (!(a.debug & 16)) store_a2_row(a2, a2 + 128 * WKC, tid, v);
           fence_async_smem();
-          mbar_arrive(bars + BAR_A2_FULL + ab);
-          ++q;
+          mbar_arrive(bars + BAR_A2_FULL + rA2.slot);
+          rA2.next();
         }
         ++npass;
       }
@@ -423,44 +437,42 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
     }
   } else if (warp == 4) {
     // =========================== producer ===========================
+    // stage sequence per tile and pass (the MMA warp walks the same sequence):
+    //   G1(0..NG-1), then per chunk c: S2(p,c) and, when c closes a group, G1(c/cpg + NG); then S3 chunks of the pass
     if (lane == 0) {
-      uint32_t sq = 0;
-      const uint32_t s1b = (uint32_t)im.s1_floats * 4u, s3b = (uint32_t)im.s3_floats * 4u;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int p = 0; p < passes; ++p) {
-          for (int c = 0; c < nch; ++c, ++sq) {
-            float* dst;
-            uint32_t slot;
-            if (a.resident) {
-              slot = (uint32_t)c;
-              dst = ring + (size_t)c * im.s1_floats;
-            } else {
-              slot = sq % (uint32_t)a.NS;
-              dst = ring + (size_t)slot * im.s1_floats;
-              if ((a.debug & 1) && sq >= (uint32_t)a.NS) continue;
-              mbar_wait(bars + BAR_W_EMPTY + slot, ((sq / (uint32_t)a.NS) & 1) ^ 1);
+      if (a.resident) {
+        // the whole block region [G1 | S2 | S3] of this conditioner stays in shared memory
+        const uint32_t total = (uint32_t)im.blocks_floats * 4u;
+        mbar_expect_tx(bars + BAR_W_FULL, total);
+        uint32_t done = 0;
+        while (done < total) {  // pieces of <= 64 KB
+          const uint32_t piece = min(total - done, 65536u);
+          bulk_g2s(reinterpret_cast<char*>(ring) + done, reinterpret_cast<const char*>(gimg + im.g1_off) + done, piece,
+                   bars + BAR_W_FULL);
+          done += piece;
+        }
+      } else {
+        Ring rW{0, 0, (uint32_t)a.NS};
+        const uint32_t g1b = (uint32_t)im.g1_floats * 4u, s2b = (uint32_t)im.s2_floats * 4u, s3b = (uint32_t)im.s3_floats * 4u;
+        auto put = [&](const float* src, uint32_t bytes) {
+          mbar_wait(bars + BAR_W_EMPTY + rW.slot, rW.par ^ 1);
+          mbar_expect_tx(bars + BAR_W_FULL + rW.slot, bytes);
+          bulk_g2s(ring + (size_t)rW.slot * im.slot_floats, src, bytes, bars + BAR_W_FULL + rW.slot);
+          rW.next();
+        };
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+          for (int p = 0; p < passes; ++p) {
+            for (int g = 0; g < NG && g < ng; ++g) put(gimg + im.g1_off + (size_t)g * im.g1_floats, g1b);
+            for (int c = 0; c < nch; ++c) {
+              put(gimg + im.s2_off + (size_t)(p * nch + c) * im.s2_floats, s2b);
+              if ((c + 1) % cpg == 0) {
+                const int gn = c / cpg + NG;
+                if (gn < ng) put(gimg + im.g1_off + (size_t)gn * im.g1_floats, g1b);
+              }
             }
-            mbar_expect_tx(bars + BAR_W_FULL + slot, s1b);
-            bulk_g2s(dst, gimg + im.s1_off + (size_t)(p * nch + c) * im.s1_floats, s1b, bars + BAR_W_FULL + slot);
-          }
-          for (int cc = 0; cc < nch_pass; ++cc, ++sq) {
-            const int gc = p * nch_pass + cc;
-            float* dst;
-            uint32_t slot;
-            if (a.resident) {
-              slot = (uint32_t)(nch + gc);
-              dst = ring + (size_t)nch * im.s1_floats + (size_t)gc * im.s3_floats;
-            } else {
-              slot = sq % (uint32_t)a.NS;
-              dst = ring + (size_t)slot * im.s1_floats;
-              if ((a.debug & 1) && sq >= (uint32_t)a.NS) continue;
-              mbar_wait(bars + BAR_W_EMPTY + slot, ((sq / (uint32_t)a.NS) & 1) ^ 1);
-            }
-            mbar_expect_tx(bars + BAR_W_FULL + slot, s3b);
-            bulk_g2s(dst, gimg + im.s3_off + (size_t)gc * im.s3_floats, s3b, bars + BAR_W_FULL + slot);
+            for (int cc = 0; cc < nch_pass; ++cc) put(gimg + im.s3_off + (size_t)(p * nch_pass + cc) * im.s3_floats, s3b);
           }
         }
-        if (a.resident) break;  // loaded once, kept for every tile of this CTA
       }
     }
   } else {
@@ -469,98 +481,95 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
     const uint32_t hiK0 = desc_hi(K0p), hi16 = desc_hi(WKC);
     const uint64_t dA1h = desc_at(hiK0, smem_u32(A1h)), dA1l = desc_at(hiK0, smem_u32(A1l));
     const uint32_t a2_u32 = smem_u32(A2), ring_u32 = smem_u32(ring);
-    const uint32_t id1 = instr_desc_tf32(WKC), id2 = instr_desc_tf32(NH), id3 = instr_desc_tf32(N3p);
+    const uint32_t id1 = instr_desc_tf32(GW), id2 = instr_desc_tf32(NH), id3 = instr_desc_tf32(N3p);
     const int k1steps = K0p >> 3;
-    const uint32_t w1_bytes = (uint32_t)(WKC * K0p) * 4u, w2_bytes = (uint32_t)(NH * WKC) * 4u,
+    const uint32_t g1h_bytes = (uint32_t)(GW * K0p) * 4u, w2_bytes = (uint32_t)(NH * WKC) * 4u,
                    w3_bytes = (uint32_t)(N3p * WKC) * 4u, a2_bytes = 128u * WKC * 4u;
-    const uint32_t s1_bytes = (uint32_t)im.s1_floats * 4u, s3_bytes = (uint32_t)im.s3_floats * 4u;
-    uint32_t q = 0, j1 = 0, sq = 0, npass = 0, tcount = 0;
-    bool first = true;
+    const uint32_t g1b = (uint32_t)im.g1_floats * 4u, s2b = (uint32_t)im.s2_floats * 4u, s3b = (uint32_t)im.s3_floats * 4u;
+    const uint32_t slot_bytes = (uint32_t)im.slot_floats * 4u;
+    const uint32_t res_s2 = (uint32_t)(im.s2_off - im.g1_off) * 4u, res_s3 = (uint32_t)(im.s3_off - im.g1_off) * 4u;
+    Ring rW{0, 0, (uint32_t)(a.resident ? 1 : a.NS)}, rA2{0, 0, (uint32_t)NA}, rD1{0, 0, (uint32_t)NG};
+    uint32_t npass = 0, tcount = 0;
+    if (a.resident) {
+      mbar_wait(bars + BAR_W_FULL, 0);
+    }
+    // next stage of the weight ring -> shared-memory address (resident: fixed position inside the block region)
+    auto stage_addr = [&](uint32_t res_off) -> uint32_t {
+      if (a.resident) return ring_u32 + res_off;
+      mbar_wait(bars + BAR_W_FULL + rW.slot, rW.par);
+      return ring_u32 + rW.slot * slot_bytes;
+    };
+    auto stage_release = [&]() {  // call inside the elected lane after the MMAs that read the stage
+      if (!a.resident) mma_commit(bars + BAR_W_EMPTY + rW.slot);
+    };
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       mbar_wait(bars + BAR_A1_FULL, tcount & 1);
       tc_fence_after();
       for (int p = 0; p < passes; ++p) {
+        auto issue_d1 = [&](int g) {
+          const uint32_t st = stage_addr((uint32_t)g * g1b);
+          mbar_wait(bars + BAR_D1_EMPTY + rD1.slot, rD1.par ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            if (!(a.debug & 2))
+              gemm3_desc(tbase + TM_D1 + rD1.slot * (uint32_t)GW, dA1h, dA1l, desc_at(hiK0, st), desc_at(hiK0, st + g1h_bytes),
+                         k1steps, id1, 0u);
+            mma_commit(bars + BAR_D1_FULL + rD1.slot);
+            stage_release();
+            if (g == ng - 1 && p == passes - 1) mma_commit(bars + BAR_A1_EMPTY);
+          }
+          __syncwarp();
+          if (!a.resident) rW.next();
+          rD1.next();
+        };
+        for (int g = 0; g < NG && g < ng; ++g) issue_d1(g);
         mbar_wait(bars + BAR_D2_EMPTY, (npass & 1) ^ 1);
         tc_fence_after();
-        uint32_t prev_stage = 0, prev_slot = 0;
-        for (int c = 0; c <= nch; ++c) {
-          uint32_t stage = 0, slot = 0;
-          if (c < nch) {
-            if (a.resident) {
-              slot = (uint32_t)c;
-              stage = ring_u32 + (uint32_t)c * s1_bytes;
-              if (first) mbar_wait(bars + BAR_W_FULL + slot, 0);
-            } else {
-              slot = sq % (uint32_t)a.NS;
-              stage = ring_u32 + slot * s1_bytes;
-              if (!((a.debug & 1) && sq >= (uint32_t)a.NS)) mbar_wait(bars + BAR_W_FULL + slot, (sq / (uint32_t)a.NS) & 1);
-            }
-            ++sq;
-            const uint32_t b = j1 & 1;
-            mbar_wait(bars + BAR_D1_EMPTY + b, ((j1 >> 1) & 1) ^ 1);
-            tc_fence_after();
-            if (elect_one()) {
-              gemm3_desc(tbase + TM_D1 + b * 32, dA1h, dA1l, desc_at(hiK0, stage), desc_at(hiK0, stage + w1_bytes), k1steps,
-                         id1, 0u);
-              mma_commit(bars + BAR_D1_FULL + b);
-              if (c == nch - 1 && p == passes - 1) mma_commit(bars + BAR_A1_EMPTY);
-            }
-            __syncwarp();
-            ++j1;
+        for (int c = 0; c < nch; ++c) {
+          const uint32_t st = stage_addr(res_s2 + (uint32_t)(p * nch + c) * s2b);
+          mbar_wait(bars + BAR_A2_FULL + rA2.slot, rA2.par);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a2 = a2_u32 + rA2.slot * 2u * a2_bytes;
+            if (!(a.debug & 8))
+              gemm3_desc(tbase + TM_D2, desc_at(hi16, a2), desc_at(hi16, a2 + a2_bytes), desc_at(hi16, st),
+                         desc_at(hi16, st + w2_bytes), WKC / 8, id2, c > 0 ? 1u : 0u);
+            mma_commit(bars + BAR_A2_EMPTY + rA2.slot);
+            stage_release();
+            if (c == nch - 1) mma_commit(bars + BAR_D2_FULL);
           }
-          if (c >= 1) {
-            // D2 += h1 chunk (c-1) * M2 chunk
-            const uint32_t ab = q & 1;
-            mbar_wait(bars + BAR_A2_FULL + ab, (q >> 1) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t a2 = a2_u32 + ab * 2u * a2_bytes, w2 = prev_stage + 2u * w1_bytes;
-              gemm3_desc(tbase + TM_D2, desc_at(hi16, a2), desc_at(hi16, a2 + a2_bytes), desc_at(hi16, w2),
-                         desc_at(hi16, w2 + w2_bytes), WKC / 8, id2, c > 1 ? 1u : 0u);
-              mma_commit(bars + BAR_A2_EMPTY + ab);
-              if (!a.resident) mma_commit(bars + BAR_W_EMPTY + prev_slot);
-              if (c == nch) mma_commit(bars + BAR_D2_FULL);
-            }
-            __syncwarp();
-            ++q;
+          __syncwarp();
+          if (!a.resident) rW.next();
+          rA2.next();
+          if ((c + 1) % cpg == 0) {
+            const int gn = c / cpg + NG;
+            if (gn < ng) issue_d1(gn);
           }
-          prev_stage = stage;
-          prev_slot = slot;
         }
         for (int cc = 0; cc < nch_pass; ++cc) {
           const int gc = p * nch_pass + cc;
-          uint32_t stage, slot;
-          if (a.resident) {
-            slot = (uint32_t)(nch + gc);
-            stage = ring_u32 + (uint32_t)nch * s1_bytes + (uint32_t)gc * s3_bytes;
-            if (first) mbar_wait(bars + BAR_W_FULL + slot, 0);
-          } else {
-            slot = sq % (uint32_t)a.NS;
-            stage = ring_u32 + slot * s1_bytes;
-            if (!((a.debug & 1) && sq >= (uint32_t)a.NS)) mbar_wait(bars + BAR_W_FULL + slot, (sq / (uint32_t)a.NS) & 1);
-          }
-          ++sq;
-          const uint32_t ab = q & 1;
-          mbar_wait(bars + BAR_A2_FULL + ab, (q >> 1) & 1);
+          const uint32_t st = stage_addr(res_s3 + (uint32_t)gc * s3b);
+          mbar_wait(bars + BAR_A2_FULL + rA2.slot, rA2.par);
           tc_fence_after();
           if (gc == 0) {
             mbar_wait(bars + BAR_D3_EMPTY, (tcount & 1) ^ 1);
             tc_fence_after();
           }
           if (elect_one()) {
-            const uint32_t a2 = a2_u32 + ab * 2u * a2_bytes;
-            gemm3_desc(tbase + TM_D3, desc_at(hi16, a2), desc_at(hi16, a2 + a2_bytes), desc_at(hi16, stage),
-                       desc_at(hi16, stage + w3_bytes), WKC / 8, id3, gc > 0 ? 1u : 0u);
-            mma_commit(bars + BAR_A2_EMPTY + ab);
-            if (!a.resident) mma_commit(bars + BAR_W_EMPTY + slot);
+            const uint32_t a2 = a2_u32 + rA2.slot * 2u * a2_bytes;
+            if (!(a.debug & 4))
+              gemm3_desc(tbase + TM_D3, desc_at(hi16, a2), desc_at(hi16, a2 + a2_bytes), desc_at(hi16, st),
+                         desc_at(hi16, st + w3_bytes), WKC / 8, id3, gc > 0 ? 1u : 0u);
+            mma_commit(bars + BAR_A2_EMPTY + rA2.slot);
+            stage_release();
             if (gc == nch - 1) mma_commit(bars + BAR_D3_FULL);
           }
           __syncwarp();
-          ++q;
+          if (!a.resident) rW.next();
+          rA2.next();
         }
         ++npass;
       }
-      first = false;
     }
   }
 
@@ -851,43 +860,74 @@ static void fill_img(TcNetImg& im, int K0, int H, int N3, long long& off, int k0
   im.passes = H / im.NH;
   im.nch = H / WKC;
   im.nch_pass = im.NH / WKC;
-  im.s1_floats = 2 * WKC * im.K0p + 2 * im.NH * WKC;
+  im.GW = (H % 64 == 0) ? 64 : 32;
+  im.ng = H / im.GW;
+  im.g1_floats = 2 * im.GW * im.K0p;
+  im.s2_floats = 2 * im.NH * WKC;
   im.s3_floats = 2 * im.N3p * WKC;
+  im.slot_floats = std::max(im.g1_floats, std::max(im.s2_floats, im.s3_floats));
   int o = 0;
   im.bias_off = o;
   o += (2 * H + im.N3p + 3) & ~3;
-  im.s1_off = o;
-  o += im.passes * im.nch * im.s1_floats;
+  im.g1_off = o;
+  o += im.ng * im.g1_floats;
+  im.s2_off = o;
+  o += im.passes * im.nch * im.s2_floats;
   im.s3_off = o;
   o += im.nch * im.s3_floats;
+  im.blocks_floats = o - im.g1_off;
   im.total = o;
   off += o;
 }
 
 struct TcLaunchCfg {
   size_t smem;
-  int resident, NS, tmem_cols, ctas_per_sm;
+  int resident, NS, NA, NG, tm_d3, tm_d2, tmem_cols, ctas_per_sm;
 };
 
 static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg& cfg) {
-  const size_t base = (size_t)(2 * 128 * im.K0p + 4 * 128 * WKC + ((2 * im.H + im.N3p + 3) & ~3)) * 4;
   const size_t bar_bytes = (size_t)BAR_COUNT * 8 + 16;
   const size_t cap = (size_t)c->max_smem_optin;
-  const size_t ring_res = (size_t)(im.passes * im.nch * im.s1_floats + im.nch * im.s3_floats) * 4;
-  const int T = im.passes * im.nch + im.nch;
-  cfg.tmem_cols = (TM_D2 + (uint32_t)im.NH) <= 256 ? 256 : 512;
-  if (im.passes == 1 && T <= NSMAX && base + ring_res + bar_bytes <= cap) {
-    cfg.resident = 1;
-    cfg.NS = T;
-    cfg.smem = base + ring_res + bar_bytes;
+  auto base_bytes = [&](int na) {
+    return (size_t)(2 * 128 * im.K0p + na * 2 * 128 * WKC + ((2 * im.H + im.N3p + 3) & ~3)) * 4;
+  };
+  // TMEM: compact map (256 columns, two CTAs per SM) for narrow nets, full map otherwise
+  if (im.NH <= 64) {
+    cfg.NG = 2;
+    cfg.tm_d3 = 128;
+    cfg.tm_d2 = 192;
+    cfg.tmem_cols = 256;
   } else {
-    const size_t room = cap > base + bar_bytes ? cap - base - bar_bytes : 0;
-    int ns = (int)(room / ((size_t)im.s1_floats * 4));
-    if (ns > 6) ns = 6;
-    if (ns < 3) return false;
-    cfg.resident = 0;
-    cfg.NS = ns;
-    cfg.smem = base + (size_t)ns * im.s1_floats * 4 + bar_bytes;
+    cfg.NG = 3;
+    cfg.tm_d3 = 192;
+    cfg.tm_d2 = 256;
+    cfg.tmem_cols = 512;
+  }
+  const size_t res = (size_t)im.blocks_floats * 4;
+  cfg.resident = 0;
+  for (int na = 4; na >= 2 && !cfg.resident; na -= 2) {
+    if (im.passes == 1 && res < (1u << 20) && base_bytes(na) + res + bar_bytes <= cap) {
+      cfg.resident = 1;
+      cfg.NA = na;
+      cfg.NS = 1;
+      cfg.smem = base_bytes(na) + res + bar_bytes;
+    }
+  }
+  if (!cfg.resident) {
+    bool ok = false;
+    for (int na = 4; na >= 2 && !ok; na -= 2) {
+      const size_t b = base_bytes(na) + bar_bytes;
+      const size_t room = cap > b ? cap - b : 0;
+      int ns = (int)(room / ((size_t)im.slot_floats * 4));
+      if (ns > 6) ns = 6;
+      if (ns >= (na == 4 ? 4 : 3)) {
+        ok = true;
+        cfg.NA = na;
+        cfg.NS = ns;
+        cfg.smem = b + (size_t)ns * im.slot_floats * 4;
+      }
+    }
+    if (!ok) return false;
   }
   // co-residency: limited by shared memory (228 KB per SM, 1 KB reserved per CTA) and by TMEM columns
   const int by_tmem = 512 / cfg.tmem_cols;
@@ -1042,6 +1082,10 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st) {
   }
   a.resident = cfg.resident;
   a.NS = cfg.NS;
+  a.NA = cfg.NA;
+  a.NG = cfg.NG;
+  a.tm_d3 = cfg.tm_d3;
+  a.tm_d2 = cfg.tm_d2;
   a.debug = c->tc_debug;
   a.tmem_cols = cfg.tmem_cols;
   CKT(cudaFuncSetAttribute(tc_net_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
@@ -1123,7 +1167,7 @@ static void train_layout(const dflow_chain* c, long long B, TcTrainLayout& T) {
   const long long per = (L + 1) * Hd.d + 1 + Hd.d + Hd.n + L * tp->a16max + L * tp->k0pmax + L * 4 * tp->hmax +
                         L * 4 * (tp->hmax / 32) + 4 * tp->hmax + 2 * tp->a16max;
   long long MB = ((B + 127) / 128) * 128;
-  const long long budget = (long long)12 << 30;  // bytes
+  const long long budget = (long long)24 << 30;  // bytes
   long long cap = budget / (per * 4);
   cap = std::max<long long>(128, (cap / 128) * 128);
   if (MB > cap) MB = cap;

@@ -25,10 +25,14 @@ struct TcNetImg {
   int H;          // hidden width
   int N3, N3p;    // GEMM-3 outputs, padded to a multiple of 16
   int NH, passes, nch, nch_pass;
-  int s1_floats;  // stage-1 block: [M1 chunk hi | lo] (WKC x K0p each) + [M2 chunk hi | lo] (NH x WKC each)
-  int s3_floats;  // stage-3 block: [M3 chunk hi | lo] (N3p x WKC each)
-  int bias_off;   // [b1 (H) | b2 (H) | b3 (N3p)] (forward orientation; zeros otherwise)
-  int s1_off, s3_off;
+  int GW, ng;       // D1 is produced in groups of GW hidden units (64, or 32 when H % 64 != 0); ng = H / GW
+  int g1_floats;    // G1 block: [M1 group hi | lo] (GW x K0p each)
+  int s2_floats;    // S2 block: [M2 chunk hi | lo] (NH x WKC each)
+  int s3_floats;    // S3 block: [M3 chunk hi | lo] (N3p x WKC each)
+  int slot_floats;  // ring slot = largest block
+  int bias_off;     // [b1 (H) | b2 (H) | b3 (N3p)] (forward orientation; zeros otherwise)
+  int g1_off, s2_off, s3_off;
+  int blocks_floats;  // size of the contiguous [G1 | S2 | S3] region
   int total;      // floats
 };
 

@@ -145,8 +145,10 @@ def test_descriptor_and_error_codes_without_a_device():
     bad = _desc_for([l])
     bad.elems[0].s_net.widths[0] = 7  # conditioner input does not match length(axis_nn)
     assert lib.dflow_chain_create(C.byref(bad.desc), C.byref(h)) == L.E_INVALID_ARG
-    wide = df.CouplingLayer(5, [1, 2], n=0, hidden_dim_s=128, hidden_dim_t=128)
+    # hidden > 64 runs on the tensor-core path, which needs a multiple of 32 (dflow_tc.cu): 100 is refused up front
+    wide = df.CouplingLayer(5, [1, 2], n=0, hidden_dim_s=100, hidden_dim_t=100)
     assert lib.dflow_chain_create(C.byref(_desc_for([wide]).desc), C.byref(h)) == L.E_UNSUPPORTED
+    assert b"multiple of 32" in lib.dflow_last_error()
     with pytest.raises(df.DflowUnsupported):
         L.check(L.E_UNSUPPORTED)
     act = _desc_for([l])
