@@ -382,7 +382,7 @@ def run_ours(args):
                      "fma_frac": tfl / FP32_FMA_PEAK_TFLOPS},
         "ops": ops,
     }
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:  # reported on rank 0 at N=1 only (bounded sample)
         line["cpu_baseline"] = cpu_baseline(sample_s=12.0)
     if rank == 0:
         print(json.dumps(line), flush=True)
