@@ -72,6 +72,8 @@ struct TcArgs {
   int sampling, flags;
   int resident, NS, tmem_cols;
   int NG, NA, tm_d3, tm_d2;  // D1 group buffers, A2 ring depth, TMEM columns of D3 / D2
+  int s3ps;                  // S3 blocks (W3 chunks) per ring stage when streamed
+  int cluster;               // 1: launched as CTA pairs that share the weight stream (bulk-copy multicast)
   int debug;  // timing experiments only: bit 0 = weights loaded once per CTA (wrong results when streamed)
   unsigned char af[DMAX], id[DMAX];
   float theta_min[NMAX], theta_rng[NMAX];
@@ -85,8 +87,8 @@ struct TcArgs {
   float* inbuf;
   float* h1buf;
   float* h2buf;
-  uint32_t* m1buf;
-  uint32_t* m2buf;
+  uint16_t* m1buf;  // relu masks, one 16-bit word per (chunk, sample): [tiles][H/16][128]
+  uint16_t* m2buf;
   float* d1buf;
   float* d2buf;
   float* d3buf;
@@ -171,7 +173,7 @@ struct Ring {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
   const TcNetImg& im = a.im;
@@ -195,198 +197,233 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
   if (tid == 0) {
     for (int i = 0; i < NSMAX; ++i) {
       mbar_init(bars + BAR_W_FULL + i, 1);
-      mbar_init(bars + BAR_W_EMPTY + i, 1);
+      mbar_init(bars + BAR_W_EMPTY + i, a.cluster ? 2 : 1);  // pair: released by both CTAs' MMA warps
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(bars + BAR_D1_FULL + i, 1);
-      mbar_init(bars + BAR_D1_EMPTY + i, 128);
+      mbar_init(bars + BAR_D1_EMPTY + i, 256);
       mbar_init(bars + BAR_A2_FULL + i, 128);
       mbar_init(bars + BAR_A2_EMPTY + i, 1);
     }
     mbar_init(bars + BAR_D2_FULL, 1);
-    mbar_init(bars + BAR_D2_EMPTY, 128);
+    mbar_init(bars + BAR_D2_EMPTY, 256);
     mbar_init(bars + BAR_D3_FULL, 1);
     mbar_init(bars + BAR_D3_EMPTY, 128);
     mbar_init(bars + BAR_A1_FULL, 128);
     mbar_init(bars + BAR_A1_EMPTY, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  if (warp == 13) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   for (int i = tid; i < nbias; i += TC_THREADS) biasS[i] = i < 2 * H + N3p ? __ldg(gimg + im.bias_off + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
+  if (a.cluster) cluster_sync_all();  // the peer's barriers exist before any multicast copy / commit can reach them
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
   const long long ntiles = (a.B + 127) / 128;
+  // every CTA walks the same number of tiles (a pair must issue identical stage sequences); tiles >= ntiles are dummies
+  const long long iters = (ntiles + gridDim.x - 1) / gridDim.x;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =========================== epilogue warps ===========================
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    Ring rA2{0, 0, (uint32_t)NA}, rD1{0, 0, (uint32_t)NG};
+    // Two warpgroups share the 128 sample rows (thread row = tid & 127 = TMEM lane): warpgroup w handles the chunks
+    // with (chunk index & 1) == w, so every SM sub-partition has two epilogue warps to hide TMEM / barrier latency.
+    const int wg = warp >> 2, row = tid & 127;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t na_mask = (uint32_t)NA - 1u, na_log = NA == 4 ? 2u : 1u;
+    uint32_t q = (uint32_t)wg;  // A2 chunk sequence number of this warpgroup (advances by 2)
+    Ring rD1{0, 0, (uint32_t)NG};
     uint32_t npass = 0, tcount = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-      const long long gi = tile * 128 + tid;
-      const bool valid = gi < a.B;
-      mbar_wait(bars + BAR_A1_EMPTY, (tcount & 1) ^ 1);
-      // ---- A1: this sample's GEMM-1 input row ----
-      if constexpr (MODE == TC_BWD) {
-        // delta3 of this conditioner (src/affine/RNVP.jl:118-127): s: -zbar_af * z_af - jbar, t: -zbar_af * exp(-s)
-        for (int k0 = 0; k0 < K0p; k0 += 4) {
-          float v[4];
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const int j = k0 + qq;
-            float val = 0.0f;
-            if (valid && j < a.a) {
-              const int k = a.af[j];
-              const float zb = a.zbar[gi * d + k];
-              if (a.net_id == 0) {
-                val = -zb * a.zout[gi * d + k] + a.inv_btot;
-              } else {
-                const float sv = a.has_s ? a.sbuf[((size_t)tile * a.a16 + j) * 128 + tid] : 0.0f;
-                val = -zb * expf(-sv);
-              }
-            }
-            v[qq] = val;
-            a.d3buf[((size_t)tile * K0p + j) * 128 + tid] = val;
-            // bias gradient of the last Dense: sum over the tile's samples
-            float r = val;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-            if (lane == 0 && j < a.a && r != 0.0f) atomicAdd(a.grad + a.p_b3 + j, r);
-          }
-          float4 hi, lo;
-          hi.x = to_tf32(v[0]); lo.x = v[0] - hi.x;
-          hi.y = to_tf32(v[1]); lo.y = v[1] - hi.y;
-          hi.z = to_tf32(v[2]); lo.z = v[2] - hi.z;
-          hi.w = to_tf32(v[3]); lo.w = v[3] - hi.w;
-          const int idx = core_idx(tid, k0, K0p);
-          *reinterpret_cast<float4*>(A1h + idx) = hi;
-          *reinterpret_cast<float4*>(A1l + idx) = lo;
-        }
-      } else {
-        // conditioner input row [theta_0..theta_{n-1}, x[axis_id...], 0 pad] (src/affine/RNVP.jl:157)
-        if (a.x_out != a.x_in && a.net_id == 1 && valid)
-          for (int k = 0; k < d; ++k) a.x_out[gi * d + k] = a.x_in[gi * d + k];
-        for (int k0 = 0; k0 < K0p; k0 += 4) {
-          float v[4];
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const int k = k0 + qq;
-            float val = 0.0f;
-            if (valid && k < a.nin) {
-              if (k < n) {
-                val = a.theta_const ? __ldg(a.theta_const + k) : __ldg(a.theta + gi * n + k);
-                if (a.flags & DFLOW_THETA_NORMALIZE)
-                  val = (a.theta_rng[k] == 0.0f) ? 0.0f : (val - a.theta_min[k]) / a.theta_rng[k];
-              } else {
-                val = a.x_in[gi * d + a.id[k - n]];
-              }
-            }
-            v[qq] = val;
-            if constexpr (MODE == TC_FWD_STORE)
-              if (a.net_id == 1) a.inbuf[((size_t)tile * K0p + k) * 128 + tid] = val;
-          }
-          float4 hi, lo;
-          hi.x = to_tf32(v[0]); lo.x = v[0] - hi.x;
-          hi.y = to_tf32(v[1]); lo.y = v[1] - hi.y;
-          hi.z = to_tf32(v[2]); lo.z = v[2] - hi.z;
-          hi.w = to_tf32(v[3]); lo.w = v[3] - hi.w;
-          const int idx = core_idx(tid, k0, K0p);
-          *reinterpret_cast<float4*>(A1h + idx) = hi;
-          *reinterpret_cast<float4*>(A1l + idx) = lo;
-        }
-      }
+    // activation chunk -> next free slot of the A2 ring
+    auto handoff = [&](const float (&v)[16]) {
+      const uint32_t slot = q & na_mask, par = (q >> na_log) & 1u;
+      mbar_wait(bars + BAR_A2_EMPTY + slot, par ^ 1u);
+      float* a2 = A2 + slot * 2 * 128 * WKC;
+      if (!(a.debug & 16)) store_a2_row(a2, a2 + 128 * WKC, row, v);
       fence_async_smem();
-      mbar_arrive(bars + BAR_A1_FULL);
-
-      uint32_t mword = 0;
+      mbar_arrive(bars + BAR_A2_FULL + slot);
+      q += 2;
+    };
+    for (long long it = 0; it < iters; ++it, ++tcount) {
+      const long long tile = blockIdx.x + it * gridDim.x;
+      const bool live = tile < ntiles && !(a.debug & 128);  // dummy tiles touch no global memory
+      const long long gi = tile * 128 + row;
+      const bool valid = gi < a.B && !(a.debug & 128);  // (debug bit 128: timing without the per-sample global traffic)
       for (int p = 0; p < passes; ++p) {
-        // ---- epilogue 1: hidden-1 units, one D1 group (GW columns) at a time ----
+        // ---- epilogue 1: hidden-1 units, one D1 group (GW columns) at a time; this warpgroup's chunks of the group
+        //      are loaded together (one tcgen05.wait::ld per group) ----
         for (int g = 0; g < ng; ++g) {
           mbar_wait(bars + BAR_D1_FULL + rD1.slot, rD1.par);
           tc_fence_after();
-          for (int cg = 0; cg < cpg; ++cg) {
-            const int c = g * cpg + cg;
-            float v[16];
-            tmem_ld16(tbase + lane_off + TM_D1 + rD1.slot * (uint32_t)GW + (uint32_t)(cg * WKC), v);
-            if (cg == cpg - 1) {
-              tc_fence_before();
-              mbar_arrive(bars + BAR_D1_EMPTY + rD1.slot);
-            }
-            if constexpr (MODE == TC_BWD) {
-              if (!(c & 1)) mword = a.m2buf[((size_t)tile * (H >> 5) + (c >> 1)) * 128 + tid];
+          uint32_t r[2][16];
+          const uint32_t tcol = tbase + lane_off + rD1.slot * (uint32_t)GW;
+          tmem_ld16_nowait(tcol + (uint32_t)(wg * WKC), r[0]);
+          if (cpg > 2) tmem_ld16_nowait(tcol + (uint32_t)((wg + 2) * WKC), r[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(bars + BAR_D1_EMPTY + rD1.slot);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                v[j] = ((mword >> ((c & 1) * 16 + j)) & 1u) ? v[j] : 0.0f;
-                a.d2buf[((size_t)tile * H + c * WKC + j) * 128 + tid] = v[j];
-              }
-            } else {
+          for (int i = 0; i < 2; ++i) {
+            if (i * 2 < cpg) {
+              const int c = g * cpg + wg + 2 * i;
+              float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + biasS[c * WKC + j], 0.0f);
-              if constexpr (MODE == TC_FWD_STORE) {
-                if (p == 0) {
-                  if (!(c & 1)) mword = 0;
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[i][j]);
+              if constexpr (MODE == TC_BWD) {
+                const uint32_t mword = live ? a.m2buf[((size_t)tile * nch + c) * 128 + row] : 0u;
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    a.h1buf[((size_t)tile * H + c * WKC + j) * 128 + tid] = v[j];
-                    mword |= (v[j] > 0.0f ? 1u : 0u) << ((c & 1) * 16 + j);
+                for (int j = 0; j < 16; ++j) {
+                  v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
+                  if (live) a.d2buf[((size_t)tile * H + c * WKC + j) * 128 + row] = v[j];
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + biasS[c * WKC + j], 0.0f);
+                if constexpr (MODE == TC_FWD_STORE) {
+                  if (p == 0 && live) {
+                    uint32_t mword = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      a.h1buf[((size_t)tile * H + c * WKC + j) * 128 + row] = v[j];
+                      mword |= (v[j] > 0.0f ? 1u : 0u) << j;
+                    }
+                    a.m1buf[((size_t)tile * nch + c) * 128 + row] = (uint16_t)mword;
                   }
-                  if (c & 1) a.m1buf[((size_t)tile * (H >> 5) + (c >> 1)) * 128 + tid] = mword;
                 }
               }
+              handoff(v);
             }
-            mbar_wait(bars + BAR_A2_EMPTY + rA2.slot, rA2.par ^ 1);
-            float* a2 = A2 + rA2.slot * 2 * 128 * WKC;
-            if (!(a.debug & 16)) store_a2_row(a2, a2 + 128 * WKC, tid, v);
-            fence_async_smem();
-            mbar_arrive(bars + BAR_A2_FULL + rA2.slot);
-            rA2.next();
           }
           rD1.next();
         }
         // ---- epilogue 2: hidden-2 chunks of this pass ----
         mbar_wait(bars + BAR_D2_FULL, npass & 1);
         tc_fence_after();
-        for (int cc = 0; cc < nch_pass; ++cc) {
+        for (int cc = wg; cc < nch_pass; cc += 2) {
           const int gc = p * nch_pass + cc;
           float v[16];
           tmem_ld16(tbase + lane_off + TM_D2 + cc * WKC, v);
-          if (cc == nch_pass - 1) {
+          if (cc + 2 >= nch_pass) {
             tc_fence_before();
             mbar_arrive(bars + BAR_D2_EMPTY);
           }
           if constexpr (MODE == TC_BWD) {
-            if (!(gc & 1)) mword = a.m1buf[((size_t)tile * (H >> 5) + (gc >> 1)) * 128 + tid];
+            const uint32_t mword = live ? a.m1buf[((size_t)tile * nch + gc) * 128 + row] : 0u;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              v[j] = ((mword >> ((gc & 1) * 16 + j)) & 1u) ? v[j] : 0.0f;
-              a.d1buf[((size_t)tile * H + gc * WKC + j) * 128 + tid] = v[j];
+              v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
+              if (live) a.d1buf[((size_t)tile * H + gc * WKC + j) * 128 + row] = v[j];
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + biasS[H + gc * WKC + j], 0.0f);
-            if constexpr (MODE == TC_FWD_STORE) {
-              if (!(gc & 1)) mword = 0;
+            if (MODE == TC_FWD_STORE && live) {
+              uint32_t mword = 0;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                a.h2buf[((size_t)tile * H + gc * WKC + j) * 128 + tid] = v[j];
-                mword |= (v[j] > 0.0f ? 1u : 0u) << ((gc & 1) * 16 + j);
+                a.h2buf[((size_t)tile * H + gc * WKC + j) * 128 + row] = v[j];
+                mword |= (v[j] > 0.0f ? 1u : 0u) << j;
               }
-              if (gc & 1) a.m2buf[((size_t)tile * (H >> 5) + (gc >> 1)) * 128 + tid] = mword;
+              a.m2buf[((size_t)tile * nch + gc) * 128 + row] = (uint16_t)mword;
             }
           }
-          mbar_wait(bars + BAR_A2_EMPTY + rA2.slot, rA2.par ^ 1);
-          float* a2 = A2 + rA2.slot * 2 * 128 * WKC;
-          if (!(a.debug & 16)) store_a2_row(a2, a2 + 128 * WKC, tid, v);
-          fence_async_smem();
-          mbar_arrive(bars + BAR_A2_FULL + rA2.slot);
-          rA2.next();
+          handoff(v);
         }
         ++npass;
       }
-      // ---- outputs of the conditioner ----
-      mbar_wait(bars + BAR_D3_FULL, tcount & 1);
+    }
+  } else if (warp < 12) {
+    // =========================== loader / output warpgroup ===========================
+    // Builds the GEMM-1 operand of tile t+1 (gathers from global memory) while the pipeline works on tile t, then
+    // applies tile t's conditioner outputs; thread row = sample = TMEM lane.
+    const int row = tid & 127;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    auto build_a1 = [&](long long it, uint32_t tc) {
+      const long long tile = blockIdx.x + it * gridDim.x;
+      const bool live = tile < ntiles && !(a.debug & 128);
+      const long long gi = tile * 128 + row;
+      const bool valid = gi < a.B && !(a.debug & 128);
+      (void)live;
+        mbar_wait(bars + BAR_A1_EMPTY, (tc & 1) ^ 1);
+        // ---- A1: this sample's GEMM-1 input row ----
+        if constexpr (MODE == TC_BWD) {
+          // delta3 of this conditioner (src/affine/RNVP.jl:118-127): s: -zbar_af * z_af - jbar, t: -zbar_af * exp(-s)
+          for (int k0 = 0; k0 < K0p; k0 += 4) {
+            float v[4];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const int j = k0 + qq;
+              float val = 0.0f;
+              if (valid && j < a.a) {
+                const int k = a.af[j];
+                const float zb = a.zbar[gi * d + k];
+                if (a.net_id == 0) {
+                  val = -zb * a.zout[gi * d + k] + a.inv_btot;
+                } else {
+                  const float sv = a.has_s ? a.sbuf[((size_t)tile * a.a16 + j) * 128 + row] : 0.0f;
+                  val = -zb * expf(-sv);
+                }
+              }
+              v[qq] = val;
+              if (live) a.d3buf[((size_t)tile * K0p + j) * 128 + row] = val;
+              // bias gradient of the last Dense: sum over the tile's samples
+              float r = val;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+              if (lane == 0 && j < a.a && r != 0.0f) atomicAdd(a.grad + a.p_b3 + j, r);
+            }
+            float4 hi, lo;
+            hi.x = to_tf32(v[0]); lo.x = v[0] - hi.x;
+            hi.y = to_tf32(v[1]); lo.y = v[1] - hi.y;
+            hi.z = to_tf32(v[2]); lo.z = v[2] - hi.z;
+            hi.w = to_tf32(v[3]); lo.w = v[3] - hi.w;
+            const int idx = core_idx(row, k0, K0p);
+            *reinterpret_cast<float4*>(A1h + idx) = hi;
+            *reinterpret_cast<float4*>(A1l + idx) = lo;
+          }
+        } else {
+          // conditioner input row [theta_0..theta_{n-1}, x[axis_id...], 0 pad] (src/affine/RNVP.jl:157)
+          if (a.x_out != a.x_in && a.net_id == 1 && valid)
+            for (int k = 0; k < d; ++k) a.x_out[gi * d + k] = a.x_in[gi * d + k];
+          for (int k0 = 0; k0 < K0p; k0 += 4) {
+            float v[4];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const int k = k0 + qq;
+              float val = 0.0f;
+              if (valid && k < a.nin) {
+                if (k < n) {
+                  val = a.theta_const ? __ldg(a.theta_const + k) : __ldg(a.theta + gi * n + k);
+                  if (a.flags & DFLOW_THETA_NORMALIZE)
+                    val = (a.theta_rng[k] == 0.0f) ? 0.0f : (val - a.theta_min[k]) / a.theta_rng[k];
+                } else {
+                  val = a.x_in[gi * d + a.id[k - n]];
+                }
+              }
+              v[qq] = val;
+              if constexpr (MODE == TC_FWD_STORE)
+                if (a.net_id == 1 && live) a.inbuf[((size_t)tile * K0p + k) * 128 + row] = val;
+            }
+            float4 hi, lo;
+            hi.x = to_tf32(v[0]); lo.x = v[0] - hi.x;
+            hi.y = to_tf32(v[1]); lo.y = v[1] - hi.y;
+            hi.z = to_tf32(v[2]); lo.z = v[2] - hi.z;
+            hi.w = to_tf32(v[3]); lo.w = v[3] - hi.w;
+            const int idx = core_idx(row, k0, K0p);
+            *reinterpret_cast<float4*>(A1h + idx) = hi;
+            *reinterpret_cast<float4*>(A1l + idx) = lo;
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(bars + BAR_A1_FULL);
+    };
+    auto final_out = [&](long long it, uint32_t tc) {
+      const long long tile = blockIdx.x + it * gridDim.x;
+      const bool live = tile < ntiles && !(a.debug & 128);
+      const long long gi = tile * 128 + row;
+      const bool valid = gi < a.B && !(a.debug & 128);
+      (void)live;
+      mbar_wait(bars + BAR_D3_FULL, tc & 1);
       tc_fence_after();
       float lsum = 0.0f;
       for (int o0 = 0; o0 < N3p; o0 += 16) {
@@ -406,8 +443,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
             }
           }
         } else if (a.net_id == 0) {
+          if (live)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) a.sbuf[((size_t)tile * a.a16 + o0 + j) * 128 + tid] = v[j] + biasS[2 * H + o0 + j];
+            for (int j = 0; j < 16; ++j) a.sbuf[((size_t)tile * a.a16 + o0 + j) * 128 + row] = v[j] + biasS[2 * H + o0 + j];
         } else if (valid) {
           // coupling transform (src/affine/RNVP.jl:92,184; NICE: s = 0)
 #pragma unroll
@@ -416,7 +454,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
             if (jj < a.a) {
               const int k = a.af[jj];
               const float tv = v[j] + biasS[2 * H + jj];
-              const float sv = a.has_s ? a.sbuf[((size_t)tile * a.a16 + jj) * 128 + tid] : 0.0f;
+              const float sv = a.has_s ? a.sbuf[((size_t)tile * a.a16 + jj) * 128 + row] : 0.0f;
               const float xv = a.x_in[gi * d + k];
               a.x_out[gi * d + k] = a.sampling ? xv * expf(sv) + tv : (xv - tv) * expf(-sv);
               lsum += sv;
@@ -428,14 +466,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
         // cotangent of the transformed coordinates: ubar_af = zbar_af * exp(-s) (src/affine/RNVP.jl:134)
         if (a.net_id == 1 && a.has_s && valid)
           for (int j = 0; j < a.a; ++j) {
-            const float sv = a.sbuf[((size_t)tile * a.a16 + j) * 128 + tid];
+            const float sv = a.sbuf[((size_t)tile * a.a16 + j) * 128 + row];
             a.zbar[gi * d + a.af[j]] *= expf(-sv);
           }
       } else {
         if (a.net_id == 1 && a.ldj && valid) a.ldj[gi] += a.sampling ? lsum : -lsum;
       }
+    };
+    if (iters > 0) build_a1(0, 0);
+    for (long long it = 0; it < iters; ++it) {
+      if (it + 1 < iters) build_a1(it + 1, (uint32_t)(it + 1));
+      final_out(it, (uint32_t)it);
     }
-  } else if (warp == 4) {
+  } else if (warp == 12) {
     // =========================== producer ===========================
     // stage sequence per tile and pass (the MMA warp walks the same sequence):
     //   G1(0..NG-1), then per chunk c: S2(p,c) and, when c closes a group, G1(c/cpg + NG); then S3 chunks of the pass
@@ -454,13 +497,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
       } else {
         Ring rW{0, 0, (uint32_t)a.NS};
         const uint32_t g1b = (uint32_t)im.g1_floats * 4u, s2b = (uint32_t)im.s2_floats * 4u, s3b = (uint32_t)im.s3_floats * 4u;
+        const uint32_t crank = a.cluster ? cluster_ctarank() : 0u;
         auto put = [&](const float* src, uint32_t bytes) {
+          if (a.debug & 64) bytes = (bytes >> 3) & ~31u;  // timing experiment: an eighth of the weight stream
           mbar_wait(bars + BAR_W_EMPTY + rW.slot, rW.par ^ 1);
           mbar_expect_tx(bars + BAR_W_FULL + rW.slot, bytes);
-          bulk_g2s(ring + (size_t)rW.slot * im.slot_floats, src, bytes, bars + BAR_W_FULL + rW.slot);
+          char* dst = reinterpret_cast<char*>(ring + (size_t)rW.slot * im.slot_floats);
+          if (a.cluster) {
+            // each CTA of the pair fetches one half of the block and delivers it to both
+            const uint32_t half = bytes >> 1;
+            bulk_g2s_multicast(dst + crank * half, reinterpret_cast<const char*>(src) + crank * half, half,
+                               bars + BAR_W_FULL + rW.slot, (uint16_t)3);
+          } else {
+            bulk_g2s(dst, src, bytes, bars + BAR_W_FULL + rW.slot);
+          }
           rW.next();
         };
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (long long it = 0; it < iters; ++it) {
           for (int p = 0; p < passes; ++p) {
             for (int g = 0; g < NG && g < ng; ++g) put(gimg + im.g1_off + (size_t)g * im.g1_floats, g1b);
             for (int c = 0; c < nch; ++c) {
@@ -470,102 +523,155 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
                 if (gn < ng) put(gimg + im.g1_off + (size_t)gn * im.g1_floats, g1b);
               }
             }
-            for (int cc = 0; cc < nch_pass; ++cc) put(gimg + im.s3_off + (size_t)(p * nch_pass + cc) * im.s3_floats, s3b);
+            for (int cc = 0; cc < nch_pass; cc += a.s3ps)  // several W3 chunks per stage: one ring round trip for all of them
+              put(gimg + im.s3_off + (size_t)(p * nch_pass + cc) * im.s3_floats, (uint32_t)min(a.s3ps, nch_pass - cc) * s3b);
           }
         }
       }
     }
   } else {
     // =========================== MMA issuer ===========================
-    // The whole warp runs this loop uniformly (descriptors live in uniform registers); one elected lane issues.
+    // The whole warp runs this loop uniformly; one elected lane issues.  The loop is the serial resource of the CTA
+    // (one warp, dependent uniform-datapath arithmetic), so everything is precomputed in descriptor units (16 B):
+    // a descriptor is `base + offset`, barriers are 32-bit shared addresses.
     const uint32_t hiK0 = desc_hi(K0p), hi16 = desc_hi(WKC);
     const uint64_t dA1h = desc_at(hiK0, smem_u32(A1h)), dA1l = desc_at(hiK0, smem_u32(A1l));
-    const uint32_t a2_u32 = smem_u32(A2), ring_u32 = smem_u32(ring);
+    const uint64_t dA2_0 = desc_at(hi16, smem_u32(A2));        // A2 slot s hi: + s * a2_step, lo: + a2_lo
+    const uint64_t dRing16 = desc_at(hi16, smem_u32(ring));    // weight stage read with a 16-float row pitch (S2, S3)
+    const uint64_t dRingK0 = desc_at(hiK0, smem_u32(ring));    // ... with a K0p-float row pitch (G1)
+    const uint32_t a2_lo = (128u * WKC * 4u) >> 4, a2_step = 2u * a2_lo;
+    const uint32_t g1_lo = ((uint32_t)(GW * K0p) * 4u) >> 4, w2_lo = ((uint32_t)(NH * WKC) * 4u) >> 4,
+                   w3_lo = ((uint32_t)(N3p * WKC) * 4u) >> 4;
+    const uint32_t slot_step = ((uint32_t)im.slot_floats * 4u) >> 4;
+    const uint32_t g1_step = ((uint32_t)im.g1_floats * 4u) >> 4, s2_step = ((uint32_t)im.s2_floats * 4u) >> 4,
+                   s3_step = ((uint32_t)im.s3_floats * 4u) >> 4;
+    const uint32_t res_s2 = ((uint32_t)(im.s2_off - im.g1_off) * 4u) >> 4, res_s3 = ((uint32_t)(im.s3_off - im.g1_off) * 4u) >> 4;
     const uint32_t id1 = instr_desc_tf32(GW), id2 = instr_desc_tf32(NH), id3 = instr_desc_tf32(N3p);
     const int k1steps = K0p >> 3;
-    const uint32_t g1h_bytes = (uint32_t)(GW * K0p) * 4u, w2_bytes = (uint32_t)(NH * WKC) * 4u,
-                   w3_bytes = (uint32_t)(N3p * WKC) * 4u, a2_bytes = 128u * WKC * 4u;
-    const uint32_t g1b = (uint32_t)im.g1_floats * 4u, s2b = (uint32_t)im.s2_floats * 4u, s3b = (uint32_t)im.s3_floats * 4u;
-    const uint32_t slot_bytes = (uint32_t)im.slot_floats * 4u;
-    const uint32_t res_s2 = (uint32_t)(im.s2_off - im.g1_off) * 4u, res_s3 = (uint32_t)(im.s3_off - im.g1_off) * 4u;
-    Ring rW{0, 0, (uint32_t)(a.resident ? 1 : a.NS)}, rA2{0, 0, (uint32_t)NA}, rD1{0, 0, (uint32_t)NG};
+    const uint32_t bars_u32 = smem_u32(bars);
+    const uint32_t bW_FULL = bars_u32 + BAR_W_FULL * 8, bW_EMPTY = bars_u32 + BAR_W_EMPTY * 8,
+                   bD1_FULL = bars_u32 + BAR_D1_FULL * 8, bD1_EMPTY = bars_u32 + BAR_D1_EMPTY * 8,
+                   bA2_FULL = bars_u32 + BAR_A2_FULL * 8, bA2_EMPTY = bars_u32 + BAR_A2_EMPTY * 8;
+    const uint32_t tD1 = tbase + TM_D1, tD2 = tbase + TM_D2, tD3 = tbase + TM_D3;
+    const bool resident = a.resident != 0, pair = a.cluster != 0;
+    const bool skip1 = (a.debug & 2) != 0, skip2 = (a.debug & 8) != 0, skip3 = (a.debug & 4) != 0;
+    Ring rW{0, 0, (uint32_t)(resident ? 1 : a.NS)}, rA2{0, 0, (uint32_t)NA}, rD1{0, 0, (uint32_t)NG};
     uint32_t npass = 0, tcount = 0;
-    if (a.resident) {
-      mbar_wait(bars + BAR_W_FULL, 0);
-    }
-    // next stage of the weight ring -> shared-memory address (resident: fixed position inside the block region)
-    auto stage_addr = [&](uint32_t res_off) -> uint32_t {
-      if (a.resident) return ring_u32 + res_off;
-      mbar_wait(bars + BAR_W_FULL + rW.slot, rW.par);
-      return ring_u32 + rW.slot * slot_bytes;
-    };
-    auto stage_release = [&]() {  // call inside the elected lane after the MMAs that read the stage
-      if (!a.resident) mma_commit(bars + BAR_W_EMPTY + rW.slot);
-    };
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    if (resident) mbar_wait(bars + BAR_W_FULL, 0);
+    for (long long it = 0; it < iters; ++it, ++tcount) {
       mbar_wait(bars + BAR_A1_FULL, tcount & 1);
       tc_fence_after();
       for (int p = 0; p < passes; ++p) {
         auto issue_d1 = [&](int g) {
-          const uint32_t st = stage_addr((uint32_t)g * g1b);
-          mbar_wait(bars + BAR_D1_EMPTY + rD1.slot, rD1.par ^ 1);
+          uint32_t woff;  // weight block position in descriptor units
+          if (resident) {
+            woff = (uint32_t)g * g1_step;
+          } else {
+            mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
+            woff = rW.slot * slot_step;
+          }
+          mbar_wait_a(bD1_EMPTY + rD1.slot * 8, rD1.par ^ 1);
           tc_fence_after();
           if (elect_one()) {
-            if (!(a.debug & 2))
-              gemm3_desc(tbase + TM_D1 + rD1.slot * (uint32_t)GW, dA1h, dA1l, desc_at(hiK0, st), desc_at(hiK0, st + g1h_bytes),
-                         k1steps, id1, 0u);
-            mma_commit(bars + BAR_D1_FULL + rD1.slot);
-            stage_release();
+            const uint64_t db = dRingK0 + woff;
+            if (!skip1) gemm3_desc(tD1 + rD1.slot * (uint32_t)GW, dA1h, dA1l, db, db + g1_lo, k1steps, id1, 0u);
+            mma_commit_a(bD1_FULL + rD1.slot * 8);
+            if (!resident) {
+              if (pair) mma_commit_multicast_a(bW_EMPTY + rW.slot * 8, (uint16_t)3);
+              else mma_commit_a(bW_EMPTY + rW.slot * 8);
+            }
             if (g == ng - 1 && p == passes - 1) mma_commit(bars + BAR_A1_EMPTY);
           }
           __syncwarp();
-          if (!a.resident) rW.next();
+          if (!resident) rW.next();
           rD1.next();
         };
         for (int g = 0; g < NG && g < ng; ++g) issue_d1(g);
         mbar_wait(bars + BAR_D2_EMPTY, (npass & 1) ^ 1);
         tc_fence_after();
+        int cg = 0, gnext = NG;
         for (int c = 0; c < nch; ++c) {
-          const uint32_t st = stage_addr(res_s2 + (uint32_t)(p * nch + c) * s2b);
-          mbar_wait(bars + BAR_A2_FULL + rA2.slot, rA2.par);
+          uint32_t woff;
+          if (resident) {
+            woff = res_s2 + (uint32_t)(p * nch + c) * s2_step;
+          } else {
+            mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
+            woff = rW.slot * slot_step;
+          }
+          mbar_wait_a(bA2_FULL + rA2.slot * 8, rA2.par);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a2 = a2_u32 + rA2.slot * 2u * a2_bytes;
-            if (!(a.debug & 8))
-              gemm3_desc(tbase + TM_D2, desc_at(hi16, a2), desc_at(hi16, a2 + a2_bytes), desc_at(hi16, st),
-                         desc_at(hi16, st + w2_bytes), WKC / 8, id2, c > 0 ? 1u : 0u);
-            mma_commit(bars + BAR_A2_EMPTY + rA2.slot);
-            stage_release();
+            const uint64_t da = dA2_0 + rA2.slot * a2_step, db = dRing16 + woff;
+            if (!skip2) {
+              const uint32_t acc = c > 0 ? 1u : 0u;
+              mma_tf32(tD2, da + a2_lo, db, id2, acc);
+              mma_tf32(tD2, da, db + w2_lo, id2, 1u);
+              mma_tf32(tD2, da, db, id2, 1u);
+              mma_tf32(tD2, da + a2_lo + 16, db + 16, id2, 1u);
+              mma_tf32(tD2, da + 16, db + w2_lo + 16, id2, 1u);
+              mma_tf32(tD2, da + 16, db + 16, id2, 1u);
+            }
+            mma_commit_a(bA2_EMPTY + rA2.slot * 8);
+            if (!resident) {
+              if (pair) mma_commit_multicast_a(bW_EMPTY + rW.slot * 8, (uint16_t)3);
+              else mma_commit_a(bW_EMPTY + rW.slot * 8);
+            }
             if (c == nch - 1) mma_commit(bars + BAR_D2_FULL);
           }
           __syncwarp();
-          if (!a.resident) rW.next();
+          if (!resident) rW.next();
           rA2.next();
-          if ((c + 1) % cpg == 0) {
-            const int gn = c / cpg + NG;
-            if (gn < ng) issue_d1(gn);
+          if (++cg == cpg) {
+            cg = 0;
+            if (gnext < ng) issue_d1(gnext);
+            ++gnext;
           }
         }
-        for (int cc = 0; cc < nch_pass; ++cc) {
+        uint32_t woff3 = 0;
+        for (int cc = 0, ci = 0; cc < nch_pass; ++cc) {
           const int gc = p * nch_pass + cc;
-          const uint32_t st = stage_addr(res_s3 + (uint32_t)gc * s3b);
-          mbar_wait(bars + BAR_A2_FULL + rA2.slot, rA2.par);
+          uint32_t woff;
+          if (resident) {
+            woff = res_s3 + (uint32_t)gc * s3_step;
+          } else {
+            if (ci == 0) {
+              mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
+              woff3 = rW.slot * slot_step;
+            }
+            woff = woff3 + (uint32_t)ci * s3_step;
+          }
+          const bool last_of_stage = (ci + 1 == a.s3ps) || (cc + 1 == nch_pass);
+          mbar_wait_a(bA2_FULL + rA2.slot * 8, rA2.par);
           tc_fence_after();
           if (gc == 0) {
             mbar_wait(bars + BAR_D3_EMPTY, (tcount & 1) ^ 1);
             tc_fence_after();
           }
           if (elect_one()) {
-            const uint32_t a2 = a2_u32 + rA2.slot * 2u * a2_bytes;
-            if (!(a.debug & 4))
-              gemm3_desc(tbase + TM_D3, desc_at(hi16, a2), desc_at(hi16, a2 + a2_bytes), desc_at(hi16, st),
-                         desc_at(hi16, st + w3_bytes), WKC / 8, id3, gc > 0 ? 1u : 0u);
-            mma_commit(bars + BAR_A2_EMPTY + rA2.slot);
-            stage_release();
+            const uint64_t da = dA2_0 + rA2.slot * a2_step, db = dRing16 + woff;
+            if (!skip3) {
+              const uint32_t acc = gc > 0 ? 1u : 0u;
+              mma_tf32(tD3, da + a2_lo, db, id3, acc);
+              mma_tf32(tD3, da, db + w3_lo, id3, 1u);
+              mma_tf32(tD3, da, db, id3, 1u);
+              mma_tf32(tD3, da + a2_lo + 16, db + 16, id3, 1u);
+              mma_tf32(tD3, da + 16, db + w3_lo + 16, id3, 1u);
+              mma_tf32(tD3, da + 16, db + 16, id3, 1u);
+            }
+            mma_commit_a(bA2_EMPTY + rA2.slot * 8);
+            if (!resident && last_of_stage) {
+              if (pair) mma_commit_multicast_a(bW_EMPTY + rW.slot * 8, (uint16_t)3);
+              else mma_commit_a(bW_EMPTY + rW.slot * 8);
+            }
             if (gc == nch - 1) mma_commit(bars + BAR_D3_FULL);
           }
           __syncwarp();
-          if (!a.resident) rW.next();
+          if (last_of_stage) {
+            if (!resident) rW.next();
+            ci = 0;
+          } else {
+            ++ci;
+          }
           rA2.next();
         }
         ++npass;
@@ -575,10 +681,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_net_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 13) {
     __syncwarp();
     tmem_dealloc(tbase, (uint32_t)a.tmem_cols);
   }
+  if (a.cluster) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
 }
 
 // ---- weight gradients: K = samples GEMMs ------------------------------------------------------------------------
@@ -1086,13 +1193,34 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st) {
   a.NG = cfg.NG;
   a.tm_d3 = cfg.tm_d3;
   a.tm_d2 = cfg.tm_d2;
+  a.s3ps = std::max(1, a.im.slot_floats / a.im.s3_floats);
   a.debug = c->tc_debug;
   a.tmem_cols = cfg.tmem_cols;
   CKT(cudaFuncSetAttribute(tc_net_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
   long long grid = (a.B + 127) / 128;
   const long long cap = (long long)c->sm_count * cfg.ctas_per_sm;
   if (grid > cap) grid = cap;
-  tc_net_kernel<MODE><<<(unsigned)grid, TC_THREADS, cfg.smem, st>>>(a);
+  // streamed weights: CTA pairs share the stream (each fetches half of every block and multicasts it)
+  a.cluster = (!cfg.resident && c->tc_cluster && grid >= 2) ? 1 : 0;
+  if (a.cluster) {
+    grid &= ~1LL;
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)grid);
+    lc.blockDim = dim3(TC_THREADS);
+    lc.dynamicSmemBytes = cfg.smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    CKT(cudaLaunchKernelEx(&lc, tc_net_kernel<MODE>, a));
+  } else {
+    tc_net_kernel<MODE><<<(unsigned)grid, TC_THREADS, cfg.smem, st>>>(a);
+  }
   CKT(cudaGetLastError());
   c->launches++;
   return DFLOW_OK;
@@ -1228,7 +1356,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       return wsf + T.hbuf + ((size_t)(e * 2 + net) * 2 + which) * (size_t)hmax * T.MB;
     };
     auto mbuf_of = [&](int e, int net, int which) {
-      return reinterpret_cast<uint32_t*>(wsf + T.mbuf) + ((size_t)(e * 2 + net) * 2 + which) * (size_t)(hmax / 32) * T.MB;
+      return reinterpret_cast<uint16_t*>(wsf + T.mbuf) + ((size_t)(e * 2 + net) * 2 + which) * (size_t)(hmax / 16) * T.MB;
     };
     auto dbuf_of = [&](int net, int which) { return wsf + T.dbuf + (size_t)(net * 2 + which) * (size_t)hmax * T.MB; };
     auto d3buf_of = [&](int net) { return wsf + T.d3buf + (size_t)net * a16m * T.MB; };

@@ -16,7 +16,7 @@ namespace dflow {
 
 constexpr int TC_WKC = 16;     // hidden units per pipeline chunk (N of GEMM 1, K of GEMMs 2 and 3)
 constexpr int TC_NSMAX = 16;   // ring slots
-constexpr int TC_THREADS = 192;  // 4 epilogue warps + producer warp + MMA warp
+constexpr int TC_THREADS = 448;  // 8 chunk-epilogue warps (two warpgroups) + 4 loader/output warps + producer + MMA warp
 constexpr int TC_DW_KS = 16;   // samples per stage of the weight-gradient kernel
 
 struct TcNetImg {
@@ -64,7 +64,7 @@ struct TcTrainLayout {
   size_t sbuf;         // [L][a16max * MB]
   size_t inbuf;        // [L][K0pmax * MB]
   size_t hbuf;         // [L][2 nets][2][hmax * MB]   post-relu activations h1, h2
-  size_t mbuf;         // [L][2 nets][2][(hmax/32) * MB]  relu masks (uint32)
+  size_t mbuf;         // [L][2 nets][2][(hmax/32) * MB]  relu masks (uint16 per 16-unit chunk)
   size_t dbuf;         // [2 nets][2][hmax * MB]      delta1, delta2 of the current layer
   size_t d3buf;        // [2 nets][a16max * MB]
   size_t total;        // floats
