@@ -611,10 +611,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
               mma_tf32(tD2, da + 16, db + w2_lo + 16, id2, 1u);
               mma_tf32(tD2, da + 16, db + 16, id2, 1u);
             }
+            if (a.debug & 256) {  // timing experiment (MMAs off): plain arrives instead of tcgen05.commit
+              mbar_arrive_a(bA2_EMPTY + rA2.slot * 8);
+              if (!resident) mbar_arrive_a(bW_EMPTY + rW.slot * 8);
+            } else {
             mma_commit_a(bA2_EMPTY + rA2.slot * 8);
             if (!resident) {
               if (pair) mma_commit_multicast_a(bW_EMPTY + rW.slot * 8, (uint16_t)3);
               else mma_commit_a(bW_EMPTY + rW.slot * 8);
+            }
             }
             if (c == nch - 1) mma_commit(bars + BAR_D2_FULL);
           }
@@ -697,12 +702,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
 //   dW3^T[mt] (128 x a16) += h2[mt] * delta3^T
 // accumulated in TMEM over the CTA's whole sample range and flushed once with red.global.add.
 constexpr int DW_KS = TC_DW_KS;
-constexpr int DW_STAGE_THREADS = 256;
+constexpr int DW_STAGE_WARPS = 8;
+constexpr int DW_STAGE_THREADS = DW_STAGE_WARPS * 32;
 constexpr int DW_THREADS = DW_STAGE_THREADS + 32;
-constexpr uint32_t DWT_W2 = 0, DWT_W1 = 256, DWT_W3 = 320, DWT_B2 = 384, DWT_B1 = 400;
+constexpr int DW_MAXRB = 12;  // row-blocks (8 rows x 16 samples) per staging warp and stage
+constexpr uint32_t DWT_W2 = 0, DWT_W1 = 256, DWT_W3 = 320;
 
 struct DwArgs {
-  int H, K0p, K0, a, a16, mtiles, units, ksplit;
+  int H, K0p, K0, a, a16, mtiles, units, ksplit, nstage;
   long long ntiles;
   const float* h1buf[2];
   const float* h2buf[2];
@@ -715,26 +722,11 @@ struct DwArgs {
   float* grad;
 };
 
-__device__ __forceinline__ void dw_stage_rows(float* dst_hi, float* dst_lo, const float* __restrict__ src, int rows,
-                                              int rows_valid, int s0, int stid) {
-  // rows x 16 samples: group g = (row, quad of 4 samples); a warp covers 8 rows x 4 quads = 512 contiguous bytes
-  const int ngroups = rows * 4;
-  for (int g = stid; g < ngroups; g += DW_STAGE_THREADS) {
-    const int blk = g >> 5, l = g & 31;
-    const int row = blk * 8 + (l & 7), quad = l >> 3;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < rows_valid) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * 128 + s0 + quad * 4));
-    float4 hi, lo;
-    hi.x = to_tf32(v.x); lo.x = v.x - hi.x;
-    hi.y = to_tf32(v.y); lo.y = v.y - hi.y;
-    hi.z = to_tf32(v.z); lo.z = v.z - hi.z;
-    hi.w = to_tf32(v.w); lo.w = v.w - hi.w;
-    const int idx = core_idx(row, quad * 4, DW_KS);
-    *reinterpret_cast<float4*>(dst_hi + idx) = hi;
-    *reinterpret_cast<float4*>(dst_lo + idx) = lo;
-  }
-}
-
+// Stage layout (floats), operands K-major with K = DW_KS samples, each [hi | lo]:
+//   A segments (rows = RA = this m-tile's valid rows rounded to 8): delta2, delta1, h2
+//   B segments: h1 (H rows), in (K0p rows), delta3 (a16 rows)
+// The M = 128 MMAs read 128 rows from each A segment; rows beyond RA alias the following (finite) data and only
+// feed accumulator rows that are never flushed.
 __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_constant__ DwArgs a) {
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
@@ -743,29 +735,37 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
   const int unit = blockIdx.x % a.units, ks = blockIdx.x / a.units;
   const int net = a.first_net + unit / a.mtiles, mt = unit % a.mtiles;
   const int rows_valid = min(128, H - mt * 128);
-  // per stage (floats): A operands 3 x [128 x KS] hi/lo, B operands [H | K0p | a16] x KS hi/lo
-  const int a_fl = 128 * DW_KS, stage_fl = 2 * (3 * a_fl + (H + K0p + a16) * DW_KS);
-  float* stage0 = smem;
-  float* ones = smem + 2 * stage_fl;  // [16 x KS] hi only: row 0 = 1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + 16 * DW_KS);
-  uint64_t* full = bars;       // [2]
-  uint64_t* empty = bars + 2;  // [2]
-  uint64_t* done = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int RA = (rows_valid + 7) & ~7;
+  const int seg_rows[6] = {RA, RA, RA, H, K0p, a16};
+  int seg_dst[6], seg_rb0[7];
+  {
+    int o = 0, rb = 0;
+    for (int sgi = 0; sgi < 6; ++sgi) {
+      seg_dst[sgi] = o;
+      seg_rb0[sgi] = rb;
+      o += 2 * seg_rows[sgi] * DW_KS;
+      rb += seg_rows[sgi] >> 3;
+    }
+    seg_rb0[6] = rb;
+  }
+  const int stage_fl = 2 * (3 * RA + H + K0p + a16) * DW_KS;
+  const int RB = seg_rb0[6];
+  const int NST = a.nstage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NST * stage_fl);
+  uint64_t* full = bars;         // [NST]
+  uint64_t* empty = bars + 4;    // [NST]
+  uint64_t* done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(full + i, DW_STAGE_THREADS);
       mbar_init(empty + i, 1);
     }
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < 16 * DW_KS; i += DW_THREADS) ones[i] = 0.0f;
-  __syncthreads();
-  if (tid < DW_KS) ones[core_idx(0, tid, DW_KS)] = 1.0f;
-  fence_async_smem();
+  if (warp == DW_STAGE_WARPS) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -775,32 +775,85 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
   const long long t0 = ks * per, t1 = min(a.ntiles, t0 + per);
   const long long nstages = (t1 > t0) ? (t1 - t0) * (128 / DW_KS) : 0;
 
-  if (warp < 8) {
-    const float* d2 = a.d2buf[net];
-    const float* d1 = a.d1buf[net];
-    const float* h2 = a.h2buf[net];
-    const float* h1 = a.h1buf[net];
-    const float* d3 = a.d3buf[net];
-    for (long long s = 0; s < nstages; ++s) {
-      const uint32_t slot = (uint32_t)(s & 1);
+  if (warp < DW_STAGE_WARPS) {
+    // ---- staging warps: global (fp32) -> hi/lo split -> shared operand layout, loads issued one stage ahead ----
+    // this warp's row-blocks: rb = warp + 8 i  (everything per row-block is resolved once, outside the stage loop)
+    const float* my_ptr[DW_MAXRB];
+    int my_ts[DW_MAXRB], my_seg[DW_MAXRB], my_dst[DW_MAXRB], my_lo[DW_MAXRB], my_row[DW_MAXRB];
+    bool my_ok[DW_MAXRB];
+    const int lofs = (lane >> 3) * 32 + (lane & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < DW_MAXRB; ++i) {
+      const int rb = warp + DW_STAGE_WARPS * i;
+      int sgi = 0;
+#pragma unroll
+      for (int k = 1; k < 6; ++k)
+        if (rb >= seg_rb0[k]) sgi = k;
+      const int rb0 = sgi == 0 ? seg_rb0[0] : sgi == 1 ? seg_rb0[1] : sgi == 2 ? seg_rb0[2] : sgi == 3 ? seg_rb0[3]
+                      : sgi == 4 ? seg_rb0[4] : seg_rb0[5];
+      const int dst0 = sgi == 0 ? seg_dst[0] : sgi == 1 ? seg_dst[1] : sgi == 2 ? seg_dst[2] : sgi == 3 ? seg_dst[3]
+                       : sgi == 4 ? seg_dst[4] : seg_dst[5];
+      const int srows = sgi < 3 ? RA : sgi == 3 ? H : sgi == 4 ? K0p : a16;          // rows of the segment in the stage
+      const int valid = sgi < 3 ? rows_valid : srows;                                  // rows that exist in the source
+      const int trows = sgi < 4 ? H : sgi == 4 ? K0p : a16;                            // rows per tile in the source buffer
+      const float* base = sgi == 0 ? a.d2buf[net] : sgi == 1 ? a.d1buf[net] : sgi == 2 ? a.h2buf[net]
+                          : sgi == 3 ? a.h1buf[net] : sgi == 4 ? a.inbuf : a.d3buf[net];
+      const int r0 = (rb - rb0) * 8;
+      my_seg[i] = rb < RB ? sgi : -1;
+      my_row[i] = r0 + (lane & 7);
+      my_ok[i] = rb < RB && my_row[i] < valid;
+      my_dst[i] = dst0 + (r0 >> 3) * 128 + lofs;
+      my_lo[i] = srows * DW_KS;
+      my_ts[i] = trows * 128;
+      my_ptr[i] = base + (size_t)((sgi < 3 ? mt * 128 : 0) + my_row[i]) * 128 + (lane >> 3) * 4;
+    }
+    float4 v[DW_MAXRB];
+    float bacc[DW_MAXRB];
+#pragma unroll
+    for (int i = 0; i < DW_MAXRB; ++i) bacc[i] = 0.0f;
+    auto load_stage = [&](long long s) {
       const long long tile = t0 + s / (128 / DW_KS);
       const int s0 = (int)(s % (128 / DW_KS)) * DW_KS;
-      mbar_wait(empty + slot, (uint32_t)(((s >> 1) & 1) ^ 1));
-      float* st = stage0 + (size_t)slot * stage_fl;
-      float* A_d2 = st;
-      float* A_d1 = st + 2 * a_fl;
-      float* A_h2 = st + 4 * a_fl;
-      float* B_h1 = st + 6 * a_fl;
-      float* B_in = B_h1 + 2 * H * DW_KS;
-      float* B_d3 = B_in + 2 * K0p * DW_KS;
-      dw_stage_rows(A_d2, A_d2 + a_fl, d2 + ((size_t)tile * H + mt * 128) * 128, 128, rows_valid, s0, tid);
-      dw_stage_rows(A_d1, A_d1 + a_fl, d1 + ((size_t)tile * H + mt * 128) * 128, 128, rows_valid, s0, tid);
-      dw_stage_rows(A_h2, A_h2 + a_fl, h2 + ((size_t)tile * H + mt * 128) * 128, 128, rows_valid, s0, tid);
-      dw_stage_rows(B_h1, B_h1 + H * DW_KS, h1 + (size_t)tile * H * 128, H, H, s0, tid);
-      dw_stage_rows(B_in, B_in + K0p * DW_KS, a.inbuf + (size_t)tile * K0p * 128, K0p, K0p, s0, tid);
-      dw_stage_rows(B_d3, B_d3 + a16 * DW_KS, d3 + (size_t)tile * a16 * 128, a16, a16, s0, tid);
+#pragma unroll
+      for (int i = 0; i < DW_MAXRB; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (my_ok[i]) v[i] = __ldg(reinterpret_cast<const float4*>(my_ptr[i] + (size_t)tile * my_ts[i] + s0));
+      }
+    };
+    if (nstages > 0) load_stage(0);
+    uint32_t slot = 0, par = 0;
+    for (long long s = 0; s < nstages; ++s) {
+      mbar_wait(empty + slot, par ^ 1);
+      float* st = smem + (size_t)slot * stage_fl;
+#pragma unroll
+      for (int i = 0; i < DW_MAXRB; ++i) {
+        if (my_seg[i] >= 0) {
+          float4 hi, lo;
+          hi.x = to_tf32(v[i].x); lo.x = v[i].x - hi.x;
+          hi.y = to_tf32(v[i].y); lo.y = v[i].y - hi.y;
+          hi.z = to_tf32(v[i].z); lo.z = v[i].z - hi.z;
+          hi.w = to_tf32(v[i].w); lo.w = v[i].w - hi.w;
+          *reinterpret_cast<float4*>(st + my_dst[i]) = hi;
+          *reinterpret_cast<float4*>(st + my_dst[i] + my_lo[i]) = lo;
+          if (my_seg[i] < 2) bacc[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);  // bias gradients: sums of delta2 / delta1
+        }
+      }
       fence_async_smem();
       mbar_arrive(full + slot);
+      if (s + 1 < nstages) load_stage(s + 1);
+      if (++slot == (uint32_t)NST) {
+        slot = 0;
+        par ^= 1;
+      }
+    }
+    // bias gradients: reduce the four sample quads of a row, one atomic per row
+#pragma unroll
+    for (int i = 0; i < DW_MAXRB; ++i) {
+      float r = bacc[i];
+      r += __shfl_xor_sync(0xffffffffu, r, 8);
+      r += __shfl_xor_sync(0xffffffffu, r, 16);
+      if (my_seg[i] >= 0 && my_seg[i] < 2 && lane < 8 && my_ok[i] && nstages > 0)
+        atomicAdd(a.grad + a.p_b[net][my_seg[i] == 0 ? 1 : 0] + mt * 128 + my_row[i], r);
     }
     // ---- flush: warps 0-3 own TMEM lanes 32w..32w+31 = hidden unit rows of this m-tile ----
     if (warp < 4 && nstages > 0) {
@@ -809,78 +862,66 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
       const int o = mt * 128 + tid;  // hidden unit (row of delta2 / delta1 / h2)
       const bool ok = tid < rows_valid;
-      float v[16];
+      float w[16];
       for (int i0 = 0; i0 < H; i0 += 16) {  // dW2[o][i] at p_w2 + o + H * i
-        tmem_ld16(tbase + lane_off + DWT_W2 + i0, v);
+        tmem_ld16(tbase + lane_off + DWT_W2 + i0, w);
         if (ok)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(a.grad + a.p_w[net][1] + o + (size_t)H * (i0 + j), v[j]);
+          for (int j = 0; j < 16; ++j) atomicAdd(a.grad + a.p_w[net][1] + o + (size_t)H * (i0 + j), w[j]);
       }
-      for (int k0 = 0; k0 < K0p; k0 += 16) {  // dW1[o][k] at p_w1 + o + H * k   (K0p may be 8 mod 16: guard)
-        tmem_ld16(tbase + lane_off + DWT_W1 + k0, v);
+      for (int k0 = 0; k0 < K0p; k0 += 16) {  // dW1[o][k] at p_w1 + o + H * k
+        tmem_ld16(tbase + lane_off + DWT_W1 + k0, w);
         if (ok)
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (k0 + j < a.K0) atomicAdd(a.grad + a.p_w[net][0] + o + (size_t)H * (k0 + j), v[j]);
+            if (k0 + j < a.K0) atomicAdd(a.grad + a.p_w[net][0] + o + (size_t)H * (k0 + j), w[j]);
       }
       for (int j0 = 0; j0 < a16; j0 += 16) {  // dW3[j][i=o] at p_w3 + j + a * o
-        tmem_ld16(tbase + lane_off + DWT_W3 + j0, v);
+        tmem_ld16(tbase + lane_off + DWT_W3 + j0, w);
         if (ok)
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (j0 + j < a.a) atomicAdd(a.grad + a.p_w[net][2] + (j0 + j) + (size_t)a.a * o, v[j]);
+            if (j0 + j < a.a) atomicAdd(a.grad + a.p_w[net][2] + (j0 + j) + (size_t)a.a * o, w[j]);
       }
-      tmem_ld16(tbase + lane_off + DWT_B2, v);
-      if (ok) atomicAdd(a.grad + a.p_b[net][1] + o, v[0]);
-      tmem_ld16(tbase + lane_off + DWT_B1, v);
-      if (ok) atomicAdd(a.grad + a.p_b[net][0] + o, v[0]);
     }
   } else {
-    // MMA issuer: the warp runs the loop uniformly, one elected lane issues
-    const int K0n = (K0p + 15) & ~15;  // N of the dW1 GEMM (M = 128 needs N % 16 == 0); extra rows read B_d3 (finite)
+    // ---- MMA issuer: the warp runs the loop uniformly, one elected lane issues ----
+    const int K0n = (K0p + 15) & ~15;  // N of the dW1 GEMM (M = 128 needs N % 16 == 0); extra rows read finite data
     const uint32_t hi = desc_hi(DW_KS);
-    const uint32_t idW2 = instr_desc_tf32(H), idW1 = instr_desc_tf32(K0n), idW3 = instr_desc_tf32(a16),
-                   idB = instr_desc_tf32(16);
-    const uint32_t st_u32 = smem_u32(stage0), ones_u32 = smem_u32(ones);
-    const uint32_t a_b = (uint32_t)a_fl * 4u;
-    const uint32_t oB_h1 = 6u * a_b, oB_in = oB_h1 + 2u * (uint32_t)(H * DW_KS) * 4u,
-                   oB_d3 = oB_in + 2u * (uint32_t)(K0p * DW_KS) * 4u;
-    const uint64_t dOnes = desc_at(hi, ones_u32);
+    const uint32_t idW2 = instr_desc_tf32(H), idW1 = instr_desc_tf32(K0n), idW3 = instr_desc_tf32(a16);
+    const uint64_t d0 = desc_at(hi, smem_u32(smem));
+    const uint32_t stage_step = ((uint32_t)stage_fl * 4u) >> 4;
+    uint32_t so[6], sl[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      so[k] = ((uint32_t)seg_dst[k] * 4u) >> 4;
+      sl[k] = ((uint32_t)(seg_rows[k] * DW_KS) * 4u) >> 4;
+    }
+    const uint32_t full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
+    uint32_t slot = 0, par = 0;
     for (long long s = 0; s < nstages; ++s) {
-      const uint32_t slot = (uint32_t)(s & 1);
-      mbar_wait(full + slot, (uint32_t)((s >> 1) & 1));
+      mbar_wait_a(full_u32 + slot * 8, par);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t st = st_u32 + slot * (uint32_t)stage_fl * 4u;
+        const uint64_t b = d0 + slot * stage_step;
         const uint32_t acc = s > 0 ? 1u : 0u;
-        const uint64_t dD2h = desc_at(hi, st), dD2l = desc_at(hi, st + a_b);
-        const uint64_t dD1h = desc_at(hi, st + 2u * a_b), dD1l = desc_at(hi, st + 3u * a_b);
-        const uint64_t dH2h = desc_at(hi, st + 4u * a_b), dH2l = desc_at(hi, st + 5u * a_b);
-        gemm3_desc(tbase + DWT_W2, dD2h, dD2l, desc_at(hi, st + oB_h1), desc_at(hi, st + oB_h1 + (uint32_t)(H * DW_KS) * 4u),
-                   DW_KS / 8, idW2, acc);
-        gemm3_desc(tbase + DWT_W1, dD1h, dD1l, desc_at(hi, st + oB_in), desc_at(hi, st + oB_in + (uint32_t)(K0p * DW_KS) * 4u),
-                   DW_KS / 8, idW1, acc);
-        gemm3_desc(tbase + DWT_W3, dH2h, dH2l, desc_at(hi, st + oB_d3), desc_at(hi, st + oB_d3 + (uint32_t)(a16 * DW_KS) * 4u),
-                   DW_KS / 8, idW3, acc);
-        // column sums: (lo + hi) * 1
-#pragma unroll
-        for (int k8 = 0; k8 < DW_KS / 8; ++k8) {
-          const uint64_t o = (uint64_t)(k8 * 16);
-          const uint32_t acc2 = (acc || k8 > 0) ? 1u : 0u;
-          mma_tf32(tbase + DWT_B2, dD2l + o, dOnes + o, idB, acc2);
-          mma_tf32(tbase + DWT_B2, dD2h + o, dOnes + o, idB, 1u);
-          mma_tf32(tbase + DWT_B1, dD1l + o, dOnes + o, idB, acc2);
-          mma_tf32(tbase + DWT_B1, dD1h + o, dOnes + o, idB, 1u);
-        }
-        mma_commit(empty + slot);
+        // dW2 += delta2 * h1^T ; dW1 += delta1 * in^T ; dW3^T += h2 * delta3^T   (each: lo*hi + hi*lo + hi*hi, 2 K steps)
+        gemm3_desc(tbase + DWT_W2, b + so[0], b + so[0] + sl[0], b + so[3], b + so[3] + sl[3], DW_KS / 8, idW2, acc);
+        gemm3_desc(tbase + DWT_W1, b + so[1], b + so[1] + sl[1], b + so[4], b + so[4] + sl[4], DW_KS / 8, idW1, acc);
+        gemm3_desc(tbase + DWT_W3, b + so[2], b + so[2] + sl[2], b + so[5], b + so[5] + sl[5], DW_KS / 8, idW3, acc);
+        mma_commit_a(empty_u32 + slot * 8);
         if (s == nstages - 1) mma_commit(done);
       }
       __syncwarp();
+      if (++slot == (uint32_t)NST) {
+        slot = 0;
+        par ^= 1;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == DW_STAGE_WARPS) {
     __syncwarp();
     tmem_dealloc(tbase, 512);
   }
@@ -1472,12 +1513,18 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       }
       w.inbuf = inbuf_of(ei);
       w.grad = grad_out;
-      const size_t stage_fl = 2 * (3 * 128 * DW_KS + (size_t)(w.H + w.K0p + w.a16) * DW_KS);
-      const size_t smem = (2 * stage_fl + 16 * DW_KS) * 4 + 64;
-      if (smem > (size_t)c->max_smem_optin) {
-        set_error("weight-gradient stage needs %zu bytes of shared memory", smem);
+      const int RA = std::min(128, w.H);  // rows of the A segments (a multiple of 8: H % 32 == 0)
+      const size_t stage_bytes = 2 * (size_t)(3 * RA + w.H + w.K0p + w.a16) * DW_KS * 4;
+      // the M = 128 MMAs read 128 rows of every A segment: keep that overrun inside the allocation
+      const size_t overrun = (size_t)(128 - RA) * DW_KS * 4 * 2;
+      int nst = (int)(((size_t)c->max_smem_optin - 128 - overrun) / stage_bytes);
+      if (nst > 4) nst = 4;
+      if (nst < 2 || (3 * RA + w.H + w.K0p + w.a16) / 8 > DW_MAXRB * DW_STAGE_WARPS) {
+        set_error("weight-gradient stage does not fit (%zu bytes per stage)", stage_bytes);
         return DFLOW_E_UNSUPPORTED;
       }
+      w.nstage = nst;
+      const size_t smem = nst * stage_bytes + overrun + 128;
       CKT(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       tc_dw_kernel<<<(unsigned)(w.units * w.ksplit), DW_THREADS, smem, st>>>(w);
       CKT(cudaGetLastError());

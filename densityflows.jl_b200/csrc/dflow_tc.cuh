@@ -61,6 +61,9 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
 __device__ __forceinline__ void mma_commit_a(uint32_t addr) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
 __device__ __forceinline__ void mma_commit_multicast_a(uint32_t addr, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    addr),
