@@ -38,7 +38,8 @@ namespace dflow {
 
 using namespace tc;
 
-constexpr int WKC = TC_WKC;
+constexpr int WKC = TC_WKC;  // hidden units per weight block (K of one block's MMAs)
+constexpr int WKA = 32;      // hidden units per activation chunk (two weight blocks)
 constexpr int NSMAX = TC_NSMAX;
 
 enum { TC_FWD = 0, TC_FWD_STORE = 1, TC_BWD = 2 };
@@ -87,8 +88,8 @@ struct TcArgs {
   float* inbuf;
   float* h1buf;
   float* h2buf;
-  uint16_t* m1buf;  // relu masks, one 16-bit word per (chunk, sample): [tiles][H/16][128]
-  uint16_t* m2buf;
+  uint32_t* m1buf;  // relu masks, one word per (32-unit chunk, sample): [tiles][H/32][128]
+  uint32_t* m2buf;
   float* d1buf;
   float* d2buf;
   float* d3buf;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
   const TcNetImg& im = a.im;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K0p = im.K0p, H = im.H, N3p = im.N3p, NH = im.NH, passes = im.passes, nch = im.nch,
-            nch_pass = im.nch_pass, GW = im.GW, ng = im.ng, cpg = im.GW / WKC;
+            nch_pass = im.nch_pass, GW = im.GW, ng = im.ng;
   const int d = a.d, n = a.n, NG = a.NG, NA = a.NA;
   const uint32_t TM_D1 = 0, TM_D3 = (uint32_t)a.tm_d3, TM_D2 = (uint32_t)a.tm_d2;
 
@@ -225,106 +226,131 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
   const long long iters = (ntiles + gridDim.x - 1) / gridDim.x;
 
   if (warp < 8) {
-    // =========================== epilogue warps ===========================
-    // Two warpgroups share the 128 sample rows (thread row = tid & 127 = TMEM lane): warpgroup w handles the chunks
-    // with (chunk index & 1) == w, so every SM sub-partition has two epilogue warps to hide TMEM / barrier latency.
+    // =========================== chunk-epilogue warps ===========================
+    // Activation chunks are WKA = 32 hidden units wide (two 16-unit weight blocks per MMA-warp iteration: the issuer's
+    // fixed cost per iteration is ~700 clk, so each iteration has to carry >= 12 full-width MMAs).  Two warpgroups
+    // share the 128 sample rows (thread row = tid & 127 = TMEM lane); chunk q of the global chunk sequence belongs to
+    // warpgroup q & 1 and to A2 slot q & 1.
     const int wg = warp >> 2, row = tid & 127;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t na_mask = (uint32_t)NA - 1u, na_log = NA == 4 ? 2u : 1u;
-    uint32_t q = (uint32_t)wg;  // A2 chunk sequence number of this warpgroup (advances by 2)
+    const int cpg = GW / WKA, ncp = NH / WKA;
+    uint32_t q = 0;      // global chunk counter (identical in both warpgroups and in the MMA warp)
+    uint32_t uses = 0;   // hand-offs of this warpgroup = uses of its A2 slot
     Ring rD1{0, 0, (uint32_t)NG};
-    uint32_t npass = 0, tcount = 0;
-    // activation chunk -> next free slot of the A2 ring
-    auto handoff = [&](const float (&v)[16]) {
-      const uint32_t slot = q & na_mask, par = (q >> na_log) & 1u;
-      mbar_wait(bars + BAR_A2_EMPTY + slot, par ^ 1u);
-      float* a2 = A2 + slot * 2 * 128 * WKC;
-      if (!(a.debug & 16)) store_a2_row(a2, a2 + 128 * WKC, row, v);
+    uint32_t npass = 0;
+    float* a2h = A2 + wg * 2 * 128 * WKA;
+    float* a2l = a2h + 128 * WKA;
+    // one 32-unit chunk of this thread's row -> A2 slot (hi / lo, K-major core layout with Kc = 32)
+    auto handoff = [&](const float (&v)[32]) {
+      mbar_wait(bars + BAR_A2_EMPTY + wg, (uses & 1u) ^ 1u);
+      if (!(a.debug & 16)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 hi, lo;
+          hi.x = to_tf32(v[4 * j + 0]); lo.x = v[4 * j + 0] - hi.x;
+          hi.y = to_tf32(v[4 * j + 1]); lo.y = v[4 * j + 1] - hi.y;
+          hi.z = to_tf32(v[4 * j + 2]); lo.z = v[4 * j + 2] - hi.z;
+          hi.w = to_tf32(v[4 * j + 3]); lo.w = v[4 * j + 3] - hi.w;
+          const int idx = core_idx(row, 4 * j, WKA);
+          *reinterpret_cast<float4*>(a2h + idx) = hi;
+          *reinterpret_cast<float4*>(a2l + idx) = lo;
+        }
+      }
       fence_async_smem();
-      mbar_arrive(bars + BAR_A2_FULL + slot);
-      q += 2;
+      mbar_arrive(bars + BAR_A2_FULL + wg);
+      ++uses;
     };
-    for (long long it = 0; it < iters; ++it, ++tcount) {
+    auto ld32 = [&](uint32_t taddr, float (&v)[32]) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16_nowait(taddr, r0);
+      tmem_ld16_nowait(taddr + 16, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = __uint_as_float(r0[j]);
+        v[16 + j] = __uint_as_float(r1[j]);
+      }
+    };
+    for (long long it = 0; it < iters; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const bool live = tile < ntiles && !(a.debug & 128);  // dummy tiles touch no global memory
-      const long long gi = tile * 128 + row;
-      const bool valid = gi < a.B && !(a.debug & 128);  // (debug bit 128: timing without the per-sample global traffic)
       for (int p = 0; p < passes; ++p) {
-        // ---- epilogue 1: hidden-1 units, one D1 group (GW columns) at a time; this warpgroup's chunks of the group
-        //      are loaded together (one tcgen05.wait::ld per group) ----
+        // ---- epilogue 1: hidden-1 units, one D1 group (GW columns) at a time ----
         for (int g = 0; g < ng; ++g) {
           mbar_wait(bars + BAR_D1_FULL + rD1.slot, rD1.par);
           tc_fence_after();
-          uint32_t r[2][16];
-          const uint32_t tcol = tbase + lane_off + rD1.slot * (uint32_t)GW;
-          tmem_ld16_nowait(tcol + (uint32_t)(wg * WKC), r[0]);
-          if (cpg > 2) tmem_ld16_nowait(tcol + (uint32_t)((wg + 2) * WKC), r[1]);
-          tmem_ld_wait();
+          // at most one chunk of a group belongs to this warpgroup (cpg <= 2)
+          const int cg = (cpg == 2) ? (int)((q ^ (uint32_t)wg) & 1u) : 0;
+          const bool mine = (cpg == 2) || (((q & 1u) == (uint32_t)wg));
+          float v[32];
+          if (mine) ld32(tbase + lane_off + TM_D1 + rD1.slot * (uint32_t)GW + (uint32_t)(cg * WKA), v);
           tc_fence_before();
           mbar_arrive(bars + BAR_D1_EMPTY + rD1.slot);
+          if (mine) {
+            const int c = g * cpg + cg;  // 32-unit chunk index inside the hidden layer
+            if constexpr (MODE == TC_BWD) {
+              const uint32_t mword = live ? a.m2buf[((size_t)tile * (H >> 5) + c) * 128 + row] : 0u;
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            if (i * 2 < cpg) {
-              const int c = g * cpg + wg + 2 * i;
-              float v[16];
+              for (int j = 0; j < 32; ++j) {
+                v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
+                if (live) a.d2buf[((size_t)tile * H + c * WKA + j) * 128 + row] = v[j];
+              }
+            } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[i][j]);
-              if constexpr (MODE == TC_BWD) {
-                const uint32_t mword = live ? a.m2buf[((size_t)tile * nch + c) * 128 + row] : 0u;
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[c * WKA + j], 0.0f);
+              if constexpr (MODE == TC_FWD_STORE) {
+                if (p == 0 && live) {
+                  uint32_t mword = 0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
-                  if (live) a.d2buf[((size_t)tile * H + c * WKC + j) * 128 + row] = v[j];
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + biasS[c * WKC + j], 0.0f);
-                if constexpr (MODE == TC_FWD_STORE) {
-                  if (p == 0 && live) {
-                    uint32_t mword = 0;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                      a.h1buf[((size_t)tile * H + c * WKC + j) * 128 + row] = v[j];
-                      mword |= (v[j] > 0.0f ? 1u : 0u) << j;
-                    }
-                    a.m1buf[((size_t)tile * nch + c) * 128 + row] = (uint16_t)mword;
+                  for (int j = 0; j < 32; ++j) {
+                    a.h1buf[((size_t)tile * H + c * WKA + j) * 128 + row] = v[j];
+                    mword |= (v[j] > 0.0f ? 1u : 0u) << j;
                   }
+                  a.m1buf[((size_t)tile * (H >> 5) + c) * 128 + row] = mword;
                 }
               }
-              handoff(v);
             }
+            handoff(v);
           }
+          q += (uint32_t)cpg;
           rD1.next();
         }
         // ---- epilogue 2: hidden-2 chunks of this pass ----
         mbar_wait(bars + BAR_D2_FULL, npass & 1);
         tc_fence_after();
-        for (int cc = wg; cc < nch_pass; cc += 2) {
-          const int gc = p * nch_pass + cc;
-          float v[16];
-          tmem_ld16(tbase + lane_off + TM_D2 + cc * WKC, v);
-          if (cc + 2 >= nch_pass) {
+        // this warpgroup's last chunk of the pass (its D2 reads end there); -1: it has none and releases D2 at once
+        int my_last = (((q + (uint32_t)(ncp - 1)) & 1u) == (uint32_t)wg) ? ncp - 1 : ncp - 2;
+        if (my_last < 0) {
+          tc_fence_before();
+          mbar_arrive(bars + BAR_D2_EMPTY);
+        }
+        for (int cc = 0; cc < ncp; ++cc, ++q) {
+          if ((q & 1u) != (uint32_t)wg) continue;
+          const int gc = p * ncp + cc;
+          float v[32];
+          ld32(tbase + lane_off + TM_D2 + cc * WKA, v);
+          if (cc == my_last) {
             tc_fence_before();
             mbar_arrive(bars + BAR_D2_EMPTY);
           }
           if constexpr (MODE == TC_BWD) {
-            const uint32_t mword = live ? a.m1buf[((size_t)tile * nch + gc) * 128 + row] : 0u;
+            const uint32_t mword = live ? a.m1buf[((size_t)tile * (H >> 5) + gc) * 128 + row] : 0u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 32; ++j) {
               v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
-              if (live) a.d1buf[((size_t)tile * H + gc * WKC + j) * 128 + row] = v[j];
+              if (live) a.d1buf[((size_t)tile * H + gc * WKA + j) * 128 + row] = v[j];
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + biasS[H + gc * WKC + j], 0.0f);
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[H + gc * WKA + j], 0.0f);
             if (MODE == TC_FWD_STORE && live) {
               uint32_t mword = 0;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                a.h2buf[((size_t)tile * H + gc * WKC + j) * 128 + row] = v[j];
+              for (int j = 0; j < 32; ++j) {
+                a.h2buf[((size_t)tile * H + gc * WKA + j) * 128 + row] = v[j];
                 mword |= (v[j] > 0.0f ? 1u : 0u) << j;
               }
-              a.m2buf[((size_t)tile * nch + gc) * 128 + row] = (uint16_t)mword;
+              a.m2buf[((size_t)tile * (H >> 5) + gc) * 128 + row] = mword;
             }
           }
           handoff(v);
@@ -496,6 +522,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
         }
       } else {
         Ring rW{0, 0, (uint32_t)a.NS};
+        const int cpg16 = GW / WKC;  // weight blocks per D1 group
         const uint32_t g1b = (uint32_t)im.g1_floats * 4u, s2b = (uint32_t)im.s2_floats * 4u, s3b = (uint32_t)im.s3_floats * 4u;
         const uint32_t crank = a.cluster ? cluster_ctarank() : 0u;
         auto put = [&](const float* src, uint32_t bytes) {
@@ -518,8 +545,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
             for (int g = 0; g < NG && g < ng; ++g) put(gimg + im.g1_off + (size_t)g * im.g1_floats, g1b);
             for (int c = 0; c < nch; ++c) {
               put(gimg + im.s2_off + (size_t)(p * nch + c) * im.s2_floats, s2b);
-              if ((c + 1) % cpg == 0) {
-                const int gn = c / cpg + NG;
+              if ((c + 1) % cpg16 == 0) {
+                const int gn = c / cpg16 + NG;
                 if (gn < ng) put(gimg + im.g1_off + (size_t)gn * im.g1_floats, g1b);
               }
             }
@@ -536,10 +563,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
     // a descriptor is `base + offset`, barriers are 32-bit shared addresses.
     const uint32_t hiK0 = desc_hi(K0p), hi16 = desc_hi(WKC);
     const uint64_t dA1h = desc_at(hiK0, smem_u32(A1h)), dA1l = desc_at(hiK0, smem_u32(A1l));
-    const uint64_t dA2_0 = desc_at(hi16, smem_u32(A2));        // A2 slot s hi: + s * a2_step, lo: + a2_lo
+    const uint64_t dA2_0 = desc_at(desc_hi(WKA), smem_u32(A2));  // A2 slot s (128 x 32) hi: + s * a2_step, lo: + a2_lo
     const uint64_t dRing16 = desc_at(hi16, smem_u32(ring));    // weight stage read with a 16-float row pitch (S2, S3)
     const uint64_t dRingK0 = desc_at(hiK0, smem_u32(ring));    // ... with a K0p-float row pitch (G1)
-    const uint32_t a2_lo = (128u * WKC * 4u) >> 4, a2_step = 2u * a2_lo;
+    const uint32_t a2_lo = (128u * WKA * 4u) >> 4, a2_step = 2u * a2_lo;
+    const int nch32 = H / WKA, ncp = NH / WKA, cpg = GW / WKA;
+    uint32_t q = 0;  // global 32-unit chunk counter (A2 slot q & 1, use q >> 1)
     const uint32_t g1_lo = ((uint32_t)(GW * K0p) * 4u) >> 4, w2_lo = ((uint32_t)(NH * WKC) * 4u) >> 4,
                    w3_lo = ((uint32_t)(N3p * WKC) * 4u) >> 4;
     const uint32_t slot_step = ((uint32_t)im.slot_floats * 4u) >> 4;
@@ -555,7 +584,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
     const uint32_t tD1 = tbase + TM_D1, tD2 = tbase + TM_D2, tD3 = tbase + TM_D3;
     const bool resident = a.resident != 0, pair = a.cluster != 0;
     const bool skip1 = (a.debug & 2) != 0, skip2 = (a.debug & 8) != 0, skip3 = (a.debug & 4) != 0;
-    Ring rW{0, 0, (uint32_t)(resident ? 1 : a.NS)}, rA2{0, 0, (uint32_t)NA}, rD1{0, 0, (uint32_t)NG};
+    Ring rW{0, 0, (uint32_t)(resident ? 1 : a.NS)}, rD1{0, 0, (uint32_t)NG};
     uint32_t npass = 0, tcount = 0;
     if (resident) mbar_wait(bars + BAR_W_FULL, 0);
     for (long long it = 0; it < iters; ++it, ++tcount) {
@@ -589,55 +618,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
         for (int g = 0; g < NG && g < ng; ++g) issue_d1(g);
         mbar_wait(bars + BAR_D2_EMPTY, (npass & 1) ^ 1);
         tc_fence_after();
+        // ---- D2 += h1 chunk (32 units) * two 16-unit M2 blocks ----
         int cg = 0, gnext = NG;
-        for (int c = 0; c < nch; ++c) {
-          uint32_t woff;
+        for (int c = 0; c < nch32; ++c, ++q) {
+          uint32_t woff0, woff1, slot0 = 0, slot1 = 0;
           if (resident) {
-            woff = res_s2 + (uint32_t)(p * nch + c) * s2_step;
+            woff0 = res_s2 + (uint32_t)(p * nch + 2 * c) * s2_step;
+            woff1 = woff0 + s2_step;
           } else {
             mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
-            woff = rW.slot * slot_step;
+            slot0 = rW.slot;
+            woff0 = slot0 * slot_step;
+            rW.next();
+            mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
+            slot1 = rW.slot;
+            woff1 = slot1 * slot_step;
+            rW.next();
           }
-          mbar_wait_a(bA2_FULL + rA2.slot * 8, rA2.par);
+          const uint32_t as = q & 1u;
+          mbar_wait_a(bA2_FULL + as * 8, (q >> 1) & 1u);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t da = dA2_0 + rA2.slot * a2_step, db = dRing16 + woff;
+            const uint64_t da = dA2_0 + as * a2_step;
             if (!skip2) {
-              const uint32_t acc = c > 0 ? 1u : 0u;
-              mma_tf32(tD2, da + a2_lo, db, id2, acc);
-              mma_tf32(tD2, da, db + w2_lo, id2, 1u);
-              mma_tf32(tD2, da, db, id2, 1u);
-              mma_tf32(tD2, da + a2_lo + 16, db + 16, id2, 1u);
-              mma_tf32(tD2, da + 16, db + w2_lo + 16, id2, 1u);
-              mma_tf32(tD2, da + 16, db + 16, id2, 1u);
+              uint32_t acc = c > 0 ? 1u : 0u;
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const uint64_t db = dRing16 + (hf ? woff1 : woff0);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint32_t ao = (uint32_t)(hf * 2 + ks) * 16u, bo = (uint32_t)ks * 16u;
+                  mma_tf32(tD2, da + a2_lo + ao, db + bo, id2, acc);
+                  mma_tf32(tD2, da + ao, db + w2_lo + bo, id2, 1u);
+                  mma_tf32(tD2, da + ao, db + bo, id2, 1u);
+                  acc = 1u;
+                }
+              }
             }
-            if (a.debug & 256) {  // timing experiment (MMAs off): plain arrives instead of tcgen05.commit
-              mbar_arrive_a(bA2_EMPTY + rA2.slot * 8);
-              if (!resident) mbar_arrive_a(bW_EMPTY + rW.slot * 8);
-            } else {
-            mma_commit_a(bA2_EMPTY + rA2.slot * 8);
+            mma_commit_a(bA2_EMPTY + as * 8);
             if (!resident) {
-              if (pair) mma_commit_multicast_a(bW_EMPTY + rW.slot * 8, (uint16_t)3);
-              else mma_commit_a(bW_EMPTY + rW.slot * 8);
+              if (pair) {
+                mma_commit_multicast_a(bW_EMPTY + slot0 * 8, (uint16_t)3);
+                mma_commit_multicast_a(bW_EMPTY + slot1 * 8, (uint16_t)3);
+              } else {
+                mma_commit_a(bW_EMPTY + slot0 * 8);
+                mma_commit_a(bW_EMPTY + slot1 * 8);
+              }
             }
-            }
-            if (c == nch - 1) mma_commit(bars + BAR_D2_FULL);
+            if (c == nch32 - 1) mma_commit(bars + BAR_D2_FULL);
           }
           __syncwarp();
-          if (!resident) rW.next();
-          rA2.next();
           if (++cg == cpg) {
             cg = 0;
             if (gnext < ng) issue_d1(gnext);
             ++gnext;
           }
         }
+        // ---- D3 += h2 chunk (32 units) * two 16-unit M3 blocks ----
         uint32_t woff3 = 0;
-        for (int cc = 0, ci = 0; cc < nch_pass; ++cc) {
-          const int gc = p * nch_pass + cc;
+        for (int cc = 0, ci = 0; cc < ncp; ++cc, ++q) {
+          const int gc = p * ncp + cc;  // 32-unit chunk of hidden layer 2
           uint32_t woff;
           if (resident) {
-            woff = res_s3 + (uint32_t)gc * s3_step;
+            woff = res_s3 + (uint32_t)(2 * gc) * s3_step;
           } else {
             if (ci == 0) {
               mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
@@ -645,39 +688,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
             }
             woff = woff3 + (uint32_t)ci * s3_step;
           }
-          const bool last_of_stage = (ci + 1 == a.s3ps) || (cc + 1 == nch_pass);
-          mbar_wait_a(bA2_FULL + rA2.slot * 8, rA2.par);
+          const bool last_of_stage = (ci + 2 >= a.s3ps) || (cc + 1 == ncp);
+          const uint32_t as = q & 1u;
+          mbar_wait_a(bA2_FULL + as * 8, (q >> 1) & 1u);
           tc_fence_after();
           if (gc == 0) {
             mbar_wait(bars + BAR_D3_EMPTY, (tcount & 1) ^ 1);
             tc_fence_after();
           }
           if (elect_one()) {
-            const uint64_t da = dA2_0 + rA2.slot * a2_step, db = dRing16 + woff;
+            const uint64_t da = dA2_0 + as * a2_step;
             if (!skip3) {
-              const uint32_t acc = gc > 0 ? 1u : 0u;
-              mma_tf32(tD3, da + a2_lo, db, id3, acc);
-              mma_tf32(tD3, da, db + w3_lo, id3, 1u);
-              mma_tf32(tD3, da, db, id3, 1u);
-              mma_tf32(tD3, da + a2_lo + 16, db + 16, id3, 1u);
-              mma_tf32(tD3, da + 16, db + w3_lo + 16, id3, 1u);
-              mma_tf32(tD3, da + 16, db + 16, id3, 1u);
+              uint32_t acc = gc > 0 ? 1u : 0u;
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const uint64_t db = dRing16 + woff + (uint32_t)hf * s3_step;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint32_t ao = (uint32_t)(hf * 2 + ks) * 16u, bo = (uint32_t)ks * 16u;
+                  mma_tf32(tD3, da + a2_lo + ao, db + bo, id3, acc);
+                  mma_tf32(tD3, da + ao, db + w3_lo + bo, id3, 1u);
+                  mma_tf32(tD3, da + ao, db + bo, id3, 1u);
+                  acc = 1u;
+                }
+              }
             }
-            mma_commit_a(bA2_EMPTY + rA2.slot * 8);
+            mma_commit_a(bA2_EMPTY + as * 8);
             if (!resident && last_of_stage) {
               if (pair) mma_commit_multicast_a(bW_EMPTY + rW.slot * 8, (uint16_t)3);
               else mma_commit_a(bW_EMPTY + rW.slot * 8);
             }
-            if (gc == nch - 1) mma_commit(bars + BAR_D3_FULL);
+            if (gc == (H >> 5) - 1) mma_commit(bars + BAR_D3_FULL);
           }
           __syncwarp();
           if (last_of_stage) {
             if (!resident) rW.next();
             ci = 0;
           } else {
-            ++ci;
+            ci += 2;
           }
-          rA2.next();
         }
         ++npass;
       }
@@ -1053,7 +1102,7 @@ static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg&
   }
   const size_t res = (size_t)im.blocks_floats * 4;
   cfg.resident = 0;
-  for (int na = 4; na >= 2 && !cfg.resident; na -= 2) {
+  for (int na = 4; na >= 4 && !cfg.resident; na -= 2) {  // A2 = two 32-unit slots
     if (im.passes == 1 && res < (1u << 20) && base_bytes(na) + res + bar_bytes <= cap) {
       cfg.resident = 1;
       cfg.NA = na;
@@ -1063,12 +1112,12 @@ static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg&
   }
   if (!cfg.resident) {
     bool ok = false;
-    for (int na = 4; na >= 2 && !ok; na -= 2) {
+    for (int na = 4; na >= 4 && !ok; na -= 2) {
       const size_t b = base_bytes(na) + bar_bytes;
       const size_t room = cap > b ? cap - b : 0;
       int ns = (int)(room / ((size_t)im.slot_floats * 4));
       if (ns > 6) ns = 6;
-      if (ns >= (na == 4 ? 4 : 3)) {
+      if (ns >= 3) {
         ok = true;
         cfg.NA = na;
         cfg.NS = ns;
@@ -1234,7 +1283,7 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st) {
   a.NG = cfg.NG;
   a.tm_d3 = cfg.tm_d3;
   a.tm_d2 = cfg.tm_d2;
-  a.s3ps = std::max(1, a.im.slot_floats / a.im.s3_floats);
+  a.s3ps = std::max(2, (a.im.slot_floats / a.im.s3_floats) & ~1);  // an even number of 16-unit blocks
   a.debug = c->tc_debug;
   a.tmem_cols = cfg.tmem_cols;
   CKT(cudaFuncSetAttribute(tc_net_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
@@ -1397,7 +1446,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       return wsf + T.hbuf + ((size_t)(e * 2 + net) * 2 + which) * (size_t)hmax * T.MB;
     };
     auto mbuf_of = [&](int e, int net, int which) {
-      return reinterpret_cast<uint16_t*>(wsf + T.mbuf) + ((size_t)(e * 2 + net) * 2 + which) * (size_t)(hmax / 16) * T.MB;
+      return reinterpret_cast<uint32_t*>(wsf + T.mbuf) + ((size_t)(e * 2 + net) * 2 + which) * (size_t)(hmax / 32) * T.MB;
     };
     auto dbuf_of = [&](int net, int which) { return wsf + T.dbuf + (size_t)(net * 2 + which) * (size_t)hmax * T.MB; };
     auto d3buf_of = [&](int net) { return wsf + T.d3buf + (size_t)net * a16m * T.MB; };
