@@ -280,15 +280,16 @@ def run_ours(args):
             ts3(x3, th3, None, Bg, flags)
 
         ms3 = timed(step_c3, 2, 1, dist)
+        # default routing: at hidden 64 and a batch this large the adjoint runs on the tensor cores (dflow_tc.cu)
         ops["train_step_c3"] = {"samples_per_s": Bg / (ms3 * 1e-3), "ms_per_step": ms3, "global_batch": Bg,
-                                "scaling": "strong", "allreduce_bytes": 4 * (pc3.P + 2)}
-
-        # the same step with the conditioners on the tensor cores (tcgen05, 3xTF32): dflow_tc.cu
-        pc3.tune(tc_mode=1)
+                                "scaling": "strong", "allreduce_bytes": 4 * (pc3.P + 2),
+                                "path": "tcgen05 3xTF32 adjoint (automatic for hidden 64, B >= 32768)"}
+        # the same step forced onto the CUDA-core adjoint kernel (tc_mode=-1)
+        pc3.tune(tc_mode=-1)
         ts3b = TrainStep(pc3, df.setup(df.Adam(1e-3), c3))
-        ms3b = timed(step_c3_tc := (lambda: ts3b(x3, th3, None, Bg, flags)), 2, 1, dist)
-        ops["train_step_c3_tensor"] = {"samples_per_s": Bg / (ms3b * 1e-3), "ms_per_step": ms3b, "global_batch": Bg,
-                                       "scaling": "strong", "path": "tcgen05 3xTF32 (tc_mode=1)"}
+        ms3b = timed(lambda: ts3b(x3, th3, None, Bg, flags), 2, 1, dist)
+        ops["train_step_c3_cuda_cores"] = {"samples_per_s": Bg / (ms3b * 1e-3), "ms_per_step": ms3b, "global_batch": Bg,
+                                           "scaling": "strong", "path": "FP32 FFMA adjoint kernel (tc_mode=-1)"}
         del x3, th3, pc3, ts3, ts3b
         torch.cuda.empty_cache()
 

@@ -478,6 +478,7 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
     return DFLOW_E_CUDA;
   }
   c->must_wide = wide ? 1 : 0;
+  c->hidden_max = hidden_max;
   if (tc_eligible) {
     int rc = build_wide_plan(c);
     if (!rc) rc = tc_build_plan(c);
@@ -735,7 +736,7 @@ int dflow_sample_rng(dflow_chain* c, const float* W, uint64_t seed, uint32_t off
 
 size_t dflow_workspace_bytes(const dflow_chain* c, int64_t B) {
   if (!c) return 0;
-  if (c->use_tc()) return tc_workspace_bytes(c, B);
+  if (c->use_tc_grad(B)) return tc_workspace_bytes(c, B);
   // one checkpoint slab per resident CTA (not per sample): grid <= sm_count * 4 CTAs of <= 256 threads
   return (size_t)c->sm_count * 4 * 512 * (size_t)c->hc()->h.ck_total * sizeof(float) + 256;
 }
@@ -756,7 +757,7 @@ int dflow_loss_grad(dflow_chain* c, const float* W, const float* x, const float*
   }
   if (B == 0) return DFLOW_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (c->use_tc()) return tc_loss_grad(c, W, x, theta, B, idx, inv_btot, flags, loss_out, grad_out, ws, ws_bytes, st);
+  if (c->use_tc_grad(B)) return tc_loss_grad(c, W, x, theta, B, idx, inv_btot, flags, loss_out, grad_out, ws, ws_bytes, st);
   rc = launch_prepack(c, W, st);
   if (rc) return rc;
   GradArgs a{};

@@ -144,6 +144,13 @@ struct dflow_chain {
   int tc_debug = 0;    // timing experiments (dflow_tc.cu)
   int tc_mode = 0;     // 0: automatic (tensor cores iff must_wide), 1: force tensor cores, -1: force CUDA cores
   bool use_tc() const { return wide && tcp && (must_wide || tc_mode > 0); }
+  // adjoint: at hidden 64 the tensor-core kernels beat the CUDA-core adjoint (3.8e7 vs 2.1e7 samples/s on C3) once the
+  // batch fills the machine; narrower or smaller stays on CUDA cores
+  int hidden_max = 0;
+  bool use_tc_grad(long long B) const {
+    if (use_tc()) return true;
+    return wide && tcp && tc_mode == 0 && hidden_max == 64 && B >= 32768;
+  }
   const dflow::DevChain* hc() const { return reinterpret_cast<const dflow::DevChain*>(host_chain.data()); }
   dflow::DevChain* hc() { return reinterpret_cast<dflow::DevChain*>(host_chain.data()); }
 };
