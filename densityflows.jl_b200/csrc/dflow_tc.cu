@@ -621,30 +621,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
         // ---- D2 += h1 chunk (32 units) * two 16-unit M2 blocks ----
         int cg = 0, gnext = NG;
         for (int c = 0; c < nch32; ++c, ++q) {
-          uint32_t woff0, woff1, slot0 = 0, slot1 = 0;
-          if (resident) {
-            woff0 = res_s2 + (uint32_t)(p * nch + 2 * c) * s2_step;
-            woff1 = woff0 + s2_step;
-          } else {
-            mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
-            slot0 = rW.slot;
-            woff0 = slot0 * slot_step;
-            rW.next();
-            mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
-            slot1 = rW.slot;
-            woff1 = slot1 * slot_step;
-            rW.next();
-          }
           const uint32_t as = q & 1u;
-          mbar_wait_a(bA2_FULL + as * 8, (q >> 1) & 1u);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t da = dA2_0 + as * a2_step;
-            if (!skip2) {
-              uint32_t acc = c > 0 ? 1u : 0u;
+          const uint64_t da = dA2_0 + as * a2_step;
+          // each 16-unit weight block is released as soon as its own six MMAs are queued, so the producer can refill
+          // the slot while the second block of the chunk is still being multiplied
 #pragma unroll
-              for (int hf = 0; hf < 2; ++hf) {
-                const uint64_t db = dRing16 + (hf ? woff1 : woff0);
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t woff, slot = 0;
+            if (resident) {
+              woff = res_s2 + (uint32_t)(p * nch + 2 * c + hf) * s2_step;
+            } else {
+              mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
+              slot = rW.slot;
+              woff = slot * slot_step;
+              rW.next();
+            }
+            if (hf == 0) mbar_wait_a(bA2_FULL + as * 8, (q >> 1) & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t db = dRing16 + woff;
+              if (!skip2) {
+                uint32_t acc = (c > 0 || hf > 0) ? 1u : 0u;
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
                   const uint32_t ao = (uint32_t)(hf * 2 + ks) * 16u, bo = (uint32_t)ks * 16u;
@@ -654,20 +651,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
                   acc = 1u;
                 }
               }
-            }
-            mma_commit_a(bA2_EMPTY + as * 8);
-            if (!resident) {
-              if (pair) {
-                mma_commit_multicast_a(bW_EMPTY + slot0 * 8, (uint16_t)3);
-                mma_commit_multicast_a(bW_EMPTY + slot1 * 8, (uint16_t)3);
-              } else {
-                mma_commit_a(bW_EMPTY + slot0 * 8);
-                mma_commit_a(bW_EMPTY + slot1 * 8);
+              if (!resident) {
+                if (pair) mma_commit_multicast_a(bW_EMPTY + slot * 8, (uint16_t)3);
+                else mma_commit_a(bW_EMPTY + slot * 8);
+              }
+              if (hf == 1) {
+                mma_commit_a(bA2_EMPTY + as * 8);
+                if (c == nch32 - 1) mma_commit(bars + BAR_D2_FULL);
               }
             }
-            if (c == nch32 - 1) mma_commit(bars + BAR_D2_FULL);
+            __syncwarp();
           }
-          __syncwarp();
           if (++cg == cpg) {
             cg = 0;
             if (gnext < ng) issue_d1(gnext);
