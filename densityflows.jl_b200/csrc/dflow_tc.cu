@@ -162,6 +162,12 @@ __device__ __forceinline__ void store_a2_row(float* a_hi, float* a_lo, int row, 
   }
 }
 
+// Training buffers (h1, h2, delta1, delta2, delta3, conditioner inputs) are laid out for the weight-gradient kernel:
+// [tile][block of 16 samples][row][16 samples], so that one K = 16 stage of a row range is one contiguous run.
+__device__ __forceinline__ size_t tbuf_idx(long long tile, int rows, int r, int s) {
+  return (((size_t)tile * 8 + (size_t)(s >> 4)) * (size_t)rows + (size_t)r) * 16 + (size_t)(s & 15);
+}
+
 // ring cursor: slot index + phase parity, advanced without divisions
 struct Ring {
   uint32_t slot, par, n;
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
-                if (live) a.d2buf[((size_t)tile * H + c * WKA + j) * 128 + row] = v[j];
+                if (live) a.d2buf[tbuf_idx(tile, H, c * WKA + j, row)] = v[j];
               }
             } else {
 #pragma unroll
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
                   uint32_t mword = 0;
 #pragma unroll
                   for (int j = 0; j < 32; ++j) {
-                    a.h1buf[((size_t)tile * H + c * WKA + j) * 128 + row] = v[j];
+                    a.h1buf[tbuf_idx(tile, H, c * WKA + j, row)] = v[j];
                     mword |= (v[j] > 0.0f ? 1u : 0u) << j;
                   }
                   a.m1buf[((size_t)tile * (H >> 5) + c) * 128 + row] = mword;
@@ -338,7 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
-              if (live) a.d1buf[((size_t)tile * H + gc * WKA + j) * 128 + row] = v[j];
+              if (live) a.d1buf[tbuf_idx(tile, H, gc * WKA + j, row)] = v[j];
             }
           } else {
 #pragma unroll
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
               uint32_t mword = 0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                a.h2buf[((size_t)tile * H + gc * WKA + j) * 128 + row] = v[j];
+                a.h2buf[tbuf_idx(tile, H, gc * WKA + j, row)] = v[j];
                 mword |= (v[j] > 0.0f ? 1u : 0u) << j;
               }
               a.m2buf[((size_t)tile * (H >> 5) + gc) * 128 + row] = mword;
@@ -391,7 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
                 }
               }
               v[qq] = val;
-              if (live) a.d3buf[((size_t)tile * K0p + j) * 128 + row] = val;
+              if (live) a.d3buf[tbuf_idx(tile, K0p, j, row)] = val;
               // bias gradient of the last Dense: sum over the tile's samples
               float r = val;
 #pragma unroll
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
               }
               v[qq] = val;
               if constexpr (MODE == TC_FWD_STORE)
-                if (a.net_id == 1 && live) a.inbuf[((size_t)tile * K0p + k) * 128 + row] = val;
+                if (a.net_id == 1 && live) a.inbuf[tbuf_idx(tile, K0p, k, row)] = val;
             }
             float4 hi, lo;
             hi.x = to_tf32(v[0]); lo.x = v[0] - hi.x;
@@ -745,10 +751,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
 //   dW3^T[mt] (128 x a16) += h2[mt] * delta3^T
 // accumulated in TMEM over the CTA's whole sample range and flushed once with red.global.add.
 constexpr int DW_KS = TC_DW_KS;
-constexpr int DW_STAGE_WARPS = 8;
+constexpr int DW_STAGE_WARPS = 16;
 constexpr int DW_STAGE_THREADS = DW_STAGE_WARPS * 32;
 constexpr int DW_THREADS = DW_STAGE_THREADS + 32;
-constexpr int DW_MAXRB = 12;  // row-blocks (8 rows x 16 samples) per staging warp and stage
+constexpr int DW_MAXRB = 6;   // row-blocks (8 rows x 16 samples) per staging warp and stage
 constexpr uint32_t DWT_W2 = 0, DWT_W1 = 256, DWT_W3 = 320;
 
 struct DwArgs {
@@ -847,20 +853,19 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       my_ok[i] = rb < RB && my_row[i] < valid;
       my_dst[i] = dst0 + (r0 >> 3) * 128 + lofs;
       my_lo[i] = srows * DW_KS;
-      my_ts[i] = trows * 128;
-      my_ptr[i] = base + (size_t)((sgi < 3 ? mt * 128 : 0) + my_row[i]) * 128 + (lane >> 3) * 4;
+      my_ts[i] = trows * 16;  // floats per [rows x 16 samples] block of the source buffer
+      my_ptr[i] = base + (size_t)((sgi < 3 ? mt * 128 : 0) + my_row[i]) * 16 + (lane >> 3) * 4;
     }
     float4 v[DW_MAXRB];
     float bacc[DW_MAXRB];
 #pragma unroll
     for (int i = 0; i < DW_MAXRB; ++i) bacc[i] = 0.0f;
     auto load_stage = [&](long long s) {
-      const long long tile = t0 + s / (128 / DW_KS);
-      const int s0 = (int)(s % (128 / DW_KS)) * DW_KS;
+      const size_t blk = (size_t)(t0 * (128 / DW_KS) + s);  // [tile][16-sample block] index (tbuf_idx)
 #pragma unroll
       for (int i = 0; i < DW_MAXRB; ++i) {
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (my_ok[i]) v[i] = __ldg(reinterpret_cast<const float4*>(my_ptr[i] + (size_t)tile * my_ts[i] + s0));
+        if (my_ok[i]) v[i] = __ldg(reinterpret_cast<const float4*>(my_ptr[i] + blk * my_ts[i]));
       }
     };
     if (nstages > 0) load_stage(0);
