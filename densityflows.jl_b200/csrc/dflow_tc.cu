@@ -1384,7 +1384,7 @@ static void train_layout(const dflow_chain* c, long long B, TcTrainLayout& T) {
   const long long per = (L + 1) * Hd.d + 1 + Hd.d + Hd.n + L * tp->a16max + L * tp->k0pmax + L * 4 * tp->hmax +
                         L * 4 * (tp->hmax / 32) + 4 * tp->hmax + 2 * tp->a16max;
   long long MB = ((B + 127) / 128) * 128;
-  const long long budget = (long long)24 << 30;  // bytes
+  const long long budget = c->tc_ws_budget_mb > 0 ? (long long)c->tc_ws_budget_mb << 20 : (long long)24 << 30;  // bytes
   long long cap = budget / (per * 4);
   cap = std::max<long long>(128, (cap / 128) * 128);
   if (MB > cap) MB = cap;

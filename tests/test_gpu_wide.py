@@ -131,6 +131,54 @@ def test_wide_loss_grad(name, B):
     _check_grad(name, ochain, chain.packed(), x, th, B)
 
 
+def _mixed_wide_chain(x):
+    """RNVP + NICE coupling layers with a NormalizationLayer in the middle and one at the end, hidden 128."""
+    rng = np.random.default_rng(7)
+    l1 = O.coupling_layer(O.coupling_axes(8, [1, 2, 3, 4], n=2), hidden_dim_s=128, hidden_dim_t=128, rng=rng,
+                          bias_scale=0.1, s_out_scale=0.3)
+    l2 = O.coupling_layer(O.coupling_axes(8, [8, 5, 6], n=2), kind="nice", hidden_dim_t=128, rng=rng, bias_scale=0.1)
+    l3 = O.coupling_layer(O.coupling_axes(8, [7, 2, 4, 6, 1], n=2), hidden_dim_s=128, hidden_dim_t=128, rng=rng,
+                          bias_scale=0.1, s_out_scale=0.3)
+    return O.Chain([l1, O.norm_layer_from_data(x, -2.0, 3.0), l2, l3, O.norm_layer_from_data(x)])
+
+
+def test_wide_nice_layer_and_inner_normalization():
+    """NICE (no s-net) layers and a NormalizationLayer inside the chain on the tensor-core kernels, both directions
+    and the adjoint (the cotangent is scaled through the inner NormalizationLayer)."""
+    xn = O.synthetic_data(8, 2, 1000, seed=99)[0]
+    ochain = _mixed_wide_chain(xn)
+    B = 700
+    x, th = O.synthetic_data(8, 2, B, seed=13)
+    chain = chain_from_oracle(ochain)
+    z, ldj = df.backward(chain, x, th)
+    zo, lo = O.chain_backward(ochain, x, th, np.float64)
+    zo32, lo32 = O.chain_backward(ochain, x, th)
+    slack = np.abs(zo32 - zo).max() + np.abs(lo32 - lo).max()
+    assert_close(df.to_numpy(z), zo, 1e-5, 1e-5 + slack, "mixed z")
+    assert_close(df.to_numpy(ldj), lo, 1e-5, 1e-5 + slack, "mixed ldj")
+    x2, ldj2 = df.forward(chain, df.to_numpy(z), th)
+    assert_close(df.to_numpy(x2), x, 1e-4, 1e-4, "mixed round trip")
+    _check_grad("mixed_h128", ochain, chain.packed(), x, th, B)
+
+
+def test_wide_adjoint_macro_batches():
+    """A workspace cap forces the adjoint to run in several macro-batches; the gradient is the same sum."""
+    ochain, chain, x, th = _setup("h128_d8", 3000, seed=5)
+    pc = chain.packed()
+    full = torch.zeros(pc.P, device=DEV)
+    l_full = torch.zeros(2, device=DEV)
+    pc.loss_grad(x, th, full, l_full)
+    pc.tune(tc_ws_budget_mb=8)  # 8 MiB: a few hundred samples per macro-batch
+    part = torch.zeros(pc.P, device=DEV)
+    l_part = torch.zeros(2, device=DEV)
+    n0 = pc.launch_count()
+    pc.loss_grad(x, th, part, l_part)
+    assert pc.launch_count() - n0 > 2 * 20  # several sweeps
+    pc.tune(tc_ws_budget_mb=0)
+    assert torch.allclose(part, full, rtol=1e-4, atol=2e-6 * full.abs().max().item())
+    assert abs(l_part[0].item() - l_full[0].item()) <= 1e-5 * abs(l_full[0].item())
+
+
 def test_wide_grad_idx_and_dp_seed():
     """Gather through an index + data-parallel seed: two shards with inv_btot = 1/B sum to the full gradient."""
     ochain, chain, x, th = _setup("h128_d8", 600, seed=4)
