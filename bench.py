@@ -163,7 +163,7 @@ def timed(fn, steps, warmup, dist):
 
 def run_ours(args):
     import densityflows.jl_b200 as df
-    from densityflows.jl_b200.flows import TrainStep
+    from densityflows.jl_b200.flows import PeerTrainStep, make_train_step
     from tests.helpers import chain_from_oracle
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -201,6 +201,13 @@ def run_ours(args):
     assert torch.isfinite(out[:: max(1, B // 4096)]).all()
 
     ops = {}
+
+    def coll(step):
+        if world == 1:
+            return "none (1 GPU)"
+        return ("fused NVLink peer all-reduce + Adam kernel (dflow_dp.cu)" if isinstance(step, PeerTrainStep)
+                else "NCCL all-reduce + Adam kernel")
+
     # ---- sample(): in-kernel Philox base draw + sampling direction, fixed θ (src/Flows.jl:174-185) ----
     thc = torch.tensor([0.5, 0.5], device=dev)
 
@@ -219,7 +226,7 @@ def run_ours(args):
     # ---- train step on C2 (per-GPU shard of a 2^24-sample minibatch, weak) ----
     Bt = 1 << 24
     state = df.setup(df.Adam(1e-3), chain)
-    ts = TrainStep(pc, state)
+    ts = make_train_step(pc, state)
     w_save = pc.W.clone()
 
     def step_train():
@@ -227,7 +234,7 @@ def run_ours(args):
 
     ms_t = timed(step_train, 3, 3, dist)
     ops["train_step_c2"] = {"samples_per_s": world * Bt / (ms_t * 1e-3), "ms_per_step": ms_t, "B_per_gpu": Bt,
-                            "scaling": "weak", "allreduce_bytes": 4 * (pc.P + 2)}
+                            "scaling": "weak", "allreduce_bytes": 4 * (pc.P + 2), "collective": coll(ts)}
     pc.W.copy_(w_save)
 
     # ---- e2e: host buffers through the C-ABI host entry point (pinned host -> HBM -> host every step) ----
@@ -274,7 +281,7 @@ def run_ours(args):
         x3, th3 = device_inputs(16, 4, Bl, dev, 99 + rank)
         t3min, t3max = np.full(4, -1.0, np.float32), np.full(4, 2.0, np.float32)
         pc3 = df.PackedChain(c3._leaves(), dev, t3min, t3max)
-        ts3 = TrainStep(pc3, df.setup(df.Adam(1e-3), c3))
+        ts3 = make_train_step(pc3, df.setup(df.Adam(1e-3), c3))
 
         def step_c3():
             ts3(x3, th3, None, Bg, flags)
@@ -282,11 +289,11 @@ def run_ours(args):
         ms3 = timed(step_c3, 2, 1, dist)
         # default routing: at hidden 64 and a batch this large the adjoint runs on the tensor cores (dflow_tc.cu)
         ops["train_step_c3"] = {"samples_per_s": Bg / (ms3 * 1e-3), "ms_per_step": ms3, "global_batch": Bg,
-                                "scaling": "strong", "allreduce_bytes": 4 * (pc3.P + 2),
+                                "scaling": "strong", "allreduce_bytes": 4 * (pc3.P + 2), "collective": coll(ts3),
                                 "path": "tcgen05 3xTF32 adjoint (automatic for hidden 64, B >= 32768)"}
         # the same step forced onto the CUDA-core adjoint kernel (tc_mode=-1)
         pc3.tune(tc_mode=-1)
-        ts3b = TrainStep(pc3, df.setup(df.Adam(1e-3), c3))
+        ts3b = make_train_step(pc3, df.setup(df.Adam(1e-3), c3))
         ms3b = timed(lambda: ts3b(x3, th3, None, Bg, flags), 2, 1, dist)
         ops["train_step_c3_cuda_cores"] = {"samples_per_s": Bg / (ms3b * 1e-3), "ms_per_step": ms3b, "global_batch": Bg,
                                            "scaling": "strong", "path": "FP32 FFMA adjoint kernel (tc_mode=-1)"}
@@ -321,14 +328,14 @@ def run_ours(args):
                             "tensor_tflops_3xtf32_per_gpu": 3 * f4 * B4 / (ms4 * 1e-3) / 1e12,
                             "tensor_frac_of_measured_tf32": 3 * f4 * B4 / (ms4 * 1e-3) / 1e12 / tf32_peak,
                             "tf32_peak_tflops": tf32_peak, "tf32_peak_source": "MEASURED_PEAKS.json bf16_tflops / 2"}
-        ts4 = TrainStep(pc4, df.setup(df.Adam(1e-3), c4))
+        ts4 = make_train_step(pc4, df.setup(df.Adam(1e-3), c4))
 
         def step_c4_train():
             ts4(x4, th4, None, B4 * world, flags)
 
         ms4t = timed(step_c4_train, 2, 1, dist)
         ops["train_step_c4"] = {"samples_per_s": world * B4 / (ms4t * 1e-3), "ms_per_step": ms4t, "B_per_gpu": B4,
-                                "scaling": "weak", "allreduce_bytes": 4 * (pc4.P + 2),
+                                "scaling": "weak", "allreduce_bytes": 4 * (pc4.P + 2), "collective": coll(ts4),
                                 "tensor_tflops_3xtf32_per_gpu": 9 * f4 * B4 / (ms4t * 1e-3) / 1e12,
                                 "tensor_frac_of_measured_tf32": 9 * f4 * B4 / (ms4t * 1e-3) / 1e12 / tf32_peak}
         del x4, th4, pc4, ts4, out4

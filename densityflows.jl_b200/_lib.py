@@ -85,6 +85,12 @@ SYMBOLS = [
     ("dflow_minmax", C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, vp]),
     ("dflow_logpdf_host", C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int32, vp, C.c_int64]),
     ("dflow_sample_host", C.c_int, [vp, vp, C.c_uint64, vp, C.c_int64, C.c_int32, vp, C.c_int64]),
+    ("dflow_dp_create", C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(vp), vp]),
+    ("dflow_dp_connect", C.c_int, [vp, vp]),
+    ("dflow_dp_grad_buffer", vp, [vp]),
+    ("dflow_dp_allreduce_adam", C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp, vp]),
+    ("dflow_dp_status", C.c_int, [vp, vp]),
+    ("dflow_dp_destroy", C.c_int, [vp]),
     ("dflow_set_tuning", C.c_int, [vp, C.c_char_p, C.c_int32]),
     ("dflow_launch_count", C.c_int64, [vp]),
 ]

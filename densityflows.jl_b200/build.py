@@ -48,6 +48,8 @@ def _units():
         units.append(("dflow_wide.o", "dflow_wide.cu", []))
     if os.path.exists(os.path.join(CSRC, "dflow_tc.cu")):
         units.append(("dflow_tc.o", "dflow_tc.cu", []))
+    if os.path.exists(os.path.join(CSRC, "dflow_dp.cu")):
+        units.append(("dflow_dp.o", "dflow_dp.cu", []))
     return units
 
 

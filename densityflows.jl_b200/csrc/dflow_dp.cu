@@ -1,0 +1,260 @@
+// Data-parallel train step, collective part: gradient all-reduce over NVLink peer memory fused with the Adam update
+// (src/Flows.jl:413-415: gradient -> Optimisers.update!).  One process per GPU; every rank owns one communication
+// buffer (cudaMalloc + CUDA IPC handle, opened by its peers):
+//
+//   [ flags: uint32[64] | go: uint32 | pad to 512 B ] [ half 0: P + 2 floats, padded ] [ half 1: P + 2 floats, padded ]
+//
+// Step e writes its local gradient sum [grad | sum logp | #non-finite] into half e & 1 (the adjoint kernels accumulate
+// there directly), then ONE kernel per rank: (1) thread 0 of CTA 0 publishes flags[rank] = e in every peer's buffer
+// (st.release.sys after a system fence) and waits until all peers have published e in its own buffer
+// (ld.acquire.sys); (2) every thread sums element i over the ranks' halves in rank order 0..N-1 -- peer loads over
+// NVLink, identical order on every rank => bit-identical replicas without a broadcast -- and applies Adam to its own
+// replica.  No separate all-reduce launch, no reduced-gradient round trip through HBM.
+// Halves ping-pong: a rank can only start step e+2 (which overwrites half e & 1) after the barrier of step e+1, which
+// every peer reaches only after it has finished reading step e.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "dflow_internal.h"
+
+namespace dflow {
+
+constexpr int DP_MAX_RANKS = 16;
+constexpr size_t DP_HDR_BYTES = 512;
+
+struct DpArgs {
+  const char* bufs[DP_MAX_RANKS];  // every rank's communication buffer (own buffer at index rank)
+  int rank, nranks;
+  uint32_t epoch;
+  long long P;
+  size_t half_floats;  // padded size of one half
+  float* W;
+  float* m;
+  float* v;
+  float lr, b1, b2, eps, c1, c2;
+  float* loss2_out;   // [2] reduced sum logp / #non-finite, or null
+  int* status;        // device int: set to 1 if the barrier timed out
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer(const float* p) {  // bypass L1: peer data is not kept coherent there
+  float v;
+  asm volatile("ld.global.cv.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(256) dp_allreduce_adam_kernel(const DpArgs a) {
+  uint32_t* my_flags = reinterpret_cast<uint32_t*>(const_cast<char*>(a.bufs[a.rank]));
+  uint32_t* go = my_flags + 64;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();  // the adjoint kernels' gradient (earlier launches on this stream) before the flag
+    for (int j = 0; j < a.nranks; ++j)
+      st_release_sys(reinterpret_cast<uint32_t*>(const_cast<char*>(a.bufs[j])) + a.rank, a.epoch);
+    const long long t0 = clock64();
+    bool ok = true;
+    for (int j = 0; j < a.nranks && ok; ++j) {
+      while ((int32_t)(ld_acquire_sys(my_flags + j) - a.epoch) < 0) {
+        if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer is gone
+          ok = false;
+          break;
+        }
+      }
+    }
+    if (!ok && a.status) *a.status = 1;
+    __threadfence();
+    atomicExch(go, a.epoch);
+  }
+  // all CTAs are co-resident (grid <= SM count): wait for the release by CTA 0
+  if (threadIdx.x == 0) {
+    while ((int32_t)(ld_acquire_gpu(go) - a.epoch) < 0) {
+    }
+  }
+  __syncthreads();
+  const size_t half_off = DP_HDR_BYTES / sizeof(float) + (size_t)(a.epoch & 1u) * a.half_floats;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.P + 2; i += (long long)gridDim.x * blockDim.x) {
+    float g = 0.0f;
+    for (int j = 0; j < a.nranks; ++j) {
+      const float* h = reinterpret_cast<const float*>(a.bufs[j]) + half_off;
+      g += (j == a.rank) ? h[i] : ld_peer(h + i);
+    }
+    if (i >= a.P) {
+      if (a.loss2_out) a.loss2_out[i - a.P] = g;
+      continue;
+    }
+    // Optimisers.Adam, same explicit round-to-nearest sequence as adam_kernel (dflow_kernels.cu)
+    const float mi = __fadd_rn(__fmul_rn(a.b1, a.m[i]), __fmul_rn(1.0f - a.b1, g));
+    const float vi = __fadd_rn(__fmul_rn(a.b2, a.v[i]), __fmul_rn(1.0f - a.b2, __fmul_rn(g, g)));
+    a.m[i] = mi;
+    a.v[i] = vi;
+    const float den = __fadd_rn(__fsqrt_rn(__fdiv_rn(vi, a.c2)), a.eps);
+    const float stepv = __fmul_rn(__fdiv_rn(__fdiv_rn(mi, a.c1), den), a.lr);
+    a.W[i] = __fsub_rn(a.W[i], stepv);
+  }
+}
+
+}  // namespace dflow
+
+using namespace dflow;
+
+struct dflow_dp {
+  int rank = 0, nranks = 1;
+  long long P = 0;
+  size_t half_floats = 0, bytes = 0;
+  char* own = nullptr;
+  char* peers[DP_MAX_RANKS] = {nullptr};
+  bool opened[DP_MAX_RANKS] = {false};
+  int* d_status = nullptr;
+  uint32_t epoch = 0;
+  int sm_count = 148;
+};
+
+extern "C" {
+
+int dflow_dp_create(int32_t rank, int32_t nranks, int64_t P, dflow_dp** out, void* ipc_handle_out) {
+  if (!out || !ipc_handle_out || rank < 0 || nranks < 1 || nranks > DP_MAX_RANKS || rank >= nranks || P < 0) {
+    set_error("bad dflow_dp_create arguments (at most %d ranks)", DP_MAX_RANKS);
+    return DFLOW_E_INVALID_ARG;
+  }
+  dflow_dp* d = new (std::nothrow) dflow_dp();
+  if (!d) return DFLOW_E_NOMEM;
+  d->rank = rank;
+  d->nranks = nranks;
+  d->P = P;
+  d->half_floats = (size_t)((P + 2 + 63) & ~63LL);
+  d->bytes = DP_HDR_BYTES + 2 * d->half_floats * sizeof(float);
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    delete d;
+    return DFLOW_E_CUDA;
+  }
+  d->sm_count = prop.multiProcessorCount;
+  cudaIpcMemHandle_t h;
+  if (cudaMalloc(&d->own, d->bytes) != cudaSuccess || cudaMalloc(&d->d_status, sizeof(int)) != cudaSuccess ||
+      cudaMemset(d->own, 0, d->bytes) != cudaSuccess || cudaMemset(d->d_status, 0, sizeof(int)) != cudaSuccess ||
+      cudaIpcGetMemHandle(&h, d->own) != cudaSuccess) {
+    set_error("communication buffer setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (d->own) cudaFree(d->own);
+    if (d->d_status) cudaFree(d->d_status);
+    delete d;
+    return DFLOW_E_CUDA;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(ipc_handle_out, &h, 64);
+  d->peers[rank] = d->own;
+  *out = d;
+  return DFLOW_OK;
+}
+
+/* handles: nranks x 64 bytes in rank order (the own entry is ignored) */
+int dflow_dp_connect(dflow_dp* d, const void* handles) {
+  if (!d || !handles) {
+    set_error("null argument");
+    return DFLOW_E_INVALID_ARG;
+  }
+  for (int j = 0; j < d->nranks; ++j) {
+    if (j == d->rank || d->opened[j]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + 64 * (size_t)j, 64);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", j, cudaGetErrorString(cudaGetLastError()));
+      return DFLOW_E_CUDA;
+    }
+    d->peers[j] = static_cast<char*>(p);
+    d->opened[j] = true;
+  }
+  return DFLOW_OK;
+}
+
+/* device pointer of the [grad (P) | sum logp | #non-finite] accumulation area of the NEXT step; the caller zeroes it and
+ * passes grad / loss2 pointers into it to dflow_loss_grad */
+float* dflow_dp_grad_buffer(dflow_dp* d) {
+  if (!d) return nullptr;
+  return reinterpret_cast<float*>(d->own + DP_HDR_BYTES) + (size_t)((d->epoch + 1) & 1u) * d->half_floats;
+}
+
+int dflow_dp_allreduce_adam(dflow_dp* d, float* W, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                            int64_t t, float* loss2_out, void* stream) {
+  if (!d || !W || !m || !v || t < 1) {
+    set_error("bad dflow_dp_allreduce_adam arguments");
+    return DFLOW_E_INVALID_ARG;
+  }
+  for (int j = 0; j < d->nranks; ++j)
+    if (!d->peers[j]) {
+      set_error("rank %d is not connected (dflow_dp_connect)", j);
+      return DFLOW_E_INVALID_ARG;
+    }
+  d->epoch += 1;
+  DpArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int j = 0; j < d->nranks; ++j) a.bufs[j] = d->peers[j];
+  a.rank = d->rank;
+  a.nranks = d->nranks;
+  a.epoch = d->epoch;
+  a.P = d->P;
+  a.half_floats = d->half_floats;
+  a.W = W;
+  a.m = m;
+  a.v = v;
+  a.lr = lr;
+  a.b1 = beta1;
+  a.b2 = beta2;
+  a.eps = eps;
+  float b1t = 1.0f, b2t = 1.0f;  // Float32 running products like Optimisers.jl (launch_adam)
+  for (long long i = 0; i < t; ++i) {
+    b1t *= beta1;
+    b2t *= beta2;
+  }
+  a.c1 = 1.0f - b1t;
+  a.c2 = 1.0f - b2t;
+  a.loss2_out = loss2_out;
+  a.status = d->d_status;
+  long long blocks = (d->P + 2 + 1023) / 1024;
+  if (blocks > d->sm_count) blocks = d->sm_count;  // co-resident: CTAs wait for CTA 0
+  if (blocks < 1) blocks = 1;
+  dp_allreduce_adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  if (cudaGetLastError() != cudaSuccess) {
+    set_error("dp_allreduce_adam launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return DFLOW_E_CUDA;
+  }
+  return DFLOW_OK;
+}
+
+/* 0 = fine, 1 = a peer did not reach the barrier within ~10 s (synchronises the stream) */
+int dflow_dp_status(dflow_dp* d, void* stream) {
+  if (!d) return DFLOW_E_INVALID_ARG;
+  int s = 0;
+  if (cudaMemcpyAsync(&s, d->d_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+      cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+    set_error("status read failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return DFLOW_E_CUDA;
+  }
+  return s;
+}
+
+int dflow_dp_destroy(dflow_dp* d) {
+  if (!d) return DFLOW_OK;
+  for (int j = 0; j < d->nranks; ++j)
+    if (d->opened[j] && d->peers[j]) cudaIpcCloseMemHandle(d->peers[j]);
+  if (d->own) cudaFree(d->own);
+  if (d->d_status) cudaFree(d->d_status);
+  delete d;
+  return DFLOW_OK;
+}
+
+}  // extern "C"

@@ -251,6 +251,99 @@ class TrainStep:
         pc.adam_step(self.grad, st.m, st.v, st.t, r.eta, r.beta, r.epsilon)
 
 
+class _DevView:
+    """Float32 view of raw device memory for torch.as_tensor (no copy)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+
+class PeerTrainStep:
+    """The same step with the collective fused into the optimiser kernel: every rank publishes its gradient buffer
+    over CUDA IPC, and ONE kernel per rank waits for the peers' buffers of this step, sums them over NVLink peer
+    loads in rank order and applies Adam (csrc/dflow_dp.cu).  No NCCL call on the step; replicas stay bit-identical.
+    Construct it on every rank (it exchanges the IPC handles through torch.distributed)."""
+
+    def __init__(self, pc: PackedChain, state: OptimiserState):
+        import ctypes as C
+
+        d = _dist()
+        if d is None:
+            raise RuntimeError("PeerTrainStep needs an initialised torch.distributed group with world_size > 1")
+        self.pc, self.state = pc, state
+        state._ensure(pc)
+        self.rank, self.world = d.get_rank(), d.get_world_size()
+        self.P = max(pc.P, 1)
+        handle = C.create_string_buffer(64)
+        self.dp = C.c_void_p()
+        with torch.cuda.device(pc.device):
+            L.check(L.lib().dflow_dp_create(self.rank, self.world, self.P, C.byref(self.dp), handle))
+            handles: list = [None] * self.world
+            d.all_gather_object(handles, handle.raw)
+            self._handles = b"".join(handles)
+            L.check(L.lib().dflow_dp_connect(self.dp, self._handles))
+        self._views = {}
+        self.loss2 = torch.zeros(2, device=pc.device, dtype=torch.float32)
+        d.barrier()
+
+    def _next_buffer(self) -> torch.Tensor:
+        ptr = int(L.lib().dflow_dp_grad_buffer(self.dp))
+        v = self._views.get(ptr)
+        if v is None:
+            v = torch.as_tensor(_DevView(ptr, self.P + 2), device=self.pc.device)
+            self._views[ptr] = v
+        return v
+
+    def __call__(self, x, θ, idx: Optional[torch.Tensor], B_global: int, flags: int = 0) -> None:
+        pc, st = self.pc, self.state
+        buf = self._next_buffer()
+        buf.zero_()
+        nb = n_samples(x) if idx is None else int(idx.numel())
+        if nb > 0:
+            pc.loss_grad(x, θ, buf[: self.P], buf[self.P:], 1.0 / B_global, flags, idx)
+        st.t += 1
+        r = st.rule
+        with torch.cuda.device(pc.device):
+            L.check(L.lib().dflow_dp_allreduce_adam(self.dp, pc.W.data_ptr(), st.m.data_ptr(), st.v.data_ptr(), r.eta,
+                                                    r.beta[0], r.beta[1], r.epsilon, st.t, self.loss2.data_ptr(),
+                                                    pc._stream()))
+
+    def check(self) -> None:
+        """Raises if a peer failed to reach a step's barrier (synchronises the stream)."""
+        with torch.cuda.device(self.pc.device):
+            s = L.lib().dflow_dp_status(self.dp, self.pc._stream())
+        if s != 0:
+            raise RuntimeError("data-parallel step: a peer did not publish its gradient (timeout)")
+
+    def __del__(self):
+        try:
+            if getattr(self, "dp", None):
+                L.lib().dflow_dp_destroy(self.dp)
+                self.dp = None
+        except Exception:
+            pass
+
+
+def make_train_step(pc: PackedChain, state: OptimiserState):
+    """PeerTrainStep when several GPU ranks of one node train together (DFLOW_DP=nccl keeps the NCCL all-reduce),
+    else TrainStep."""
+    import os
+
+    d = _dist()
+    if d is None or pc.device.type != "cuda" or os.environ.get("DFLOW_DP", "peer") == "nccl":
+        return TrainStep(pc, state)
+    ok = torch.ones(1, device=pc.device)
+    step = None
+    try:
+        step = PeerTrainStep(pc, state)
+    except Exception:
+        ok.zero_()
+    d.all_reduce(ok, op=d.ReduceOp.MIN)
+    if ok.item() < 1:  # some rank could not map its peers (no P2P): every rank falls back to the NCCL collective
+        return TrainStep(pc, state)
+    return step
+
+
 def _full_loss(pc: PackedChain, x, θ, idx: torch.Tensor, n_global: int, flags: int, tmp: torch.Tensor) -> float:
     """loss = -mean(logpdf(base, z) + ldj) over a whole partition (src/Flows.jl:419-430), sharded over ranks."""
     tmp.zero_()
@@ -274,7 +367,7 @@ def train_(flow: Flow, data: DataArrays, optimiser_state: OptimiserState, epochs
         raise NotImplementedError("train! partitions along dim 2; only (d, N) arrays are supported (src/Data.jl:167)")
     tr = data.partition.training.to(pc.device)
     va = data.partition.validation.to(pc.device)
-    step = TrainStep(pc, optimiser_state)
+    step = make_train_step(pc, optimiser_state)
     d = _dist()
     rank, world = (d.get_rank(), d.get_world_size()) if d is not None else (0, 1)
     n_tr, n_va = int(tr.numel()), int(va.numel())

@@ -148,6 +148,25 @@ int dflow_loss_grad(dflow_chain* chain, const float* W, const float* x, const fl
 int dflow_adam_step(float* W, const float* g, float* m, float* v, int64_t P, float lr, float beta1, float beta2,
                     float eps, int64_t t, void* stream);
 
+/* ---- data-parallel train step: gradient all-reduce over NVLink peer memory fused with the Adam update ------------
+ * (one process per GPU; replaces NCCL all-reduce + dflow_adam_step for src/Flows.jl:413-415).  Protocol per rank:
+ *   dflow_dp_create(rank, nranks, P, &dp, handle64)     allocates this rank's communication buffer, returns its
+ *                                                        64-byte CUDA IPC handle
+ *   (exchange the handles, e.g. all_gather)  ->  dflow_dp_connect(dp, handles)    nranks x 64 bytes in rank order
+ *   every step: buf = dflow_dp_grad_buffer(dp); zero P+2 floats; dflow_loss_grad(..., loss_out = buf + P,
+ *               grad_out = buf, ...) with inv_btot = 1/B_global; dflow_dp_allreduce_adam(dp, W, m, v, ...).
+ * The kernel waits until every peer has published its gradient of the same step, sums the ranks' buffers in rank order
+ * over peer loads (bit-identical replicas, no broadcast) and applies Adam; loss2_out (device float[2], may be NULL)
+ * receives the reduced [sum logp, #non-finite].  All ranks must call it the same number of times. */
+typedef struct dflow_dp dflow_dp; /* opaque */
+int dflow_dp_create(int32_t rank, int32_t nranks, int64_t P, dflow_dp** out, void* ipc_handle_out);
+int dflow_dp_connect(dflow_dp* dp, const void* handles);
+float* dflow_dp_grad_buffer(dflow_dp* dp);
+int dflow_dp_allreduce_adam(dflow_dp* dp, float* W, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                            int64_t t, float* loss2_out, void* stream);
+int dflow_dp_status(dflow_dp* dp, void* stream);
+int dflow_dp_destroy(dflow_dp* dp);
+
 /* ---- per-row min / max over B samples (NormalizationLayer ctor src/norm/Normalization.jl:52-53; minimum_θ /
  * maximum_θ src/Data.jl:182-183).  min_out / max_out: device float[rows]. */
 int dflow_minmax(const float* x, int32_t rows, int64_t B, float* min_out, float* max_out, void* stream);

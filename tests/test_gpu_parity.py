@@ -285,3 +285,39 @@ def test_smoke_entry():
     import __graft_entry__ as g
 
     g.smoke()
+
+
+def test_fused_peer_allreduce_adam_single_rank_equals_adam_kernel():
+    """dflow_dp_* with one rank: the fused all-reduce + Adam kernel (csrc/dflow_dp.cu) must reproduce dflow_adam_step
+    bit for bit and pass the reduced loss terms through; two steps exercise the ping-pong halves."""
+    import ctypes as C
+
+    lib = df._lib.lib()
+    P = 5000
+    rng = np.random.default_rng(3)
+    w0 = rng.standard_normal(P).astype(np.float32)
+    wa, wb = torch.tensor(w0, device=DEV), torch.tensor(w0, device=DEV)
+    ma, va, mb, vb = (torch.zeros(P, device=DEV) for _ in range(4))
+    dp = C.c_void_p()
+    handle = C.create_string_buffer(64)
+    df._lib.check(lib.dflow_dp_create(0, 1, P, C.byref(dp), handle))
+    df._lib.check(lib.dflow_dp_connect(dp, handle.raw))
+    loss2 = torch.zeros(2, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    from densityflows.jl_b200.flows import _DevView
+
+    for t in (1, 2, 3):
+        g = torch.tensor(rng.standard_normal(P).astype(np.float32) * 0.1, device=DEV)
+        buf = torch.as_tensor(_DevView(int(lib.dflow_dp_grad_buffer(dp)), P + 2), device=DEV)
+        buf[:P] = g
+        buf[P] = -123.5 * t
+        buf[P + 1] = 0.0
+        df._lib.check(lib.dflow_dp_allreduce_adam(dp, wa.data_ptr(), ma.data_ptr(), va.data_ptr(), 1e-3, 0.9, 0.999, 1e-8,
+                                                  t, loss2.data_ptr(), st))
+        df._lib.check(lib.dflow_adam_step(wb.data_ptr(), g.data_ptr(), mb.data_ptr(), vb.data_ptr(), P, 1e-3, 0.9, 0.999,
+                                          1e-8, t, st))
+        torch.cuda.synchronize()
+        assert torch.equal(wa, wb) and torch.equal(ma, mb) and torch.equal(va, vb)
+        assert loss2[0].item() == -123.5 * t and loss2[1].item() == 0.0
+    assert lib.dflow_dp_status(dp, st) == 0
+    df._lib.check(lib.dflow_dp_destroy(dp))
