@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
     };
     for (long long it = 0; it < iters; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
-      const bool live = tile < ntiles && !(a.debug & 128);  // dummy tiles touch no global memory
+      const bool live = tile < ntiles && !(a.debug & (128 | 512));  // dummy tiles touch no global memory (512: timing
+                                                                    // experiment without the training stores)
       for (int p = 0; p < passes; ++p) {
         // ---- epilogue 1: hidden-1 units, one D1 group (GW columns) at a time ----
         for (int g = 0; g < ng; ++g) {

@@ -16,8 +16,16 @@ if h <= 64:
 g = torch.Generator(device="cuda").manual_seed(0)
 x = df.jl_empty((d, B), "cuda:0"); x.normal_(generator=g)
 th = df.jl_empty((n, B), "cuda:0"); th.uniform_(0, 1, generator=g)
+pc.tune(tc_debug=int(os.environ.get("DFLOW_TC_DEBUG", "0")))
 grad = torch.zeros(pc.P, device="cuda:0"); l2 = torch.zeros(2, device="cuda:0")
-for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 1):
-    pc.loss_grad(x, th, grad, l2)
+pc.loss_grad(x, th, grad, l2)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+for _ in range(nrep):
+    pc.loss_grad(x, th, grad, l2)
+e1.record()
+torch.cuda.synchronize()
+print("ms per loss_grad", e0.elapsed_time(e1) / nrep)
 print("ok", name, l2.tolist())
