@@ -963,7 +963,7 @@ int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
   else if (!strcmp(key, "tc_ws_budget_mb"))
     c->tc_ws_budget_mb = value;
   else if (!strcmp(key, "tc_cluster"))
-    c->tc_cluster = value ? 1 : 0;
+    c->tc_cluster = value < 0 ? 0 : value > 2 ? 2 : value;
   else if (!strcmp(key, "tc_debug"))
     c->tc_debug = value;
   else if (!strcmp(key, "wide_gen"))

@@ -140,7 +140,8 @@ struct dflow_chain {
   dflow::TcPlan* tcp = nullptr;
   int wide_gen = 2;    // 1: dflow_wide.cu kernels, 2: dflow_tc.cu kernels
   int must_wide = 0;   // some hidden width > 64: the CUDA-core kernels cannot run this chain
-  int tc_cluster = 1;  // CTA pairs share the weight stream of streamed conditioners (bulk-copy multicast)
+  int tc_cluster = 0;  // streamed conditioners: 0 independent CTAs (default, fastest measured), 1 CTA pairs sharing the
+                       // weight stream by bulk-copy multicast, 2 cta_group::2 pairs (one issuer, M = 256)
   int tc_ws_budget_mb = 0;  // adjoint workspace cap in MiB (0: 24 GiB); larger batches are processed in macro-batches
   int tc_debug = 0;    // timing experiments (dflow_tc.cu)
   int tc_mode = 0;     // 0: automatic (tensor cores iff must_wide), 1: force tensor cores, -1: force CUDA cores

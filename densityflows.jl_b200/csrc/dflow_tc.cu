@@ -61,12 +61,14 @@ enum {
   BAR_D3_EMPTY,
   BAR_A1_FULL,
   BAR_A1_EMPTY,
-  BAR_TMEM_SLOT,
+  BAR_W_PEER,                           // [NSMAX] CTA pair: the peer's half of a weight stage has landed
+  BAR_TMEM_SLOT = BAR_W_PEER + NSMAX,
   BAR_COUNT
 };
 
 struct TcArgs {
   TcNetImg im;
+  TcNetImg im2[2];  // cluster == 2: the two CTAs' half-row images
   const float* img;
   long long B;
   int net_id, has_s, d, n, a, a16, nin;
@@ -74,7 +76,8 @@ struct TcArgs {
   int resident, NS, tmem_cols;
   int NG, NA, tm_d3, tm_d2;  // D1 group buffers, A2 ring depth, TMEM columns of D3 / D2
   int s3ps;                  // S3 blocks (W3 chunks) per ring stage when streamed
-  int cluster;               // 1: launched as CTA pairs that share the weight stream (bulk-copy multicast)
+  int cluster;               // 1: CTA pairs share the weight stream (bulk-copy multicast); 2: cta_group::2 pairs (one
+                             // issuer, M = 256, each CTA holds half of the weight rows)
   int debug;  // timing experiments only: bit 0 = weights loaded once per CTA (wrong results when streamed)
   unsigned char af[DMAX], id[DMAX];
   float theta_min[NMAX], theta_rng[NMAX];
@@ -114,54 +117,46 @@ __global__ void tc_prepack_kernel(const TcPackJob* jobs, const float* __restrict
     base[im.bias_off + H + i] = J.pb2 >= 0 ? W[J.pb2 + i] : 0.0f;
   }
   for (int i = t0; i < N3p; i += ts) base[im.bias_off + 2 * H + i] = (J.pb3 >= 0 && i < J.nb3) ? W[J.pb3 + i] : 0.0f;
+  const int hv = im.halves > 1 ? im.halves : 1, rk = im.rank;
+  const int gwr = im.GW / hv, nhr = NH / hv, n3r = N3p / hv;  // rows per block in this image
   // M1 [H x K0p]: group g = rows g*GW..
   for (int i = t0; i < H * K0p; i += ts) {
     const int u = i / K0p, k = i - u * K0p;
+    const int g = u / im.GW, within = u - g * im.GW, sub = within / gwr, r = within - sub * gwr;
+    if (sub != rk) continue;
     const float w = k < J.vk1 ? W[J.base1 + u * J.sn1 + k * J.sk1] : 0.0f;
     const float hi = to_tf32(w);
-    const int g = u / im.GW, r = u - g * im.GW;
     float* blk = base + im.g1_off + (size_t)g * im.g1_floats;
     blk[core_idx(r, k, K0p)] = hi;
-    blk[im.GW * K0p + core_idx(r, k, K0p)] = w - hi;
+    blk[gwr * K0p + core_idx(r, k, K0p)] = w - hi;
   }
   // M2 [H x H]: (pass p, chunk c) holds rows p*NH.. (n index), columns c*WKC.. (k index)
   for (int i = t0; i < H * H; i += ts) {
     const int nn = i / H, k = i - nn * H;
+    const int p = nn / NH, within = nn - p * NH, sub = within / nhr, r = within - sub * nhr;
+    if (sub != rk) continue;
     const float w = W[J.base2 + nn * J.sn2 + k * J.sk2];
     const float hi = to_tf32(w);
-    const int p = nn / NH, r = nn - p * NH, c = k / WKC, kk = k - c * WKC;
+    const int c = k / WKC, kk = k - c * WKC;
     float* blk = base + im.s2_off + (size_t)(p * nch + c) * im.s2_floats;
     blk[core_idx(r, kk, WKC)] = hi;
-    blk[NH * WKC + core_idx(r, kk, WKC)] = w - hi;
+    blk[nhr * WKC + core_idx(r, kk, WKC)] = w - hi;
   }
   // M3 [N3p x H]: chunk gc holds columns gc*WKC..
   for (int i = t0; i < N3p * H; i += ts) {
     const int nn = i / H, k = i - nn * H;
+    const int sub = nn / n3r, r = nn - sub * n3r;
+    if (sub != rk) continue;
     const float w = nn < J.vn3 ? W[J.base3 + nn * J.sn3 + k * J.sk3] : 0.0f;
     const float hi = to_tf32(w);
     const int c = k / WKC, kk = k - c * WKC;
     float* blk = base + im.s3_off + (size_t)c * im.s3_floats;
-    blk[core_idx(nn, kk, WKC)] = hi;
-    blk[N3p * WKC + core_idx(nn, kk, WKC)] = w - hi;
+    blk[core_idx(r, kk, WKC)] = hi;
+    blk[n3r * WKC + core_idx(r, kk, WKC)] = w - hi;
   }
 }
 
 // ---- the net kernel ------------------------------------------------------------------------------------------
-// this thread's row of a 16-unit activation chunk as hi / lo operands (K-major core layout, Kc = 16)
-__device__ __forceinline__ void store_a2_row(float* a_hi, float* a_lo, int row, const float (&v)[16]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float4 hi, lo;
-    hi.x = to_tf32(v[4 * q + 0]); lo.x = v[4 * q + 0] - hi.x;
-    hi.y = to_tf32(v[4 * q + 1]); lo.y = v[4 * q + 1] - hi.y;
-    hi.z = to_tf32(v[4 * q + 2]); lo.z = v[4 * q + 2] - hi.z;
-    hi.w = to_tf32(v[4 * q + 3]); lo.w = v[4 * q + 3] - hi.w;
-    const int idx = core_idx(row, 4 * q, WKC);
-    *reinterpret_cast<float4*>(a_hi + idx) = hi;
-    *reinterpret_cast<float4*>(a_lo + idx) = lo;
-  }
-}
-
 // Training buffers (h1, h2, delta1, delta2, delta3, conditioner inputs) are laid out for the weight-gradient kernel:
 // [tile][block of 16 samples][row][16 samples], so that one K = 16 stage of a row range is one contiguous run.
 __device__ __forceinline__ size_t tbuf_idx(long long tile, int rows, int r, int s) {
@@ -179,11 +174,15 @@ struct Ring {
   }
 };
 
-template <int MODE>
+// PAIR2 kernels contain cta_group::2 instructions and can only be launched as clusters of two CTAs.
+template <int MODE, bool PAIR2>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
-  const TcNetImg& im = a.im;
+  constexpr bool pair2 = PAIR2;                             // cta_group::2: rank 0 of the pair issues for both CTAs
+  const uint32_t crank = a.cluster ? cluster_ctarank() : 0u;
+  const TcNetImg& im = pair2 ? a.im2[crank] : a.im;         // (logical sizes are the same in all three images)
+  const int hv = pair2 ? 2 : 1;                             // weight-block rows held by this CTA = logical rows / hv
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K0p = im.K0p, H = im.H, N3p = im.N3p, NH = im.NH, passes = im.passes, nch = im.nch,
             nch_pass = im.nch_pass, GW = im.GW, ng = im.ng;
@@ -192,8 +191,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
 
   float* A1h = smem;
   float* A1l = A1h + 128 * K0p;
-  float* A2 = A1l + 128 * K0p;  // ring slot s: hi at A2 + s * 2*128*WKC, lo 128*WKC further
-  float* biasS = A2 + NA * 2 * 128 * WKC;
+  float* A2 = A1l + 128 * K0p;  // NA slots of one 32-unit chunk: hi at A2 + s * 2*128*WKA, lo 128*WKA further
+  float* biasS = A2 + NA * 2 * 128 * WKA;
   const int nbias = (2 * H + N3p + 3) & ~3;
   float* ring = biasS + nbias;
   const int ring_floats = a.resident ? im.blocks_floats : a.NS * im.slot_floats;
@@ -204,23 +203,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
   if (tid == 0) {
     for (int i = 0; i < NSMAX; ++i) {
       mbar_init(bars + BAR_W_FULL + i, 1);
-      mbar_init(bars + BAR_W_EMPTY + i, a.cluster ? 2 : 1);  // pair: released by both CTAs' MMA warps
+      mbar_init(bars + BAR_W_EMPTY + i, a.cluster == 1 ? 2 : 1);  // multicast pair: released by both CTAs' MMA warps
+      mbar_init(bars + BAR_W_PEER + i, 1);
     }
+    const uint32_t two = pair2 ? 2u : 1u;  // cta_group::2: both CTAs' threads arrive on the leader's barriers
     for (int i = 0; i < 4; ++i) {
       mbar_init(bars + BAR_D1_FULL + i, 1);
-      mbar_init(bars + BAR_D1_EMPTY + i, 256);
-      mbar_init(bars + BAR_A2_FULL + i, 128);
+      mbar_init(bars + BAR_D1_EMPTY + i, 8 * two);  // warps
+      mbar_init(bars + BAR_A2_FULL + i, 4 * two);
       mbar_init(bars + BAR_A2_EMPTY + i, 1);
     }
     mbar_init(bars + BAR_D2_FULL, 1);
-    mbar_init(bars + BAR_D2_EMPTY, 256);
+    mbar_init(bars + BAR_D2_EMPTY, 8 * two);
     mbar_init(bars + BAR_D3_FULL, 1);
-    mbar_init(bars + BAR_D3_EMPTY, 128);
-    mbar_init(bars + BAR_A1_FULL, 128);
+    mbar_init(bars + BAR_D3_EMPTY, 4 * two);
+    mbar_init(bars + BAR_A1_FULL, 4 * two);
     mbar_init(bars + BAR_A1_EMPTY, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 13) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  if (warp == 13) {
+    if constexpr (pair2) tmem_alloc2(tmem_slot, (uint32_t)a.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  }
   for (int i = tid; i < nbias; i += TC_THREADS) biasS[i] = i < 2 * H + N3p ? __ldg(gimg + im.bias_off + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
@@ -230,6 +234,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
   const long long ntiles = (a.B + 127) / 128;
   // every CTA walks the same number of tiles (a pair must issue identical stage sequences); tiles >= ntiles are dummies
   const long long iters = (ntiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t bars_u32g = smem_u32(bars);
+  // arrival on a barrier the MMA issuer waits on: in a cta_group::2 pair that is always the leader's barrier
+  // (one arrival per warp: __syncwarp orders the lanes' earlier shared-memory / TMEM accesses before lane 0's release)
+  auto arrive_issuer = [&](int bar_index) {
+    __syncwarp();
+    if (lane == 0) {
+      if (pair2) mbar_arrive_cluster(bars_u32g + (uint32_t)bar_index * 8u, 0u);
+      else mbar_arrive(bars + bar_index);
+    }
+  };
 
   if (warp < 8) {
     // =========================== chunk-epilogue warps ===========================
@@ -244,11 +258,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
     uint32_t uses = 0;   // hand-offs of this warpgroup = uses of its A2 slot
     Ring rD1{0, 0, (uint32_t)NG};
     uint32_t npass = 0;
-    float* a2h = A2 + wg * 2 * 128 * WKA;
-    float* a2l = a2h + 128 * WKA;
+    const uint32_t na_half = (uint32_t)NA >> 1;  // slots owned by this warpgroup: wg, wg + 2, ...
     // one 32-unit chunk of this thread's row -> A2 slot (hi / lo, K-major core layout with Kc = 32)
     auto handoff = [&](const float (&v)[32]) {
-      mbar_wait(bars + BAR_A2_EMPTY + wg, (uses & 1u) ^ 1u);
+      const uint32_t slot = (uint32_t)wg + 2u * (uses % na_half), par = (uses / na_half) & 1u;
+      float* a2h = A2 + slot * 2 * 128 * WKA;
+      float* a2l = a2h + 128 * WKA;
+      mbar_wait(bars + BAR_A2_EMPTY + slot, par ^ 1u);
       if (!(a.debug & 16)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -263,7 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
         }
       }
       fence_async_smem();
-      mbar_arrive(bars + BAR_A2_FULL + wg);
+      arrive_issuer(BAR_A2_FULL + (int)slot);
       ++uses;
     };
     auto ld32 = [&](uint32_t taddr, float (&v)[32]) {
@@ -292,7 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
           float v[32];
           if (mine) ld32(tbase + lane_off + TM_D1 + rD1.slot * (uint32_t)GW + (uint32_t)(cg * WKA), v);
           tc_fence_before();
-          mbar_arrive(bars + BAR_D1_EMPTY + rD1.slot);
+          arrive_issuer(BAR_D1_EMPTY + (int)rD1.slot);
           if (mine) {
             const int c = g * cpg + cg;  // 32-unit chunk index inside the hidden layer
             if constexpr (MODE == TC_BWD) {
@@ -329,7 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
         int my_last = (((q + (uint32_t)(ncp - 1)) & 1u) == (uint32_t)wg) ? ncp - 1 : ncp - 2;
         if (my_last < 0) {
           tc_fence_before();
-          mbar_arrive(bars + BAR_D2_EMPTY);
+          arrive_issuer(BAR_D2_EMPTY);
         }
         for (int cc = 0; cc < ncp; ++cc, ++q) {
           if ((q & 1u) != (uint32_t)wg) continue;
@@ -338,7 +354,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
           ld32(tbase + lane_off + TM_D2 + cc * WKA, v);
           if (cc == my_last) {
             tc_fence_before();
-            mbar_arrive(bars + BAR_D2_EMPTY);
+            arrive_issuer(BAR_D2_EMPTY);
           }
           if constexpr (MODE == TC_BWD) {
             const uint32_t mword = live ? a.m1buf[((size_t)tile * (H >> 5) + gc) * 128 + row] : 0u;
@@ -448,7 +464,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
           }
         }
         fence_async_smem();
-        mbar_arrive(bars + BAR_A1_FULL);
+        arrive_issuer(BAR_A1_FULL);
     };
     auto final_out = [&](long long it, uint32_t tc) {
       const long long tile = blockIdx.x + it * gridDim.x;
@@ -464,7 +480,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
         tmem_ld16(tbase + lane_off + TM_D3 + o0, v);
         if (o0 + 16 >= N3p) {
           tc_fence_before();
-          mbar_arrive(bars + BAR_D3_EMPTY);
+          arrive_issuer(BAR_D3_EMPTY);
         }
         if constexpr (MODE == TC_BWD) {
           // cotangent of the conditioner input: rows n.. go to the identity coordinates (theta rows are dropped)
@@ -531,13 +547,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
         Ring rW{0, 0, (uint32_t)a.NS};
         const int cpg16 = GW / WKC;  // weight blocks per D1 group
         const uint32_t g1b = (uint32_t)im.g1_floats * 4u, s2b = (uint32_t)im.s2_floats * 4u, s3b = (uint32_t)im.s3_floats * 4u;
-        const uint32_t crank = a.cluster ? cluster_ctarank() : 0u;
         auto put = [&](const float* src, uint32_t bytes) {
           if (a.debug & 64) bytes = (bytes >> 3) & ~31u;  // timing experiment: an eighth of the weight stream
           mbar_wait(bars + BAR_W_EMPTY + rW.slot, rW.par ^ 1);
           mbar_expect_tx(bars + BAR_W_FULL + rW.slot, bytes);
           char* dst = reinterpret_cast<char*>(ring + (size_t)rW.slot * im.slot_floats);
-          if (a.cluster) {
+          if (a.cluster == 1) {
             // each CTA of the pair fetches one half of the block and delivers it to both
             const uint32_t half = bytes >> 1;
             bulk_g2s_multicast(dst + crank * half, reinterpret_cast<const char*>(src) + crank * half, half,
@@ -575,161 +590,206 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
     const uint64_t dRingK0 = desc_at(hiK0, smem_u32(ring));    // ... with a K0p-float row pitch (G1)
     const uint32_t a2_lo = (128u * WKA * 4u) >> 4, a2_step = 2u * a2_lo;
     const int nch32 = H / WKA, ncp = NH / WKA, cpg = GW / WKA;
-    uint32_t q = 0;  // global 32-unit chunk counter (A2 slot q & 1, use q >> 1)
-    const uint32_t g1_lo = ((uint32_t)(GW * K0p) * 4u) >> 4, w2_lo = ((uint32_t)(NH * WKC) * 4u) >> 4,
-                   w3_lo = ((uint32_t)(N3p * WKC) * 4u) >> 4;
+    uint32_t q = 0;  // global 32-unit chunk counter (A2 slot q % NA, use q / NA)
+    const uint32_t na_mask = (uint32_t)NA - 1u, na_log = NA == 4 ? 2u : 1u;
+    const uint32_t g1_lo = ((uint32_t)(GW / hv * K0p) * 4u) >> 4, w2_lo = ((uint32_t)(NH / hv * WKC) * 4u) >> 4,
+                   w3_lo = ((uint32_t)(N3p / hv * WKC) * 4u) >> 4;  // hi -> lo distance inside a block (rows held here)
     const uint32_t slot_step = ((uint32_t)im.slot_floats * 4u) >> 4;
     const uint32_t g1_step = ((uint32_t)im.g1_floats * 4u) >> 4, s2_step = ((uint32_t)im.s2_floats * 4u) >> 4,
                    s3_step = ((uint32_t)im.s3_floats * 4u) >> 4;
     const uint32_t res_s2 = ((uint32_t)(im.s2_off - im.g1_off) * 4u) >> 4, res_s3 = ((uint32_t)(im.s3_off - im.g1_off) * 4u) >> 4;
-    const uint32_t id1 = instr_desc_tf32(GW), id2 = instr_desc_tf32(NH), id3 = instr_desc_tf32(N3p);
+    const uint32_t id1 = pair2 ? instr_desc_tf32_m256(GW) : instr_desc_tf32(GW),
+                   id2 = pair2 ? instr_desc_tf32_m256(NH) : instr_desc_tf32(NH),
+                   id3 = pair2 ? instr_desc_tf32_m256(N3p) : instr_desc_tf32(N3p);
     const int k1steps = K0p >> 3;
     const uint32_t bars_u32 = smem_u32(bars);
     const uint32_t bW_FULL = bars_u32 + BAR_W_FULL * 8, bW_EMPTY = bars_u32 + BAR_W_EMPTY * 8,
                    bD1_FULL = bars_u32 + BAR_D1_FULL * 8, bD1_EMPTY = bars_u32 + BAR_D1_EMPTY * 8,
-                   bA2_FULL = bars_u32 + BAR_A2_FULL * 8, bA2_EMPTY = bars_u32 + BAR_A2_EMPTY * 8;
+                   bA2_FULL = bars_u32 + BAR_A2_FULL * 8, bA2_EMPTY = bars_u32 + BAR_A2_EMPTY * 8,
+                   bW_PEER = bars_u32 + BAR_W_PEER * 8;
     const uint32_t tD1 = tbase + TM_D1, tD2 = tbase + TM_D2, tD3 = tbase + TM_D3;
-    const bool resident = a.resident != 0, pair = a.cluster != 0;
+    const bool resident = a.resident != 0, pair = a.cluster == 1;
+    // issue / commit variants: one CTA, or the cta_group::2 pair (commits are multicast to both CTAs' barriers)
+    auto MMA = [&](uint32_t dt, uint64_t da_, uint64_t db_, uint32_t id_, uint32_t acc_) {
+      if constexpr (pair2) mma_tf32_2(dt, da_, db_, id_, acc_);
+      else mma_tf32(dt, da_, db_, id_, acc_);
+    };
+    auto COMMIT = [&](uint32_t addr) {
+      if constexpr (pair2) mma_commit2_multicast_a(addr, (uint16_t)3);
+      else mma_commit_a(addr);
+    };
+    auto release_stage = [&](uint32_t slot_) {
+      if (resident) return;
+      if (pair) mma_commit_multicast_a(bW_EMPTY + slot_ * 8, (uint16_t)3);
+      else COMMIT(bW_EMPTY + slot_ * 8);
+    };
+    // wait until a ring stage has landed (cta_group::2: in both CTAs)
+    auto wait_stage = [&](uint32_t slot_, uint32_t par_) {
+      mbar_wait_a(bW_FULL + slot_ * 8, par_);
+      if (pair2) mbar_wait_a(bW_PEER + slot_ * 8, par_);
+    };
     const bool skip1 = (a.debug & 2) != 0, skip2 = (a.debug & 8) != 0, skip3 = (a.debug & 4) != 0;
     Ring rW{0, 0, (uint32_t)(resident ? 1 : a.NS)}, rD1{0, 0, (uint32_t)NG};
     uint32_t npass = 0, tcount = 0;
-    if (resident) mbar_wait(bars + BAR_W_FULL, 0);
-    for (long long it = 0; it < iters; ++it, ++tcount) {
-      mbar_wait(bars + BAR_A1_FULL, tcount & 1);
-      tc_fence_after();
-      for (int p = 0; p < passes; ++p) {
-        auto issue_d1 = [&](int g) {
-          uint32_t woff;  // weight block position in descriptor units
-          if (resident) {
-            woff = (uint32_t)g * g1_step;
-          } else {
-            mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
-            woff = rW.slot * slot_step;
+    if (pair2 && crank != 0) {
+      // ---- peer CTA of a cta_group::2 pair: no MMAs here; tell the leader when this CTA's half of a stage has landed ----
+      const int cpg16 = GW / WKC;
+      auto relay = [&]() {
+        mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
+        if (elect_one()) mbar_arrive_cluster(bW_PEER + rW.slot * 8, 0u);
+        __syncwarp();
+        rW.next();
+      };
+      for (long long it = 0; it < iters; ++it) {
+        for (int p = 0; p < passes; ++p) {
+          for (int g = 0; g < NG && g < ng; ++g) relay();
+          for (int c = 0; c < nch; ++c) {
+            relay();
+            if ((c + 1) % cpg16 == 0 && c / cpg16 + NG < ng) relay();
           }
-          mbar_wait_a(bD1_EMPTY + rD1.slot * 8, rD1.par ^ 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t db = dRingK0 + woff;
-            if (!skip1) gemm3_desc(tD1 + rD1.slot * (uint32_t)GW, dA1h, dA1l, db, db + g1_lo, k1steps, id1, 0u);
-            mma_commit_a(bD1_FULL + rD1.slot * 8);
-            if (!resident) {
-              if (pair) mma_commit_multicast_a(bW_EMPTY + rW.slot * 8, (uint16_t)3);
-              else mma_commit_a(bW_EMPTY + rW.slot * 8);
-            }
-            if (g == ng - 1 && p == passes - 1) mma_commit(bars + BAR_A1_EMPTY);
-          }
-          __syncwarp();
-          if (!resident) rW.next();
-          rD1.next();
-        };
-        for (int g = 0; g < NG && g < ng; ++g) issue_d1(g);
-        mbar_wait(bars + BAR_D2_EMPTY, (npass & 1) ^ 1);
+          for (int cc = 0; cc < nch_pass; cc += a.s3ps) relay();
+        }
+      }
+    } else {
+      if (resident) mbar_wait(bars + BAR_W_FULL, 0);
+      for (long long it = 0; it < iters; ++it, ++tcount) {
+        mbar_wait(bars + BAR_A1_FULL, tcount & 1);
         tc_fence_after();
-        // ---- D2 += h1 chunk (32 units) * two 16-unit M2 blocks ----
-        int cg = 0, gnext = NG;
-        for (int c = 0; c < nch32; ++c, ++q) {
-          const uint32_t as = q & 1u;
-          const uint64_t da = dA2_0 + as * a2_step;
-          // each 16-unit weight block is released as soon as its own six MMAs are queued, so the producer can refill
-          // the slot while the second block of the chunk is still being multiplied
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t woff, slot = 0;
+        for (int p = 0; p < passes; ++p) {
+          auto issue_d1 = [&](int g) {
+            uint32_t woff;  // weight block position in descriptor units
             if (resident) {
-              woff = res_s2 + (uint32_t)(p * nch + 2 * c + hf) * s2_step;
+              woff = (uint32_t)g * g1_step;
             } else {
-              mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
-              slot = rW.slot;
-              woff = slot * slot_step;
-              rW.next();
+              wait_stage(rW.slot, rW.par);
+              woff = rW.slot * slot_step;
             }
-            if (hf == 0) mbar_wait_a(bA2_FULL + as * 8, (q >> 1) & 1u);
+            mbar_wait_a(bD1_EMPTY + rD1.slot * 8, rD1.par ^ 1);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t db = dRing16 + woff;
-              if (!skip2) {
-                uint32_t acc = (c > 0 || hf > 0) ? 1u : 0u;
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint32_t ao = (uint32_t)(hf * 2 + ks) * 16u, bo = (uint32_t)ks * 16u;
-                  mma_tf32(tD2, da + a2_lo + ao, db + bo, id2, acc);
-                  mma_tf32(tD2, da + ao, db + w2_lo + bo, id2, 1u);
-                  mma_tf32(tD2, da + ao, db + bo, id2, 1u);
+              const uint64_t db = dRingK0 + woff;
+              if (!skip1) {
+                const uint32_t td = tD1 + rD1.slot * (uint32_t)GW;
+                uint32_t acc = 0u;
+                for (int ks = 0; ks < k1steps; ++ks) {
+                  const uint64_t o = (uint64_t)(ks * 16);
+                  MMA(td, dA1l + o, db + o, id1, acc);
+                  MMA(td, dA1h + o, db + g1_lo + o, id1, 1u);
+                  MMA(td, dA1h + o, db + o, id1, 1u);
                   acc = 1u;
                 }
               }
-              if (!resident) {
-                if (pair) mma_commit_multicast_a(bW_EMPTY + slot * 8, (uint16_t)3);
-                else mma_commit_a(bW_EMPTY + slot * 8);
-              }
-              if (hf == 1) {
-                mma_commit_a(bA2_EMPTY + as * 8);
-                if (c == nch32 - 1) mma_commit(bars + BAR_D2_FULL);
-              }
+              COMMIT(bD1_FULL + rD1.slot * 8);
+              release_stage(rW.slot);
+              if (g == ng - 1 && p == passes - 1) COMMIT(bars_u32 + BAR_A1_EMPTY * 8);
             }
             __syncwarp();
-          }
-          if (++cg == cpg) {
-            cg = 0;
-            if (gnext < ng) issue_d1(gnext);
-            ++gnext;
-          }
-        }
-        // ---- D3 += h2 chunk (32 units) * two 16-unit M3 blocks ----
-        uint32_t woff3 = 0;
-        for (int cc = 0, ci = 0; cc < ncp; ++cc, ++q) {
-          const int gc = p * ncp + cc;  // 32-unit chunk of hidden layer 2
-          uint32_t woff;
-          if (resident) {
-            woff = res_s3 + (uint32_t)(2 * gc) * s3_step;
-          } else {
-            if (ci == 0) {
-              mbar_wait_a(bW_FULL + rW.slot * 8, rW.par);
-              woff3 = rW.slot * slot_step;
-            }
-            woff = woff3 + (uint32_t)ci * s3_step;
-          }
-          const bool last_of_stage = (ci + 2 >= a.s3ps) || (cc + 1 == ncp);
-          const uint32_t as = q & 1u;
-          mbar_wait_a(bA2_FULL + as * 8, (q >> 1) & 1u);
+            if (!resident) rW.next();
+            rD1.next();
+          };
+          for (int g = 0; g < NG && g < ng; ++g) issue_d1(g);
+          mbar_wait(bars + BAR_D2_EMPTY, (npass & 1) ^ 1);
           tc_fence_after();
-          if (gc == 0) {
-            mbar_wait(bars + BAR_D3_EMPTY, (tcount & 1) ^ 1);
-            tc_fence_after();
-          }
-          if (elect_one()) {
+          // ---- D2 += h1 chunk (32 units) * two 16-unit M2 blocks ----
+          int cg = 0, gnext = NG;
+          for (int c = 0; c < nch32; ++c, ++q) {
+            const uint32_t as = q & na_mask, apar = (q >> na_log) & 1u;
             const uint64_t da = dA2_0 + as * a2_step;
-            if (!skip3) {
-              uint32_t acc = gc > 0 ? 1u : 0u;
+            // each 16-unit weight block is released as soon as its own six MMAs are queued, so the producer can refill
+            // the slot while the second block of the chunk is still being multiplied
 #pragma unroll
-              for (int hf = 0; hf < 2; ++hf) {
-                const uint64_t db = dRing16 + woff + (uint32_t)hf * s3_step;
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t woff, slot = 0;
+              if (resident) {
+                woff = res_s2 + (uint32_t)(p * nch + 2 * c + hf) * s2_step;
+              } else {
+                wait_stage(rW.slot, rW.par);
+                slot = rW.slot;
+                woff = slot * slot_step;
+                rW.next();
+              }
+              if (hf == 0) mbar_wait_a(bA2_FULL + as * 8, apar);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t db = dRing16 + woff;
+                if (!skip2) {
+                  uint32_t acc = (c > 0 || hf > 0) ? 1u : 0u;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint32_t ao = (uint32_t)(hf * 2 + ks) * 16u, bo = (uint32_t)ks * 16u;
-                  mma_tf32(tD3, da + a2_lo + ao, db + bo, id3, acc);
-                  mma_tf32(tD3, da + ao, db + w3_lo + bo, id3, 1u);
-                  mma_tf32(tD3, da + ao, db + bo, id3, 1u);
-                  acc = 1u;
+                  for (int ks = 0; ks < 2; ++ks) {
+                    const uint32_t ao = (uint32_t)(hf * 2 + ks) * 16u, bo = (uint32_t)ks * 16u;
+                    MMA(tD2, da + a2_lo + ao, db + bo, id2, acc);
+                    MMA(tD2, da + ao, db + w2_lo + bo, id2, 1u);
+                    MMA(tD2, da + ao, db + bo, id2, 1u);
+                    acc = 1u;
+                  }
+                }
+                release_stage(slot);
+                if (hf == 1) {
+                  COMMIT(bA2_EMPTY + as * 8);
+                  if (c == nch32 - 1) COMMIT(bars_u32 + BAR_D2_FULL * 8);
                 }
               }
+              __syncwarp();
             }
-            mma_commit_a(bA2_EMPTY + as * 8);
-            if (!resident && last_of_stage) {
-              if (pair) mma_commit_multicast_a(bW_EMPTY + rW.slot * 8, (uint16_t)3);
-              else mma_commit_a(bW_EMPTY + rW.slot * 8);
+            if (++cg == cpg) {
+              cg = 0;
+              if (gnext < ng) issue_d1(gnext);
+              ++gnext;
             }
-            if (gc == (H >> 5) - 1) mma_commit(bars + BAR_D3_FULL);
           }
-          __syncwarp();
-          if (last_of_stage) {
-            if (!resident) rW.next();
-            ci = 0;
-          } else {
-            ci += 2;
+          // ---- D3 += h2 chunk (32 units) * two 16-unit M3 blocks ----
+          uint32_t woff3 = 0;
+          for (int cc = 0, ci = 0; cc < ncp; ++cc, ++q) {
+            const int gc = p * ncp + cc;  // 32-unit chunk of hidden layer 2
+            uint32_t woff;
+            if (resident) {
+              woff = res_s3 + (uint32_t)(2 * gc) * s3_step;
+            } else {
+              if (ci == 0) {
+                wait_stage(rW.slot, rW.par);
+                woff3 = rW.slot * slot_step;
+              }
+              woff = woff3 + (uint32_t)ci * s3_step;
+            }
+            const bool last_of_stage = (ci + 2 >= a.s3ps) || (cc + 1 == ncp);
+            const uint32_t as = q & na_mask;
+            mbar_wait_a(bA2_FULL + as * 8, (q >> na_log) & 1u);
+            tc_fence_after();
+            if (gc == 0) {
+              mbar_wait(bars + BAR_D3_EMPTY, (tcount & 1) ^ 1);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              const uint64_t da = dA2_0 + as * a2_step;
+              if (!skip3) {
+                uint32_t acc = gc > 0 ? 1u : 0u;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  const uint64_t db = dRing16 + woff + (uint32_t)hf * s3_step;
+#pragma unroll
+                  for (int ks = 0; ks < 2; ++ks) {
+                    const uint32_t ao = (uint32_t)(hf * 2 + ks) * 16u, bo = (uint32_t)ks * 16u;
+                    MMA(tD3, da + a2_lo + ao, db + bo, id3, acc);
+                    MMA(tD3, da + ao, db + w3_lo + bo, id3, 1u);
+                    MMA(tD3, da + ao, db + bo, id3, 1u);
+                    acc = 1u;
+                  }
+                }
+              }
+              COMMIT(bA2_EMPTY + as * 8);
+              if (last_of_stage) release_stage(rW.slot);
+              if (gc == (H >> 5) - 1) COMMIT(bars_u32 + BAR_D3_FULL * 8);
+            }
+            __syncwarp();
+            if (last_of_stage) {
+              if (!resident) rW.next();
+              ci = 0;
+            } else {
+              ci += 2;
+            }
           }
+          ++npass;
         }
-        ++npass;
       }
     }
   }
@@ -738,7 +798,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
   __syncthreads();
   if (warp == 13) {
     __syncwarp();
-    tmem_dealloc(tbase, (uint32_t)a.tmem_cols);
+    if constexpr (pair2) tmem_dealloc2(tbase, (uint32_t)a.tmem_cols);
+    else tmem_dealloc(tbase, (uint32_t)a.tmem_cols);
   }
   if (a.cluster) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
 }
@@ -1046,7 +1107,8 @@ __global__ void tc_gather_kernel(const float* __restrict__ src, const int32_t* _
     }                                                                                      \
   } while (0)
 
-static void fill_img(TcNetImg& im, int K0, int H, int N3, long long& off, int k0_align = 8) {
+static void fill_img(TcNetImg& im, int K0, int H, int N3, long long& off, int k0_align = 8, int halves = 1,
+                     int rank = 0) {
   im.off = off;
   im.K0 = K0;
   im.K0p = (K0 + k0_align - 1) & ~(k0_align - 1);
@@ -1059,9 +1121,11 @@ static void fill_img(TcNetImg& im, int K0, int H, int N3, long long& off, int k0
   im.nch_pass = im.NH / WKC;
   im.GW = (H % 64 == 0) ? 64 : 32;
   im.ng = H / im.GW;
-  im.g1_floats = 2 * im.GW * im.K0p;
-  im.s2_floats = 2 * im.NH * WKC;
-  im.s3_floats = 2 * im.N3p * WKC;
+  im.halves = halves;
+  im.rank = rank;
+  im.g1_floats = 2 * (im.GW / halves) * im.K0p;  // a CTA of a cta_group::2 pair holds half of every block's rows
+  im.s2_floats = 2 * (im.NH / halves) * WKC;
+  im.s3_floats = 2 * (im.N3p / halves) * WKC;
   im.slot_floats = std::max(im.g1_floats, std::max(im.s2_floats, im.s3_floats));
   int o = 0;
   im.bias_off = o;
@@ -1082,11 +1146,11 @@ struct TcLaunchCfg {
   int resident, NS, NA, NG, tm_d3, tm_d2, tmem_cols, ctas_per_sm;
 };
 
-static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg& cfg) {
+static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg& cfg, bool allow_resident = true) {
   const size_t bar_bytes = (size_t)BAR_COUNT * 8 + 16;
   const size_t cap = (size_t)c->max_smem_optin;
-  auto base_bytes = [&](int na) {
-    return (size_t)(2 * 128 * im.K0p + na * 2 * 128 * WKC + ((2 * im.H + im.N3p + 3) & ~3)) * 4;
+  auto base_bytes = [&](int na) {  // na = A2 slots of one 32-unit chunk (2 or 4)
+    return (size_t)(2 * 128 * im.K0p + na * 2 * 128 * WKA + ((2 * im.H + im.N3p + 3) & ~3)) * 4;
   };
   // TMEM: compact map (256 columns, two CTAs per SM) for narrow nets, full map otherwise
   if (im.NH <= 64) {
@@ -1102,8 +1166,8 @@ static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg&
   }
   const size_t res = (size_t)im.blocks_floats * 4;
   cfg.resident = 0;
-  for (int na = 4; na >= 4 && !cfg.resident; na -= 2) {  // A2 = two 32-unit slots
-    if (im.passes == 1 && res < (1u << 20) && base_bytes(na) + res + bar_bytes <= cap) {
+  for (int na = 2; na >= 2 && !cfg.resident; na -= 2) {
+    if (allow_resident && im.passes == 1 && res < (1u << 20) && base_bytes(na) + res + bar_bytes <= cap) {
       cfg.resident = 1;
       cfg.NA = na;
       cfg.NS = 1;
@@ -1112,12 +1176,13 @@ static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg&
   }
   if (!cfg.resident) {
     bool ok = false;
-    for (int na = 4; na >= 4 && !ok; na -= 2) {
+    // a cta_group::2 pair (half-size weight slots) can afford four A2 slots, which absorb the cross-CTA latencies
+    for (int na = (im.halves == 2 ? 4 : 2); na >= 2 && !ok; na -= 2) {
       const size_t b = base_bytes(na) + bar_bytes;
       const size_t room = cap > b ? cap - b : 0;
       int ns = (int)(room / ((size_t)im.slot_floats * 4));
-      if (ns > 6) ns = 6;
-      if (ns >= 3) {
+      if (ns > 8) ns = 8;
+      if (ns >= (na == 4 ? 4 : 3)) {
         ok = true;
         cfg.NA = na;
         cfg.NS = ns;
@@ -1187,6 +1252,11 @@ int tc_build_plan(dflow_chain* c) {
       J.pb1 = net.p_b[0]; J.pb2 = net.p_b[1]; J.pb3 = net.p_b[2]; J.nb3 = a;
       tp->jobs_fwd.push_back(J);
       tp->k0pmax = std::max(tp->k0pmax, Ld.fwd[ni].K0p);
+      for (int r = 0; r < 2; ++r) {  // half-row images of the two CTAs of a cta_group::2 pair
+        fill_img(Ld.fwd2[ni][r], Ld.nin, h, a, off, 8, 2, r);
+        J.im = Ld.fwd2[ni][r];
+        tp->jobs_fwd.push_back(J);
+      }
       if (h <= 256) {
         // adjoint orientation: M1[u][o] = W3[o][u], M2[i][o] = W2[o][i], M3[k][u] = W1[u][k]
         fill_img(Ld.bwd[ni], a, h, Ld.nin, off, 16);  // K0p = a16: delta3 rows double as the dW3 operand
@@ -1197,6 +1267,11 @@ int tc_build_plan(dflow_chain* c) {
         J.base3 = net.p_w[0]; J.sn3 = h; J.sk3 = 1; J.vn3 = Ld.nin;
         J.pb1 = J.pb2 = J.pb3 = -1;
         tp->jobs_bwd.push_back(J);
+        for (int r = 0; r < 2; ++r) {
+          fill_img(Ld.bwd2[ni][r], a, h, Ld.nin, off, 16, 2, r);
+          J.im = Ld.bwd2[ni][r];
+          tp->jobs_bwd.push_back(J);
+        }
       }
     }
     TcLaunchCfg cfg;
@@ -1271,27 +1346,42 @@ static void fill_common(const dflow_chain* c, const TcLayer& Ld, TcArgs& a) {
 }
 
 template <int MODE>
-static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st) {
+static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st, const TcNetImg* half = nullptr) {
   TcLaunchCfg cfg;
   if (!tc_launch_cfg(c, a.im, cfg)) {
     set_error("conditioner does not fit the tensor-core pipeline's shared memory");
     return DFLOW_E_UNSUPPORTED;
   }
+  long long grid = (a.B + 127) / 128;
+  // streamed weights, CTA pairs: tc_cluster = 2 -> cta_group::2 (one issuer for two SMs, half of the weight rows per
+  // CTA), tc_cluster = 1 -> independent CTAs that share the weight stream by bulk-copy multicast
+  a.cluster = 0;
+  if (!cfg.resident && grid >= 2 && c->tc_cluster == 2 && half) {
+    TcLaunchCfg c2;
+    if (tc_launch_cfg(c, half[0], c2, false)) {
+      cfg = c2;
+      a.cluster = 2;
+      a.im2[0] = half[0];
+      a.im2[1] = half[1];
+    }
+  }
+  if (!a.cluster && !cfg.resident && grid >= 2 && c->tc_cluster == 1) a.cluster = 1;
   a.resident = cfg.resident;
   a.NS = cfg.NS;
   a.NA = cfg.NA;
   a.NG = cfg.NG;
   a.tm_d3 = cfg.tm_d3;
   a.tm_d2 = cfg.tm_d2;
-  a.s3ps = std::max(2, (a.im.slot_floats / a.im.s3_floats) & ~1);  // an even number of 16-unit blocks
+  const TcNetImg& imu = a.cluster == 2 ? a.im2[0] : a.im;
+  a.s3ps = std::max(2, (imu.slot_floats / imu.s3_floats) & ~1);  // an even number of 16-unit blocks
   a.debug = c->tc_debug;
   a.tmem_cols = cfg.tmem_cols;
-  CKT(cudaFuncSetAttribute(tc_net_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-  long long grid = (a.B + 127) / 128;
+  if (a.cluster == 2)
+    CKT(cudaFuncSetAttribute(tc_net_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+  else
+    CKT(cudaFuncSetAttribute(tc_net_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
   const long long cap = (long long)c->sm_count * cfg.ctas_per_sm;
   if (grid > cap) grid = cap;
-  // streamed weights: CTA pairs share the stream (each fetches half of every block and multicasts it)
-  a.cluster = (!cfg.resident && c->tc_cluster && grid >= 2) ? 1 : 0;
   if (a.cluster) {
     grid &= ~1LL;
     cudaLaunchConfig_t lc;
@@ -1307,9 +1397,12 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     lc.attrs = attr;
     lc.numAttrs = 1;
-    CKT(cudaLaunchKernelEx(&lc, tc_net_kernel<MODE>, a));
+    if (a.cluster == 2)
+      CKT(cudaLaunchKernelEx(&lc, tc_net_kernel<MODE, true>, a));
+    else
+      CKT(cudaLaunchKernelEx(&lc, tc_net_kernel<MODE, false>, a));
   } else {
-    tc_net_kernel<MODE><<<(unsigned)grid, TC_THREADS, cfg.smem, st>>>(a);
+    tc_net_kernel<MODE, false><<<(unsigned)grid, TC_THREADS, cfg.smem, st>>>(a);
   }
   CKT(cudaGetLastError());
   c->launches++;
@@ -1369,7 +1462,7 @@ int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* thet
       a.theta_const = theta_const;
       a.ldj = ldj;
       a.sbuf = tp->d_sbuf;
-      rc = launch_net<TC_FWD>(c, a, st);
+      rc = launch_net<TC_FWD>(c, a, st, Ld.fwd2[ni]);
       if (rc) return rc;
     }
   }
@@ -1494,7 +1587,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         a.h2buf = hbuf_of(ei, ni, 1);
         a.m1buf = mbuf_of(ei, ni, 0);
         a.m2buf = mbuf_of(ei, ni, 1);
-        rc = launch_net<TC_FWD_STORE>(c, a, st);
+        rc = launch_net<TC_FWD_STORE>(c, a, st, Ld.fwd2[ni]);
         if (rc) return rc;
       }
     }
@@ -1533,7 +1626,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         a.inv_btot = inv_btot;
         a.grad = grad_out;
         a.p_b3 = Ld.p_b[ni][2];
-        rc = launch_net<TC_BWD>(c, a, st);
+        rc = launch_net<TC_BWD>(c, a, st, Ld.bwd2[ni]);
         if (rc) return rc;
       }
       // weight gradients of this layer

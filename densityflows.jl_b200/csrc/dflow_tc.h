@@ -33,6 +33,7 @@ struct TcNetImg {
   int bias_off;     // [b1 (H) | b2 (H) | b3 (N3p)] (forward orientation; zeros otherwise)
   int g1_off, s2_off, s3_off;
   int blocks_floats;  // size of the contiguous [G1 | S2 | S3] region
+  int halves, rank;   // CTA-pair images: every block holds rows [rank * R/2, (rank+1) * R/2) of its R logical rows
   int total;      // floats
 };
 
@@ -52,6 +53,7 @@ struct TcLayer {
   unsigned char af[DMAX], id[DMAX];
   int p_w[2][3], p_b[2][3];
   TcNetImg fwd[2], bwd[2];
+  TcNetImg fwd2[2][2], bwd2[2][2];  // [net][rank of the CTA pair]: half-row images for cta_group::2
 };
 
 // per-layer training buffers (offsets in floats inside the caller's workspace)

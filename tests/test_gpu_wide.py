@@ -232,6 +232,27 @@ def test_narrow_chain_on_tensor_cores(name):
     pc.tune(tc_mode=0)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_wide_cta_pair_modes_match(mode):
+    """tc_cluster=1 (CTA pairs sharing the weight stream by bulk-copy multicast) and tc_cluster=2 (cta_group::2: one
+    issuer, M = 256 MMAs, half of the weight rows per CTA) give the same numbers as independent CTAs, forward and
+    adjoint."""
+    ochain, chain, x, th = _setup("c4_like_h256", 700)
+    pc = chain.packed()
+    a = pc.logpdf(x, th).clone()
+    g0 = torch.zeros(pc.P, device=DEV)
+    l0 = torch.zeros(2, device=DEV)
+    pc.loss_grad(x, th, g0, l0)
+    pc.tune(tc_cluster=mode)
+    b = pc.logpdf(x, th).clone()
+    g1 = torch.zeros(pc.P, device=DEV)
+    l1 = torch.zeros(2, device=DEV)
+    pc.loss_grad(x, th, g1, l1)
+    pc.tune(tc_cluster=0)
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-5)
+    assert torch.allclose(g0, g1, rtol=1e-4, atol=2e-6 * g0.abs().max().item())
+
+
 def test_wide_generation_1_kernels_still_match():
     """The first-generation (serialised) kernels stay selectable with wide_gen=1 and give the same numbers."""
     ochain, chain, x, th = _setup("h128_d8", 300)
