@@ -287,6 +287,16 @@ def run_ours(args):
             ts3(x3, th3, None, Bg, flags)
 
         ms3 = timed(step_c3, 2, 1, dist)
+        out3 = torch.empty(Bl, device=dev)
+        x3p, t3p = df.arrays.flat_view(x3).data_ptr(), df.arrays.flat_view(th3).data_ptr()
+
+        def step_c3_logpdf():
+            df._lib.check(lib.dflow_logpdf(pc3.handle, pc3.W.data_ptr(), x3p, t3p, Bl, None, flags, out3.data_ptr(), st))
+
+        ms3l = timed(step_c3_logpdf, 3, 2, dist)
+        ops["logpdf_c3"] = {"samples_per_s": world * Bl / (ms3l * 1e-3), "ms_per_step": ms3l, "B_per_gpu": Bl,
+                            "path": "tcgen05 3xTF32 (automatic for hidden 64, B >= 65536)",
+                            "fp32_equiv_tflops_per_gpu": 172032.0 * Bl / (ms3l * 1e-3) / 1e12}
         # default routing: at hidden 64 and a batch this large the adjoint runs on the tensor cores (dflow_tc.cu)
         ops["train_step_c3"] = {"samples_per_s": Bg / (ms3 * 1e-3), "ms_per_step": ms3, "global_batch": Bg,
                                 "scaling": "strong", "allreduce_bytes": 4 * (pc3.P + 2), "collective": coll(ts3),

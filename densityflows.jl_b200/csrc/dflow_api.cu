@@ -610,7 +610,7 @@ static int check_common(dflow_chain* c, const float* W, const float* theta, cons
 
 static int run_fwd(dflow_chain* c, const float* W, FwdArgs& a, void* stream) {
   if (a.B == 0) return DFLOW_OK;
-  if (c->use_tc()) return wide_fwd(c, W, a, stream);
+  if (c->use_tc_fwd(a.B)) return wide_fwd(c, W, a, stream);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_prepack(c, W, st);
   if (rc) return rc;

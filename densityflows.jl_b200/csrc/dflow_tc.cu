@@ -175,8 +175,9 @@ struct Ring {
 };
 
 // PAIR2 kernels contain cta_group::2 instructions and can only be launched as clusters of two CTAs.
-template <int MODE, bool PAIR2>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_constant__ TcArgs a) {
+// NWG = chunk-epilogue warpgroups: 2 (448 threads, one CTA per SM) or 1 (320 threads, two CTAs per SM for narrow nets).
+template <int MODE, bool PAIR2, int NWG>
+__global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
   constexpr bool pair2 = PAIR2;                             // cta_group::2: rank 0 of the pair issues for both CTAs
@@ -184,6 +185,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
   const TcNetImg& im = pair2 ? a.im2[crank] : a.im;         // (logical sizes are the same in all three images)
   const int hv = pair2 ? 2 : 1;                             // weight-block rows held by this CTA = logical rows / hv
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int EW = 4 * NWG;           // chunk-epilogue warps; then 4 loader/output warps, the producer, the MMA issuer
+  constexpr int NTHREADS = (EW + 6) * 32;
   const int K0p = im.K0p, H = im.H, N3p = im.N3p, NH = im.NH, passes = im.passes, nch = im.nch,
             nch_pass = im.nch_pass, GW = im.GW, ng = im.ng;
   const int d = a.d, n = a.n, NG = a.NG, NA = a.NA;
@@ -209,23 +212,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
     const uint32_t two = pair2 ? 2u : 1u;  // cta_group::2: both CTAs' threads arrive on the leader's barriers
     for (int i = 0; i < 4; ++i) {
       mbar_init(bars + BAR_D1_FULL + i, 1);
-      mbar_init(bars + BAR_D1_EMPTY + i, 8 * two);  // warps
+      mbar_init(bars + BAR_D1_EMPTY + i, EW * two);  // warps
       mbar_init(bars + BAR_A2_FULL + i, 4 * two);
       mbar_init(bars + BAR_A2_EMPTY + i, 1);
     }
     mbar_init(bars + BAR_D2_FULL, 1);
-    mbar_init(bars + BAR_D2_EMPTY, 8 * two);
+    mbar_init(bars + BAR_D2_EMPTY, EW * two);
     mbar_init(bars + BAR_D3_FULL, 1);
     mbar_init(bars + BAR_D3_EMPTY, 4 * two);
     mbar_init(bars + BAR_A1_FULL, 4 * two);
     mbar_init(bars + BAR_A1_EMPTY, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 13) {
+  if (warp == EW + 5) {
     if constexpr (pair2) tmem_alloc2(tmem_slot, (uint32_t)a.tmem_cols);
     else tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   }
-  for (int i = tid; i < nbias; i += TC_THREADS) biasS[i] = i < 2 * H + N3p ? __ldg(gimg + im.bias_off + i) : 0.0f;
+  for (int i = tid; i < nbias; i += NTHREADS) biasS[i] = i < 2 * H + N3p ? __ldg(gimg + im.bias_off + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
   if (a.cluster) cluster_sync_all();  // the peer's barriers exist before any multicast copy / commit can reach them
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
     }
   };
 
-  if (warp < 8) {
+  if (warp < EW) {
     // =========================== chunk-epilogue warps ===========================
     // Activation chunks are WKA = 32 hidden units wide (two 16-unit weight blocks per MMA-warp iteration: the issuer's
     // fixed cost per iteration is ~700 clk, so each iteration has to carry >= 12 full-width MMAs).  Two warpgroups
@@ -258,10 +261,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
     uint32_t uses = 0;   // hand-offs of this warpgroup = uses of its A2 slot
     Ring rD1{0, 0, (uint32_t)NG};
     uint32_t npass = 0;
-    const uint32_t na_half = (uint32_t)NA >> 1;  // slots owned by this warpgroup: wg, wg + 2, ...
+    const uint32_t nown = NWG == 2 ? (uint32_t)NA >> 1 : (uint32_t)NA;  // A2 slots owned by this warpgroup
     // one 32-unit chunk of this thread's row -> A2 slot (hi / lo, K-major core layout with Kc = 32)
     auto handoff = [&](const float (&v)[32]) {
-      const uint32_t slot = (uint32_t)wg + 2u * (uses % na_half), par = (uses / na_half) & 1u;
+      const uint32_t slot = NWG == 2 ? (uint32_t)wg + 2u * (uses % nown) : uses % nown, par = (uses / nown) & 1u;
       float* a2h = A2 + slot * 2 * 128 * WKA;
       float* a2l = a2h + 128 * WKA;
       mbar_wait(bars + BAR_A2_EMPTY + slot, par ^ 1u);
@@ -302,14 +305,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
         for (int g = 0; g < ng; ++g) {
           mbar_wait(bars + BAR_D1_FULL + rD1.slot, rD1.par);
           tc_fence_after();
-          // at most one chunk of a group belongs to this warpgroup (cpg <= 2)
-          const int cg = (cpg == 2) ? (int)((q ^ (uint32_t)wg) & 1u) : 0;
-          const bool mine = (cpg == 2) || (((q & 1u) == (uint32_t)wg));
-          float v[32];
-          if (mine) ld32(tbase + lane_off + TM_D1 + rD1.slot * (uint32_t)GW + (uint32_t)(cg * WKA), v);
-          tc_fence_before();
-          arrive_issuer(BAR_D1_EMPTY + (int)rD1.slot);
-          if (mine) {
+          // chunks of this group that belong to this warpgroup: with two warpgroups at most one (cpg <= 2)
+          for (int cg = 0; cg < cpg; ++cg) {
+            const bool mine = NWG == 1 || (((q + (uint32_t)cg) & 1u) == (uint32_t)wg);
+            const bool last_ld = cg == cpg - 1;
+            float v[32];
+            if (mine) ld32(tbase + lane_off + TM_D1 + rD1.slot * (uint32_t)GW + (uint32_t)(cg * WKA), v);
+            if (last_ld) {
+              tc_fence_before();
+              arrive_issuer(BAR_D1_EMPTY + (int)rD1.slot);
+            }
+            if (!mine) continue;
             const int c = g * cpg + cg;  // 32-unit chunk index inside the hidden layer
             if constexpr (MODE == TC_BWD) {
               const uint32_t mword = live ? a.m2buf[((size_t)tile * (H >> 5) + c) * 128 + row] : 0u;
@@ -342,13 +348,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
         mbar_wait(bars + BAR_D2_FULL, npass & 1);
         tc_fence_after();
         // this warpgroup's last chunk of the pass (its D2 reads end there); -1: it has none and releases D2 at once
-        int my_last = (((q + (uint32_t)(ncp - 1)) & 1u) == (uint32_t)wg) ? ncp - 1 : ncp - 2;
+        int my_last = (NWG == 1 || ((q + (uint32_t)(ncp - 1)) & 1u) == (uint32_t)wg) ? ncp - 1 : ncp - 2;
         if (my_last < 0) {
           tc_fence_before();
           arrive_issuer(BAR_D2_EMPTY);
         }
         for (int cc = 0; cc < ncp; ++cc, ++q) {
-          if ((q & 1u) != (uint32_t)wg) continue;
+          if (NWG == 2 && (q & 1u) != (uint32_t)wg) continue;
           const int gc = p * ncp + cc;
           float v[32];
           ld32(tbase + lane_off + TM_D2 + cc * WKA, v);
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
         ++npass;
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < EW + 4) {
     // =========================== loader / output warpgroup ===========================
     // Builds the GEMM-1 operand of tile t+1 (gathers from global memory) while the pipeline works on tile t, then
     // applies tile t's conditioner outputs; thread row = sample = TMEM lane.
@@ -527,7 +533,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
       if (it + 1 < iters) build_a1(it + 1, (uint32_t)(it + 1));
       final_out(it, (uint32_t)it);
     }
-  } else if (warp == 12) {
+  } else if (warp == EW + 4) {
     // =========================== producer ===========================
     // stage sequence per tile and pass (the MMA warp walks the same sequence):
     //   G1(0..NG-1), then per chunk c: S2(p,c) and, when c closes a group, G1(c/cpg + NG); then S3 chunks of the pass
@@ -796,7 +802,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_net_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == EW + 5) {
     __syncwarp();
     if constexpr (pair2) tmem_dealloc2(tbase, (uint32_t)a.tmem_cols);
     else tmem_dealloc(tbase, (uint32_t)a.tmem_cols);
@@ -1144,6 +1150,7 @@ static void fill_img(TcNetImg& im, int K0, int H, int N3, long long& off, int k0
 struct TcLaunchCfg {
   size_t smem;
   int resident, NS, NA, NG, tm_d3, tm_d2, tmem_cols, ctas_per_sm;
+  int nwg;  // chunk-epilogue warpgroups: 2 (448 threads) or 1 (320 threads, two CTAs per SM)
 };
 
 static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg& cfg, bool allow_resident = true) {
@@ -1166,6 +1173,32 @@ static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg&
   }
   const size_t res = (size_t)im.blocks_floats * 4;
   cfg.resident = 0;
+  cfg.nwg = 2;
+  // narrow nets (hidden <= 64): the pipeline is latency bound, so run two small CTAs per SM (one chunk-epilogue
+  // warpgroup each, 256 TMEM columns each) if the shared memory of both fits
+  if (im.NH <= 64 && im.halves <= 1 && allow_resident) {
+    const size_t half_cap = 233472 / 2 - 1024;
+    const size_t b = base_bytes(2) + bar_bytes;
+    if (im.passes == 1 && b + res <= half_cap) {
+      cfg.resident = 1;
+      cfg.NA = 2;
+      cfg.NS = 1;
+      cfg.smem = b + res;
+      cfg.nwg = 1;
+    } else if (b + 3 * (size_t)im.slot_floats * 4 <= half_cap) {
+      int ns = (int)((half_cap - b) / ((size_t)im.slot_floats * 4));
+      if (ns > 6) ns = 6;
+      cfg.NA = 2;
+      cfg.NS = ns;
+      cfg.smem = b + (size_t)ns * im.slot_floats * 4;
+      cfg.nwg = 1;
+    }
+    if (cfg.nwg == 1) {
+      cfg.ctas_per_sm = 2;
+      if (cfg.smem < 76900) cfg.smem = 76900;  // never three CTAs per SM: TMEM serves two (256 columns each)
+      return true;
+    }
+  }
   for (int na = 2; na >= 2 && !cfg.resident; na -= 2) {
     if (allow_resident && im.passes == 1 && res < (1u << 20) && base_bytes(na) + res + bar_bytes <= cap) {
       cfg.resident = 1;
@@ -1376,10 +1409,11 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st, const TcNetImg
   a.s3ps = std::max(2, (imu.slot_floats / imu.s3_floats) & ~1);  // an even number of 16-unit blocks
   a.debug = c->tc_debug;
   a.tmem_cols = cfg.tmem_cols;
-  if (a.cluster == 2)
-    CKT(cudaFuncSetAttribute(tc_net_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-  else
-    CKT(cudaFuncSetAttribute(tc_net_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+  void (*kern)(TcArgs) = a.cluster == 2 ? tc_net_kernel<MODE, true, 2>
+                         : cfg.nwg == 1 ? tc_net_kernel<MODE, false, 1>
+                                        : tc_net_kernel<MODE, false, 2>;
+  const unsigned nthreads = (unsigned)(4 * cfg.nwg + 6) * 32u;
+  CKT(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
   const long long cap = (long long)c->sm_count * cfg.ctas_per_sm;
   if (grid > cap) grid = cap;
   if (a.cluster) {
@@ -1387,7 +1421,7 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st, const TcNetImg
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
     lc.gridDim = dim3((unsigned)grid);
-    lc.blockDim = dim3(TC_THREADS);
+    lc.blockDim = dim3(nthreads);
     lc.dynamicSmemBytes = cfg.smem;
     lc.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1397,12 +1431,9 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st, const TcNetImg
     attr[0].val.clusterDim.z = 1;
     lc.attrs = attr;
     lc.numAttrs = 1;
-    if (a.cluster == 2)
-      CKT(cudaLaunchKernelEx(&lc, tc_net_kernel<MODE, true>, a));
-    else
-      CKT(cudaLaunchKernelEx(&lc, tc_net_kernel<MODE, false>, a));
+    CKT(cudaLaunchKernelEx(&lc, kern, a));
   } else {
-    tc_net_kernel<MODE, false><<<(unsigned)grid, TC_THREADS, cfg.smem, st>>>(a);
+    kern<<<(unsigned)grid, nthreads, cfg.smem, st>>>(a);
   }
   CKT(cudaGetLastError());
   c->launches++;
