@@ -153,7 +153,7 @@ struct dflow_chain {
   // against 1.95e8 for the CUDA-core chain kernel once the batch fills the machine
   bool use_tc_fwd(long long B) const {
     if (use_tc()) return true;
-    return wide && tcp && tc_mode == 0 && hidden_max == 64 && B >= 65536;
+    return wide && tcp && tc_mode == 0 && hidden_max == 64 && B >= 524288;  // below: 17 launches cost more than they save
   }
   bool use_tc_grad(long long B) const {
     if (use_tc()) return true;
