@@ -421,11 +421,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
               }
               v[qq] = val;
               if (live) a.d3buf[tbuf_idx(tile, K0p, j, row)] = val;
-              // bias gradient of the last Dense: sum over the tile's samples
-              float r = val;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-              if (lane == 0 && j < a.a && r != 0.0f) atomicAdd(a.grad + a.p_b3 + j, r);
+              // (the bias gradient of the last Dense, sum_samples delta3, is accumulated by tc_dw_kernel while staging)
             }
             float4 hi, lo;
             hi.x = to_tf32(v[0]); lo.x = v[0] - hi.x;
@@ -951,7 +947,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
           hi.w = to_tf32(v[i].w); lo.w = v[i].w - hi.w;
           *reinterpret_cast<float4*>(st + my_dst[i]) = hi;
           *reinterpret_cast<float4*>(st + my_dst[i] + my_lo[i]) = lo;
-          if (my_seg[i] < 2) bacc[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);  // bias gradients: sums of delta2 / delta1
+          // bias gradients: sums over the samples of delta2 / delta1 (this m-tile's rows) and delta3 (m-tile 0 only)
+          if (my_seg[i] < 2 || (my_seg[i] == 5 && mt == 0)) bacc[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
       }
       fence_async_smem();
@@ -970,6 +967,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       r += __shfl_xor_sync(0xffffffffu, r, 16);
       if (my_seg[i] >= 0 && my_seg[i] < 2 && lane < 8 && my_ok[i] && nstages > 0)
         atomicAdd(a.grad + a.p_b[net][my_seg[i] == 0 ? 1 : 0] + mt * 128 + my_row[i], r);
+      if (my_seg[i] == 5 && mt == 0 && lane < 8 && my_row[i] < a.a && nstages > 0)
+        atomicAdd(a.grad + a.p_b[net][2] + my_row[i], r);
     }
     // ---- flush: warps 0-3 own TMEM lanes 32w..32w+31 = hidden unit rows of this m-tile ----
     if (warp < 4 && nstages > 0) {
