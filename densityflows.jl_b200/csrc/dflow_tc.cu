@@ -301,6 +301,13 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
       const bool live = tile < ntiles && !(a.debug & (128 | 512));  // dummy tiles touch no global memory (512: timing
                                                                     // experiment without the training stores)
       for (int p = 0; p < passes; ++p) {
+        // relu masks of the adjoint chain are fetched one chunk ahead (the global-load latency would otherwise sit
+        // in the per-chunk chain); this warpgroup's chunks are first_c, first_c + NWG, ...
+        uint32_t mnext = 0;
+        if constexpr (MODE == TC_BWD) {
+          const int first_c = NWG == 1 ? 0 : (int)((q ^ (uint32_t)wg) & 1u);
+          if (live && first_c < (H >> 5)) mnext = a.m2buf[((size_t)tile * (H >> 5) + first_c) * 128 + row];
+        }
         // ---- epilogue 1: hidden-1 units, one D1 group (GW columns) at a time ----
         for (int g = 0; g < ng; ++g) {
           mbar_wait(bars + BAR_D1_FULL + rD1.slot, rD1.par);
@@ -318,7 +325,8 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             if (!mine) continue;
             const int c = g * cpg + cg;  // 32-unit chunk index inside the hidden layer
             if constexpr (MODE == TC_BWD) {
-              const uint32_t mword = live ? a.m2buf[((size_t)tile * (H >> 5) + c) * 128 + row] : 0u;
+              const uint32_t mword = mnext;
+              if (live && c + NWG < (H >> 5)) mnext = a.m2buf[((size_t)tile * (H >> 5) + c + NWG) * 128 + row];
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
@@ -345,6 +353,10 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
           rD1.next();
         }
         // ---- epilogue 2: hidden-2 chunks of this pass ----
+        if constexpr (MODE == TC_BWD) {
+          const int first_cc = NWG == 1 ? 0 : (int)((q ^ (uint32_t)wg) & 1u);
+          mnext = (live && first_cc < ncp) ? a.m1buf[((size_t)tile * (H >> 5) + p * ncp + first_cc) * 128 + row] : 0u;
+        }
         mbar_wait(bars + BAR_D2_FULL, npass & 1);
         tc_fence_after();
         // this warpgroup's last chunk of the pass (its D2 reads end there); -1: it has none and releases D2 at once
@@ -363,7 +375,8 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             arrive_issuer(BAR_D2_EMPTY);
           }
           if constexpr (MODE == TC_BWD) {
-            const uint32_t mword = live ? a.m1buf[((size_t)tile * (H >> 5) + gc) * 128 + row] : 0u;
+            const uint32_t mword = mnext;
+            if (live && cc + NWG < ncp) mnext = a.m1buf[((size_t)tile * (H >> 5) + gc + NWG) * 128 + row];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
