@@ -1,24 +1,33 @@
-// Tensor-core path, generation 2 (sm_100a): warp-specialised tcgen05 / TMEM pipeline for conditioners with
-// hidden width >= 64, forward (both directions) and adjoint.
+// Tensor-core path, generation 2 (sm_100a): warp-specialised tcgen05 / TMEM pipeline for conditioners with hidden
+// width >= 32 (default for hidden > 64; hidden 64 at large batch), forward in both directions and the adjoint.
 //
-// One launch per (coupling layer, conditioner).  CTA = 6 warps:
-//   warps 0-3  epilogue: thread t <-> sample row t of the 128-sample tile <-> TMEM lane t
-//   warp  4    producer: streams pre-split weight stage blocks global -> shared with cp.async.bulk (TMA engine),
-//              completion on mbarriers; nets that fit stay resident in shared memory for the life of the CTA
-//   warp  5    MMA issuer (one lane): tcgen05.mma kind::tf32, accumulators in TMEM
+// One launch per (coupling layer, conditioner), persistent CTAs over 128-sample tiles.  Warps of a CTA:
+//   chunk-epilogue warpgroup(s)  thread row <-> sample row of the tile <-> TMEM lane; two warpgroups alternate 32-unit
+//                                chunks (448-thread CTA, one per SM), or one warpgroup in the 320-thread variant that
+//                                runs two CTAs per SM for narrow nets (hidden <= 64)
+//   loader / output warpgroup    builds the GEMM-1 operand of tile t+1 (gathers theta / x, or the adjoint seeds delta3)
+//                                while the pipeline works on tile t; applies the coupling transform / cotangents of t
+//   producer warp                streams pre-split weight blocks global -> shared with cp.async.bulk (TMA engine),
+//                                completion on mbarriers; nets that fit stay resident for the life of the CTA
+//   MMA warp                     runs uniformly, one elected lane issues tcgen05.mma kind::tf32 (accumulators in TMEM)
 //
 // Float32 parity on a TF32 tensor core: every operand is split into hi = cvt.rna.tf32(x), lo = x - hi and each
 // product is issued as lo*hi + hi*lo + hi*hi (the dropped lo*lo term is ~2^-22 relative).
 //
-// Pipeline per 128-sample tile and conditioner (chunks of WKC = 16 hidden units):
-//   D1[c&1] (128 x 16)   = A1 (128 x K0) * M1_c^T             TMEM cols [0,16) / [32,48), double buffered
-//   epilogue 1           : tcgen05.ld, bias + relu (or relu mask), split -> A2[q&1] in shared memory
-//   D2 (128 x NH)       += A2 (128 x 16) * M2_c^T             TMEM cols [128, 128+NH)
-//   epilogue 2 (per 16)  : tcgen05.ld, bias + relu (or mask), split -> A2[q&1]
-//   D3 (128 x N3)       += A2 * M3_cc^T                       TMEM cols [64, 64+N3)
-// While the tensor pipe runs D2 of chunk c the epilogue warps already process D1 of chunk c+1.
-// The adjoint's input-gradient chain  delta3 -> (.W3) mask2 -> (.W2) mask1 -> (.W1)  is the same pipeline on
-// the transposed matrices (dflow_tc.h).  Weight gradients are K = samples GEMMs in tc_dw_kernel.
+// Pipeline per tile and conditioner (hidden width H, NH = min(H, 256) output columns per pass):
+//   D1 group (128 x GW)   = A1 (128 x K0) * M1_g^T        GW = 64 hidden units per group, NG-deep ring in TMEM,
+//                                                          issued ahead of the epilogue
+//   epilogue 1 (32 units) : tcgen05.ld, bias + relu (adjoint: relu mask), hi/lo split -> A2 slot in shared memory
+//   D2 (128 x NH)        += A2 (128 x 32) * two 16-unit M2 blocks^T      (12 MMAs per issuer iteration)
+//   epilogue 2 (32 units) : tcgen05.ld, bias + relu (or mask), split -> A2 slot
+//   D3 (128 x N3)        += A2 * two 16-unit M3 blocks^T
+//   output                : D3 + b3 -> s (kept for the t launch) or the coupling transform / log-det
+// All hand-offs are mbarriers (tcgen05.commit on the MMA side, fence.proxy.async + one arrival per warp on the thread
+// side).  The adjoint's input-gradient chain  delta3 -> (.W3) mask2 -> (.W2) mask1 -> (.W1)  is the same pipeline on
+// the transposed matrices (dflow_tc.h); the forward sweep of a train step additionally stores the activations, their
+// relu masks and the conditioner inputs; weight gradients are K = samples GEMMs in tc_dw_kernel.
+// tc_cluster = 1 / 2 launch CTA pairs (weight stream shared by bulk-copy multicast / cta_group::2 with M = 256 MMAs):
+// both parity-green and both slower than independent CTAs on B200 (profiles/r01_tc_summary.md), so off by default.
 //
 // Reference math: src/affine/RNVP.jl:77-96 (normalising), :99-147 (adjoint), :150-205 (gather, sampling);
 // src/affine/NICE.jl:63-170; src/norm/Normalization.jl:64-103; src/Flows.jl:272-281,352-359.
