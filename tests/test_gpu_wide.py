@@ -232,6 +232,51 @@ def test_narrow_chain_on_tensor_cores(name):
     pc.tune(tc_mode=0)
 
 
+@pytest.mark.parametrize("name", ["c4_like_h256", "c5_like_h512", "h128_d8", "h64_forced"])
+def test_wide_many_tiles_per_cta_equal_small_launches(name):
+    """Size-independent property at a batch where every persistent CTA walks several tiles (ring slots and barrier
+    phases wrap many times, last tile partial): per-sample results must not depend on how the batch is cut, so one
+    big call equals the concatenation of small calls bit for bit; the gradient of the big batch equals the sum of the
+    chunks' gradients."""
+    if name == "h64_forced":
+        d, n, L, h = 16, 4, 2, 64
+    else:
+        d, n, L, h = CASES[name]
+    xn = O.synthetic_data(d, n, 1000, seed=99)[0]
+    ochain = O.block_chain(d, n, L, h, xn, s_out_scale=0.3)
+    chain = chain_from_oracle(ochain)
+    pc = chain.packed()
+    if h <= 64:
+        pc.tune(tc_mode=1)
+    B = 148 * 128 * 5 + 77
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = df.jl_empty((d, B), DEV)
+    x.normal_(generator=g)
+    th = df.jl_empty((n, B), DEV)
+    th.uniform_(0, 1, generator=g)
+    big = pc.logpdf(x, th).clone()
+    step = 9000
+    parts = [pc.logpdf(df.to_jl(x[:, i:i + step].clone(), DEV), df.to_jl(th[:, i:i + step].clone(), DEV))
+             for i in range(0, B, step)]
+    small = torch.cat([p_.reshape(-1) for p_ in parts])
+    assert torch.equal(big.reshape(-1), small)
+    xs = pc.sample_rng(B, 5, None, torch.full((n,), 0.4, device=DEV))
+    xs2 = torch.cat([df.to_jl(pc.sample_rng(min(step, B - i), 5, None, torch.full((n,), 0.4, device=DEV), first_sample=i), DEV)
+                     for i in range(0, B, step)], dim=1)
+    assert torch.equal(df.to_jl(xs, DEV), xs2)
+    if h <= 256:
+        gb = torch.zeros(pc.P, device=DEV)
+        lb = torch.zeros(2, device=DEV)
+        pc.loss_grad(x, th, gb, lb)
+        gs = torch.zeros(pc.P, device=DEV)
+        ls = torch.zeros(2, device=DEV)
+        for i in range(0, B, 3 * step):
+            pc.loss_grad(df.to_jl(x[:, i:i + 3 * step].clone(), DEV), df.to_jl(th[:, i:i + 3 * step].clone(), DEV), gs, ls,
+                         1.0 / B)
+        assert torch.allclose(gb, gs, rtol=1e-4, atol=3e-6 * gb.abs().max().item())
+        assert abs(lb[0].item() - ls[0].item()) <= 1e-5 * abs(lb[0].item())
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 def test_wide_cta_pair_modes_match(mode):
     """tc_cluster=1 (CTA pairs sharing the weight stream by bulk-copy multicast) and tc_cluster=2 (cta_group::2: one
