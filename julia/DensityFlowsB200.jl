@@ -279,4 +279,45 @@ function train!(flow::Flow{Float32}, data::CuDataArrays, st::AdamState; epochs::
     return nothing
 end
 
+# ---- data-parallel step over NVLink peer memory (include/dflow.h: dflow_dp_*) -------------------------------------
+# One Julia process per GPU (e.g. MPI.jl).  `exchange(handle::Vector{UInt8})::Vector{UInt8}` must return the ranks'
+# 64-byte IPC handles concatenated in rank order (an MPI.Allgather of 64 bytes).  Every step accumulates the local
+# gradient straight into the communication buffer and ONE kernel per rank reduces the peers' buffers and applies Adam.
+mutable struct PeerStep
+    dp::Ptr{Cvoid}
+    P::Int
+end
+
+function PeerStep(pc, rank::Integer, nranks::Integer, exchange)
+    dp = Ref{Ptr{Cvoid}}(C_NULL); handle = zeros(UInt8, 64)
+    check(ccall((:dflow_dp_create, libdflow), Cint, (Int32, Int32, Int64, Ptr{Ptr{Cvoid}}, Ptr{UInt8}),
+                rank, nranks, max(pc.P, 1), dp, handle))
+    check(ccall((:dflow_dp_connect, libdflow), Cint, (Ptr{Cvoid}, Ptr{UInt8}), dp[], exchange(handle)))
+    return PeerStep(dp[], max(pc.P, 1))
+end
+
+function peer_train_step!(ps::PeerStep, pc, st::AdamState, x, θ, idx, B_global::Integer, flags::Int32, loss2)
+    buf = ccall((:dflow_dp_grad_buffer, libdflow), CuPtr{Float32}, (Ptr{Cvoid},), ps.dp)
+    CUDA.memset(buf, UInt32(0), ps.P + 2)              # [grad | Σlogp | #non-finite] of this step
+    nb = length(idx)
+    need = ccall((:dflow_workspace_bytes, libdflow), Csize_t, (Ptr{Cvoid}, Int64), pc.handle, nb)
+    length(pc.ws) < need && (pc.ws = CuVector{UInt8}(undef, need))
+    check(ccall((:dflow_loss_grad, libdflow), Cint,
+                (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, CuPtr{Int32}, Float32, Int32,
+                 CuPtr{Float32}, CuPtr{Float32}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                pc.handle, pc.W, x, θptr(θ), nb, idx, 1f0 / B_global, flags, buf + 4 * ps.P, buf, pc.ws, length(pc.ws), stream()))
+    st.t += 1
+    check(ccall((:dflow_dp_allreduce_adam, libdflow), Cint,
+                (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Float32, Float32, Float32, Float32, Int64,
+                 CuPtr{Float32}, Ptr{Cvoid}),
+                ps.dp, pc.W, st.m, st.v, st.η, st.β[1], st.β[2], st.ϵ, st.t, loss2, stream()))
+    return nothing
+end
+
+# tuning knobs (dflow_set_tuning): "tc_mode" 1 / 0 / -1 forces an eligible hidden <= 64 chain onto / off the tensor cores,
+# "tc_ws_budget_mb" caps the adjoint workspace, "tc_cluster" 0 / 1 / 2 selects independent CTAs / multicast pairs /
+# cta_group::2 pairs for streamed conditioners.
+tune!(pc, key::AbstractString, value::Integer) =
+    check(ccall((:dflow_set_tuning, libdflow), Cint, (Ptr{Cvoid}, Cstring, Int32), pc.handle, key, value))
+
 end # module
