@@ -456,8 +456,15 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
           }
         } else {
           // conditioner input row [theta_0..theta_{n-1}, x[axis_id...], 0 pad] (src/affine/RNVP.jl:157)
-          if (a.x_out != a.x_in && a.net_id == 1 && valid)
-            for (int k = 0; k < d; ++k) a.x_out[gi * d + k] = a.x_in[gi * d + k];
+          if (a.x_out != a.x_in && a.net_id == 1 && valid) {  // out-of-place (training sweep): carry the whole state row
+            if ((d & 3) == 0) {
+              const float4* src = reinterpret_cast<const float4*>(a.x_in + gi * d);
+              float4* dst = reinterpret_cast<float4*>(a.x_out + gi * d);
+              for (int k = 0; k < (d >> 2); ++k) dst[k] = src[k];
+            } else {
+              for (int k = 0; k < d; ++k) a.x_out[gi * d + k] = a.x_in[gi * d + k];
+            }
+          }
           for (int k0 = 0; k0 < K0p; k0 += 4) {
             float v[4];
 #pragma unroll
