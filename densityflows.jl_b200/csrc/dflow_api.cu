@@ -960,6 +960,8 @@ int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
     c->grad_spt = value;
   else if (!strcmp(key, "ctas_per_sm"))
     c->ctas_per_sm = value;
+  else if (!strcmp(key, "tc_ns_max"))
+    c->tc_ns_max = value;
   else if (!strcmp(key, "tc_ws_budget_mb"))
     c->tc_ws_budget_mb = value;
   else if (!strcmp(key, "tc_cluster"))

@@ -1243,6 +1243,7 @@ static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg&
       const size_t room = cap > b ? cap - b : 0;
       int ns = (int)(room / ((size_t)im.slot_floats * 4));
       if (ns > 8) ns = 8;
+      if (c->tc_ns_max > 0 && ns > c->tc_ns_max) ns = c->tc_ns_max;
       if (ns >= (na == 4 ? 4 : 3)) {
         ok = true;
         cfg.NA = na;

@@ -27,6 +27,7 @@ for name in (sys.argv[1:] or ["c4", "c5"]):
     pc = chain.packed("cuda:0")
     pc.tune(wide_gen=GEN)
     pc.tune(tc_debug=int(os.environ.get("DFLOW_TC_DEBUG", "0")))
+    pc.tune(tc_ns_max=int(os.environ.get("DFLOW_TC_NS_MAX", "0")))
     pc.tune(tc_cluster=int(os.environ.get("DFLOW_TC_CLUSTER", "0")))
     if h <= 64:
         pc.tune(tc_mode=TCMODE)
