@@ -194,10 +194,11 @@ static int wide_scratch(dflow_chain* c, size_t floats, float** out) {
 static int wide_fwd(dflow_chain* c, const float* W, FwdArgs& a, void* stream) {
   if (a.B == 0) return DFLOW_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (c->wide_gen >= 2) return tc_fwd(c, W, a, st);  // generation 2 works on its own tile-blocked state (dflow_tc.cu)
   const DevChainHdr& H = c->hc()->h;
   const long long B = a.B;
   const int d = H.d, n = H.n;
-  int rc = c->wide_gen >= 2 ? tc_prepack(c, W, false, st) : wide_prepack(c, W, st);
+  int rc = wide_prepack(c, W, st);
   if (rc) return rc;
   const bool sampling = a.mode >= MODE_SAMPLE;
   const bool need_copy = (a.mode == MODE_LOGPDF || a.mode == MODE_LOGPDF_SUM);
@@ -236,8 +237,7 @@ static int wide_fwd(dflow_chain* c, const float* W, FwdArgs& a, void* stream) {
       return DFLOW_E_CUDA;
     }
   }
-  rc = c->wide_gen >= 2 ? tc_run_chain(c, xw, theta, a.theta_const, ldj_dst, B, sampling ? 1 : 0, a.flags, st)
-                        : wide_run_chain(c, xw, theta, a.theta_const, ldj_dst, B, sampling ? 1 : 0, a.flags, st);
+  rc = wide_run_chain(c, xw, theta, a.theta_const, ldj_dst, B, sampling ? 1 : 0, a.flags, st);
   if (rc) return rc;
   if (a.mode == MODE_LOGPDF) return wide_logpdf(c, xw, ldj, B, a.aux_out, nullptr, st);
   if (a.mode == MODE_LOGPDF_SUM) return wide_logpdf(c, xw, ldj, B, nullptr, a.aux_out, st);

@@ -40,6 +40,7 @@
 #include <algorithm>
 #include <new>
 
+#include "dflow_chain_kernels.cuh"
 #include "dflow_tc.cuh"
 #include "dflow_tc.h"
 
@@ -170,6 +171,13 @@ __global__ void tc_prepack_kernel(const TcPackJob* jobs, const float* __restrict
 // [tile][block of 16 samples][row][16 samples], so that one K = 16 stage of a row range is one contiguous run.
 __device__ __forceinline__ size_t tbuf_idx(long long tile, int rows, int r, int s) {
   return (((size_t)tile * 8 + (size_t)(s >> 4)) * (size_t)rows + (size_t)r) * 16 + (size_t)(s & 15);
+}
+
+// Working layout of the state (x / z / zbar) and of theta inside the tensor-core path: tile-blocked, dimension-major
+// [tile][k][128 samples], so that the thread that owns a sample reads and writes coalesced 4-byte elements (a warp =
+// one 128-byte line per dimension) instead of one 4d-byte row per thread.  Entry points transpose in / out.
+__device__ __forceinline__ size_t tidx(long long tile, int rows, int k, int r) {
+  return ((size_t)tile * (size_t)rows + (size_t)k) * 128 + (size_t)r;
 }
 
 // ring cursor: slot index + phase parity, advanced without divisions
@@ -425,73 +433,96 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
         // ---- A1: this sample's GEMM-1 input row ----
         if constexpr (MODE == TC_BWD) {
           // delta3 of this conditioner (src/affine/RNVP.jl:118-127): s: -zbar_af * z_af - jbar, t: -zbar_af * exp(-s)
-          for (int k0 = 0; k0 < K0p; k0 += 4) {
-            float v[4];
+          // (loads of a group of 8 are issued back to back before any store: one memory round trip per group)
+          for (int k0 = 0; k0 < K0p; k0 += 8) {
+            float zb[8], zo[8], sv[8], v[8];
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
+            for (int qq = 0; qq < 8; ++qq) {
               const int j = k0 + qq;
-              float val = 0.0f;
+              zb[qq] = zo[qq] = sv[qq] = 0.0f;
               if (valid && j < a.a) {
                 const int k = a.af[j];
-                const float zb = a.zbar[gi * d + k];
-                if (a.net_id == 0) {
-                  val = -zb * a.zout[gi * d + k] + a.inv_btot;
-                } else {
-                  const float sv = a.has_s ? a.sbuf[((size_t)tile * a.a16 + j) * 128 + row] : 0.0f;
-                  val = -zb * expf(-sv);
-                }
+                zb[qq] = a.zbar[tidx(tile, d, k, row)];
+                if (a.net_id == 0)
+                  zo[qq] = a.zout[tidx(tile, d, k, row)];
+                else if (a.has_s)
+                  sv[qq] = a.sbuf[((size_t)tile * a.a16 + j) * 128 + row];
               }
-              v[qq] = val;
-              if (live) a.d3buf[tbuf_idx(tile, K0p, j, row)] = val;
-              // (the bias gradient of the last Dense, sum_samples delta3, is accumulated by tc_dw_kernel while staging)
             }
-            float4 hi, lo;
-            hi.x = to_tf32(v[0]); lo.x = v[0] - hi.x;
-            hi.y = to_tf32(v[1]); lo.y = v[1] - hi.y;
-            hi.z = to_tf32(v[2]); lo.z = v[2] - hi.z;
-            hi.w = to_tf32(v[3]); lo.w = v[3] - hi.w;
-            const int idx = core_idx(row, k0, K0p);
-            *reinterpret_cast<float4*>(A1h + idx) = hi;
-            *reinterpret_cast<float4*>(A1l + idx) = lo;
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+              const int j = k0 + qq;
+              float val = 0.0f;
+              if (valid && j < a.a) val = a.net_id == 0 ? -zb[qq] * zo[qq] + a.inv_btot : -zb[qq] * expf(-sv[qq]);
+              v[qq] = val;
+            }
+            // (the bias gradient of the last Dense, sum_samples delta3, is accumulated by tc_dw_kernel while staging)
+            if (live) {
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) a.d3buf[tbuf_idx(tile, K0p, k0 + qq, row)] = v[qq];
+            }
+#pragma unroll
+            for (int h4 = 0; h4 < 8; h4 += 4) {
+              float4 hi, lo;
+              hi.x = to_tf32(v[h4 + 0]); lo.x = v[h4 + 0] - hi.x;
+              hi.y = to_tf32(v[h4 + 1]); lo.y = v[h4 + 1] - hi.y;
+              hi.z = to_tf32(v[h4 + 2]); lo.z = v[h4 + 2] - hi.z;
+              hi.w = to_tf32(v[h4 + 3]); lo.w = v[h4 + 3] - hi.w;
+              const int idx = core_idx(row, k0 + h4, K0p);
+              *reinterpret_cast<float4*>(A1h + idx) = hi;
+              *reinterpret_cast<float4*>(A1l + idx) = lo;
+            }
           }
         } else {
           // conditioner input row [theta_0..theta_{n-1}, x[axis_id...], 0 pad] (src/affine/RNVP.jl:157)
-          if (a.x_out != a.x_in && a.net_id == 1 && valid) {  // out-of-place (training sweep): carry the whole state row
-            if ((d & 3) == 0) {
-              const float4* src = reinterpret_cast<const float4*>(a.x_in + gi * d);
-              float4* dst = reinterpret_cast<float4*>(a.x_out + gi * d);
-              for (int k = 0; k < (d >> 2); ++k) dst[k] = src[k];
-            } else {
-              for (int k = 0; k < d; ++k) a.x_out[gi * d + k] = a.x_in[gi * d + k];
+          if (a.x_out != a.x_in && a.net_id == 1 && live) {  // out-of-place (training sweep): carry the whole state
+            for (int k0 = 0; k0 < d; k0 += 8) {
+              float v[8];
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) v[qq] = (k0 + qq < d) ? a.x_in[tidx(tile, d, k0 + qq, row)] : 0.0f;
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq)
+                if (k0 + qq < d) a.x_out[tidx(tile, d, k0 + qq, row)] = v[qq];
             }
           }
-          for (int k0 = 0; k0 < K0p; k0 += 4) {
-            float v[4];
+          for (int k0 = 0; k0 < K0p; k0 += 8) {
+            float v[8];
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
+            for (int qq = 0; qq < 8; ++qq) {
               const int k = k0 + qq;
               float val = 0.0f;
               if (valid && k < a.nin) {
-                if (k < n) {
-                  val = a.theta_const ? __ldg(a.theta_const + k) : __ldg(a.theta + gi * n + k);
-                  if (a.flags & DFLOW_THETA_NORMALIZE)
-                    val = (a.theta_rng[k] == 0.0f) ? 0.0f : (val - a.theta_min[k]) / a.theta_rng[k];
-                } else {
-                  val = a.x_in[gi * d + a.id[k - n]];
-                }
+                if (k < n)
+                  val = a.theta_const ? __ldg(a.theta_const + k) : __ldg(a.theta + tidx(tile, n, k, row));
+                else
+                  val = a.x_in[tidx(tile, d, a.id[k - n], row)];
               }
               v[qq] = val;
-              if constexpr (MODE == TC_FWD_STORE)
-                if (a.net_id == 1 && live) a.inbuf[tbuf_idx(tile, K0p, k, row)] = val;
             }
-            float4 hi, lo;
-            hi.x = to_tf32(v[0]); lo.x = v[0] - hi.x;
-            hi.y = to_tf32(v[1]); lo.y = v[1] - hi.y;
-            hi.z = to_tf32(v[2]); lo.z = v[2] - hi.z;
-            hi.w = to_tf32(v[3]); lo.w = v[3] - hi.w;
-            const int idx = core_idx(row, k0, K0p);
-            *reinterpret_cast<float4*>(A1h + idx) = hi;
-            *reinterpret_cast<float4*>(A1l + idx) = lo;
+            if (a.flags & DFLOW_THETA_NORMALIZE) {
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) {
+                const int k = k0 + qq;
+                if (valid && k < n) v[qq] = (a.theta_rng[k] == 0.0f) ? 0.0f : (v[qq] - a.theta_min[k]) / a.theta_rng[k];
+              }
+            }
+            if constexpr (MODE == TC_FWD_STORE) {
+              if (a.net_id == 1 && live) {
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) a.inbuf[tbuf_idx(tile, K0p, k0 + qq, row)] = v[qq];
+              }
+            }
+#pragma unroll
+            for (int h4 = 0; h4 < 8; h4 += 4) {
+              float4 hi, lo;
+              hi.x = to_tf32(v[h4 + 0]); lo.x = v[h4 + 0] - hi.x;
+              hi.y = to_tf32(v[h4 + 1]); lo.y = v[h4 + 1] - hi.y;
+              hi.z = to_tf32(v[h4 + 2]); lo.z = v[h4 + 2] - hi.z;
+              hi.w = to_tf32(v[h4 + 3]); lo.w = v[h4 + 3] - hi.w;
+              const int idx = core_idx(row, k0 + h4, K0p);
+              *reinterpret_cast<float4*>(A1h + idx) = hi;
+              *reinterpret_cast<float4*>(A1l + idx) = lo;
+            }
           }
         }
         fence_async_smem();
@@ -516,10 +547,16 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
         if constexpr (MODE == TC_BWD) {
           // cotangent of the conditioner input: rows n.. go to the identity coordinates (theta rows are dropped)
           if (valid) {
+            float zb[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int k = o0 + j;
-              if (k >= n && k < a.nin) a.zbar[gi * d + a.id[k - n]] += v[j];
+              zb[j] = (k >= n && k < a.nin) ? a.zbar[tidx(tile, d, a.id[k - n], row)] : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int k = o0 + j;
+              if (k >= n && k < a.nin) a.zbar[tidx(tile, d, a.id[k - n], row)] = zb[j] + v[j];
             }
           }
         } else if (a.net_id == 0) {
@@ -528,16 +565,20 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             for (int j = 0; j < 16; ++j) a.sbuf[((size_t)tile * a.a16 + o0 + j) * 128 + row] = v[j] + biasS[2 * H + o0 + j];
         } else if (valid) {
           // coupling transform (src/affine/RNVP.jl:92,184; NICE: s = 0)
+          float sv[16], xv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int jj = o0 + j;
+            sv[j] = (jj < a.a && a.has_s) ? a.sbuf[((size_t)tile * a.a16 + jj) * 128 + row] : 0.0f;
+            xv[j] = (jj < a.a) ? a.x_in[tidx(tile, d, a.af[jj], row)] : 0.0f;
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int jj = o0 + j;
             if (jj < a.a) {
-              const int k = a.af[jj];
               const float tv = v[j] + biasS[2 * H + jj];
-              const float sv = a.has_s ? a.sbuf[((size_t)tile * a.a16 + jj) * 128 + row] : 0.0f;
-              const float xv = a.x_in[gi * d + k];
-              a.x_out[gi * d + k] = a.sampling ? xv * expf(sv) + tv : (xv - tv) * expf(-sv);
-              lsum += sv;
+              a.x_out[tidx(tile, d, a.af[jj], row)] = a.sampling ? xv[j] * expf(sv[j]) + tv : (xv[j] - tv) * expf(-sv[j]);
+              lsum += sv[j];
             }
           }
         }
@@ -545,9 +586,17 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
       if constexpr (MODE == TC_BWD) {
         // cotangent of the transformed coordinates: ubar_af = zbar_af * exp(-s) (src/affine/RNVP.jl:134)
         if (a.net_id == 1 && a.has_s && valid)
-          for (int j = 0; j < a.a; ++j) {
-            const float sv = a.sbuf[((size_t)tile * a.a16 + j) * 128 + row];
-            a.zbar[gi * d + a.af[j]] *= expf(-sv);
+          for (int j0 = 0; j0 < a.a; j0 += 8) {
+            float sv[8], zb[8];
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+              const int j = j0 + qq;
+              sv[qq] = j < a.a ? a.sbuf[((size_t)tile * a.a16 + j) * 128 + row] : 0.0f;
+              zb[qq] = j < a.a ? a.zbar[tidx(tile, d, a.af[j], row)] : 0.0f;
+            }
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq)
+              if (j0 + qq < a.a) a.zbar[tidx(tile, d, a.af[j0 + qq], row)] = zb[qq] * expf(-sv[qq]);
           }
       } else {
         if (a.net_id == 1 && a.ldj && valid) a.ldj[gi] += a.sampling ? lsum : -lsum;
@@ -1072,62 +1121,126 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
 }
 
 // ---- small element-wise kernels ------------------------------------------------------------------------------
+// All element-wise kernels below work on the tile-blocked layout (tidx): element i of a [tiles][rows][128] array.
 __global__ void tc_norm_kernel(const float* x_in, float* x_out, float* ldj, long long B, int d,
                                const float* __restrict__ blk, int sampling) {
   // blk = [x_min(d) | x_max(d) | alpha, beta, ldj_const]   (src/norm/Normalization.jl:64-103)
   const float alpha = blk[2 * d], beta = blk[2 * d + 1], c = blk[2 * d + 2];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * d; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % d);
+  const long long total = ((B + 127) / 128) * 128 * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i & 127), k = (int)((i >> 7) % d);
+    const long long b = (i >> 7) / d * 128 + r;
     const float xmin = blk[k], xmax = blk[d + k], v = x_in[i];
     x_out[i] = sampling ? ((xmax - xmin) * v - alpha * xmax + beta * xmin) / (beta - alpha)
                         : (beta * (v - xmin) + alpha * (xmax - v)) / (xmax - xmin);
-    if (k == 0 && ldj) ldj[i / d] += sampling ? c : -c;
+    if (k == 0 && ldj && b < B) ldj[b] += sampling ? c : -c;
   }
 }
 
 // cotangent through a NormalizationLayer in the normalising direction: dz/dx = (beta - alpha) / (x_max - x_min)
 __global__ void tc_norm_bwd_kernel(float* zbar, long long B, int d, const float* __restrict__ blk) {
   const float alpha = blk[2 * d], beta = blk[2 * d + 1];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * d; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % d);
+  const long long total = ((B + 127) / 128) * 128 * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)((i >> 7) % d);
     zbar[i] *= (beta - alpha) / (blk[d + k] - blk[k]);
   }
 }
 
-// loss terms and adjoint seeds: logp_b = c0 - 0.5 |z_b|^2 + ldj_b (src/Flows.jl:279); zbar = z * inv_btot
-__global__ void tc_seed_kernel(const float* __restrict__ z, const float* __restrict__ ldj, long long B, int d, float c0,
-                               float inv_btot, float* zbar, float* loss2) {
+// log-density terms: logp_b = c0 - 0.5 |z_b|^2 + ldj_b (src/Flows.jl:279).  out: per-sample values; sum2: [sum, #non-finite];
+// zbar (training): adjoint seeds z * inv_btot.
+__global__ void tc_logpdf_kernel(const float* __restrict__ z, const float* __restrict__ ldj, long long B, int d, float c0,
+                                 float inv_btot, float* zbar, float* out, float* sum2) {
   float ls = 0.0f, bad = 0.0f;
   for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    const long long tile = b >> 7;
+    const int r = (int)(b & 127);
     float qd = 0.0f;
     for (int k = 0; k < d; ++k) {
-      const float v = z[b * d + k];
+      const float v = z[tidx(tile, d, k, r)];
       qd = fmaf(v, v, qd);
-      zbar[b * d + k] = v * inv_btot;
+      if (zbar) zbar[tidx(tile, d, k, r)] = v * inv_btot;
     }
     const float lp = c0 - 0.5f * qd + ldj[b];
+    if (out) out[b] = lp;
     if (isfinite(lp))
       ls += lp;
     else
       bad += 1.0f;
   }
+  if (sum2) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ls += __shfl_xor_sync(0xffffffffu, ls, o);
-    bad += __shfl_xor_sync(0xffffffffu, bad, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(loss2, ls);
-    if (bad != 0.0f) atomicAdd(loss2 + 1, bad);
+    for (int o = 16; o > 0; o >>= 1) {
+      ls += __shfl_xor_sync(0xffffffffu, ls, o);
+      bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(sum2, ls);
+      if (bad != 0.0f) atomicAdd(sum2 + 1, bad);
+    }
   }
 }
 
-__global__ void tc_gather_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, long long first,
-                                 long long B, int rows, float* dst) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < B * rows; i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / rows;
-    const long long col = idx ? (long long)idx[first + b] : first + b;
-    dst[i] = src[col * rows + (i - b * rows)];
+// sample-major (rows, B) [optionally through an index] -> tile-blocked; padding samples are zero.  One 128-sample tile
+// per CTA iteration, transposed through shared memory (row stride odd: conflict-free) so that both sides are coalesced.
+__global__ void __launch_bounds__(256) tc_gather_t_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                                          long long first, long long B, int rows, float* dst) {
+  extern __shared__ float tsm[];
+  const int ld = rows | 1;
+  const long long ntiles = (B + 127) / 128;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int i = threadIdx.x; i < 128 * rows; i += 256) {
+      const int r = i / rows, k = i - r * rows;
+      const long long b = tile * 128 + r;
+      float v = 0.0f;
+      if (b < B) {
+        const long long col = idx ? (long long)idx[first + b] : first + b;
+        v = src[col * rows + k];
+      }
+      tsm[r * ld + k] = v;
+    }
+    __syncthreads();
+    float* out = dst + (size_t)tile * rows * 128;
+    for (int i = threadIdx.x; i < 128 * rows; i += 256) out[i] = tsm[(i & 127) * ld + (i >> 7)];
+    __syncthreads();
+  }
+}
+
+// tile-blocked -> sample-major (rows, B)
+__global__ void __launch_bounds__(256) tc_scatter_t_kernel(const float* __restrict__ src, long long B, int rows, float* dst) {
+  extern __shared__ float tsm[];
+  const int ld = rows | 1;
+  const long long ntiles = (B + 127) / 128;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const float* in = src + (size_t)tile * rows * 128;
+    for (int i = threadIdx.x; i < 128 * rows; i += 256) tsm[(i & 127) * ld + (i >> 7)] = in[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * rows; i += 256) {
+      const int r = i / rows, k = i - r * rows;
+      const long long b = tile * 128 + r;
+      if (b < B) dst[b * rows + k] = tsm[r * ld + k];
+    }
+    __syncthreads();
+  }
+}
+
+// base draw z ~ N(0, I) in the tile-blocked layout: Philox4x32-10 + Box-Muller, counter = global sample index
+__global__ void tc_philox_kernel(float* z, long long B, int d, unsigned long long seed, unsigned int offset,
+                                 unsigned long long first) {
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long ctr = first + (unsigned long long)b;
+    const long long tile = b >> 7;
+    const int r = (int)(b & 127);
+    for (int g = 0; g < (d + 3) / 4; ++g) {
+      unsigned int rr[4];
+      philox4x32_10((unsigned int)ctr, (unsigned int)(ctr >> 32), (unsigned int)g, offset, (unsigned int)seed,
+                    (unsigned int)(seed >> 32), rr);
+      float v[4];
+      box_muller(rr[0], rr[1], v[0], v[1]);
+      box_muller(rr[2], rr[3], v[2], v[3]);
+      for (int qq = 0; qq < 4; ++qq)
+        if (4 * g + qq < d) z[tidx(tile, d, 4 * g + qq, r)] = v[qq];
+    }
   }
 }
 
@@ -1371,6 +1484,7 @@ void tc_free_plan(dflow_chain* c) {
   if (tp->d_jobs_fwd) cudaFree(tp->d_jobs_fwd);
   if (tp->d_jobs_bwd) cudaFree(tp->d_jobs_bwd);
   if (tp->d_sbuf) cudaFree(tp->d_sbuf);
+  if (tp->d_work) cudaFree(tp->d_work);
   delete tp;
   c->tcp = nullptr;
 }
@@ -1489,7 +1603,18 @@ static unsigned ew_blocks(long long work) {
   return (unsigned)blocks;
 }
 
-// Runs the whole chain on `x` in place (x already holds the input), accumulating ldj.
+static size_t tsm_bytes(int rows) { return (size_t)128 * (rows | 1) * sizeof(float); }
+static unsigned tile_blocks(long long B) { return (unsigned)std::max<long long>(1, std::min<long long>((B + 127) / 128, 148 * 8)); }
+
+static int gather_t(dflow_chain* c, const float* src, const int32_t* idx, long long first, long long B, int rows, float* dst,
+                    cudaStream_t st) {
+  tc_gather_t_kernel<<<tile_blocks(B), 256, tsm_bytes(rows), st>>>(src, idx, first, B, rows, dst);
+  CKT(cudaGetLastError());
+  c->launches++;
+  return DFLOW_OK;
+}
+
+// Runs the whole chain on the tile-blocked state `x` in place (x already holds the input), accumulating ldj (per sample).
 int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* theta_const, float* ldj, long long B,
                  int sampling, int flags, cudaStream_t st) {
   TcPlan* tp = c->tcp;
@@ -1502,7 +1627,7 @@ int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* thet
     const int ei = sampling ? step : (L - 1 - step);  // src/Chains.jl:155-161 vs :174-180
     const TcLayer& Ld = tp->layers[ei];
     if (!Ld.is_coupling) {
-      tc_norm_kernel<<<ew_blocks(B * Hd.d), 256, 0, st>>>(x, x, ldj, B, Hd.d, c->d_staged + Ld.norm_off, sampling);
+      tc_norm_kernel<<<ew_blocks(Bp * Hd.d), 256, 0, st>>>(x, x, ldj, B, Hd.d, c->d_staged + Ld.norm_off, sampling);
       CKT(cudaGetLastError());
       c->launches++;
       continue;
@@ -1526,6 +1651,66 @@ int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* thet
       if (rc) return rc;
     }
   }
+  return DFLOW_OK;
+}
+
+// Forward-type entry points (normalise / log-density / sample) on the tensor-core kernels: transpose the caller's
+// sample-major arrays into the tile-blocked working layout, run the chain in place, transpose (or reduce) out.
+// Working buffer (grow-only, owned by the plan): [x (d*Bp)] [ldj (Bp)] [theta (n*Bp)].
+int tc_fwd(dflow_chain* c, const float* W, FwdArgs& a, cudaStream_t st) {
+  if (a.B == 0) return DFLOW_OK;
+  TcPlan* tp = c->tcp;
+  const DevChainHdr& Hd = c->hc()->h;
+  const long long B = a.B, Bp = ((B + 127) / 128) * 128;
+  const int d = Hd.d, n = Hd.n;
+  int rc = tc_prepack(c, W, false, st);
+  if (rc) return rc;
+  const bool sampling = a.mode >= MODE_SAMPLE;
+  const bool own_ldj = (a.mode == MODE_LOGPDF || a.mode == MODE_LOGPDF_SUM);
+  const bool want_ldj = !(a.mode == MODE_SAMPLE || a.mode == MODE_SAMPLE_RNG);
+  const bool per_sample_theta = n > 0 && a.theta && !a.theta_const;
+  const size_t need = (size_t)(d + 1 + n) * Bp + 64;
+  if (tp->work_floats < need) {
+    if (tp->d_work) cudaFree(tp->d_work);
+    tp->d_work = nullptr;
+    tp->work_floats = 0;
+    if (cudaMalloc(&tp->d_work, need * sizeof(float)) != cudaSuccess) {
+      set_error("cudaMalloc failed for %zu floats of tensor-core working state", need);
+      return DFLOW_E_NOMEM;
+    }
+    tp->work_floats = need;
+  }
+  float* xw = tp->d_work;
+  float* ldj = xw + (size_t)d * Bp;
+  float* thw = ldj + Bp;
+  if (a.mode == MODE_SAMPLE_RNG) {
+    tc_philox_kernel<<<ew_blocks(B), 256, 0, st>>>(xw, B, d, a.seed, a.rng_offset, a.first_sample);
+    CKT(cudaGetLastError());
+    c->launches++;
+  } else {
+    rc = gather_t(c, a.x_in, a.idx, 0, B, d, xw, st);
+    if (rc) return rc;
+  }
+  if (per_sample_theta) {
+    rc = gather_t(c, a.theta, a.idx, 0, B, n, thw, st);
+    if (rc) return rc;
+  }
+  float* ldj_dst = nullptr;
+  if (want_ldj) {
+    ldj_dst = own_ldj ? ldj : a.aux_out;
+    CKT(cudaMemsetAsync(ldj_dst, 0, sizeof(float) * B, st));
+  }
+  rc = tc_run_chain(c, xw, per_sample_theta ? thw : nullptr, a.theta_const, ldj_dst, B, sampling ? 1 : 0, a.flags, st);
+  if (rc) return rc;
+  if (own_ldj) {
+    tc_logpdf_kernel<<<ew_blocks(B), 256, 0, st>>>(xw, ldj, B, d, Hd.logpdf_c0, 0.0f, nullptr,
+                                                   a.mode == MODE_LOGPDF ? a.aux_out : nullptr,
+                                                   a.mode == MODE_LOGPDF_SUM ? a.aux_out : nullptr);
+  } else {
+    tc_scatter_t_kernel<<<tile_blocks(B), 256, tsm_bytes(d), st>>>(xw, B, d, a.x_out);
+  }
+  CKT(cudaGetLastError());
+  c->launches++;
   return DFLOW_OK;
 }
 
@@ -1604,26 +1789,20 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
     auto dbuf_of = [&](int net, int which) { return wsf + T.dbuf + (size_t)(net * 2 + which) * (size_t)hmax * T.MB; };
     auto d3buf_of = [&](int net) { return wsf + T.d3buf + (size_t)net * a16m * T.MB; };
     // input slot L: gather (or copy) this macro-batch
-    tc_gather_kernel<<<ew_blocks(mb * d), 256, 0, st>>>(x, idx, first, mb, d, slot(L));
-    CKT(cudaGetLastError());
-    c->launches++;
+    rc = gather_t(c, x, idx, first, mb, d, slot(L), st);
+    if (rc) return rc;
     const float* th = nullptr;
     if (n > 0) {
-      if (idx) {
-        tc_gather_kernel<<<ew_blocks(mb * n), 256, 0, st>>>(theta, idx, first, mb, n, thg);
-        CKT(cudaGetLastError());
-        c->launches++;
-        th = thg;
-      } else {
-        th = theta + (size_t)first * n;
-      }
+      rc = gather_t(c, theta, idx, first, mb, n, thg, st);
+      if (rc) return rc;
+      th = thg;
     }
     CKT(cudaMemsetAsync(ldj, 0, sizeof(float) * mb, st));
     // ---- forward (normalising) sweep with stored activations: elements L-1 .. 0 ----
     for (int ei = L - 1; ei >= 0; --ei) {
       const TcLayer& Ld = tp->layers[ei];
       if (!Ld.is_coupling) {
-        tc_norm_kernel<<<ew_blocks(mb * d), 256, 0, st>>>(slot(ei + 1), slot(ei), ldj, mb, d, c->d_staged + Ld.norm_off, 0);
+        tc_norm_kernel<<<ew_blocks(ntiles * 128 * d), 256, 0, st>>>(slot(ei + 1), slot(ei), ldj, mb, d, c->d_staged + Ld.norm_off, 0);
         CKT(cudaGetLastError());
         c->launches++;
         continue;
@@ -1652,7 +1831,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       }
     }
     // ---- loss and seeds ----
-    tc_seed_kernel<<<ew_blocks(mb), 256, 0, st>>>(slot(0), ldj, mb, d, Hd.logpdf_c0, inv_btot, zbar, loss_out);
+    tc_logpdf_kernel<<<ew_blocks(mb), 256, 0, st>>>(slot(0), ldj, mb, d, Hd.logpdf_c0, inv_btot, zbar, nullptr, loss_out);
     CKT(cudaGetLastError());
     c->launches++;
     // ---- reverse sweep in chain order ----
@@ -1662,7 +1841,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
     for (int ei = 0; ei <= last_coupling; ++ei) {
       const TcLayer& Ld = tp->layers[ei];
       if (!Ld.is_coupling) {
-        tc_norm_bwd_kernel<<<ew_blocks(mb * d), 256, 0, st>>>(zbar, mb, d, c->d_staged + Ld.norm_off);
+        tc_norm_bwd_kernel<<<ew_blocks(ntiles * 128 * d), 256, 0, st>>>(zbar, mb, d, c->d_staged + Ld.norm_off);
         CKT(cudaGetLastError());
         c->launches++;
         continue;

@@ -62,7 +62,7 @@ struct TcTrainLayout {
   size_t traj;         // [L+1][d * MB]   states: slot e = output of element e (normalising direction), slot L = input
   size_t ldj;          // [MB]
   size_t zbar;         // [d * MB]
-  size_t theta;        // [n * MB] gathered theta (idx != null)
+  size_t theta;        // [n * MB] theta in the tile-blocked layout
   size_t sbuf;         // [L][a16max * MB]
   size_t inbuf;        // [L][K0pmax * MB]
   size_t hbuf;         // [L][2 nets][2][hmax * MB]   post-relu activations h1, h2
@@ -81,6 +81,8 @@ struct TcPlan {
   size_t img_floats = 0;
   float* d_sbuf = nullptr;  // s values of the current layer (forward-type calls), grow-only
   size_t sbuf_floats = 0;
+  float* d_work = nullptr;  // tile-blocked working state of the forward-type calls [x | ldj | theta], grow-only
+  size_t work_floats = 0;
   int hmax = 0, a16max = 0, k0pmax = 0;
   bool train_ok = false;  // adjoint supported (h <= 256)
 };
@@ -88,6 +90,7 @@ struct TcPlan {
 int tc_build_plan(dflow_chain* c);
 void tc_free_plan(dflow_chain* c);
 int tc_prepack(dflow_chain* c, const float* W, bool with_bwd, cudaStream_t st);
+int tc_fwd(dflow_chain* c, const float* W, FwdArgs& a, cudaStream_t st);
 int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* theta_const, float* ldj, long long B,
                  int sampling, int flags, cudaStream_t st);
 size_t tc_workspace_bytes(const dflow_chain* c, long long B);
