@@ -23,6 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 # (HP, samples per thread, register-resident activations)
 FWD_INST = [(16, 1, 0), (16, 2, 0), (16, 4, 0), (16, 2, 1), (16, 4, 1), (32, 1, 0), (32, 2, 0), (32, 4, 0), (32, 2, 1),
             (64, 1, 0), (64, 2, 0)]
+CFWD_INST = [(16, 4), (32, 2)]  # constant-bank forward kernels (weights as uniform-datapath operands)
 GRAD_INST = [16, 32, 64]
 GRAD2_INST = [(16, 1), (16, 2), (16, 4), (32, 1), (32, 2), (64, 1), (64, 2)]
 
@@ -39,6 +40,9 @@ def _units():
     for hp, s, reg in FWD_INST:
         units.append((f"inst_fwd_{hp}_{s}_{reg}.o", "dflow_inst.cu",
                       ["-DDFLOW_INST_FWD", f"-DDFLOW_HP={hp}", f"-DDFLOW_S={s}", f"-DDFLOW_REG={reg}"]))
+    for hp, s in CFWD_INST:
+        units.append((f"inst_cfwd_{hp}_{s}.o", "dflow_inst.cu",
+                      ["-DDFLOW_INST_CFWD", "-DDFLOW_CBANK", f"-DDFLOW_HP={hp}", f"-DDFLOW_S={s}"]))
     for hp in GRAD_INST:
         units.append((f"inst_grad_{hp}.o", "dflow_inst.cu", ["-DDFLOW_INST_GRAD", f"-DDFLOW_HP={hp}"]))
     for hp, s in GRAD2_INST:

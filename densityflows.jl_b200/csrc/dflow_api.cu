@@ -444,6 +444,18 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
   c->chain_bytes = (int)((img.size() + 15) & ~(size_t)15);
   img.resize(c->chain_bytes, 0);
   c->host_chain = img;
+  {
+    // constant-bank forward kernel (dflow_chain_kernels.cuh): relu conditioners of >= 2 Dense, hidden template 16 / 32,
+    // descriptor + staged image inside the 60 KB bank
+    bool ok = !wide && relu_only && (hp == 16 || hp == 32) && (size_t)c->chain_bytes + (size_t)total * 4 <= 60 * 1024;
+    for (int ei = 0; ei < L && ok; ++ei) {
+      const DevElem& E = C->e[ei];
+      if (E.kind == DFLOW_ELEM_NORM) continue;
+      if (E.kind == DFLOW_ELEM_RNVP && E.s.depth < 2) ok = false;
+      if (E.t.depth < 2) ok = false;
+    }
+    c->cbank_ok = ok ? 1 : 0;
+  }
   if (desc->theta_min && desc->theta_max) dflow_chain_set_theta_range(c, desc->theta_min, desc->theta_max);
 
   cudaError_t e1 = cudaMalloc(&c->d_chain, c->chain_bytes);
@@ -952,6 +964,8 @@ int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
   }
   if (!strcmp(key, "fwd_spt"))
     c->fwd_spt = value;
+  else if (!strcmp(key, "fwd_const"))
+    c->fwd_const = value;
   else if (!strcmp(key, "fwd_threads"))
     c->fwd_threads = value;
   else if (!strcmp(key, "grad_threads"))

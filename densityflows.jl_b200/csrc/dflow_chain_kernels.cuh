@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <type_traits>
+
 #include "dflow_internal.h"
 
 namespace dflow {
@@ -83,7 +85,52 @@ __device__ __forceinline__ void st_samples(float* p, const float (&v)[S]) {
   }
 }
 
-// acc[o][s] += W[k][o] * in_k[s] for one input row k (NG broadcast LDS.128 -> NG*4*S FFMA)
+// Packed FP32 FMA (sm_100 FFMA2): one issue slot performs two IEEE fmas, acc[s..s+1] = v[s..s+1] * w + c[s..s+1], on an
+// even-aligned register pair; the scalar weight is a broadcast operand of the instruction (`R.F32`), so pairing over
+// the thread's adjacent samples costs no packing moves (the mov.b64 below are register-allocation hints that ptxas
+// folds away).  Each lane rounds exactly like fmaf: results are bit-identical to the scalar form.
+__device__ __forceinline__ void fma2_pair(float& r0, float& r1, float x0, float x1, float w, float c0, float c1) {
+  unsigned long long x, ww, c, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(ww), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+}
+// acc[s] = v[s] * w + acc[s] for the S samples of a thread
+template <int S>
+__device__ __forceinline__ void fma_samples(float (&acc)[S], const float (&v)[S], float w) {
+  if constexpr (S % 2 == 0) {
+#pragma unroll
+    for (int s = 0; s < S; s += 2) fma2_pair(acc[s], acc[s + 1], v[s], v[s + 1], w, acc[s], acc[s + 1]);
+  } else {
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[s] = fmaf(w, v[s], acc[s]);
+  }
+}
+// acc[s] = v[s] * w + b (first row of a Dense: the bias enters as the addend)
+template <int S>
+__device__ __forceinline__ void fma_samples_bias(float (&acc)[S], const float (&v)[S], float w, float b) {
+  if constexpr (S % 2 == 0) {
+#pragma unroll
+    for (int s = 0; s < S; s += 2) fma2_pair(acc[s], acc[s + 1], v[s], v[s + 1], w, b, b);
+  } else {
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[s] = fmaf(w, v[s], b);
+  }
+}
+
+// acc[s] = b, written as 1.0 * b + 0 (exact) so that b stays a broadcast operand of the FFMA2: the constant-bank kernels
+// must never need a bias or weight in a vector register, or ptxas switches the whole conditioner from uniform constant
+// loads (LDCU) to per-thread indexed LDC (4x too slow; see profiles/r01_ncu_fwd_summary.md)
+template <int S>
+__device__ __forceinline__ void bias_samples(float (&acc)[S], float b) {
+  static_assert(S % 2 == 0, "packed pairs");
+#pragma unroll
+  for (int s = 0; s < S; s += 2) fma2_pair(acc[s], acc[s + 1], 1.0f, 1.0f, b, 0.0f, 0.0f);
+}
+
+// acc[o][s] += W[k][o] * in_k[s] for one input row k (NG broadcast LDS.128 -> NG*4*S FMAs = NG*2*S FFMA2)
 template <int NG, int S>
 __device__ __forceinline__ void dense_row(const float* src, const float* __restrict__ wrow, int slot0, int NT,
                                           float (&acc)[NG * 4][S]) {
@@ -93,13 +140,10 @@ __device__ __forceinline__ void dense_row(const float* src, const float* __restr
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     const float4 w = wr[g];
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      acc[4 * g + 0][s] = fmaf(w.x, v[s], acc[4 * g + 0][s]);
-      acc[4 * g + 1][s] = fmaf(w.y, v[s], acc[4 * g + 1][s]);
-      acc[4 * g + 2][s] = fmaf(w.z, v[s], acc[4 * g + 2][s]);
-      acc[4 * g + 3][s] = fmaf(w.w, v[s], acc[4 * g + 3][s]);
-    }
+    fma_samples<S>(acc[4 * g + 0], v, w.x);
+    fma_samples<S>(acc[4 * g + 1], v, w.y);
+    fma_samples<S>(acc[4 * g + 2], v, w.z);
+    fma_samples<S>(acc[4 * g + 3], v, w.w);
   }
 }
 
@@ -119,13 +163,10 @@ __device__ __forceinline__ void dense_to_col(const InSel& in, int K, const float
     for (int g = 0; g < NG; ++g) {
       const float4 b = *reinterpret_cast<const float4*>(bst + 4 * g);
       const float4 w = *reinterpret_cast<const float4*>(Wst + 4 * g);
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        acc[4 * g + 0][s] = fmaf(w.x, v[s], b.x);
-        acc[4 * g + 1][s] = fmaf(w.y, v[s], b.y);
-        acc[4 * g + 2][s] = fmaf(w.z, v[s], b.z);
-        acc[4 * g + 3][s] = fmaf(w.w, v[s], b.w);
-      }
+      fma_samples_bias<S>(acc[4 * g + 0], v, w.x, b.x);
+      fma_samples_bias<S>(acc[4 * g + 1], v, w.y, b.y);
+      fma_samples_bias<S>(acc[4 * g + 2], v, w.z, b.z);
+      fma_samples_bias<S>(acc[4 * g + 3], v, w.w, b.w);
     }
   }
   if (in.first) {
@@ -252,13 +293,10 @@ __device__ __forceinline__ void last_dense_regs(const float (&h)[HP][S], const f
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       const float4 w = *reinterpret_cast<const float4*>(Wst + k * ld + 4 * g);
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        acc[4 * g + 0][s] = fmaf(w.x, h[k][s], acc[4 * g + 0][s]);
-        acc[4 * g + 1][s] = fmaf(w.y, h[k][s], acc[4 * g + 1][s]);
-        acc[4 * g + 2][s] = fmaf(w.z, h[k][s], acc[4 * g + 2][s]);
-        acc[4 * g + 3][s] = fmaf(w.w, h[k][s], acc[4 * g + 3][s]);
-      }
+      fma_samples<S>(acc[4 * g + 0], h[k], w.x);
+      fma_samples<S>(acc[4 * g + 1], h[k], w.y);
+      fma_samples<S>(acc[4 * g + 2], h[k], w.z);
+      fma_samples<S>(acc[4 * g + 3], h[k], w.w);
     }
   }
 #pragma unroll
@@ -307,13 +345,10 @@ __device__ __forceinline__ void run_net_reg(const DevNet& net, const float* __re
 #pragma unroll
       for (int g = 0; g < HP / 4; ++g) {
         const float4 w = *reinterpret_cast<const float4*>(Wj + k * HP + 4 * g);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          o[4 * g + 0][s] = fmaf(w.x, h[k][s], o[4 * g + 0][s]);
-          o[4 * g + 1][s] = fmaf(w.y, h[k][s], o[4 * g + 1][s]);
-          o[4 * g + 2][s] = fmaf(w.z, h[k][s], o[4 * g + 2][s]);
-          o[4 * g + 3][s] = fmaf(w.w, h[k][s], o[4 * g + 3][s]);
-        }
+        fma_samples<S>(o[4 * g + 0], h[k], w.x);
+        fma_samples<S>(o[4 * g + 1], h[k], w.y);
+        fma_samples<S>(o[4 * g + 2], h[k], w.z);
+        fma_samples<S>(o[4 * g + 3], h[k], w.w);
       }
     }
     act_regs<HP, S>(o, net.act[j]);
@@ -336,6 +371,114 @@ __device__ __forceinline__ void run_net_reg(const DevNet& net, const float* __re
   }
 }
 
+// ---- constant-bank variant (weights never touch shared memory or vector registers) ----------------------------
+// Chains whose descriptor + staged weight image fit the 64 KB constant bank (every hidden <= 32 README-class chain)
+// run with the weights as *uniform-datapath* operands: the Dense loops are fully unrolled over register-resident
+// activations, every weight is fetched by `LDCU` (uniform constant load, index provably warp-uniform) into a uniform
+// register and enters `FFMA2 R, R.F32x2, UR.F32, R` as a broadcast operand.  Per hidden Dense: zero shared-memory
+// wavefronts (the shared-memory-column kernel spends 12 per input row), zero weight registers.  Measured inner loop
+// (scripts/ubench_ldcu.cu, B200): 109 FMA/clk/SM against 92 with broadcast LDS.128 weights.
+// The bank image is [DevChain | pad to 16 B | staged weights] and is uploaded by the launcher right before the kernel.
+#ifdef DFLOW_CBANK
+constexpr int CBANK_BYTES = 60 * 1024;
+__constant__ uint4 g_cbank[CBANK_BYTES / 16];
+__device__ __forceinline__ float cbw(int off) { return reinterpret_cast<const float*>(g_cbank)[off]; }
+// four consecutive weights (off is a multiple of 4 floats: staged blocks, rows and biases are 16-byte aligned) with one
+// wide uniform load instead of four LDCU.32 (the 32-bit form made LDCU 24 % of all issued instructions)
+__device__ __forceinline__ float4 cbw4(int off) { return reinterpret_cast<const float4*>(g_cbank)[off >> 2]; }
+template <int S>
+__device__ __forceinline__ void bias4_samples(float (&a0)[S], float (&a1)[S], float (&a2)[S], float (&a3)[S], int off) {
+  const float4 b = cbw4(off);
+  bias_samples<S>(a0, b.x);
+  bias_samples<S>(a1, b.y);
+  bias_samples<S>(a2, b.z);
+  bias_samples<S>(a3, b.w);
+}
+template <int S>
+__device__ __forceinline__ void fma4_samples(float (&a0)[S], float (&a1)[S], float (&a2)[S], float (&a3)[S],
+                                             const float (&v)[S], int off) {
+  const float4 w = cbw4(off);
+  fma_samples<S>(a0, v, w.x);
+  fma_samples<S>(a1, v, w.y);
+  fma_samples<S>(a2, v, w.z);
+  fma_samples<S>(a3, v, w.w);
+}
+
+template <int HP, int S>
+__device__ __forceinline__ void run_net_const(const DevNet& net, int wofs, const InSel& in, float* outcol, int CS,
+                                              int slot0) {
+  const int D = net.depth;  // >= 2 (host-side eligibility)
+  float h[HP][S];
+  // first Dense: inputs are the gathered theta / x columns (runtime depth), outputs in registers; the bias is the
+  // addend of the first row
+  {
+    const int w0 = wofs + net.s_w[0], b0 = wofs + net.s_b[0];
+    const int n = in.n, K = net.w[0];
+#pragma unroll
+    for (int o = 0; o < HP; o += 4) bias4_samples<S>(h[o], h[o + 1], h[o + 2], h[o + 3], b0 + o);
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      const float* src = k < n ? in.th + k * CS : in.xs + (int)in.id[k - n] * CS;
+      float v[S];
+      ld_samples<S>(src + slot0 * S, v);
+#pragma unroll
+      for (int o = 0; o < HP; o += 4) fma4_samples<S>(h[o], h[o + 1], h[o + 2], h[o + 3], v, w0 + k * HP + o);
+    }
+  }
+  act_regs<HP, S>(h, net.act[0]);
+  // hidden Dense layers: registers -> registers (weight rows are zero-padded to HP)
+#pragma unroll 1
+  for (int j = 1; j < D - 1; ++j) {
+    float o[HP][S];
+    const int wj = wofs + net.s_w[j], bj = wofs + net.s_b[j];
+#pragma unroll
+    for (int oo = 0; oo < HP; oo += 4) bias4_samples<S>(o[oo], o[oo + 1], o[oo + 2], o[oo + 3], bj + oo);
+#pragma unroll
+    for (int k = 0; k < HP; ++k)
+#pragma unroll
+      for (int oo = 0; oo < HP; oo += 4) fma4_samples<S>(o[oo], o[oo + 1], o[oo + 2], o[oo + 3], h[k], wj + k * HP + oo);
+    act_regs<HP, S>(o, net.act[j]);
+#pragma unroll
+    for (int k = 0; k < HP; ++k)
+#pragma unroll
+      for (int s = 0; s < S; ++s) h[k][s] = o[k][s];
+  }
+  // last Dense (padded width op in {4, 8, 16, 32, 64}) in groups of 4 outputs straight from the registers; the row
+  // stride is a compile-time constant for the common widths so that every weight address is base + immediate
+  {
+    const int jl = D - 1, op = net.op[jl], act = net.act[jl];
+    const int wl = wofs + net.s_w[jl], bl = wofs + net.s_b[jl];
+    auto group = [&](int o0, auto ldc) {
+      constexpr int LD = decltype(ldc)::value;  // 0: runtime stride
+      float acc[4][S];
+      bias4_samples<S>(acc[0], acc[1], acc[2], acc[3], bl + o0);
+#pragma unroll
+      for (int k = 0; k < HP; ++k) fma4_samples<S>(acc[0], acc[1], acc[2], acc[3], h[k], wl + k * (LD ? LD : op) + o0);
+#pragma unroll
+      for (int oo = 0; oo < 4; ++oo) st_samples<S>(outcol + (o0 + oo) * CS + slot0 * S, acc[oo]);
+    };
+    if (op == 4) {
+      group(0, std::integral_constant<int, 4>{});
+    } else if (op == 8) {
+      group(0, std::integral_constant<int, 8>{});
+      group(4, std::integral_constant<int, 8>{});
+    } else {
+#pragma unroll 1
+      for (int o0 = 0; o0 < op; o0 += 4) group(o0, std::integral_constant<int, 0>{});
+    }
+    if (act != DFLOW_ACT_IDENTITY) {
+#pragma unroll 1
+      for (int o = 0; o < op; ++o)
+#pragma unroll 1
+        for (int s = 0; s < S; ++s) {
+          float* p = outcol + o * CS + slot0 * S + s;
+          *p = act_apply(act, *p);
+        }
+    }
+  }
+}
+#endif  // DFLOW_CBANK
+
 // cooperative float4 copy global -> shared (len4 = number of float4)
 __device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ src, int len4, int tid, int nt) {
   float4* d4 = reinterpret_cast<float4*>(dst);
@@ -345,16 +488,21 @@ __device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ sr
 
 // Apply one element in the normalising (`backward`, x -> z) or sampling direction to the S samples of this
 // thread.  ldj is accumulated with the reference's signs.
-template <int HP, int S, bool REG = false>
+template <int HP, int S, bool REG = false, bool CB = false>
 __device__ __forceinline__ void elem_apply(const DevChainHdr& H, const DevElem& E, const float* __restrict__ wblk,
                                            bool sampling, float* xs, float* th, float* hc, int hstride, float* sb,
-                                           float* tb, int CS, int slot0, int NT, float (&ldj)[S]) {
+                                           float* tb, int CS, int slot0, int NT, float (&ldj)[S], int wofs = 0) {
+#ifdef DFLOW_CBANK
+#define wat(i) (CB ? cbw(wofs + (i)) : wblk[(i)])
+#else
+#define wat(i) (wblk[(i)])
+#endif
   if (E.kind == DFLOW_ELEM_NORM) {
     // src/norm/Normalization.jl:64-103
     const int d = H.d;
-    const float alpha = wblk[2 * d], beta = wblk[2 * d + 1], c = wblk[2 * d + 2];
+    const float alpha = wat(2 * d), beta = wat(2 * d + 1), c = wat(2 * d + 2);
     for (int k = 0; k < d; ++k) {
-      const float xmin = wblk[k], xmax = wblk[d + k];
+      const float xmin = wat(k), xmax = wat(d + k);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         float* p = xs + k * CS + slot0 * S + s;
@@ -369,9 +517,16 @@ __device__ __forceinline__ void elem_apply(const DevChainHdr& H, const DevElem& 
     for (int s = 0; s < S; ++s) ldj[s] += sampling ? c : -c;
     return;
   }
+#undef wat
   InSel in{th, xs, hc, E.id, H.n, CS, true};
   const bool rnvp = (E.kind == DFLOW_ELEM_RNVP);
   for (int ni = rnvp ? 0 : 1; ni < 2; ++ni) {
+#ifdef DFLOW_CBANK
+    if constexpr (CB) {
+      run_net_const<HP, S>(ni == 0 ? E.s : E.t, wofs, in, ni == 0 ? sb : tb, CS, slot0);
+      continue;
+    }
+#endif
     if constexpr (REG)
       run_net_reg<HP, S>(ni == 0 ? E.s : E.t, wblk, in, ni == 0 ? sb : tb, CS, slot0, NT);
     else
@@ -450,10 +605,11 @@ struct SmemPlan {
   __host__ __device__ size_t bytes() const { return 4ull * ((size_t)chain_f + w_f + cols_f + grad_f); }
 };
 
-__host__ __device__ inline SmemPlan plan_fwd(const DevChainHdr& h, int chain_bytes, int nts, bool reg = false) {
+__host__ __device__ inline SmemPlan plan_fwd(const DevChainHdr& h, int chain_bytes, int nts, bool reg = false,
+                                             bool cb = false) {
   SmemPlan p;
-  p.chain_f = ((chain_bytes + 15) / 16) * 4;
-  p.w_f = h.resident ? h.stage_total : h.stage_max;
+  p.chain_f = cb ? 0 : ((chain_bytes + 15) / 16) * 4;  // constant-bank variant: descriptor and weights stay out of shared
+  p.w_f = cb ? 0 : (h.resident ? h.stage_total : h.stage_max);
   p.cs = nts;
   const int rows = h.d + h.n + (reg ? 0 : h.hp) + 2 * h.amax4;  // REG keeps hidden activations in registers
   p.cols_f = rows * p.cs;
@@ -487,48 +643,11 @@ constexpr int fwd_min_ctas() {
   return (REG || HP * S > 64) ? 2 : (HP * S == 64 ? 3 : 2);  // 255 / 168 / 128 registers
 }
 
-// FIXED: blockDim.x equals fwd_max_threads, so the column stride CS = NT*S is a compile-time constant and every
-// column address `unit*CS + slot` of an unrolled loop folds into an immediate offset (the runtime-stride build spent
-// ~15 % of its instructions on LEA/IMAD/IADD3 address arithmetic; profiles/r01_ncu_fwd_summary.md).
-template <int HP, int S, bool REG, bool FIXED>
-__device__ __forceinline__ void chain_fwd_body(const FwdArgs& a) {
-  extern __shared__ float4 smem4[];
-  float* smem = reinterpret_cast<float*>(smem4);
-  const int tid = threadIdx.x, NT = FIXED ? fwd_max_threads<HP, S, REG>() : (int)blockDim.x, NTS = NT * S;
-
-  // DevChain -> shared
-  copy_f4(smem, reinterpret_cast<const float*>(a.chain), (a.chain_bytes + 15) / 16, tid, NT);
-  __syncthreads();
-  const DevChain* C = reinterpret_cast<const DevChain*>(smem);
-  const DevChainHdr& H = C->h;
-  const SmemPlan P = plan_fwd(H, a.chain_bytes, NTS, REG);
-  float* wsm = smem + P.chain_f;
-  float* cols = wsm + P.w_f;
-  const int CS = FIXED ? NTS : P.cs;
-  float* xs = cols;
-  float* th = xs + H.d * CS;
-  float* hc = th + H.n * CS;
-  float* sb = hc + (REG ? 0 : H.hp) * CS;
-  float* tb = sb + H.amax4 * CS;
-
-  if (H.resident) {
-    copy_f4(wsm, a.staged, H.stage_total / 4, tid, NT);
-    __syncthreads();
-  }
-
-  const int d = H.d, n = H.n, L = H.L;
-  const bool sampling = (a.mode >= MODE_SAMPLE);
-  // 128-bit global access needs 16-byte aligned array bases (cudaMalloc / CuArray / torch give >= 256)
-  const bool io_aligned = ((reinterpret_cast<uintptr_t>(a.x_in) | reinterpret_cast<uintptr_t>(a.theta) |
-                            reinterpret_cast<uintptr_t>(a.x_out) | reinterpret_cast<uintptr_t>(a.aux_out)) & 15) == 0;
-  const long long ntiles = (a.B + NTS - 1) / NTS;
-  float lsum_thread = 0.0f, nonfinite = 0.0f;
-
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long base = tile * NTS;
-    // ---- load ----
-    // fast path (S == 4, full tile, no gather): the thread's 4 consecutive samples are 4*d contiguous floats =
-    // d aligned float4 -> coalesced 128-bit global loads, transposed into the columns on the fly
+// Tile input: global -> shared-memory columns (x, theta), or the in-kernel base draw.
+template <int HP, int S>
+__device__ __forceinline__ void fwd_load_tile(const FwdArgs& a, const DevChainHdr& H, float* xs, float* th, int CS, int tid,
+                                              long long base, int NTS, bool io_aligned) {
+  const int d = H.d, n = H.n;
     const bool vec_io = (S == 4) && a.idx == nullptr && (base + NTS <= a.B) && io_aligned;
     if (vec_io && a.mode != MODE_SAMPLE_RNG) {
       const float4* xp4 = reinterpret_cast<const float4*>(a.x_in + (base + (long long)tid * S) * d);
@@ -601,26 +720,15 @@ __device__ __forceinline__ void chain_fwd_body(const FwdArgs& a) {
         th[k * CS + sl] = v;
       }
     }
-    float ldj[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) ldj[s] = 0.0f;
+}
 
-    // ---- chain ----
-    for (int step = 0; step < L; ++step) {
-      const int ei = sampling ? step : (L - 1 - step);  // src/Chains.jl:155-161 vs :174-180
-      const DevElem& E = C->e[ei];
-      const float* wblk;
-      if (H.resident) {
-        wblk = wsm + E.stage_off;
-      } else {
-        __syncthreads();
-        copy_f4(wsm, a.staged + E.stage_off, E.stage_len / 4, tid, NT);
-        __syncthreads();
-        wblk = wsm;
-      }
-      elem_apply<HP, S, REG>(H, E, wblk, sampling, xs, th, hc, 0, sb, tb, CS, tid, NT, ldj);
-    }
-
+// Tile output: columns -> global (z / x, ldj or logp); returns this thread's (sum logp, #non-finite) contribution.
+template <int HP, int S>
+__device__ __forceinline__ float2 fwd_store_tile(const FwdArgs& a, const DevChainHdr& H, const float* xs, int CS, int tid,
+                                                 long long base, int NTS, bool io_aligned, float4 ldj4) {
+  const int d = H.d;
+  const float ldj[4] = {ldj4.x, ldj4.y, ldj4.z, ldj4.w};
+  float lsum_thread = 0.0f, nonfinite = 0.0f;
     // ---- store ----
     const bool vec_out = (S == 4) && (base + NTS <= a.B) && io_aligned;
     float aux[S];  // per-sample scalar result: logp or ldj
@@ -671,6 +779,111 @@ __device__ __forceinline__ void chain_fwd_body(const FwdArgs& a) {
       if (a.mode != MODE_LOGPDF_SUM && a.mode != MODE_SAMPLE && a.mode != MODE_SAMPLE_RNG)
         *reinterpret_cast<float4*>(a.aux_out + base + (long long)tid * S) = make_float4(aux[0], aux[1 % S], aux[2 % S], aux[3 % S]);
     }
+  return make_float2(lsum_thread, nonfinite);
+}
+
+// Real calls for the constant-bank kernel: with the tile I/O inlined next to the chain, ptxas demotes the chain's
+// weight loads from the uniform datapath (LDCU -> FFMA2 UR operand) to per-thread LDC, which is 4x too slow.
+template <int HP, int S>
+__device__ __noinline__ void fwd_load_tile_call(const FwdArgs& a, const DevChainHdr& H, float* xs, float* th, int CS, int tid,
+                                                long long base, int NTS, bool io_aligned) {
+  fwd_load_tile<HP, S>(a, H, xs, th, CS, tid, base, NTS, io_aligned);
+}
+template <int HP, int S>
+__device__ __noinline__ float2 fwd_store_tile_call(const FwdArgs& a, const DevChainHdr& H, const float* xs, int CS, int tid,
+                                                   long long base, int NTS, bool io_aligned, float4 ldj4) {
+  return fwd_store_tile<HP, S>(a, H, xs, CS, tid, base, NTS, io_aligned, ldj4);
+}
+
+// FIXED: blockDim.x equals fwd_max_threads, so the column stride CS = NT*S is a compile-time constant and every
+// column address `unit*CS + slot` of an unrolled loop folds into an immediate offset (the runtime-stride build spent
+// ~15 % of its instructions on LEA/IMAD/IADD3 address arithmetic; profiles/r01_ncu_fwd_summary.md).
+template <int HP, int S, bool REG, bool FIXED, bool CB = false>
+__device__ __forceinline__ void chain_fwd_body(const FwdArgs& a) {
+  extern __shared__ float4 smem4[];
+  float* smem = reinterpret_cast<float*>(smem4);
+  const int tid = threadIdx.x, NT = FIXED ? fwd_max_threads<HP, S, REG>() : (int)blockDim.x, NTS = NT * S;
+
+  const DevChain* C;
+#ifdef DFLOW_CBANK
+  if constexpr (CB) {
+    C = reinterpret_cast<const DevChain*>(g_cbank);  // descriptor and weights live in the constant bank
+  } else
+#endif
+  {
+    // DevChain -> shared
+    copy_f4(smem, reinterpret_cast<const float*>(a.chain), (a.chain_bytes + 15) / 16, tid, NT);
+    __syncthreads();
+    C = reinterpret_cast<const DevChain*>(smem);
+  }
+  const DevChainHdr& H = C->h;
+  const SmemPlan P = plan_fwd(H, a.chain_bytes, NTS, REG, CB);
+  float* wsm = smem + P.chain_f;
+  float* cols = wsm + P.w_f;
+  const int CS = FIXED ? NTS : P.cs;
+  float* xs = cols;
+  float* th = xs + H.d * CS;
+  float* hc = th + H.n * CS;
+  float* sb = hc + (REG ? 0 : H.hp) * CS;
+  float* tb = sb + H.amax4 * CS;
+
+  if (!CB && H.resident) {
+    copy_f4(wsm, a.staged, H.stage_total / 4, tid, NT);
+    __syncthreads();
+  }
+
+  const int d = H.d, n = H.n, L = H.L;
+  const bool sampling = (a.mode >= MODE_SAMPLE);
+  // 128-bit global access needs 16-byte aligned array bases (cudaMalloc / CuArray / torch give >= 256)
+  const bool io_aligned = ((reinterpret_cast<uintptr_t>(a.x_in) | reinterpret_cast<uintptr_t>(a.theta) |
+                            reinterpret_cast<uintptr_t>(a.x_out) | reinterpret_cast<uintptr_t>(a.aux_out)) & 15) == 0;
+  const long long ntiles = (a.B + NTS - 1) / NTS;
+  float lsum_thread = 0.0f, nonfinite = 0.0f;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long base = tile * NTS;
+    // ---- load ----
+    // fast path (S == 4, full tile, no gather): the thread's 4 consecutive samples are 4*d contiguous floats =
+    // d aligned float4 -> coalesced 128-bit global loads, transposed into the columns on the fly
+    if constexpr (CB)
+      fwd_load_tile_call<HP, S>(a, H, xs, th, CS, tid, base, NTS, io_aligned);
+    else
+      fwd_load_tile<HP, S>(a, H, xs, th, CS, tid, base, NTS, io_aligned);
+    float ldj[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) ldj[s] = 0.0f;
+
+    // ---- chain ----
+    for (int step = 0; step < L; ++step) {
+      const int ei = sampling ? step : (L - 1 - step);  // src/Chains.jl:155-161 vs :174-180
+      const DevElem& E = C->e[ei];
+      if constexpr (CB) {
+        elem_apply<HP, S, REG, true>(H, E, nullptr, sampling, xs, th, hc, 0, sb, tb, CS, tid, NT, ldj,
+                                     a.cb_wofs + E.stage_off);
+        continue;
+      }
+      const float* wblk;
+      if (H.resident) {
+        wblk = wsm + E.stage_off;
+      } else {
+        __syncthreads();
+        copy_f4(wsm, a.staged + E.stage_off, E.stage_len / 4, tid, NT);
+        __syncthreads();
+        wblk = wsm;
+      }
+      elem_apply<HP, S, REG>(H, E, wblk, sampling, xs, th, hc, 0, sb, tb, CS, tid, NT, ldj);
+    }
+
+    // ---- store ----
+    {
+      float2 acc2;
+      if constexpr (CB)
+        acc2 = fwd_store_tile_call<HP, S>(a, H, xs, CS, tid, base, NTS, io_aligned, make_float4(ldj[0], ldj[1 % S], ldj[2 % S], ldj[3 % S]));
+      else
+        acc2 = fwd_store_tile<HP, S>(a, H, xs, CS, tid, base, NTS, io_aligned, make_float4(ldj[0], ldj[1 % S], ldj[2 % S], ldj[3 % S]));
+      lsum_thread += acc2.x;
+      nonfinite += acc2.y;
+    }
   }
 
   if (a.mode == MODE_LOGPDF_SUM) {
@@ -708,6 +921,14 @@ __global__ void __launch_bounds__((fwd_max_threads<HP, S, REG>()), (fwd_min_ctas
   else
     chain_fwd_body<HP, S, REG, false>(a);
 }
+
+#ifdef DFLOW_CBANK
+template <int HP, int S>
+__global__ void __launch_bounds__((fwd_max_threads<HP, S, true>()), 3)
+    chain_fwd_const_kernel(const __grid_constant__ FwdArgs a) {
+  chain_fwd_body<HP, S, true, true, true>(a);  // always launched with fwd_max_threads (compile-time column stride)
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------------------
 // K3: adjoint.  Forward normalising sweep, then a chain-order reverse sweep that RECOMPUTES each layer's
@@ -1015,5 +1236,8 @@ template <int HP, int S, bool REG>
 cudaError_t launch_fwd_inst(const FwdArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st);
 template <int HP>
 cudaError_t launch_grad_inst(const GradArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st);
+// constant-bank forward kernel: uploads [DevChain | staged weights] into the instantiation's bank, then launches
+template <int HP, int S>
+cudaError_t launch_fwd_const_inst(const FwdArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st, int stage_floats);
 
 }  // namespace dflow

@@ -92,6 +92,7 @@ struct FwdArgs {
   unsigned long long seed;
   unsigned int rng_offset;
   unsigned long long first_sample;
+  int cb_wofs;  // constant-bank kernels: float offset of the staged weights inside the bank
 };
 
 struct GradArgs {
@@ -131,6 +132,8 @@ struct dflow_chain {
   int chain_bytes = 0;
   // tuning
   int fwd_spt = 0, fwd_threads = 0, grad_threads = 0, grad_spt = 0, ctas_per_sm = 0;
+  int fwd_const = 0;   // -1: never use the constant-bank forward kernel (default: use it when the chain is eligible)
+  int cbank_ok = 0;    // relu chain, hidden <= 32, every conditioner >= 2 Dense, descriptor + staged image <= 60 KB
   long long launches = 0;
   // host pipeline scratch (dflow_*_host)
   void* pipe = nullptr;

@@ -166,6 +166,23 @@ static int launch_fwd_t(dflow_chain* c, FwdArgs& a, cudaStream_t st, int nt) {
   return DFLOW_OK;
 }
 
+// Constant-bank forward kernel (dflow_chain_kernels.cuh, DFLOW_CBANK): descriptor + staged weights in the 60 KB bank
+template <int HP, int S>
+static int launch_fwd_const_t(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
+  const DevChainHdr& h = c->hc()->h;
+  int nt = fwd_max_threads<HP, S, true>();
+  const SmemPlan p = plan_fwd(h, c->chain_bytes, nt * S, true, true);
+  const long long ntiles = (a.B + (long long)nt * S - 1) / ((long long)nt * S);
+  int per_sm = c->ctas_per_sm > 0 ? c->ctas_per_sm : 3;
+  long long grid = (long long)c->sm_count * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  a.cb_wofs = ((c->chain_bytes + 15) / 16) * 4;
+  CK((launch_fwd_const_inst<HP, S>(a, (unsigned)grid, nt, p.bytes(), st, h.stage_total)));
+  c->launches += 3;  // two bank uploads (descriptor, weights) + the kernel
+  return DFLOW_OK;
+}
+
 // Kernel selection (fwd_spt tuning: 0 = automatic; negative = force the shared-memory-column variant with |spt|)
 int launch_fwd(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
   const DevChainHdr& h = c->hc()->h;
@@ -173,6 +190,11 @@ int launch_fwd(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
   a.staged = c->d_staged;
   a.chain_bytes = c->chain_bytes;
   int spt = c->fwd_spt;
+  // default for chains that fit the constant bank: weights as uniform-datapath operands, activations in registers
+  if (spt == 0 && c->fwd_const >= 0 && c->cbank_ok) {
+    if (h.hp == 16) return launch_fwd_const_t<16, 4>(c, a, st);
+    if (h.hp == 32) return launch_fwd_const_t<32, 2>(c, a, st);
+  }
   if (!h.relu_only && spt < 0) spt = -spt;  // tanh / sigmoid: shared-memory-column kernels only
   int nt = c->fwd_threads > 0 ? c->fwd_threads : 256;  // clamped to the instantiation's fixed block size
   if (nt > 256) nt = 256;

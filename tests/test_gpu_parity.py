@@ -321,3 +321,31 @@ def test_fused_peer_allreduce_adam_single_rank_equals_adam_kernel():
         assert loss2[0].item() == -123.5 * t and loss2[1].item() == 0.0
     assert lib.dflow_dp_status(dp, st) == 0
     df._lib.check(lib.dflow_dp_destroy(dp))
+
+
+@pytest.mark.parametrize("name", ["readme_n2", "readme_n1", "ref_chain_d7", "blocks_d10_h32"])
+@pytest.mark.parametrize("B", [3, 513, 70001])
+def test_constant_bank_kernel_bitwise_equals_shared_memory_kernel(name, B):
+    """Eligible relu chains (hidden <= 32) default to the constant-bank forward kernel (weights as uniform-datapath
+    operands, FFMA2).  It performs the same fmas in the same order as the shared-memory-column kernel, so normalise,
+    log-density, sampling and the in-kernel draw must agree bit for bit; ragged tails and several tiles per CTA included."""
+    ochain, chain, x, th = _setup(name, B)
+    n = th.shape[0]
+    pc = chain.packed()
+    xj = df.to_jl(x, DEV)
+    tj = df.to_jl(th, DEV) if n else None
+    thc = torch.full((max(n, 1),), 0.25, device=DEV)
+    res = {}
+    for mode in (0, -1):
+        pc.tune(fwd_const=mode)
+        before = pc.launch_count()
+        lp = pc.logpdf(xj, tj)
+        launches = pc.launch_count() - before
+        z, ldj = pc.normalize(xj, tj)
+        xs, l2 = pc.forward_ldj(z, tj)
+        smp = pc.sample_rng(B, 1234, None, thc if n else None)
+        res[mode] = (lp.clone(), z.clone(), ldj.clone(), xs.clone(), l2.clone(), smp.clone(), launches)
+    pc.tune(fwd_const=0)
+    assert res[0][6] == res[-1][6] + 2, "the constant-bank path adds two bank uploads per launch"
+    for a, b in zip(res[0][:6], res[-1][:6]):
+        assert torch.equal(a, b)
