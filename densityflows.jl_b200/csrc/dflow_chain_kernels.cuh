@@ -97,6 +97,15 @@ __device__ __forceinline__ void fma2_pair(float& r0, float& r1, float x0, float 
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(ww), "l"(c));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
 }
+// (r0, r1) += (x0 * y0, x1 * y1): both factors are register pairs
+__device__ __forceinline__ void fma2_vv(float& r0, float& r1, float x0, float x1, float y0, float y1) {
+  unsigned long long x, y, c, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(y0), "f"(y1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(r0), "f"(r1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+}
 // acc[s] = v[s] * w + acc[s] for the S samples of a thread
 template <int S>
 __device__ __forceinline__ void fma_samples(float (&acc)[S], const float (&v)[S], float w) {

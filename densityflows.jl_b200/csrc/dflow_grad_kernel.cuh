@@ -54,12 +54,14 @@ __device__ __forceinline__ void dw_block(const float* __restrict__ dcol, const I
     kv[i] = (k0 + i) < K;
     hp[i] = reinterpret_cast<const float4*>(in(kv[i] ? (k0 + i) : 0) + wbase);
   }
-  float acc[TO][TK], bs[TO];
+  // packed accumulators: (even-sample partial sum, odd-sample partial sum) per dW entry; a sample quad is two FFMA2
+  // whose operands are the natural register pairs of the two LDS.128 results
+  float acc[TO][TK][2], bs[TO];
 #pragma unroll
   for (int i = 0; i < TO; ++i) {
     bs[i] = 0.0f;
 #pragma unroll
-    for (int j = 0; j < TK; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < TK; ++j) acc[i][j][0] = acc[i][j][1] = 0.0f;
   }
   const bool do_bias = with_bias && lk == 0 && kb == 0;
 #pragma unroll 2
@@ -72,7 +74,10 @@ __device__ __forceinline__ void dw_block(const float* __restrict__ dcol, const I
 #pragma unroll
     for (int i = 0; i < TO; ++i) {
 #pragma unroll
-      for (int j = 0; j < TK; ++j) acc[i][j] = dot4(dv[i], hv[j], acc[i][j]);
+      for (int j = 0; j < TK; ++j) {
+        fma2_vv(acc[i][j][0], acc[i][j][1], dv[i].x, dv[i].y, hv[j].x, hv[j].y);
+        fma2_vv(acc[i][j][0], acc[i][j][1], dv[i].z, dv[i].w, hv[j].z, hv[j].w);
+      }
       if (do_bias) bs[i] += (dv[i].x + dv[i].y) + (dv[i].z + dv[i].w);
     }
   }
@@ -83,10 +88,11 @@ __device__ __forceinline__ void dw_block(const float* __restrict__ dcol, const I
     for (int j = 0; j < TK; ++j) {
       if (!kv[j]) continue;
       const int gi = p_w + (o0 + i) + O * (k0 + j);
+      const float tot = acc[i][j][0] + acc[i][j][1];
       if (gsm)
-        atomicAdd(gsm + gi, acc[i][j]);
+        atomicAdd(gsm + gi, tot);
       else
-        atomicAdd(ggl + gi, acc[i][j]);
+        atomicAdd(ggl + gi, tot);
     }
     if (do_bias) {
       if (gsm)
@@ -157,13 +163,10 @@ __device__ __forceinline__ void dense_T2(const float* dcol, int CS, int sb, cons
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       const float4 w = wr[g];
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        a0[s] = fmaf(w.x, dl[4 * g + 0][s], a0[s]);
-        a1[s] = fmaf(w.y, dl[4 * g + 1][s], a1[s]);
-        a0[s] = fmaf(w.z, dl[4 * g + 2][s], a0[s]);
-        a1[s] = fmaf(w.w, dl[4 * g + 3][s], a1[s]);
-      }
+      fma_samples<S>(a0, dl[4 * g + 0], w.x);
+      fma_samples<S>(a1, dl[4 * g + 1], w.y);
+      fma_samples<S>(a0, dl[4 * g + 2], w.z);
+      fma_samples<S>(a1, dl[4 * g + 3], w.w);
     }
     float* dst = first ? gx + (int)id[k - n] * CS + sb : hprev + k * CS + sb;
     float cur[S];

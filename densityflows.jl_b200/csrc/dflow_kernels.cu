@@ -179,7 +179,7 @@ static int launch_fwd_const_t(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
   if (grid < 1) grid = 1;
   a.cb_wofs = ((c->chain_bytes + 15) / 16) * 4;
   CK((launch_fwd_const_inst<HP, S>(a, (unsigned)grid, nt, p.bytes(), st, h.stage_total)));
-  c->launches += 3;  // two bank uploads (descriptor, weights) + the kernel
+  c->launches++;  // kernels only: the two bank uploads are device-to-device memcpy nodes, not kernels
   return DFLOW_OK;
 }
 

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .arrays import jl_empty, n_samples, to_jl
+from .arrays import flat_view, jl_empty, n_samples, to_jl
 from .data import DataArrays, MetaData, maximum_θ, minimum_θ, number_conditions, number_dimensions
 from .model import FlowChain, PackedChain, _gen
 
@@ -157,6 +157,52 @@ def sample(*args):
                 "dimensions θ must match (n, dims...) with n number of trained parameters"
         pc.sample_rng(B, seed_, θ if flow.n > 0 else None, None, flags, out=out)
     return out
+
+
+def sample_with_rejection(*args):
+    """sample_with_rejection([rng,] condition, flow, dims, θ::Tuple[, m=100]) -- src/Flows.jl:196-229.
+
+    The reference draws ONE point per iteration and tests `condition(point, θ)`; here the same stream of points
+    (Philox counter = draw index, so draw i is the same point whatever the batching) is generated in device-side
+    batches, `condition(points (d, nb), θ)` returns a boolean mask over the batch, and the accepted points are compacted
+    in draw order.  At most m * prod(dims) points are drawn; if that is not enough the reference's ArgumentError
+    becomes a ValueError."""
+    args = list(args)
+    rng = None
+    if not callable(args[0]):
+        rng = args.pop(0)
+    condition, flow, dims, θ = args[0], args[1], _dims_tuple(args[2]), tuple(args[3])
+    m = int(args[4]) if len(args) > 4 else 100
+    if len(θ) != flow.n:
+        raise ValueError(f"θ must be an NTuple of length n={flow.n}")
+    pc = flow.packed()
+    if isinstance(rng, (int, np.integer)):
+        seed_ = int(rng)
+    else:
+        seed_ = int(torch.randint(0, 2**62, (1,), generator=rng or _gen()).item())
+    n_pts = int(np.prod(dims)) if dims else 1
+    flags = L.THETA_NORMALIZE if flow.n > 0 else 0
+    θc = torch.tensor([float(v) for v in θ], device=pc.device, dtype=torch.float32) if flow.n > 0 else None
+    out = jl_empty((flow.d, n_pts), pc.device)
+    have, drawn, budget = 0, 0, m * n_pts
+    nb = max(1024, 2 * n_pts)
+    while have < n_pts and drawn < budget:
+        cur = min(nb, budget - drawn)
+        pts = pc.sample_rng(cur, seed_, None, θc, flags, first_sample=drawn)
+        mask = torch.as_tensor(condition(pts, θ), device=pc.device).reshape(-1).to(torch.bool)
+        if mask.numel() != cur:
+            raise ValueError("condition must return one boolean per point of the batch")
+        acc = pts[:, mask]
+        take = min(int(acc.shape[1]), n_pts - have)
+        out[:, have:have + take] = acc[:, :take]
+        have += take
+        drawn += cur
+        nb = min(2 * nb, 1 << 24)
+    if have < n_pts:
+        raise ValueError("Impossible to reach convergence of rejection sampling")  # src/Flows.jl:221-224
+    res = jl_empty((flow.d,) + dims, pc.device)  # Julia reshape(r, (D, dims...)): same memory order
+    flat_view(res).copy_(flat_view(out))
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------------
