@@ -221,7 +221,13 @@ __device__ __forceinline__ void net_backward2(const DevChainHdr& H, const DevEle
 
 template <int HP, int S>
 constexpr int grad2_max_threads() {
-  return HP * S >= 64 ? 128 : 256;
+  // hidden 16, S = 2: one 384-thread CTA per SM (12 warps) instead of one 256-thread CTA -- the kernel is latency-bound
+  // and shared memory (240 B of columns per sample at C2) is what limits the resident warps
+  return HP * S >= 64 ? 128 : (HP == 16 && S == 2 ? 384 : 256);
+}
+template <int HP, int S>
+constexpr int grad2_min_ctas() {
+  return grad2_max_threads<HP, S>() > 256 ? 1 : 2;
 }
 
 template <int HP, int S, bool FIXED>
@@ -431,7 +437,7 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
 }
 
 template <int HP, int S>
-__global__ void __launch_bounds__((grad2_max_threads<HP, S>()), 2) chain_grad2_kernel(const GradArgs a) {
+__global__ void __launch_bounds__((grad2_max_threads<HP, S>()), (grad2_min_ctas<HP, S>())) chain_grad2_kernel(const GradArgs a) {
   if (blockDim.x == grad2_max_threads<HP, S>())
     chain_grad2_body<HP, S, true>(a);
   else

@@ -258,7 +258,7 @@ static int launch_grad2_t(dflow_chain* c, GradArgs& a, cudaStream_t st, int nt) 
   a.smem_grad = (h.P * 4 <= 64 * 1024) ? 1 : 0;
   SmemPlan p = plan_grad2(h, c->chain_bytes, nt * S, a.smem_grad);
   while (p.bytes() > (size_t)c->max_smem_optin && nt > 32) {
-    nt >>= 1;
+    nt = (nt > 256) ? 256 : nt >> 1;  // 384 -> 256 -> 128 -> ...
     p = plan_grad2(h, c->chain_bytes, nt * S, a.smem_grad);
   }
   if (p.bytes() > (size_t)c->max_smem_optin) {
@@ -287,7 +287,7 @@ int launch_grad(dflow_chain* c, GradArgs& a, cudaStream_t st) {
   a.staged = c->d_staged;
   a.chain_bytes = c->chain_bytes;
   if (c->grad_spt >= 0) {  // v2 adjoint (register-tiled dW); grad_spt < 0 selects the first-generation kernel
-    int nt2 = c->grad_threads > 0 ? c->grad_threads : 256;  // clamped to the instantiation's fixed block size
+    int nt2 = c->grad_threads > 0 ? c->grad_threads : 1024;  // clamped to the instantiation's fixed block size
     nt2 = (nt2 + 31) & ~31;
     const int s = c->grad_spt;
     switch (h.hp) {
