@@ -18,7 +18,7 @@ __host__ __device__ inline SmemPlan plan_grad2(const DevChainHdr& h, int chain_b
   p.w_f = h.resident ? h.stage_total : h.stage_max;
   p.cs = nts + 4;  // +4: consecutive rows start 4 banks apart (conflict-free multi-row LDS.128 in the dW phase)
   const int hd = h.max_depth > 1 ? h.max_depth - 1 : 1;
-  const int rows = 2 * h.d + h.n + hd * h.hp + 4 * h.amax4;
+  const int rows = 2 * h.d + h.n + hd * h.hp + 3 * h.amax4;  // x, xbar, theta, hidden activations, s, t, output cotangent
   p.cols_f = rows * p.cs;
   p.grad_f = smem_grad ? ((h.P + 3) / 4) * 4 : 0;
   return p;
@@ -221,7 +221,7 @@ __device__ __forceinline__ void net_backward2(const DevChainHdr& H, const DevEle
 
 template <int HP, int S>
 constexpr int grad2_max_threads() {
-  // hidden 16, S = 2: one 384-thread CTA per SM (12 warps) instead of one 256-thread CTA -- the kernel is latency-bound
+  // hidden 16, S = 2: one 384-thread CTA per SM (12 warps; 448 threads measured slower: 224 KB of shared memory leave no L1) instead of one 256-thread CTA -- the kernel is latency-bound
   // and shared memory (240 B of columns per sample at C2) is what limits the resident warps
   return HP * S >= 64 ? 128 : (HP == 16 && S == 2 ? 384 : 256);
 }
@@ -256,8 +256,8 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
   float* hc = th + n * CS;
   float* ob = hc + hd * hstride;  // s values
   float* tb = ob + H.amax4 * CS;  // t values
-  float* eb = tb + H.amax4 * CS;  // exp(-s)
-  float* gb = eb + H.amax4 * CS;  // output cotangent
+  float* gb = tb + H.amax4 * CS;  // output cotangent  (exp(-s) is recomputed from the kept s values: 4 fewer column
+                                  // rows per sample buy two more resident warps)
 
   if (H.resident) copy_f4(wsm, a.staged, H.stage_total / 4, tid, NT);
   if (a.smem_grad)
@@ -363,10 +363,6 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
       const bool rnvp = (E.kind == DFLOW_ELEM_RNVP);
       InSel in{th, xs, hc, E.id, n, CS, true};
       const int a4 = H.amax4;
-      if (!rnvp)
-        for (int j = 0; j < a4; ++j)
-#pragma unroll
-          for (int s = 0; s < S; ++s) eb[j * CS + sb + s] = 1.0f;
       for (int ni = rnvp ? 0 : 1; ni < 2; ++ni) {
         const DevNet& net = ni == 0 ? E.s : E.t;
         float* outc = ni == 0 ? ob : tb;
@@ -378,14 +374,11 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
             if (j < E.a) {
               const int k = E.af[j];
               if (ni == 0) {
-                const float em = expf(-ob[j * CS + sb + s]);
-                eb[j * CS + sb + s] = em;
                 gout = -gx[k * CS + sb + s] * xs[k * CS + sb + s] + ib[s];  // s̄ = -z̄_af z_af - j̄, RNVP.jl:134
               } else {
-                gout = -gx[k * CS + sb + s] * eb[j * CS + sb + s];  // t̄, RNVP.jl:135
+                const float em = rnvp ? expf(-ob[j * CS + sb + s]) : 1.0f;
+                gout = -gx[k * CS + sb + s] * em;  // t̄, RNVP.jl:135
               }
-            } else if (ni == 0) {
-              eb[j * CS + sb + s] = 1.0f;
             }
             gb[j * CS + sb + s] = gout;
           }
@@ -399,7 +392,7 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           xs[k * CS + sb + s] = ckb[(size_t)(E.ck_off + j) * NTS + s];
-          gx[k * CS + sb + s] *= eb[j * CS + sb + s];
+          if (rnvp) gx[k * CS + sb + s] *= expf(-ob[j * CS + sb + s]);
         }
       }
     }
