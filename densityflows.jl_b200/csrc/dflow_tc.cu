@@ -345,26 +345,30 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
               const uint32_t mword = mnext;
               if (live && c + NWG < (H >> 5)) mnext = a.m2buf[((size_t)tile * (H >> 5) + c + NWG) * 128 + row];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
-                if (live) a.d2buf[tbuf_idx(tile, H, c * WKA + j, row)] = v[j];
-              }
+              for (int j = 0; j < 32; ++j) v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[c * WKA + j], 0.0f);
-              if constexpr (MODE == TC_FWD_STORE) {
-                if (p == 0 && live) {
-                  uint32_t mword = 0;
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) {
-                    a.h1buf[tbuf_idx(tile, H, c * WKA + j, row)] = v[j];
-                    mword |= (v[j] > 0.0f ? 1u : 0u) << j;
-                  }
-                  a.m1buf[((size_t)tile * (H >> 5) + c) * 128 + row] = mword;
-                }
-              }
             }
             handoff(v);
+            // The training stores come AFTER the hand-off: its fence.proxy.async is a MEMBAR.ALL.CTA that waits for every
+            // outstanding global store of the thread, which used to put 32 store round trips into the per-chunk chain.
+            if constexpr (MODE == TC_BWD) {
+              if (live) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a.d2buf[tbuf_idx(tile, H, c * WKA + j, row)] = v[j];
+              }
+            } else if constexpr (MODE == TC_FWD_STORE) {
+              if (p == 0 && live) {
+                uint32_t mword = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  a.h1buf[tbuf_idx(tile, H, c * WKA + j, row)] = v[j];
+                  mword |= (v[j] > 0.0f ? 1u : 0u) << j;
+                }
+                a.m1buf[((size_t)tile * (H >> 5) + c) * 128 + row] = mword;
+              }
+            }
           }
           q += (uint32_t)cpg;
           rD1.next();
@@ -395,14 +399,19 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             const uint32_t mword = mnext;
             if (live && cc + NWG < ncp) mnext = a.m1buf[((size_t)tile * (H >> 5) + gc + NWG) * 128 + row];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
-              if (live) a.d1buf[tbuf_idx(tile, H, gc * WKA + j, row)] = v[j];
-            }
+            for (int j = 0; j < 32; ++j) v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[H + gc * WKA + j], 0.0f);
-            if (MODE == TC_FWD_STORE && live) {
+          }
+          handoff(v);
+          if constexpr (MODE == TC_BWD) {  // (stores after the hand-off's fence, see epilogue 1)
+            if (live) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a.d1buf[tbuf_idx(tile, H, gc * WKA + j, row)] = v[j];
+            }
+          } else if constexpr (MODE == TC_FWD_STORE) {
+            if (live) {
               uint32_t mword = 0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -412,7 +421,6 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
               a.m2buf[((size_t)tile * (H >> 5) + gc) * 128 + row] = mword;
             }
           }
-          handoff(v);
         }
         ++npass;
       }
@@ -456,11 +464,6 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
               if (valid && j < a.a) val = a.net_id == 0 ? -zb[qq] * zo[qq] + a.inv_btot : -zb[qq] * expf(-sv[qq]);
               v[qq] = val;
             }
-            // (the bias gradient of the last Dense, sum_samples delta3, is accumulated by tc_dw_kernel while staging)
-            if (live) {
-#pragma unroll
-              for (int qq = 0; qq < 8; ++qq) a.d3buf[tbuf_idx(tile, K0p, k0 + qq, row)] = v[qq];
-            }
 #pragma unroll
             for (int h4 = 0; h4 < 8; h4 += 4) {
               float4 hi, lo;
@@ -475,16 +478,6 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
           }
         } else {
           // conditioner input row [theta_0..theta_{n-1}, x[axis_id...], 0 pad] (src/affine/RNVP.jl:157)
-          if (a.x_out != a.x_in && a.net_id == 1 && live) {  // out-of-place (training sweep): carry the whole state
-            for (int k0 = 0; k0 < d; k0 += 8) {
-              float v[8];
-#pragma unroll
-              for (int qq = 0; qq < 8; ++qq) v[qq] = (k0 + qq < d) ? a.x_in[tidx(tile, d, k0 + qq, row)] : 0.0f;
-#pragma unroll
-              for (int qq = 0; qq < 8; ++qq)
-                if (k0 + qq < d) a.x_out[tidx(tile, d, k0 + qq, row)] = v[qq];
-            }
-          }
           for (int k0 = 0; k0 < K0p; k0 += 8) {
             float v[8];
 #pragma unroll
@@ -506,12 +499,6 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
                 if (valid && k < n) v[qq] = (a.theta_rng[k] == 0.0f) ? 0.0f : (v[qq] - a.theta_min[k]) / a.theta_rng[k];
               }
             }
-            if constexpr (MODE == TC_FWD_STORE) {
-              if (a.net_id == 1 && live) {
-#pragma unroll
-                for (int qq = 0; qq < 8; ++qq) a.inbuf[tbuf_idx(tile, K0p, k0 + qq, row)] = v[qq];
-              }
-            }
 #pragma unroll
             for (int h4 = 0; h4 < 8; h4 += 4) {
               float4 hi, lo;
@@ -527,6 +514,43 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
         }
         fence_async_smem();
         arrive_issuer(BAR_A1_FULL);
+        // Global stores of the training modes come after the hand-off (its fence is a MEMBAR.ALL.CTA that would wait for
+        // them).  The operand row is re-read from shared memory: hi + lo is the original Float32 value exactly, and the
+        // MMA only reads the buffer until this warpgroup rewrites it in its next call.
+        if constexpr (MODE == TC_BWD) {
+          // (the bias gradient of the last Dense, sum_samples delta3, is accumulated by tc_dw_kernel while staging)
+          if (live)
+            for (int k0 = 0; k0 < K0p; k0 += 4) {
+              const int idx = core_idx(row, k0, K0p);
+              const float4 hi = *reinterpret_cast<const float4*>(A1h + idx), lo = *reinterpret_cast<const float4*>(A1l + idx);
+              a.d3buf[tbuf_idx(tile, K0p, k0 + 0, row)] = hi.x + lo.x;
+              a.d3buf[tbuf_idx(tile, K0p, k0 + 1, row)] = hi.y + lo.y;
+              a.d3buf[tbuf_idx(tile, K0p, k0 + 2, row)] = hi.z + lo.z;
+              a.d3buf[tbuf_idx(tile, K0p, k0 + 3, row)] = hi.w + lo.w;
+            }
+        } else {
+          if constexpr (MODE == TC_FWD_STORE) {
+            if (a.net_id == 1 && live)
+              for (int k0 = 0; k0 < K0p; k0 += 4) {
+                const int idx = core_idx(row, k0, K0p);
+                const float4 hi = *reinterpret_cast<const float4*>(A1h + idx), lo = *reinterpret_cast<const float4*>(A1l + idx);
+                a.inbuf[tbuf_idx(tile, K0p, k0 + 0, row)] = hi.x + lo.x;
+                a.inbuf[tbuf_idx(tile, K0p, k0 + 1, row)] = hi.y + lo.y;
+                a.inbuf[tbuf_idx(tile, K0p, k0 + 2, row)] = hi.z + lo.z;
+                a.inbuf[tbuf_idx(tile, K0p, k0 + 3, row)] = hi.w + lo.w;
+              }
+          }
+          if (a.x_out != a.x_in && a.net_id == 1 && live) {  // out-of-place (training sweep): carry the whole state
+            for (int k0 = 0; k0 < d; k0 += 8) {
+              float v[8];
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) v[qq] = (k0 + qq < d) ? a.x_in[tidx(tile, d, k0 + qq, row)] : 0.0f;
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq)
+                if (k0 + qq < d) a.x_out[tidx(tile, d, k0 + qq, row)] = v[qq];
+            }
+          }
+        }
     };
     auto final_out = [&](long long it, uint32_t tc) {
       const long long tile = blockIdx.x + it * gridDim.x;
@@ -893,7 +917,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
 //   dW3^T[mt] (128 x a16) += h2[mt] * delta3^T
 // accumulated in TMEM over the CTA's whole sample range and flushed once with red.global.add.
 constexpr int DW_KS = TC_DW_KS;
-constexpr int DW_STAGE_WARPS = 16;
+constexpr int DW_STAGE_WARPS = 15;  // + the MMA warp = 512 threads: 128 registers per thread
 constexpr int DW_STAGE_THREADS = DW_STAGE_WARPS * 32;
 constexpr int DW_THREADS = DW_STAGE_THREADS + 32;
 constexpr int DW_MAXRB = 6;   // row-blocks (8 rows x 16 samples) per staging warp and stage
@@ -969,72 +993,106 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
   if (warp < DW_STAGE_WARPS) {
     // ---- staging warps: global (fp32) -> hi/lo split -> shared operand layout, loads issued one stage ahead ----
     // this warp's row-blocks: rb = warp + 8 i  (everything per row-block is resolved once, outside the stage loop)
+    // Per row-block metadata is packed (bit masks + a 2-bit segment-shape code) so that two stages of loaded data fit
+    // the 96-register budget next to it without spills.
     const float* my_ptr[DW_MAXRB];
-    int my_ts[DW_MAXRB], my_seg[DW_MAXRB], my_dst[DW_MAXRB], my_lo[DW_MAXRB], my_row[DW_MAXRB];
-    bool my_ok[DW_MAXRB];
+    int my_dst[DW_MAXRB];
+    uint32_t okmask = 0, segmask = 0, biasmask = 0, codes = 0;  // code: 0 RA-row A segment, 1 h1, 2 in, 3 delta3
     const int lofs = (lane >> 3) * 32 + (lane & 7) * 4;
-#pragma unroll
-    for (int i = 0; i < DW_MAXRB; ++i) {
-      const int rb = warp + DW_STAGE_WARPS * i;
+    auto seg_of = [&](int rb, int& rb0) {
       int sgi = 0;
 #pragma unroll
       for (int k = 1; k < 6; ++k)
         if (rb >= seg_rb0[k]) sgi = k;
-      const int rb0 = sgi == 0 ? seg_rb0[0] : sgi == 1 ? seg_rb0[1] : sgi == 2 ? seg_rb0[2] : sgi == 3 ? seg_rb0[3]
-                      : sgi == 4 ? seg_rb0[4] : seg_rb0[5];
+      rb0 = sgi == 0 ? seg_rb0[0] : sgi == 1 ? seg_rb0[1] : sgi == 2 ? seg_rb0[2] : sgi == 3 ? seg_rb0[3]
+            : sgi == 4 ? seg_rb0[4] : seg_rb0[5];
+      return sgi;
+    };
+#pragma unroll
+    for (int i = 0; i < DW_MAXRB; ++i) {
+      const int rb = warp + DW_STAGE_WARPS * i;
+      int rb0;
+      const int sgi = seg_of(rb, rb0);
       const int dst0 = sgi == 0 ? seg_dst[0] : sgi == 1 ? seg_dst[1] : sgi == 2 ? seg_dst[2] : sgi == 3 ? seg_dst[3]
                        : sgi == 4 ? seg_dst[4] : seg_dst[5];
       const int srows = sgi < 3 ? RA : sgi == 3 ? H : sgi == 4 ? K0p : a16;          // rows of the segment in the stage
       const int valid = sgi < 3 ? rows_valid : srows;                                  // rows that exist in the source
-      const int trows = sgi < 4 ? H : sgi == 4 ? K0p : a16;                            // rows per tile in the source buffer
       const float* base = sgi == 0 ? a.d2buf[net] : sgi == 1 ? a.d1buf[net] : sgi == 2 ? a.h2buf[net]
                           : sgi == 3 ? a.h1buf[net] : sgi == 4 ? a.inbuf : a.d3buf[net];
       const int r0 = (rb - rb0) * 8;
-      my_seg[i] = rb < RB ? sgi : -1;
-      my_row[i] = r0 + (lane & 7);
-      my_ok[i] = rb < RB && my_row[i] < valid;
+      const int row = r0 + (lane & 7);
+      if (rb < RB) segmask |= 1u << i;
+      if (rb < RB && row < valid) okmask |= 1u << i;
+      // bias gradients: sums over the samples of delta2 / delta1 (this m-tile's rows) and delta3 (m-tile 0 only)
+      if (rb < RB && (sgi < 2 || (sgi == 5 && mt == 0))) biasmask |= 1u << i;
+      codes |= (uint32_t)(sgi < 3 ? 0 : sgi - 2) << (2 * i);
       my_dst[i] = dst0 + (r0 >> 3) * 128 + lofs;
-      my_lo[i] = srows * DW_KS;
-      my_ts[i] = trows * 16;  // floats per [rows x 16 samples] block of the source buffer
-      my_ptr[i] = base + (size_t)((sgi < 3 ? mt * 128 : 0) + my_row[i]) * 16 + (lane >> 3) * 4;
+      my_ptr[i] = base + (size_t)((sgi < 3 ? mt * 128 : 0) + row) * 16 + (lane >> 3) * 4;
     }
-    float4 v[DW_MAXRB];
+    // floats per [rows x 16 samples] block of the source buffer / offset of the lo half inside the stage, by code
+    const int ts_by[4] = {H * 16, H * 16, K0p * 16, a16 * 16};
+    const int lo_by[4] = {RA * DW_KS, H * DW_KS, K0p * DW_KS, a16 * DW_KS};
+    auto pick = [](const int (&t)[4], uint32_t c) { return c == 0 ? t[0] : c == 1 ? t[1] : c == 2 ? t[2] : t[3]; };
+    // Stages are produced in PAIRS (register buffers vA / vB): both are loaded, split and stored, then ONE
+    // fence.proxy.async + two barrier arrivals, then the loads of the next pair are issued.  The fence compiles to
+    // MEMBAR.ALL.CTA, which also waits for the thread's outstanding global loads -- with one stage per fence every loop
+    // iteration paid a full DRAM latency for 44 KB per CTA (the kernel sat at ~2.6 TB/s); a pair doubles the bytes in
+    // flight per latency.  (Keeping two stages in flight ACROSS a fence does not work for the same reason.)
+    float4 vA[DW_MAXRB], vB[DW_MAXRB];
     float bacc[DW_MAXRB];
 #pragma unroll
     for (int i = 0; i < DW_MAXRB; ++i) bacc[i] = 0.0f;
-    auto load_stage = [&](long long s) {
+    auto load_stage = [&](long long s, float4 (&v)[DW_MAXRB]) {
       const size_t blk = (size_t)(t0 * (128 / DW_KS) + s);  // [tile][16-sample block] index (tbuf_idx)
 #pragma unroll
       for (int i = 0; i < DW_MAXRB; ++i) {
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (my_ok[i]) v[i] = __ldg(reinterpret_cast<const float4*>(my_ptr[i] + blk * my_ts[i]));
+        if ((okmask >> i) & 1u)
+          v[i] = __ldg(reinterpret_cast<const float4*>(my_ptr[i] + blk * (size_t)pick(ts_by, (codes >> (2 * i)) & 3u)));
       }
     };
-    if (nstages > 0) load_stage(0);
     uint32_t slot = 0, par = 0;
-    for (long long s = 0; s < nstages; ++s) {
-      mbar_wait(empty + slot, par ^ 1);
-      float* st = smem + (size_t)slot * stage_fl;
+    auto put_stage = [&](float4 (&v)[DW_MAXRB], uint32_t sl, uint32_t pr) {
+      mbar_wait(empty + sl, pr ^ 1);
+      float* st = smem + (size_t)sl * stage_fl;
 #pragma unroll
       for (int i = 0; i < DW_MAXRB; ++i) {
-        if (my_seg[i] >= 0) {
+        if ((segmask >> i) & 1u) {
           float4 hi, lo;
           hi.x = to_tf32(v[i].x); lo.x = v[i].x - hi.x;
           hi.y = to_tf32(v[i].y); lo.y = v[i].y - hi.y;
           hi.z = to_tf32(v[i].z); lo.z = v[i].z - hi.z;
           hi.w = to_tf32(v[i].w); lo.w = v[i].w - hi.w;
           *reinterpret_cast<float4*>(st + my_dst[i]) = hi;
-          *reinterpret_cast<float4*>(st + my_dst[i] + my_lo[i]) = lo;
-          // bias gradients: sums over the samples of delta2 / delta1 (this m-tile's rows) and delta3 (m-tile 0 only)
-          if (my_seg[i] < 2 || (my_seg[i] == 5 && mt == 0)) bacc[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+          *reinterpret_cast<float4*>(st + my_dst[i] + pick(lo_by, (codes >> (2 * i)) & 3u)) = lo;
+          if ((biasmask >> i) & 1u) bacc[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
       }
-      fence_async_smem();
-      mbar_arrive(full + slot);
-      if (s + 1 < nstages) load_stage(s + 1);
+    };
+    auto advance = [&]() {
       if (++slot == (uint32_t)NST) {
         slot = 0;
         par ^= 1;
+      }
+    };
+    // nstages is a multiple of 128 / DW_KS = 8: the loop handles two stages per iteration
+    if (nstages > 0) {
+      load_stage(0, vA);
+      load_stage(1, vB);
+    }
+    for (long long s = 0; s < nstages; s += 2) {
+      const uint32_t slA = slot, prA = par;
+      advance();
+      const uint32_t slB = slot, prB = par;
+      advance();
+      put_stage(vA, slA, prA);
+      put_stage(vB, slB, prB);
+      fence_async_smem();
+      mbar_arrive(full + slA);
+      mbar_arrive(full + slB);
+      if (s + 2 < nstages) {
+        load_stage(s + 2, vA);
+        load_stage(s + 3, vB);
       }
     }
     // bias gradients: reduce the four sample quads of a row, one atomic per row
@@ -1043,10 +1101,15 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       float r = bacc[i];
       r += __shfl_xor_sync(0xffffffffu, r, 8);
       r += __shfl_xor_sync(0xffffffffu, r, 16);
-      if (my_seg[i] >= 0 && my_seg[i] < 2 && lane < 8 && my_ok[i] && nstages > 0)
-        atomicAdd(a.grad + a.p_b[net][my_seg[i] == 0 ? 1 : 0] + mt * 128 + my_row[i], r);
-      if (my_seg[i] == 5 && mt == 0 && lane < 8 && my_row[i] < a.a && nstages > 0)
-        atomicAdd(a.grad + a.p_b[net][2] + my_row[i], r);
+      const int rb = warp + DW_STAGE_WARPS * i;
+      int rb0;
+      const int sgi = seg_of(rb, rb0);
+      const int row = (rb - rb0) * 8 + (lane & 7);
+      const bool seg_ok = (segmask >> i) & 1u, ok = (okmask >> i) & 1u;
+      if (seg_ok && sgi < 2 && lane < 8 && ok && nstages > 0)
+        atomicAdd(a.grad + a.p_b[net][sgi == 0 ? 1 : 0] + mt * 128 + row, r);
+      if (seg_ok && sgi == 5 && mt == 0 && lane < 8 && row < a.a && nstages > 0)
+        atomicAdd(a.grad + a.p_b[net][2] + row, r);
     }
     // ---- flush: warps 0-3 own TMEM lanes 32w..32w+31 = hidden unit rows of this m-tile ----
     if (warp < 4 && nstages > 0) {
