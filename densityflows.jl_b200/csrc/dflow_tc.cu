@@ -343,7 +343,6 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             const int c = g * cpg + cg;  // 32-unit chunk index inside the hidden layer
             if constexpr (MODE == TC_BWD) {
               const uint32_t mword = mnext;
-              if (live && c + NWG < (H >> 5)) mnext = a.m2buf[((size_t)tile * (H >> 5) + c + NWG) * 128 + row];
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
             } else {
@@ -354,6 +353,8 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             // The training stores come AFTER the hand-off: its fence.proxy.async is a MEMBAR.ALL.CTA that waits for every
             // outstanding global store of the thread, which used to put 32 store round trips into the per-chunk chain.
             if constexpr (MODE == TC_BWD) {
+              // (the next chunk's relu mask is fetched here, behind the fence, for the same reason)
+              if (live && c + NWG < (H >> 5)) mnext = a.m2buf[((size_t)tile * (H >> 5) + c + NWG) * 128 + row];
               if (live) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) a.d2buf[tbuf_idx(tile, H, c * WKA + j, row)] = v[j];
@@ -397,7 +398,6 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
           }
           if constexpr (MODE == TC_BWD) {
             const uint32_t mword = mnext;
-            if (live && cc + NWG < ncp) mnext = a.m1buf[((size_t)tile * (H >> 5) + gc + NWG) * 128 + row];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
           } else {
@@ -405,7 +405,8 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[H + gc * WKA + j], 0.0f);
           }
           handoff(v);
-          if constexpr (MODE == TC_BWD) {  // (stores after the hand-off's fence, see epilogue 1)
+          if constexpr (MODE == TC_BWD) {  // (mask prefetch and stores after the hand-off's fence, see epilogue 1)
+            if (live && cc + NWG < ncp) mnext = a.m1buf[((size_t)tile * (H >> 5) + gc + NWG) * 128 + row];
             if (live) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) a.d1buf[tbuf_idx(tile, H, gc * WKA + j, row)] = v[j];
