@@ -974,6 +974,8 @@ int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
     c->grad_spt = value;
   else if (!strcmp(key, "ctas_per_sm"))
     c->ctas_per_sm = value;
+  else if (!strcmp(key, "tc_fuse"))
+    c->tc_fuse = value < 0 ? 0 : value > 2 ? 2 : value;
   else if (!strcmp(key, "tc_ns_max"))
     c->tc_ns_max = value;
   else if (!strcmp(key, "tc_ws_budget_mb"))

@@ -146,6 +146,8 @@ struct dflow_chain {
   int tc_cluster = 0;  // streamed conditioners: 0 independent CTAs (default, fastest measured), 1 CTA pairs sharing the
                        // weight stream by bulk-copy multicast, 2 cta_group::2 pairs (one issuer, M = 256)
   int tc_ws_budget_mb = 0;  // adjoint workspace cap in MiB (0: 24 GiB); larger batches are processed in macro-batches
+  int tc_fuse = 1;     // hidden <= 128 RealNVP layers run their s and t conditioners as one block-diagonal conditioner:
+                       // 0 never, 1 in the train step (default), 2 in forward-type calls as well
   int tc_ns_max = 0;   // cap on the weight-ring depth (experiments)
   int tc_debug = 0;    // timing experiments (dflow_tc.cu)
   int tc_mode = 0;     // 0: automatic (tensor cores iff must_wide), 1: force tensor cores, -1: force CUDA cores

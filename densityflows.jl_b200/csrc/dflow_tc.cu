@@ -121,12 +121,36 @@ __global__ void tc_prepack_kernel(const TcPackJob* jobs, const float* __restrict
   const int H = im.H, K0p = im.K0p, N3p = im.N3p, NH = im.NH, nch = im.nch;
   const int part = blockIdx.y, nparts = gridDim.y;
   const int t0 = part * blockDim.x + threadIdx.x, ts = nparts * blockDim.x;
+  // element (nn, k) of a matrix: plain affine map, or (fused pair) the diagonal block of the net it falls into
+  auto getw = [&](int ba, int bb, int nn, int k, int sn, int sk, int rbs, int cbs, int vn, int vk) -> float {
+    int net = 0;
+    if (J.fuse) {
+      const int rb = rbs ? nn / rbs : -1, cb = cbs ? k / cbs : -1;
+      if (rb >= 0 && cb >= 0 && rb != cb) return 0.0f;
+      net = rb >= 0 ? rb : cb;
+      if (net > 1) return 0.0f;
+      if (rbs) nn -= rb * rbs;
+      if (cbs) k -= cb * cbs;
+    }
+    if (nn >= vn || k >= vk) return 0.0f;
+    return W[(net ? bb : ba) + nn * sn + k * sk];
+  };
+  auto getb = [&](int pa, int pb, int i, int bs, int nvalid) -> float {
+    int net = 0;
+    if (J.fuse) {
+      net = i / bs;
+      i -= net * bs;
+      if (net > 1) return 0.0f;
+    }
+    const int pp = net ? pb : pa;
+    return (pp >= 0 && i < nvalid) ? W[pp + i] : 0.0f;
+  };
   // biases
   for (int i = t0; i < H; i += ts) {
-    base[im.bias_off + i] = J.pb1 >= 0 ? W[J.pb1 + i] : 0.0f;
-    base[im.bias_off + H + i] = J.pb2 >= 0 ? W[J.pb2 + i] : 0.0f;
+    base[im.bias_off + i] = getb(J.pb1, J.pb1b, i, J.bbs12, J.fuse ? J.bbs12 : H);
+    base[im.bias_off + H + i] = getb(J.pb2, J.pb2b, i, J.bbs12, J.fuse ? J.bbs12 : H);
   }
-  for (int i = t0; i < N3p; i += ts) base[im.bias_off + 2 * H + i] = (J.pb3 >= 0 && i < J.nb3) ? W[J.pb3 + i] : 0.0f;
+  for (int i = t0; i < N3p; i += ts) base[im.bias_off + 2 * H + i] = getb(J.pb3, J.pb3b, i, J.bbs3, J.nb3);
   const int hv = im.halves > 1 ? im.halves : 1, rk = im.rank;
   const int gwr = im.GW / hv, nhr = NH / hv, n3r = N3p / hv;  // rows per block in this image
   // M1 [H x K0p]: group g = rows g*GW..
@@ -134,7 +158,7 @@ __global__ void tc_prepack_kernel(const TcPackJob* jobs, const float* __restrict
     const int u = i / K0p, k = i - u * K0p;
     const int g = u / im.GW, within = u - g * im.GW, sub = within / gwr, r = within - sub * gwr;
     if (sub != rk) continue;
-    const float w = k < J.vk1 ? W[J.base1 + u * J.sn1 + k * J.sk1] : 0.0f;
+    const float w = getw(J.base1, J.base1b, u, k, J.sn1, J.sk1, J.rbs1, J.cbs1, J.vn1, J.vk1);
     const float hi = to_tf32(w);
     float* blk = base + im.g1_off + (size_t)g * im.g1_floats;
     blk[core_idx(r, k, K0p)] = hi;
@@ -145,7 +169,7 @@ __global__ void tc_prepack_kernel(const TcPackJob* jobs, const float* __restrict
     const int nn = i / H, k = i - nn * H;
     const int p = nn / NH, within = nn - p * NH, sub = within / nhr, r = within - sub * nhr;
     if (sub != rk) continue;
-    const float w = W[J.base2 + nn * J.sn2 + k * J.sk2];
+    const float w = getw(J.base2, J.base2b, nn, k, J.sn2, J.sk2, J.rbs2, J.cbs2, J.vn2, J.vk2);
     const float hi = to_tf32(w);
     const int c = k / WKC, kk = k - c * WKC;
     float* blk = base + im.s2_off + (size_t)(p * nch + c) * im.s2_floats;
@@ -157,7 +181,7 @@ __global__ void tc_prepack_kernel(const TcPackJob* jobs, const float* __restrict
     const int nn = i / H, k = i - nn * H;
     const int sub = nn / n3r, r = nn - sub * n3r;
     if (sub != rk) continue;
-    const float w = nn < J.vn3 ? W[J.base3 + nn * J.sn3 + k * J.sk3] : 0.0f;
+    const float w = getw(J.base3, J.base3b, nn, k, J.sn3, J.sk3, J.rbs3, J.cbs3, J.vn3, J.vk3);
     const float hi = to_tf32(w);
     const int c = k / WKC, kk = k - c * WKC;
     float* blk = base + im.s3_off + (size_t)c * im.s3_floats;
@@ -449,20 +473,25 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             for (int qq = 0; qq < 8; ++qq) {
               const int j = k0 + qq;
               zb[qq] = zo[qq] = sv[qq] = 0.0f;
-              if (valid && j < a.a) {
-                const int k = a.af[j];
+              // fused pair (net_id 2): entries [0, a16) are sbar, [a16, 2 a16) are tbar
+              const bool s_form = a.net_id == 0 || (a.net_id == 2 && j < a.a16);
+              const int jj = (a.net_id == 2 && j >= a.a16) ? j - a.a16 : j;
+              if (valid && jj < a.a) {
+                const int k = a.af[jj];
                 zb[qq] = a.zbar[tidx(tile, d, k, row)];
-                if (a.net_id == 0)
+                if (s_form)
                   zo[qq] = a.zout[tidx(tile, d, k, row)];
                 else if (a.has_s)
-                  sv[qq] = a.sbuf[((size_t)tile * a.a16 + j) * 128 + row];
+                  sv[qq] = a.sbuf[((size_t)tile * a.a16 + jj) * 128 + row];
               }
             }
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) {
               const int j = k0 + qq;
+              const bool s_form = a.net_id == 0 || (a.net_id == 2 && j < a.a16);
+              const int jj = (a.net_id == 2 && j >= a.a16) ? j - a.a16 : j;
               float val = 0.0f;
-              if (valid && j < a.a) val = a.net_id == 0 ? -zb[qq] * zo[qq] + a.inv_btot : -zb[qq] * expf(-sv[qq]);
+              if (valid && jj < a.a) val = s_form ? -zb[qq] * zo[qq] + a.inv_btot : -zb[qq] * expf(-sv[qq]);
               v[qq] = val;
             }
 #pragma unroll
@@ -531,7 +560,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             }
         } else {
           if constexpr (MODE == TC_FWD_STORE) {
-            if (a.net_id == 1 && live)
+            if (a.net_id >= 1 && live)
               for (int k0 = 0; k0 < K0p; k0 += 4) {
                 const int idx = core_idx(row, k0, K0p);
                 const float4 hi = *reinterpret_cast<const float4*>(A1h + idx), lo = *reinterpret_cast<const float4*>(A1l + idx);
@@ -541,7 +570,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
                 a.inbuf[tbuf_idx(tile, K0p, k0 + 3, row)] = hi.w + lo.w;
               }
           }
-          if (a.x_out != a.x_in && a.net_id == 1 && live) {  // out-of-place (training sweep): carry the whole state
+          if (a.x_out != a.x_in && a.net_id >= 1 && live) {  // out-of-place (training sweep): carry the whole state
             for (int k0 = 0; k0 < d; k0 += 8) {
               float v[8];
 #pragma unroll
@@ -584,24 +613,26 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
               if (k >= n && k < a.nin) a.zbar[tidx(tile, d, a.id[k - n], row)] = zb[j] + v[j];
             }
           }
-        } else if (a.net_id == 0) {
+        } else if (a.net_id == 0 || (a.net_id == 2 && o0 < a.a16)) {
+          // s values (a fused pair delivers them in output columns [0, a16), the t values in [a16, 2 a16))
           if (live)
 #pragma unroll
             for (int j = 0; j < 16; ++j) a.sbuf[((size_t)tile * a.a16 + o0 + j) * 128 + row] = v[j] + biasS[2 * H + o0 + j];
         } else if (valid) {
           // coupling transform (src/affine/RNVP.jl:92,184; NICE: s = 0)
+          const int ob = a.net_id == 2 ? o0 - a.a16 : o0;
           float sv[16], xv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int jj = o0 + j;
+            const int jj = ob + j;
             sv[j] = (jj < a.a && a.has_s) ? a.sbuf[((size_t)tile * a.a16 + jj) * 128 + row] : 0.0f;
             xv[j] = (jj < a.a) ? a.x_in[tidx(tile, d, a.af[jj], row)] : 0.0f;
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int jj = o0 + j;
+            const int jj = ob + j;
             if (jj < a.a) {
-              const float tv = v[j] + biasS[2 * H + jj];
+              const float tv = v[j] + biasS[2 * H + o0 + j];
               a.x_out[tidx(tile, d, a.af[jj], row)] = a.sampling ? xv[j] * expf(sv[j]) + tv : (xv[j] - tv) * expf(-sv[j]);
               lsum += sv[j];
             }
@@ -610,7 +641,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
       }
       if constexpr (MODE == TC_BWD) {
         // cotangent of the transformed coordinates: ubar_af = zbar_af * exp(-s) (src/affine/RNVP.jl:134)
-        if (a.net_id == 1 && a.has_s && valid)
+        if (a.net_id >= 1 && a.has_s && valid)
           for (int j0 = 0; j0 < a.a; j0 += 8) {
             float sv[8], zb[8];
 #pragma unroll
@@ -624,7 +655,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
               if (j0 + qq < a.a) a.zbar[tidx(tile, d, a.af[j0 + qq], row)] = zb[qq] * expf(-sv[qq]);
           }
       } else {
-        if (a.net_id == 1 && a.ldj && valid) a.ldj[gi] += a.sampling ? lsum : -lsum;
+        if (a.net_id >= 1 && a.ldj && valid) a.ldj[gi] += a.sampling ? lsum : -lsum;
       }
     };
     if (iters > 0) build_a1(0, 0);
@@ -936,6 +967,9 @@ struct DwArgs {
   int first_net;
   int p_w[2][3], p_b[2][3];
   float* grad;
+  // fused s + t pair: one conditioner of width H = 2 hblk whose rows [0, hblk) belong to the s net and [hblk, 2 hblk) to
+  // the t net; delta3 rows [0, ablk) / [ablk, 2 ablk) likewise (a16 = 2 ablk); only the diagonal blocks are parameters
+  int fused, hblk, ablk;
 };
 
 // Stage layout (floats), operands K-major with K = DW_KS samples, each [hi | lo]:
@@ -1107,38 +1141,48 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       const int sgi = seg_of(rb, rb0);
       const int row = (rb - rb0) * 8 + (lane & 7);
       const bool seg_ok = (segmask >> i) & 1u, ok = (okmask >> i) & 1u;
-      if (seg_ok && sgi < 2 && lane < 8 && ok && nstages > 0)
-        atomicAdd(a.grad + a.p_b[net][sgi == 0 ? 1 : 0] + mt * 128 + row, r);
-      if (seg_ok && sgi == 5 && mt == 0 && lane < 8 && row < a.a && nstages > 0)
-        atomicAdd(a.grad + a.p_b[net][2] + row, r);
+      if (seg_ok && sgi < 2 && lane < 8 && ok && nstages > 0) {
+        const int hr = mt * 128 + row;
+        const int bn = a.fused ? hr / a.hblk : net, hr2 = a.fused ? hr % a.hblk : hr;
+        atomicAdd(a.grad + a.p_b[bn][sgi == 0 ? 1 : 0] + hr2, r);
+      }
+      if (seg_ok && sgi == 5 && mt == 0 && lane < 8 && nstages > 0) {
+        const int bn = a.fused ? row / a.ablk : net, r2 = a.fused ? row % a.ablk : row;
+        if (row < a16 && r2 < a.a) atomicAdd(a.grad + a.p_b[bn][2] + r2, r);
+      }
     }
     // ---- flush: warps 0-3 own TMEM lanes 32w..32w+31 = hidden unit rows of this m-tile ----
     if (warp < 4 && nstages > 0) {
       mbar_wait(done, 0);
       tc_fence_after();
       const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-      const int o = mt * 128 + tid;  // hidden unit (row of delta2 / delta1 / h2)
+      const int og = mt * 128 + tid;  // hidden unit (row of delta2 / delta1 / h2) of the (possibly fused) conditioner
       const bool ok = tid < rows_valid;
+      const int fn = a.fused ? og / a.hblk : net;           // net that owns this row
+      const int o = a.fused ? og % a.hblk : og;             // row inside that net
+      const int Hn = a.fused ? a.hblk : H;                  // width of that net
+      const int i_lo = a.fused ? fn * a.hblk : 0;           // columns of dW2 that belong to it (diagonal block)
+      const int j_lo = a.fused ? fn * a.ablk : 0, j_n = a.fused ? a.ablk : a16;
       float w[16];
-      for (int i0 = 0; i0 < H; i0 += 16) {  // dW2[o][i] at p_w2 + o + H * i
-        tmem_ld16(tbase + lane_off + DWT_W2 + i0, w);
-        if (ok)
+      for (int i0 = 0; i0 < Hn; i0 += 16) {  // dW2[o][i] at p_w2 + o + Hn * i
+        tmem_ld16(tbase + lane_off + DWT_W2 + i_lo + i0, w);
+        if (ok && fn < 2)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(a.grad + a.p_w[net][1] + o + (size_t)H * (i0 + j), w[j]);
+          for (int j = 0; j < 16; ++j) atomicAdd(a.grad + a.p_w[fn][1] + o + (size_t)Hn * (i0 + j), w[j]);
       }
-      for (int k0 = 0; k0 < K0p; k0 += 16) {  // dW1[o][k] at p_w1 + o + H * k
+      for (int k0 = 0; k0 < K0p; k0 += 16) {  // dW1[o][k] at p_w1 + o + Hn * k
         tmem_ld16(tbase + lane_off + DWT_W1 + k0, w);
-        if (ok)
+        if (ok && fn < 2)
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (k0 + j < a.K0) atomicAdd(a.grad + a.p_w[net][0] + o + (size_t)H * (k0 + j), w[j]);
+            if (k0 + j < a.K0) atomicAdd(a.grad + a.p_w[fn][0] + o + (size_t)Hn * (k0 + j), w[j]);
       }
-      for (int j0 = 0; j0 < a16; j0 += 16) {  // dW3[j][i=o] at p_w3 + j + a * o
-        tmem_ld16(tbase + lane_off + DWT_W3 + j0, w);
-        if (ok)
+      for (int j0 = 0; j0 < j_n; j0 += 16) {  // dW3[j][i=o] at p_w3 + j + a * o
+        tmem_ld16(tbase + lane_off + DWT_W3 + j_lo + j0, w);
+        if (ok && fn < 2)
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (j0 + j < a.a) atomicAdd(a.grad + a.p_w[net][2] + (j0 + j) + (size_t)a.a * o, w[j]);
+            if (j0 + j < a.a) atomicAdd(a.grad + a.p_w[fn][2] + (j0 + j) + (size_t)a.a * o, w[j]);
       }
     }
   } else {
@@ -1485,9 +1529,9 @@ int tc_build_plan(dflow_chain* c) {
       TcPackJob J;
       memset(&J, 0, sizeof(J));
       J.im = Ld.fwd[ni];
-      J.base1 = net.p_w[0]; J.sn1 = 1; J.sk1 = h; J.vk1 = Ld.nin;
-      J.base2 = net.p_w[1]; J.sn2 = 1; J.sk2 = h;
-      J.base3 = net.p_w[2]; J.sn3 = 1; J.sk3 = a; J.vn3 = a;
+      J.base1 = net.p_w[0]; J.sn1 = 1; J.sk1 = h; J.vk1 = Ld.nin; J.vn1 = h;
+      J.base2 = net.p_w[1]; J.sn2 = 1; J.sk2 = h; J.vn2 = h; J.vk2 = h;
+      J.base3 = net.p_w[2]; J.sn3 = 1; J.sk3 = a; J.vn3 = a; J.vk3 = h;
       J.pb1 = net.p_b[0]; J.pb2 = net.p_b[1]; J.pb3 = net.p_b[2]; J.nb3 = a;
       tp->jobs_fwd.push_back(J);
       tp->k0pmax = std::max(tp->k0pmax, Ld.fwd[ni].K0p);
@@ -1501,9 +1545,9 @@ int tc_build_plan(dflow_chain* c) {
         fill_img(Ld.bwd[ni], a, h, Ld.nin, off, 16);  // K0p = a16: delta3 rows double as the dW3 operand
         memset(&J, 0, sizeof(J));
         J.im = Ld.bwd[ni];
-        J.base1 = net.p_w[2]; J.sn1 = a; J.sk1 = 1; J.vk1 = a;
-        J.base2 = net.p_w[1]; J.sn2 = h; J.sk2 = 1;
-        J.base3 = net.p_w[0]; J.sn3 = h; J.sk3 = 1; J.vn3 = Ld.nin;
+        J.base1 = net.p_w[2]; J.sn1 = a; J.sk1 = 1; J.vk1 = a; J.vn1 = h;
+        J.base2 = net.p_w[1]; J.sn2 = h; J.sk2 = 1; J.vn2 = h; J.vk2 = h;
+        J.base3 = net.p_w[0]; J.sn3 = h; J.sk3 = 1; J.vn3 = Ld.nin; J.vk3 = h;
         J.pb1 = J.pb2 = J.pb3 = -1;
         tp->jobs_bwd.push_back(J);
         for (int r = 0; r < 2; ++r) {
@@ -1512,6 +1556,36 @@ int tc_build_plan(dflow_chain* c) {
           tp->jobs_bwd.push_back(J);
         }
       }
+    }
+    tp->hu = std::max(tp->hu, h);
+    // fused s + t pair: same input, same widths, 2h within one 256-column pass
+    if (Ld.has_s && E.s.w[1] == h && E.s.w[2] == h && 2 * h <= 256) {
+      const int a16 = Ld.a16;
+      TcPackJob J;
+      // forward: M1 = [W1_s ; W1_t] (2h x nin), M2 = diag(W2_s, W2_t), M3 = diag(W3_s, W3_t) with the t rows at a16
+      fill_img(Ld.ffwd, Ld.nin, 2 * h, a16 + a, off);
+      memset(&J, 0, sizeof(J));
+      J.im = Ld.ffwd;
+      J.fuse = 1;
+      J.base1 = E.s.p_w[0]; J.base1b = E.t.p_w[0]; J.sn1 = 1; J.sk1 = h; J.rbs1 = h; J.cbs1 = 0; J.vn1 = h; J.vk1 = Ld.nin;
+      J.base2 = E.s.p_w[1]; J.base2b = E.t.p_w[1]; J.sn2 = 1; J.sk2 = h; J.rbs2 = h; J.cbs2 = h; J.vn2 = h; J.vk2 = h;
+      J.base3 = E.s.p_w[2]; J.base3b = E.t.p_w[2]; J.sn3 = 1; J.sk3 = a; J.rbs3 = a16; J.cbs3 = h; J.vn3 = a; J.vk3 = h;
+      J.pb1 = E.s.p_b[0]; J.pb1b = E.t.p_b[0]; J.pb2 = E.s.p_b[1]; J.pb2b = E.t.p_b[1];
+      J.pb3 = E.s.p_b[2]; J.pb3b = E.t.p_b[2]; J.nb3 = a; J.bbs12 = h; J.bbs3 = a16;
+      tp->jobs_fwd.push_back(J);
+      // adjoint: input [sbar (a16) | tbar (a16)], M1 = diag(W3_s^T, W3_t^T), M2 = diag(W2^T), M3 = [W1_s^T | W1_t^T]
+      fill_img(Ld.fbwd, a16 + a, 2 * h, Ld.nin, off, 16);
+      memset(&J, 0, sizeof(J));
+      J.im = Ld.fbwd;
+      J.fuse = 1;
+      J.base1 = E.s.p_w[2]; J.base1b = E.t.p_w[2]; J.sn1 = a; J.sk1 = 1; J.rbs1 = h; J.cbs1 = a16; J.vn1 = h; J.vk1 = a;
+      J.base2 = E.s.p_w[1]; J.base2b = E.t.p_w[1]; J.sn2 = h; J.sk2 = 1; J.rbs2 = h; J.cbs2 = h; J.vn2 = h; J.vk2 = h;
+      J.base3 = E.s.p_w[0]; J.base3b = E.t.p_w[0]; J.sn3 = h; J.sk3 = 1; J.rbs3 = 0; J.cbs3 = h; J.vn3 = Ld.nin; J.vk3 = h;
+      J.pb1 = J.pb2 = J.pb3 = J.pb1b = J.pb2b = J.pb3b = -1;
+      J.bbs12 = h; J.bbs3 = 16;
+      tp->jobs_bwd.push_back(J);
+      TcLaunchCfg fc;
+      Ld.fused = (tc_launch_cfg(c, Ld.ffwd, fc) && tc_launch_cfg(c, Ld.fbwd, fc)) ? 1 : 0;
     }
     TcLaunchCfg cfg;
     for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
@@ -1696,11 +1770,15 @@ int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* thet
       c->launches++;
       continue;
     }
-    for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
+    // s and t conditioners as one block-diagonal conditioner: forward-type calls only on request (tc_fuse = 2) -- the
+    // zero blocks double the weight image, which costs the hidden-64 nets their resident weights and second CTA per SM
+    // (C3 log-density 6.9 ms fused vs 6.2 ms separate); the train step (tc_loss_grad) fuses by default (31.6 vs 36.8 ms)
+    const bool fz = Ld.fused && c->tc_fuse >= 2;
+    for (int ni = (fz ? 2 : Ld.has_s ? 0 : 1); ni < (fz ? 3 : 2); ++ni) {
       TcArgs a;
       memset(&a, 0, sizeof(a));
       fill_common(c, Ld, a);
-      a.im = Ld.fwd[ni];
+      a.im = fz ? Ld.ffwd : Ld.fwd[ni];
       a.net_id = ni;
       a.B = B;
       a.sampling = sampling;
@@ -1711,7 +1789,7 @@ int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* thet
       a.theta_const = theta_const;
       a.ldj = ldj;
       a.sbuf = tp->d_sbuf;
-      rc = launch_net<TC_FWD>(c, a, st, Ld.fwd2[ni]);
+      rc = launch_net<TC_FWD>(c, a, st, fz ? nullptr : Ld.fwd2[ni]);
       if (rc) return rc;
     }
   }
@@ -1784,8 +1862,8 @@ static void train_layout(const dflow_chain* c, long long B, TcTrainLayout& T) {
   const DevChainHdr& Hd = c->hc()->h;
   const long long L = (long long)tp->layers.size();
   // per-sample floats of everything that scales with the macro-batch
-  const long long per = (L + 1) * Hd.d + 1 + Hd.d + Hd.n + L * tp->a16max + L * tp->k0pmax + L * 4 * tp->hmax +
-                        L * 4 * (tp->hmax / 32) + 4 * tp->hmax + 2 * tp->a16max;
+  const long long per = (L + 1) * Hd.d + 1 + Hd.d + Hd.n + L * tp->a16max + L * tp->k0pmax + L * 4 * tp->hu +
+                        L * 4 * (tp->hu / 32) + 4 * tp->hu + 2 * tp->a16max;
   long long MB = ((B + 127) / 128) * 128;
   const long long budget = c->tc_ws_budget_mb > 0 ? (long long)c->tc_ws_budget_mb << 20 : (long long)24 << 30;  // bytes
   long long cap = budget / (per * 4);
@@ -1804,9 +1882,9 @@ static void train_layout(const dflow_chain* c, long long B, TcTrainLayout& T) {
   T.theta = take((long long)Hd.n * MB);
   T.sbuf = take(L * tp->a16max * MB);
   T.inbuf = take(L * tp->k0pmax * MB);
-  T.hbuf = take(L * 4 * tp->hmax * MB);
-  T.mbuf = take(L * 4 * (tp->hmax / 32) * MB);
-  T.dbuf = take(4LL * tp->hmax * MB);
+  T.hbuf = take(L * 4 * tp->hu * MB);
+  T.mbuf = take(L * 4 * (tp->hu / 32) * MB);
+  T.dbuf = take(4LL * tp->hu * MB);
   T.d3buf = take(2LL * tp->a16max * MB);
   T.total = o;
 }
@@ -1830,7 +1908,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
   TcTrainLayout T;
   train_layout(c, B, T);
   float* wsf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  const int L = (int)tp->layers.size(), d = Hd.d, n = Hd.n, hmax = tp->hmax, a16m = tp->a16max, k0m = tp->k0pmax;
+  const int L = (int)tp->layers.size(), d = Hd.d, n = Hd.n, hu = tp->hu, a16m = tp->a16max, k0m = tp->k0pmax;
   int rc = tc_prepack(c, W, true, st);
   if (rc) return rc;
   for (long long first = 0; first < B; first += T.MB) {
@@ -1844,13 +1922,15 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
     auto slot = [&](int e) { return traj + (size_t)e * st_d; };
     auto sbuf_of = [&](int e) { return wsf + T.sbuf + (size_t)e * a16m * T.MB; };
     auto inbuf_of = [&](int e) { return wsf + T.inbuf + (size_t)e * k0m * T.MB; };
+    // per layer four hu-wide slots: [net][h1 | h2]; a fused pair (width 2 hu) uses them as [h1 (2 slots) | h2 (2 slots)]
+    auto hslot = [](int net, int which) { return net == 2 ? which * 2 : net * 2 + which; };
     auto hbuf_of = [&](int e, int net, int which) {
-      return wsf + T.hbuf + ((size_t)(e * 2 + net) * 2 + which) * (size_t)hmax * T.MB;
+      return wsf + T.hbuf + ((size_t)e * 4 + hslot(net, which)) * (size_t)hu * T.MB;
     };
     auto mbuf_of = [&](int e, int net, int which) {
-      return reinterpret_cast<uint32_t*>(wsf + T.mbuf) + ((size_t)(e * 2 + net) * 2 + which) * (size_t)(hmax / 32) * T.MB;
+      return reinterpret_cast<uint32_t*>(wsf + T.mbuf) + ((size_t)e * 4 + hslot(net, which)) * (size_t)(hu / 32) * T.MB;
     };
-    auto dbuf_of = [&](int net, int which) { return wsf + T.dbuf + (size_t)(net * 2 + which) * (size_t)hmax * T.MB; };
+    auto dbuf_of = [&](int net, int which) { return wsf + T.dbuf + (size_t)hslot(net, which) * (size_t)hu * T.MB; };
     auto d3buf_of = [&](int net) { return wsf + T.d3buf + (size_t)net * a16m * T.MB; };
     // input slot L: gather (or copy) this macro-batch
     rc = gather_t(c, x, idx, first, mb, d, slot(L), st);
@@ -1871,11 +1951,12 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         c->launches++;
         continue;
       }
-      for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
+      const bool fz = Ld.fused && c->tc_fuse > 0;
+      for (int ni = (fz ? 2 : Ld.has_s ? 0 : 1); ni < (fz ? 3 : 2); ++ni) {
         TcArgs a;
         memset(&a, 0, sizeof(a));
         fill_common(c, Ld, a);
-        a.im = Ld.fwd[ni];
+        a.im = fz ? Ld.ffwd : Ld.fwd[ni];
         a.net_id = ni;
         a.B = mb;
         a.sampling = 0;
@@ -1890,7 +1971,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         a.h2buf = hbuf_of(ei, ni, 1);
         a.m1buf = mbuf_of(ei, ni, 0);
         a.m2buf = mbuf_of(ei, ni, 1);
-        rc = launch_net<TC_FWD_STORE>(c, a, st, Ld.fwd2[ni]);
+        rc = launch_net<TC_FWD_STORE>(c, a, st, fz ? nullptr : Ld.fwd2[ni]);
         if (rc) return rc;
       }
     }
@@ -1910,11 +1991,12 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         c->launches++;
         continue;
       }
-      for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
+      const bool fz = Ld.fused && c->tc_fuse > 0;
+      for (int ni = (fz ? 2 : Ld.has_s ? 0 : 1); ni < (fz ? 3 : 2); ++ni) {
         TcArgs a;
         memset(&a, 0, sizeof(a));
         fill_common(c, Ld, a);
-        a.im = Ld.bwd[ni];
+        a.im = fz ? Ld.fbwd : Ld.bwd[ni];
         a.net_id = ni;
         a.B = mb;
         a.flags = flags;
@@ -1923,34 +2005,39 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         a.m2buf = mbuf_of(ei, ni, 1);
         a.d1buf = dbuf_of(ni, 0);
         a.d2buf = dbuf_of(ni, 1);
-        a.d3buf = d3buf_of(ni);
+        a.d3buf = d3buf_of(fz ? 0 : ni);
         a.zbar = zbar;
         a.zout = slot(ei);
         a.inv_btot = inv_btot;
         a.grad = grad_out;
-        a.p_b3 = Ld.p_b[ni][2];
-        rc = launch_net<TC_BWD>(c, a, st, Ld.bwd2[ni]);
+        a.p_b3 = Ld.p_b[fz ? 0 : ni][2];
+        rc = launch_net<TC_BWD>(c, a, st, fz ? nullptr : Ld.bwd2[ni]);
         if (rc) return rc;
       }
       // weight gradients of this layer
       DwArgs w;
       memset(&w, 0, sizeof(w));
-      w.H = Ld.h;
+      const bool fzw = Ld.fused && c->tc_fuse > 0;
+      w.H = fzw ? 2 * Ld.h : Ld.h;
       w.K0p = Ld.fwd[1].K0p;
       w.K0 = Ld.nin;
       w.a = Ld.a;
-      w.a16 = Ld.a16;
-      w.mtiles = (Ld.h + 127) / 128;
-      w.first_net = Ld.has_s ? 0 : 1;
-      w.units = (Ld.has_s ? 2 : 1) * w.mtiles;
+      w.a16 = fzw ? 2 * Ld.a16 : Ld.a16;
+      w.fused = fzw ? 1 : 0;
+      w.hblk = Ld.h;
+      w.ablk = Ld.a16;
+      w.mtiles = (w.H + 127) / 128;
+      w.first_net = (fzw || Ld.has_s) ? 0 : 1;
+      w.units = (fzw ? 1 : Ld.has_s ? 2 : 1) * w.mtiles;
       w.ksplit = (int)std::max<long long>(1, std::min<long long>(ntiles, c->sm_count / w.units));
       w.ntiles = ntiles;
       for (int ni = 0; ni < 2; ++ni) {
-        w.h1buf[ni] = hbuf_of(ei, ni, 0);
-        w.h2buf[ni] = hbuf_of(ei, ni, 1);
-        w.d1buf[ni] = dbuf_of(ni, 0);
-        w.d2buf[ni] = dbuf_of(ni, 1);
-        w.d3buf[ni] = d3buf_of(ni);
+        const int bi = fzw ? 2 : ni;  // fused: one set of buffers (slot scheme of hbuf_of)
+        w.h1buf[ni] = hbuf_of(ei, bi, 0);
+        w.h2buf[ni] = hbuf_of(ei, bi, 1);
+        w.d1buf[ni] = dbuf_of(bi, 0);
+        w.d2buf[ni] = dbuf_of(bi, 1);
+        w.d3buf[ni] = d3buf_of(fzw ? 0 : ni);
         for (int j = 0; j < 3; ++j) {
           w.p_w[ni][j] = Ld.p_w[ni][j];
           w.p_b[ni][j] = Ld.p_b[ni][j];

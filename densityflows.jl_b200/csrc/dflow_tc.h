@@ -44,6 +44,14 @@ struct TcPackJob {
   int base2, sn2, sk2;
   int base3, sn3, sk3, vn3;
   int pb1, pb2, pb3, nb3;  // bias offsets in the packed buffer (-1: zeros), number of real b3 entries
+  // Fused s + t pair (one conditioner of width 2h with block-diagonal matrices): the `b` fields address the second net,
+  // rbs / cbs are the row / column block sizes of the three matrices (0: that dimension is shared by both nets), vn / vk
+  // the valid rows / columns inside a block.  A (row block, column block) pair off the diagonal is zero.
+  int fuse;
+  int base1b, base2b, base3b, pb1b, pb2b, pb3b;
+  int rbs1, cbs1, rbs2, cbs2, rbs3, cbs3;
+  int vn1, vn2, vk2, vk3;
+  int bbs12, bbs3;  // block sizes of the bias vectors b1/b2 and b3
 };
 
 struct TcLayer {
@@ -54,6 +62,10 @@ struct TcLayer {
   int p_w[2][3], p_b[2][3];
   TcNetImg fwd[2], bwd[2];
   TcNetImg fwd2[2][2], bwd2[2][2];  // [net][rank of the CTA pair]: half-row images for cta_group::2
+  // hidden <= 128 RealNVP layers: the s and t conditioners (same input, same widths) run as ONE conditioner of width 2h
+  // with block-diagonal W2 / W3 -- half the launches, MMA issues and pipeline hand-offs on an issue-bound shape
+  int fused;
+  TcNetImg ffwd, fbwd;
 };
 
 // per-layer training buffers (offsets in floats inside the caller's workspace)
@@ -84,6 +96,7 @@ struct TcPlan {
   float* d_work = nullptr;  // tile-blocked working state of the forward-type calls [x | ldj | theta], grow-only
   size_t work_floats = 0;
   int hmax = 0, a16max = 0, k0pmax = 0;
+  int hu = 0;  // widest single conditioner (training buffers hold 2 nets x 2 activations x hu per layer and sample)
   bool train_ok = false;  // adjoint supported (h <= 256)
 };
 

@@ -307,3 +307,42 @@ def test_wide_generation_1_kernels_still_match():
     b = pc.logpdf(x, th).clone()
     pc.tune(wide_gen=2)
     assert torch.allclose(a, b, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["h128_d8", "h96_d6_n0", "h64_d16", "h32_d10"])
+def test_fused_conditioner_pair_matches_separate_conditioners(name):
+    """tc_fuse: the s and t conditioners of a RealNVP layer (same input, same widths, 2h <= 256) run as one conditioner
+    of width 2h with block-diagonal W2 / W3 (default in the train step; tc_fuse=2 also in forward-type calls).  The zero
+    blocks contribute exact zeros, so forward results are bit-identical to the separate conditioners; gradients agree to
+    summation order."""
+    narrow = name in NARROW_ON_TC
+    d, n, L, h = NARROW_ON_TC[name] if narrow else CASES[name]
+    B = 1300
+    x, th = O.synthetic_data(d, n, B, seed=21)
+    ochain = O.block_chain(d, n, L, h, O.synthetic_data(d, n, 1000, seed=99)[0], s_out_scale=0.3)
+    chain = chain_from_oracle(ochain)
+    pc = chain.packed()
+    if narrow:
+        pc.tune(tc_mode=1)
+    xj = df.to_jl(x, DEV)
+    tj = df.to_jl(th, DEV) if n else None
+    out = {}
+    for fuse in (2, 0):
+        pc.tune(tc_fuse=fuse)
+        before = pc.launch_count()
+        lp = pc.logpdf(xj, tj).clone()
+        nl = pc.launch_count() - before
+        z, ldj = pc.normalize(xj, tj)
+        grad = torch.zeros(pc.P, device=DEV)
+        l2 = torch.zeros(2, device=DEV)
+        pc.loss_grad(xj, tj, grad, l2)
+        out[fuse] = (lp, z.clone(), ldj.clone(), grad, l2, nl)
+    pc.tune(tc_fuse=1)
+    if narrow:
+        pc.tune(tc_mode=0)
+    assert out[2][5] < out[0][5], "fused pairs need fewer launches"
+    for i in range(3):
+        assert torch.equal(out[2][i], out[0][i])
+    gmax = float(out[0][3].abs().max())
+    assert float((out[2][3] - out[0][3]).abs().max()) <= 2e-5 * gmax
+    assert abs(float(out[2][4][0] - out[0][4][0])) <= 1e-5 * abs(float(out[0][4][0]))
