@@ -394,7 +394,9 @@ __constant__ uint4 g_cbank[CBANK_BYTES / 16];
 __device__ __forceinline__ float cbw(int off) { return reinterpret_cast<const float*>(g_cbank)[off]; }
 // four consecutive weights (off is a multiple of 4 floats: staged blocks, rows and biases are 16-byte aligned) with one
 // wide uniform load instead of four LDCU.32 (the 32-bit form made LDCU 24 % of all issued instructions)
-__device__ __forceinline__ float4 cbw4(int off) { return reinterpret_cast<const float4*>(g_cbank)[off >> 2]; }
+// (offsets are passed in float4 units, base + compile-time immediate: with float offsets every load cost a uniform shift
+// and add -- USHF + UIADD3 were 17 % of all issued instructions in the ncu capture)
+__device__ __forceinline__ float4 cbw4(int off4) { return reinterpret_cast<const float4*>(g_cbank)[off4]; }
 template <int S>
 __device__ __forceinline__ void bias4_samples(float (&a0)[S], float (&a1)[S], float (&a2)[S], float (&a3)[S], int off) {
   const float4 b = cbw4(off);
@@ -421,17 +423,17 @@ __device__ __forceinline__ void run_net_const(const DevNet& net, int wofs, const
   // first Dense: inputs are the gathered theta / x columns (runtime depth), outputs in registers; the bias is the
   // addend of the first row
   {
-    const int w0 = wofs + net.s_w[0], b0 = wofs + net.s_b[0];
+    const int w0 = (wofs + net.s_w[0]) >> 2, b0 = (wofs + net.s_b[0]) >> 2;  // float4 units (16-byte aligned blocks)
     const int n = in.n, K = net.w[0];
 #pragma unroll
-    for (int o = 0; o < HP; o += 4) bias4_samples<S>(h[o], h[o + 1], h[o + 2], h[o + 3], b0 + o);
+    for (int o = 0; o < HP; o += 4) bias4_samples<S>(h[o], h[o + 1], h[o + 2], h[o + 3], b0 + o / 4);
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
       const float* src = k < n ? in.th + k * CS : in.xs + (int)in.id[k - n] * CS;
       float v[S];
       ld_samples<S>(src + slot0 * S, v);
 #pragma unroll
-      for (int o = 0; o < HP; o += 4) fma4_samples<S>(h[o], h[o + 1], h[o + 2], h[o + 3], v, w0 + k * HP + o);
+      for (int o = 0; o < HP; o += 4) fma4_samples<S>(h[o], h[o + 1], h[o + 2], h[o + 3], v, w0 + k * (HP / 4) + o / 4);
     }
   }
   act_regs<HP, S>(h, net.act[0]);
@@ -439,13 +441,14 @@ __device__ __forceinline__ void run_net_const(const DevNet& net, int wofs, const
 #pragma unroll 1
   for (int j = 1; j < D - 1; ++j) {
     float o[HP][S];
-    const int wj = wofs + net.s_w[j], bj = wofs + net.s_b[j];
+    const int wj = (wofs + net.s_w[j]) >> 2, bj = (wofs + net.s_b[j]) >> 2;
 #pragma unroll
-    for (int oo = 0; oo < HP; oo += 4) bias4_samples<S>(o[oo], o[oo + 1], o[oo + 2], o[oo + 3], bj + oo);
+    for (int oo = 0; oo < HP; oo += 4) bias4_samples<S>(o[oo], o[oo + 1], o[oo + 2], o[oo + 3], bj + oo / 4);
 #pragma unroll
     for (int k = 0; k < HP; ++k)
 #pragma unroll
-      for (int oo = 0; oo < HP; oo += 4) fma4_samples<S>(o[oo], o[oo + 1], o[oo + 2], o[oo + 3], h[k], wj + k * HP + oo);
+      for (int oo = 0; oo < HP; oo += 4)
+        fma4_samples<S>(o[oo], o[oo + 1], o[oo + 2], o[oo + 3], h[k], wj + k * (HP / 4) + oo / 4);
     act_regs<HP, S>(o, net.act[j]);
 #pragma unroll
     for (int k = 0; k < HP; ++k)
@@ -456,13 +459,14 @@ __device__ __forceinline__ void run_net_const(const DevNet& net, int wofs, const
   // stride is a compile-time constant for the common widths so that every weight address is base + immediate
   {
     const int jl = D - 1, op = net.op[jl], act = net.act[jl];
-    const int wl = wofs + net.s_w[jl], bl = wofs + net.s_b[jl];
+    const int wl = (wofs + net.s_w[jl]) >> 2, bl = (wofs + net.s_b[jl]) >> 2;
     auto group = [&](int o0, auto ldc) {
       constexpr int LD = decltype(ldc)::value;  // 0: runtime stride
       float acc[4][S];
-      bias4_samples<S>(acc[0], acc[1], acc[2], acc[3], bl + o0);
+      bias4_samples<S>(acc[0], acc[1], acc[2], acc[3], bl + (o0 >> 2));
 #pragma unroll
-      for (int k = 0; k < HP; ++k) fma4_samples<S>(acc[0], acc[1], acc[2], acc[3], h[k], wl + k * (LD ? LD : op) + o0);
+      for (int k = 0; k < HP; ++k)
+        fma4_samples<S>(acc[0], acc[1], acc[2], acc[3], h[k], wl + k * ((LD ? LD : op) >> 2) + (o0 >> 2));
 #pragma unroll
       for (int oo = 0; oo < 4; ++oo) st_samples<S>(outcol + (o0 + oo) * CS + slot0 * S, acc[oo]);
     };
