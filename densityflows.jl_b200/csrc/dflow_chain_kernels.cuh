@@ -936,8 +936,13 @@ __global__ void __launch_bounds__((fwd_max_threads<HP, S, REG>()), (fwd_min_ctas
 }
 
 #ifdef DFLOW_CBANK
+// 3 CTAs of 128 threads per SM: 142 registers, no spills.  A 128-register build (4 CTAs, 96 B of spills) measured slower
+// (7.6-7.7e9 vs 8.1e9 samples/s on C2).
+#ifndef DFLOW_CB_MINCTAS
+#define DFLOW_CB_MINCTAS 3
+#endif
 template <int HP, int S>
-__global__ void __launch_bounds__((fwd_max_threads<HP, S, true>()), 3)
+__global__ void __launch_bounds__((fwd_max_threads<HP, S, true>()), DFLOW_CB_MINCTAS)
     chain_fwd_const_kernel(const __grid_constant__ FwdArgs a) {
   chain_fwd_body<HP, S, true, true, true>(a);  // always launched with fwd_max_threads (compile-time column stride)
 }
