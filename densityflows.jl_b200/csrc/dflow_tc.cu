@@ -970,6 +970,7 @@ struct DwArgs {
   // fused s + t pair: one conditioner of width H = 2 hblk whose rows [0, hblk) belong to the s net and [hblk, 2 hblk) to
   // the t net; delta3 rows [0, ablk) / [ablk, 2 ablk) likewise (a16 = 2 ablk); only the diagonal blocks are parameters
   int fused, hblk, ablk;
+  int debug;  // timing experiments only (wrong results): 1 no MMAs, 2 no global loads, 4 no split / shared-memory stores
 };
 
 // Stage layout (floats), operands K-major with K = DW_KS samples, each [hi | lo]:
@@ -1082,7 +1083,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
 #pragma unroll
       for (int i = 0; i < DW_MAXRB; ++i) {
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((okmask >> i) & 1u)
+        if (((okmask >> i) & 1u) && !(a.debug & 2))
           v[i] = __ldg(reinterpret_cast<const float4*>(my_ptr[i] + blk * (size_t)pick(ts_by, (codes >> (2 * i)) & 3u)));
       }
     };
@@ -1092,7 +1093,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       float* st = smem + (size_t)sl * stage_fl;
 #pragma unroll
       for (int i = 0; i < DW_MAXRB; ++i) {
-        if ((segmask >> i) & 1u) {
+        if (((segmask >> i) & 1u) && !(a.debug & 4)) {
           float4 hi, lo;
           hi.x = to_tf32(v[i].x); lo.x = v[i].x - hi.x;
           hi.y = to_tf32(v[i].y); lo.y = v[i].y - hi.y;
@@ -1207,9 +1208,11 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
         const uint64_t b = d0 + slot * stage_step;
         const uint32_t acc = s > 0 ? 1u : 0u;
         // dW2 += delta2 * h1^T ; dW1 += delta1 * in^T ; dW3^T += h2 * delta3^T   (each: lo*hi + hi*lo + hi*hi, 2 K steps)
-        gemm3_desc(tbase + DWT_W2, b + so[0], b + so[0] + sl[0], b + so[3], b + so[3] + sl[3], DW_KS / 8, idW2, acc);
-        gemm3_desc(tbase + DWT_W1, b + so[1], b + so[1] + sl[1], b + so[4], b + so[4] + sl[4], DW_KS / 8, idW1, acc);
-        gemm3_desc(tbase + DWT_W3, b + so[2], b + so[2] + sl[2], b + so[5], b + so[5] + sl[5], DW_KS / 8, idW3, acc);
+        if (!(a.debug & 1)) {
+          gemm3_desc(tbase + DWT_W2, b + so[0], b + so[0] + sl[0], b + so[3], b + so[3] + sl[3], DW_KS / 8, idW2, acc);
+          gemm3_desc(tbase + DWT_W1, b + so[1], b + so[1] + sl[1], b + so[4], b + so[4] + sl[4], DW_KS / 8, idW1, acc);
+          gemm3_desc(tbase + DWT_W3, b + so[2], b + so[2] + sl[2], b + so[5], b + so[5] + sl[5], DW_KS / 8, idW3, acc);
+        }
         mma_commit_a(empty_u32 + slot * 8);
         if (s == nstages - 1) mma_commit(done);
       }
@@ -2045,6 +2048,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       }
       w.inbuf = inbuf_of(ei);
       w.grad = grad_out;
+      w.debug = (c->tc_debug >> 12) & 7;  // bits 12-14 of tc_debug: weight-gradient kernel timing experiments
       const int RA = std::min(128, w.H);  // rows of the A segments (a multiple of 8: H % 32 == 0)
       const size_t stage_bytes = 2 * (size_t)(3 * RA + w.H + w.K0p + w.a16) * DW_KS * 4;
       // the M = 128 MMAs read 128 rows of every A segment: keep that overrun inside the allocation
