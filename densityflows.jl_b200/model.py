@@ -674,6 +674,8 @@ class PackedChain:
         """grad (P floats) and loss2 (2 floats) are ACCUMULATED into; returns the batch size."""
         x, θ = self._prep(x, θ)
         B = n_samples(x) if idx is None else int(idx.numel())
+        if B == 0:
+            return 0  # nothing to accumulate (an empty shard of a data-parallel minibatch)
         ib = (1.0 / B) if inv_btot is None else float(inv_btot)
         need = int(L.lib().dflow_workspace_bytes(self.handle, B))
         if self._ws is None or self._ws.numel() < need:

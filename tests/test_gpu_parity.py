@@ -389,3 +389,36 @@ def test_sample_with_rejection():
     assert torch.equal(df.arrays.flat_view(out).reshape(-1, 5).T, keep)
     with pytest.raises(ValueError):
         df.sample_with_rejection(7, lambda pts, θ_: pts[0] > 1e9, flow, 10, θ, 3)
+
+
+def test_empty_batch_and_unaligned_arrays():
+    """B = 0 is a no-op on every entry point (the reference's zero-column arrays), and arrays that are only 4-byte
+    aligned (a view into a larger buffer) take the scalar global-memory path of the kernels: same numbers."""
+    ochain, chain, x, th = _setup("readme_n2", 1030)
+    pc = chain.packed()
+    d, n, B = 5, 2, 1030
+    # empty
+    e_x, e_t = df.jl_empty((d, 0), DEV), df.jl_empty((n, 0), DEV)
+    assert pc.logpdf(e_x, e_t).numel() == 0
+    z0, l0 = pc.normalize(e_x, e_t)
+    assert z0.shape == (d, 0) and l0.numel() == 0
+    g = torch.zeros(pc.P, device=DEV)
+    l2 = torch.zeros(2, device=DEV)
+    assert pc.loss_grad(e_x, e_t, g, l2) == 0 and float(g.abs().sum()) == 0.0
+    # unaligned: column-major (d, B) views starting one float into their storage
+    xa, ta = df.to_jl(x, DEV), df.to_jl(th, DEV)
+    ref = pc.logpdf(xa, ta).clone()
+    zr, lr = pc.normalize(xa, ta)
+    bx = torch.empty(d * B + 1, device=DEV)
+    bt = torch.empty(n * B + 1, device=DEV)
+    bx[1:].copy_(df.arrays.flat_view(xa))
+    bt[1:].copy_(df.arrays.flat_view(ta))
+    xu = bx[1:].view(B, d).t()
+    tu = bt[1:].view(B, n).t()
+    assert xu.data_ptr() % 16 != 0 and df.arrays.is_colmajor(xu)
+    for mode in (0, -1):  # constant-bank kernel and shared-memory kernel
+        pc.tune(fwd_const=mode)
+        assert torch.equal(pc.logpdf(xu, tu), ref)
+        zu, lu = pc.normalize(xu, tu)
+        assert torch.equal(zu, zr) and torch.equal(lu, lr)
+    pc.tune(fwd_const=0)
