@@ -964,6 +964,8 @@ int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
   }
   if (!strcmp(key, "fwd_spt"))
     c->fwd_spt = value;
+  else if (!strcmp(key, "grad_smem"))
+    c->grad_smem = value;
   else if (!strcmp(key, "fwd_const"))
     c->fwd_const = value;
   else if (!strcmp(key, "fwd_threads"))

@@ -132,6 +132,8 @@ struct dflow_chain {
   int chain_bytes = 0;
   // tuning
   int fwd_spt = 0, fwd_threads = 0, grad_threads = 0, grad_spt = 0, ctas_per_sm = 0;
+  int grad_smem = 0;   // -1: the narrow adjoint adds its weight gradients straight to global memory (RED) instead of a
+                       // per-CTA shared-memory accumulator (shared float atomics are compare-and-swap loops)
   int fwd_const = 0;   // -1: never use the constant-bank forward kernel (default: use it when the chain is eligible)
   int cbank_ok = 0;    // relu chain, hidden <= 32, every conditioner >= 2 Dense, descriptor + staged image <= 60 KB
   long long launches = 0;

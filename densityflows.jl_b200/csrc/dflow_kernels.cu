@@ -255,7 +255,7 @@ template <int HP, int S>
 static int launch_grad2_t(dflow_chain* c, GradArgs& a, cudaStream_t st, int nt) {
   const DevChainHdr& h = c->hc()->h;
   if (nt > grad2_max_threads<HP, S>()) nt = grad2_max_threads<HP, S>();
-  a.smem_grad = (h.P * 4 <= 64 * 1024) ? 1 : 0;
+  a.smem_grad = (h.P * 4 <= 64 * 1024 && c->grad_smem >= 0) ? 1 : 0;
   SmemPlan p = plan_grad2(h, c->chain_bytes, nt * S, a.smem_grad);
   while (p.bytes() > (size_t)c->max_smem_optin && nt > 32) {
     nt = (nt > 256) ? (nt > 384 ? 384 : 256) : nt >> 1;  // 448 -> 384 -> 256 -> 128 -> ...
