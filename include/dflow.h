@@ -179,7 +179,12 @@ int dflow_sample_host(dflow_chain* chain, const float* W, uint64_t seed, const f
 
 /* ---- tuning / introspection ------------------------------------------------------------------------------ */
 /* keys: "fwd_spt", "grad_spt" (samples per thread; negative selects the alternative kernel generation),
- * "fwd_threads", "grad_threads", "ctas_per_sm"; value 0 = automatic */
+ * "fwd_threads", "grad_threads", "ctas_per_sm"; value 0 = automatic.
+ * "fwd_const" (-1: keep small relu chains off the constant-bank forward kernel), "grad_smem" (-1: weight gradients of the
+ * narrow adjoint go straight to global memory), "tc_mode" (1 / 0 / -1: force eligible hidden <= 64 chains onto / automatic
+ * / off the tensor-core kernels), "tc_fuse" (0 / 1 / 2: s and t conditioners of a layer as one block-diagonal conditioner
+ * never / in the train step / everywhere), "tc_ws_budget_mb" (adjoint workspace cap), "tc_cluster", "tc_ns_max",
+ * "tc_debug", "wide_gen" (experiments). */
 int dflow_set_tuning(dflow_chain* chain, const char* key, int32_t value);
 /* number of kernels the library has launched on behalf of this handle since creation */
 int64_t dflow_launch_count(const dflow_chain* chain);
