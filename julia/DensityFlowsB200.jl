@@ -223,6 +223,32 @@ function sample_device(flow::Flow{Float32,D}, dims::Tuple{Vararg{Integer}}, θ::
     return out
 end
 
+"""
+sample_with_rejection(condition, flow, dims, θ::NTuple, m = 100) on the device (src/Flows.jl:196-229): the same stream
+of points as `sample_device` with that seed (Philox counter = draw index), drawn in batches; `condition(points, θ)`
+gets a `(D, nb)` CuArray and returns a Bool vector over the batch; accepted points are compacted in draw order.
+"""
+function sample_with_rejection_device(condition::Function, flow::Flow{Float32,D}, dims::Tuple{Vararg{Integer}},
+                                      θ::NTuple{Nθ,Float32}, m::Int = 100; seed::UInt64 = rand(UInt64)) where {D,Nθ}
+    pc = packed(flow); n = prod(dims); out = CuArray{Float32}(undef, D, n)
+    θc = CuArray(collect(θ))
+    have = 0; drawn = 0; nb = max(1024, 2n)
+    while have < n && drawn < m * n
+        cur = min(nb, m * n - drawn)
+        pts = CuArray{Float32}(undef, D, cur)
+        check(ccall((:dflow_sample_rng, libdflow), Cint,
+                    (Ptr{Cvoid}, CuPtr{Float32}, UInt64, UInt32, UInt64, CuPtr{Float32}, CuPtr{Float32}, Int64, Int32, CuPtr{Float32}, Ptr{Cvoid}),
+                    pc.handle, pc.W, seed, UInt32(0), UInt64(drawn), CU_NULL, Nθ > 0 ? pointer(θc) : CU_NULL, cur,
+                    Nθ > 0 ? THETA_NORMALIZE : Int32(0), pts, stream()))
+        keep = pts[:, findall(Array(condition(pts, θ)))]
+        take = min(size(keep, 2), n - have)
+        out[:, have+1:have+take] .= keep[:, 1:take]
+        have += take; drawn += cur; nb = min(2nb, 1 << 24)
+    end
+    have < n && throw(ArgumentError("Impossible to reach convergence of rejection sampling"))
+    return reshape(out, D, dims...)
+end
+
 # ---- train! on device-resident data (src/Flows.jl:380-445) -----------------------------------------------------
 "Device-resident DataArrays: x, θ on the GPU and the partition as 0-based Int32 index vectors."
 struct CuDataArrays
