@@ -223,7 +223,7 @@ template <int HP, int S>
 constexpr int grad2_max_threads() {
   // hidden 16, S = 2: one 384-thread CTA per SM (12 warps; 448 threads measured slower: 224 KB of shared memory leave no L1) instead of one 256-thread CTA -- the kernel is latency-bound
   // and shared memory (240 B of columns per sample at C2) is what limits the resident warps
-  return HP * S >= 64 ? 128 : (HP == 16 && S == 2 ? 384 : 256);
+  return (HP == 16 && S == 4) ? 192 : HP * S >= 64 ? 128 : (HP == 16 && S == 2 ? 384 : 256);
 }
 template <int HP, int S>
 constexpr int grad2_min_ctas() {
