@@ -237,6 +237,25 @@ def run_ours(args):
                             "scaling": "weak", "allreduce_bytes": 4 * (pc.P + 2), "collective": coll(ts)}
     pc.W.copy_(w_save)
 
+    # ---- C1: the README example's own training configuration (1e5 samples, 90 % training split, batchsize 64: the
+    # reference default, src/Flows.jl:380): one epoch = 1407 launch-bound minibatch steps enqueued from C ----
+    if world == 1:
+        n_tr, bs = 90000, 64
+        order = torch.randperm(n_tr, generator=torch.Generator().manual_seed(5)).to(torch.int32).to(dev)
+        m1 = torch.zeros(pc.P, device=dev)
+        v1 = torch.zeros(pc.P, device=dev)
+        tt = [0]
+
+        def step_epoch():
+            tt[0] = pc.train_epoch(x[:, :100000], th[:, :100000], order, bs, m1, v1, tt[0], 1e-3, (0.9, 0.999), 1e-8, flags)
+
+        ms_e = timed(step_epoch, 3, 1, dist)
+        nsteps = (n_tr + bs - 1) // bs
+        ops["train_epoch_c1"] = {"samples_per_s": n_tr / (ms_e * 1e-3), "ms_per_epoch": ms_e, "minibatch_steps": nsteps,
+                                 "us_per_step": ms_e * 1e3 / nsteps, "batchsize": bs,
+                                 "api": "dflow_train_epoch (loss+gradient kernel and Adam kernel per minibatch, no host round trip)"}
+        pc.W.copy_(w_save)
+
     # ---- e2e: host buffers through the C-ABI host entry point (pinned host -> HBM -> host every step) ----
     e2e = None
     if not args.no_e2e:

@@ -82,6 +82,8 @@ SYMBOLS = [
     ("dflow_workspace_bytes", C.c_size_t, [vp, C.c_int64]),
     ("dflow_loss_grad", C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_float, C.c_int32, vp, vp, vp, C.c_size_t, vp]),
     ("dflow_adam_step", C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]),
+    ("dflow_train_epoch", C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                    C.c_float, C.POINTER(C.c_int64), C.c_int32, vp, vp, vp, C.c_size_t, vp]),
     ("dflow_minmax", C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, vp]),
     ("dflow_logpdf_host", C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int32, vp, C.c_int64]),
     ("dflow_sample_host", C.c_int, [vp, vp, C.c_uint64, vp, C.c_int64, C.c_int32, vp, C.c_int64]),

@@ -785,6 +785,55 @@ int dflow_loss_grad(dflow_chain* c, const float* W, const float* x, const float*
   return launch_grad(c, a, st);
 }
 
+// One epoch of minibatch steps enqueued from C (src/Flows.jl:394-416): no host round trip between the steps.
+int dflow_train_epoch(dflow_chain* c, float* W, float* m, float* v, const float* x, const float* theta,
+                      const int32_t* order, int64_t n, int64_t batchsize, float lr, float beta1, float beta2, float eps,
+                      int64_t* t_io, int32_t flags, float* grad_scratch, float* loss2_out, void* ws, size_t ws_bytes,
+                      void* stream) {
+  if (!c || !t_io || n < 0 || batchsize < 1 || *t_io < 0) {
+    set_error("bad dflow_train_epoch arguments");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (n == 0) return DFLOW_OK;
+  const int64_t bmax = std::min<int64_t>(batchsize, n);
+  int rc = check_common(c, W, theta, nullptr, bmax, flags);
+  if (rc) return rc;
+  const long long P = c->hc()->h.P;
+  if (!x || !order || !m || !v || !grad_scratch) {
+    set_error("null pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (!ws || ws_bytes < dflow_workspace_bytes(c, bmax)) {
+    set_error("workspace too small: need %zu bytes (dflow_workspace_bytes at the batch size), got %zu",
+              dflow_workspace_bytes(c, bmax), ws_bytes);
+    return DFLOW_E_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float b1t, b2t;
+  adam_beta_powers(beta1, beta2, *t_io, &b1t, &b2t);
+  float* loss2 = grad_scratch + P;  // [grad (P) | sum logp, #non-finite] of the current minibatch
+  for (int64_t b0 = 0; b0 < n; b0 += batchsize) {
+    const int64_t nb = std::min<int64_t>(batchsize, n - b0);
+    if (cudaMemsetAsync(grad_scratch, 0, sizeof(float) * (size_t)(P + 2), st) != cudaSuccess) {
+      set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return DFLOW_E_CUDA;
+    }
+    rc = dflow_loss_grad(c, W, x, theta, nb, order + b0, (float)(1.0 / (double)nb), flags, loss2, grad_scratch, ws, ws_bytes,
+                         stream);
+    if (rc) return rc;
+    if (loss2_out) {
+      rc = launch_axpy2(loss2_out, loss2, st);
+      if (rc) return rc;
+    }
+    b1t *= beta1;
+    b2t *= beta2;
+    ++*t_io;
+    rc = launch_adam_pw(W, grad_scratch, m, v, P, lr, beta1, beta2, eps, b1t, b2t, st);
+    if (rc) return rc;
+  }
+  return DFLOW_OK;
+}
+
 int dflow_adam_step(float* W, const float* g, float* m, float* v, int64_t P, float lr, float beta1, float beta2,
                     float eps, int64_t t, void* stream) {
   if (P < 0 || t < 1 || (P > 0 && (!W || !g || !m || !v))) {

@@ -178,5 +178,9 @@ int launch_fwd(dflow_chain* c, FwdArgs& a, cudaStream_t st);
 int launch_grad(dflow_chain* c, GradArgs& a, cudaStream_t st);
 int launch_adam(float* W, const float* g, float* m, float* v, long long P, float lr, float b1, float b2, float eps,
                 long long t, cudaStream_t st);
+int launch_axpy2(float* acc, const float* v, cudaStream_t st);
+void adam_beta_powers(float b1, float b2, long long t, float* b1t, float* b2t);
+int launch_adam_pw(float* W, const float* g, float* m, float* v, long long P, float lr, float b1, float b2, float eps,
+                   float b1t, float b2t, cudaStream_t st);
 int launch_minmax(const float* x, int rows, long long B, float* mn, float* mx, cudaStream_t st);
 }  // namespace dflow

@@ -289,7 +289,10 @@ int launch_grad(dflow_chain* c, GradArgs& a, cudaStream_t st) {
   if (c->grad_spt >= 0) {  // v2 adjoint (register-tiled dW); grad_spt < 0 selects the first-generation kernel
     int nt2 = c->grad_threads > 0 ? c->grad_threads : 1024;  // clamped to the instantiation's fixed block size
     nt2 = (nt2 + 31) & ~31;
-    const int s = c->grad_spt;
+    int s = c->grad_spt;
+    // automatic: a minibatch that fits one wave of 256-thread CTAs runs one sample per thread -- a tile's latency is what
+    // such a step costs (85 us against 134 us for the S = 2 / 384-thread configuration at the reference's batchsize 64)
+    if (s == 0 && h.hp == 16 && a.B <= (long long)c->sm_count * 256) s = 1;
     switch (h.hp) {
       case 16:
         if (s == 1) return launch_grad2_t<16, 1>(c, a, st, nt2);
@@ -315,15 +318,38 @@ int launch_grad(dflow_chain* c, GradArgs& a, cudaStream_t st) {
   return DFLOW_E_UNSUPPORTED;
 }
 
+__global__ void axpy2_kernel(float* acc, const float* v) {
+  if (threadIdx.x < 2) acc[threadIdx.x] += v[threadIdx.x];
+}
+int launch_axpy2(float* acc, const float* v, cudaStream_t st) {
+  axpy2_kernel<<<1, 32, 0, st>>>(acc, v);
+  CK(cudaGetLastError());
+  return DFLOW_OK;
+}
+
+// Float32 running products beta^t of Optimisers.jl, as the host keeps them (bit-exact with t successive multiplications)
+void adam_beta_powers(float b1, float b2, long long t, float* b1t, float* b2t) {
+  float p1 = 1.0f, p2 = 1.0f;
+  for (long long i = 0; i < t; ++i) {
+    p1 *= b1;
+    p2 *= b2;
+    if (p1 == 0.0f && p2 == 0.0f) break;  // both underflowed: every further product is 0 as well
+  }
+  *b1t = p1;
+  *b2t = p2;
+}
+
 int launch_adam(float* W, const float* g, float* m, float* v, long long P, float lr, float b1, float b2, float eps,
                 long long t, cudaStream_t st) {
+  float b1t, b2t;
+  adam_beta_powers(b1, b2, t, &b1t, &b2t);
+  return launch_adam_pw(W, g, m, v, P, lr, b1, b2, eps, b1t, b2t, st);
+}
+
+int launch_adam_pw(float* W, const float* g, float* m, float* v, long long P, float lr, float b1, float b2, float eps,
+                   float b1t, float b2t, cudaStream_t st) {
   if (P <= 0) return DFLOW_OK;
   // bias corrections in Float32 like Optimisers.jl (βt is a Float32 running product)
-  float b1t = 1.0f, b2t = 1.0f;
-  for (long long i = 0; i < t; ++i) {
-    b1t *= b1;
-    b2t *= b2;
-  }
   const float c1 = 1.0f - b1t, c2 = 1.0f - b2t;
   long long blocks = (P + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;

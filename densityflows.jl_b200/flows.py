@@ -433,7 +433,14 @@ def train_(flow: Flow, data: DataArrays, optimiser_state: OptimiserState, epochs
             order = tr[perm]
         else:
             order = tr
-        for b0 in range(0, n_tr, batchsize):
+        if world == 1 and not debug and isinstance(step, TrainStep):
+            # single GPU: the whole epoch is enqueued from C (dflow_train_epoch) -- with the reference's default
+            # batchsize = 64 a step is launch-bound, and a Python round trip per minibatch would dominate it
+            st_ = optimiser_state
+            st_.t = pc.train_epoch(x, θ, order.to(torch.int32).contiguous(), batchsize, st_.m, st_.v, st_.t, st_.rule.eta,
+                                   st_.rule.beta, st_.rule.epsilon, flags, step.buf)
+            order = order[:0]
+        for b0 in range(0, int(order.numel()), batchsize):
             batch = order[b0: b0 + batchsize]
             step(x, θ, shard(batch), int(batch.numel()), flags)
             if debug:

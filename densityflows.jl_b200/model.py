@@ -693,6 +693,33 @@ class PackedChain:
                                             lr, β[0], β[1], ϵ, t, self._stream()))
 
 
+def _train_epoch(self, x, θ, order: torch.Tensor, batchsize: int, m: torch.Tensor, v: torch.Tensor, t: int, lr=1e-3,
+                 β=(0.9, 0.999), ϵ=1e-8, flags: int = 0, scratch: Optional[torch.Tensor] = None,
+                 loss2: Optional[torch.Tensor] = None) -> int:
+    """One epoch of minibatch steps enqueued from C (dflow_train_epoch): `order` = the epoch's shuffled training indices
+    (int32, device).  Returns the new Adam step count.  Same kernels and arithmetic as loss_grad + adam_step per batch."""
+    x, θ = self._prep(x, θ)
+    n = int(order.numel())
+    if n == 0:
+        return t
+    need = int(L.lib().dflow_workspace_bytes(self.handle, min(int(batchsize), n)))
+    if self._ws is None or self._ws.numel() < need:
+        self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+    if scratch is None:
+        scratch = torch.empty(max(self.P, 1) + 2, device=self.device, dtype=torch.float32)
+    tio = C.c_int64(int(t))
+    with torch.cuda.device(self.device):
+        L.check(L.lib().dflow_train_epoch(self.handle, self.W.data_ptr(), m.data_ptr(), v.data_ptr(), self._ptr(x),
+                                          self._ptr(θ), order.data_ptr(), n, int(batchsize), lr, β[0], β[1], ϵ,
+                                          C.byref(tio), flags, scratch.data_ptr(),
+                                          None if loss2 is None else loss2.data_ptr(), self._ws.data_ptr(),
+                                          self._ws.numel(), self._stream()))
+    return int(tio.value)
+
+
+PackedChain.train_epoch = _train_epoch
+
+
 def _packed_of(elem: FlowElement, device=None) -> PackedChain:
     p = elem._packed
     if p is None or (device is not None and torch.device(device) != p.device):

@@ -148,6 +148,17 @@ int dflow_loss_grad(dflow_chain* chain, const float* W, const float* x, const fl
 int dflow_adam_step(float* W, const float* g, float* m, float* v, int64_t P, float lr, float beta1, float beta2,
                     float eps, int64_t t, void* stream);
 
+/* ---- one epoch of minibatch steps, enqueued back to back from C (src/Flows.jl:394-416: `for (x, θ) in loader` with
+ * Flux.gradient + Optimisers.update! per minibatch).  order: n 0-based sample indices (the epoch's shuffled training
+ * partition); minibatch k is order[k*batchsize ..], the last one may be partial (Flux.DataLoader partial=true); each step is
+ * dflow_loss_grad with inv_btot = 1/|minibatch| followed by dflow_adam_step with t = ++*t_io.  grad_scratch: P + 2 floats.
+ * loss2_out (optional, 2 floats) accumulates [Σ logp, #non-finite] over the minibatches.  ws: dflow_workspace_bytes at
+ * min(batchsize, n).  Single device; data-parallel training shards every minibatch instead (dflow_loss_grad + dflow_dp_*). */
+int dflow_train_epoch(dflow_chain* chain, float* W, float* m, float* v, const float* x, const float* theta,
+                      const int32_t* order, int64_t n, int64_t batchsize, float lr, float beta1, float beta2, float eps,
+                      int64_t* t_io, int32_t flags, float* grad_scratch, float* loss2_out, void* ws, size_t ws_bytes,
+                      void* stream);
+
 /* ---- data-parallel train step: gradient all-reduce over NVLink peer memory fused with the Adam update ------------
  * (one process per GPU; replaces NCCL all-reduce + dflow_adam_step for src/Flows.jl:413-415).  Protocol per rank:
  *   dflow_dp_create(rank, nranks, P, &dp, handle64)     allocates this rank's communication buffer, returns its

@@ -422,3 +422,35 @@ def test_empty_batch_and_unaligned_arrays():
         zu, lu = pc.normalize(xu, tu)
         assert torch.equal(zu, zr) and torch.equal(lu, lr)
     pc.tune(fwd_const=0)
+
+
+def test_train_epoch_from_c_equals_step_by_step():
+    """dflow_train_epoch enqueues a whole epoch of minibatch steps (reference default batchsize 64, partial last batch)
+    from C; weights, Adam moments and step count must equal the per-minibatch loss_grad + adam_step path bit for bit."""
+    ochain, chain_a, x, th = _setup("readme_n2", 1000, seed=5)
+    _, chain_b, _, _ = _setup("readme_n2", 1000, seed=5)
+    pa, pb = chain_a.packed(), chain_b.packed()
+    assert torch.equal(pa.W, pb.W)
+    xj, tj = df.to_jl(x, DEV), df.to_jl(th, DEV)
+    order = torch.randperm(900, generator=torch.Generator().manual_seed(3)).to(torch.int32).to(DEV)
+    bs, P = 64, pa.P
+    ma, va = torch.zeros(P, device=DEV), torch.zeros(P, device=DEV)
+    mb, vb = torch.zeros(P, device=DEV), torch.zeros(P, device=DEV)
+    loss2 = torch.zeros(2, device=DEV)
+    t = 0
+    for _ in range(2):
+        t = pa.train_epoch(xj, tj, order, bs, ma, va, t, 1e-3, (0.9, 0.999), 1e-8, 0, None, loss2)
+    assert t == 2 * 15  # ceil(900 / 64) = 15 minibatches per epoch
+    buf = torch.zeros(P + 2, device=DEV)
+    tb, acc = 0, torch.zeros(2, device=DEV)
+    for _ in range(2):
+        for b0 in range(0, 900, bs):
+            idx = order[b0:b0 + bs]
+            buf.zero_()
+            pb.loss_grad(xj, tj, buf[:P], buf[P:], 1.0 / int(idx.numel()), 0, idx)
+            acc += buf[P:]
+            tb += 1
+            pb.adam_step(buf[:P], mb, vb, tb, 1e-3, (0.9, 0.999), 1e-8)
+    assert torch.equal(pa.W, pb.W) and torch.equal(ma, mb) and torch.equal(va, vb)
+    assert torch.equal(loss2, acc)
+    assert float((pa.W - chain_from_oracle(ochain).packed().W).abs().max()) > 0  # the weights did move
