@@ -166,7 +166,7 @@ struct dflow_chain {
   bool use_tc_grad(long long B) const {
     if (use_tc()) return true;
     // hidden 32 (d = 10, 4 blocks, 2 Mi samples): 1.94e8 samples/s on the tensor-core kernels against 1.41e8 on CUDA cores
-    return wide && tcp && tc_mode == 0 && ((hidden_max == 64 && B >= 32768) || (hidden_max == 32 && B >= 131072));
+    return wide && tcp && tc_mode == 0 && ((hidden_max == 64 && B >= 32768) || (hidden_max == 32 && B >= 65536));
   }
   const dflow::DevChain* hc() const { return reinterpret_cast<const dflow::DevChain*>(host_chain.data()); }
   dflow::DevChain* hc() { return reinterpret_cast<dflow::DevChain*>(host_chain.data()); }
