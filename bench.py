@@ -314,7 +314,7 @@ def run_ours(args):
 
         ms3l = timed(step_c3_logpdf, 3, 2, dist)
         ops["logpdf_c3"] = {"samples_per_s": world * Bl / (ms3l * 1e-3), "ms_per_step": ms3l, "B_per_gpu": Bl,
-                            "path": "tcgen05 3xTF32 (automatic for hidden 64, B >= 524288)",
+                            "path": "tcgen05 3xTF32 (automatic for hidden 64, B >= 131072)",
                             "fp32_equiv_tflops_per_gpu": 172032.0 * Bl / (ms3l * 1e-3) / 1e12}
         # default routing: at hidden 64 and a batch this large the adjoint runs on the tensor cores (dflow_tc.cu)
         ops["train_step_c3"] = {"samples_per_s": Bg / (ms3 * 1e-3), "ms_per_step": ms3, "global_batch": Bg,

@@ -161,7 +161,8 @@ struct dflow_chain {
   // against 1.95e8 for the CUDA-core chain kernel once the batch fills the machine
   bool use_tc_fwd(long long B) const {
     if (use_tc()) return true;
-    return wide && tcp && tc_mode == 0 && hidden_max == 64 && B >= 524288;  // below: 17 launches cost more than they save
+    // crossover measured with scripts/c3_fwd_threshold.py: 0.36 / 0.36 ms at 65536, 0.69 / 0.54 ms at 131072 (CUDA / tensor)
+    return wide && tcp && tc_mode == 0 && hidden_max == 64 && B >= 131072;
   }
   bool use_tc_grad(long long B) const {
     if (use_tc()) return true;
