@@ -21,10 +21,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 # (HP, samples per thread, register-resident activations)
-FWD_INST = [(16, 1, 0), (16, 2, 0), (16, 4, 0), (16, 2, 1), (16, 4, 1), (32, 1, 0), (32, 2, 0), (32, 4, 0), (32, 2, 1),
-            (64, 1, 0), (64, 2, 0)]
+FWD_INST = [(16, 1, 0), (16, 2, 0), (16, 4, 0), (32, 1, 0), (32, 2, 0), (32, 4, 0), (64, 1, 0), (64, 2, 0)]
 CFWD_INST = [(16, 4), (32, 2)]  # constant-bank forward kernels (weights as uniform-datapath operands)
-GRAD_INST = [16, 32, 64]
 GRAD2_INST = [(16, 1), (16, 2), (16, 4), (32, 1), (32, 2), (64, 1), (64, 2)]
 
 
@@ -43,13 +41,8 @@ def _units():
     for hp, s in CFWD_INST:
         units.append((f"inst_cfwd_{hp}_{s}.o", "dflow_inst.cu",
                       ["-DDFLOW_INST_CFWD", "-DDFLOW_CBANK", f"-DDFLOW_HP={hp}", f"-DDFLOW_S={s}"]))
-    for hp in GRAD_INST:
-        units.append((f"inst_grad_{hp}.o", "dflow_inst.cu", ["-DDFLOW_INST_GRAD", f"-DDFLOW_HP={hp}"]))
     for hp, s in GRAD2_INST:
         units.append((f"inst_grad2_{hp}_{s}.o", "dflow_inst.cu", ["-DDFLOW_INST_GRAD2", f"-DDFLOW_HP={hp}", f"-DDFLOW_S={s}"]))
-    extra = os.path.join(CSRC, "dflow_wide.cu")
-    if os.path.exists(extra):
-        units.append(("dflow_wide.o", "dflow_wide.cu", []))
     if os.path.exists(os.path.join(CSRC, "dflow_tc.cu")):
         units.append(("dflow_tc.o", "dflow_tc.cu", []))
     if os.path.exists(os.path.join(CSRC, "dflow_dp.cu")):

@@ -11,7 +11,6 @@
 
 #include "dflow_internal.h"
 #include "dflow_tc.h"
-#include "dflow_wide.h"
 
 namespace dflow {
 
@@ -106,142 +105,10 @@ static void layout_net(DevNet& net, int hp, int& off) {
 
 using namespace dflow;
 
-// Lay out the wide weight image (dflow_wide.cu) for a chain whose conditioners are wider than 64.
-static int build_wide_plan(dflow_chain* c) {
-  const DevChain* C = c->hc();
-  const DevChainHdr& H = C->h;
-  WidePlan* wp = new (std::nothrow) WidePlan();
-  if (!wp) return DFLOW_E_NOMEM;
-  c->wide = wp;
-  long long off = 0;
-  for (int ei = 0; ei < H.L; ++ei) {
-    const DevElem& E = C->e[ei];
-    WideLayer Ld;
-    memset(&Ld, 0, sizeof(Ld));
-    if (E.kind == DFLOW_ELEM_NORM) {
-      Ld.is_coupling = 0;
-      Ld.norm_off = E.stage_off;
-      wp->layers.push_back(Ld);
-      continue;
-    }
-    Ld.is_coupling = 1;
-    Ld.has_s = (E.kind == DFLOW_ELEM_RNVP) ? 1 : 0;
-    Ld.h = E.t.w[1];
-    Ld.nin = E.nin;
-    Ld.kinp = (E.nin + 7) & ~7;
-    Ld.a = E.a;
-    Ld.a16 = (E.a + 15) & ~15;
-    memcpy(Ld.af, E.af, sizeof(Ld.af));
-    memcpy(Ld.id, E.id, sizeof(Ld.id));
-    const int h = Ld.h, NH = h < 256 ? h : 256, passes = h / NH, nch = h / 32;
-    for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
-      const DevNet& net = ni == 0 ? E.s : E.t;
-      WideNet& N = Ld.net[ni];
-      for (int j = 0; j < 3; ++j) {
-        N.p_w[j] = net.p_w[j];
-        N.p_b[j] = net.p_b[j];
-      }
-      N.img_off = off;
-      int o = 0;
-      N.b1 = o; o += h;
-      N.b2 = o; o += h;
-      N.b3 = o; o += Ld.a16;
-      o = (o + 3) & ~3;
-      N.w1 = o; o += nch * 2 * 32 * Ld.kinp;
-      N.w2 = o; o += passes * nch * 2 * NH * 32;
-      N.w3 = o; o += nch * 2 * Ld.a16 * 32;
-      off += (o + 3) & ~3;
-    }
-    if (wide_layer_smem_bytes(Ld) > (size_t)c->max_smem_optin) {
-      set_error("element %d: wide layer needs %zu bytes of shared memory", ei, wide_layer_smem_bytes(Ld));
-      return DFLOW_E_UNSUPPORTED;
-    }
-    wp->layers.push_back(Ld);
-  }
-  wp->img_floats = (size_t)std::max<long long>(off, 4);
-  if (cudaMalloc(&wp->d_img, wp->img_floats * sizeof(float)) != cudaSuccess ||
-      cudaMalloc(&wp->d_layers, wp->layers.size() * sizeof(WideLayer)) != cudaSuccess) {
-    set_error("cudaMalloc failed for the wide weight image (%zu floats)", wp->img_floats);
-    return DFLOW_E_NOMEM;
-  }
-  if (cudaMemcpy(wp->d_layers, wp->layers.data(), wp->layers.size() * sizeof(WideLayer), cudaMemcpyHostToDevice) !=
-      cudaSuccess) {
-    set_error("cudaMemcpy failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return DFLOW_E_CUDA;
-  }
-  return DFLOW_OK;
-}
-
-// grow-only device scratch of the wide path (working copies for logpdf / gathers)
-static int wide_scratch(dflow_chain* c, size_t floats, float** out) {
-  WidePlan* wp = c->wide;
-  if (wp->scratch_floats < floats) {
-    if (wp->d_scratch) cudaFree(wp->d_scratch);
-    wp->d_scratch = nullptr;
-    wp->scratch_floats = 0;
-    if (cudaMalloc(&wp->d_scratch, floats * sizeof(float)) != cudaSuccess) {
-      set_error("cudaMalloc failed for %zu floats of wide-path scratch", floats);
-      return DFLOW_E_NOMEM;
-    }
-    wp->scratch_floats = floats;
-  }
-  *out = wp->d_scratch;
-  return DFLOW_OK;
-}
-
-// Wide-path implementation of the forward-type entry points.  Working buffer layout in scratch:
-// [x copy (d*B)] [ldj (B)] [θ gather (n*B)]
+// Forward-type entry points of chains routed to the tensor-core kernels (dflow_tc.cu works on its own tile-blocked state).
 static int wide_fwd(dflow_chain* c, const float* W, FwdArgs& a, void* stream) {
   if (a.B == 0) return DFLOW_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (c->wide_gen >= 2) return tc_fwd(c, W, a, st);  // generation 2 works on its own tile-blocked state (dflow_tc.cu)
-  const DevChainHdr& H = c->hc()->h;
-  const long long B = a.B;
-  const int d = H.d, n = H.n;
-  int rc = wide_prepack(c, W, st);
-  if (rc) return rc;
-  const bool sampling = a.mode >= MODE_SAMPLE;
-  const bool need_copy = (a.mode == MODE_LOGPDF || a.mode == MODE_LOGPDF_SUM);
-  const bool want_ldj = !(a.mode == MODE_SAMPLE || a.mode == MODE_SAMPLE_RNG);
-  float* scratch = nullptr;
-  const size_t need = (need_copy ? (size_t)d * B : 0) + (size_t)B + (a.idx ? (size_t)n * B : 0) + 16;
-  rc = wide_scratch(c, need, &scratch);
-  if (rc) return rc;
-  float* xw = need_copy ? scratch : a.x_out;
-  float* ldj = scratch + (need_copy ? (size_t)d * B : 0);
-  float* thg = ldj + B;
-  const float* theta = a.theta;
-  // input -> working buffer
-  if (a.mode == MODE_SAMPLE_RNG) {
-    rc = wide_philox(c, xw, B, a.seed, a.rng_offset, a.first_sample, st);
-    if (rc) return rc;
-  } else if (a.idx) {
-    rc = wide_gather(c, a.x_in, a.idx, B, d, xw, st);
-    if (rc) return rc;
-    if (theta && n > 0) {
-      rc = wide_gather(c, theta, a.idx, B, n, thg, st);
-      if (rc) return rc;
-      theta = thg;
-    }
-  } else if (xw != a.x_in) {
-    if (cudaMemcpyAsync(xw, a.x_in, sizeof(float) * d * B, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-      set_error("cudaMemcpyAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
-      return DFLOW_E_CUDA;
-    }
-  }
-  float* ldj_dst = nullptr;
-  if (want_ldj) {
-    ldj_dst = (a.mode == MODE_NORMALIZE || a.mode == MODE_FORWARD_LDJ) ? a.aux_out : ldj;
-    if (cudaMemsetAsync(ldj_dst, 0, sizeof(float) * B, st) != cudaSuccess) {
-      set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
-      return DFLOW_E_CUDA;
-    }
-  }
-  rc = wide_run_chain(c, xw, theta, a.theta_const, ldj_dst, B, sampling ? 1 : 0, a.flags, st);
-  if (rc) return rc;
-  if (a.mode == MODE_LOGPDF) return wide_logpdf(c, xw, ldj, B, a.aux_out, nullptr, st);
-  if (a.mode == MODE_LOGPDF_SUM) return wide_logpdf(c, xw, ldj, B, nullptr, a.aux_out, st);
-  return DFLOW_OK;
+  return tc_fwd(c, W, a, (cudaStream_t)stream);
 }
 
 extern "C" {
@@ -356,7 +223,7 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
     amax4 = std::max(amax4, round_out(a));
   }
   int hp = round_hp(hidden_max);
-  const bool wide = hp < 0;  // hidden > 64: tcgen05 path (dflow_tc.cu / dflow_wide.cu)
+  const bool wide = hp < 0;  // hidden > 64: tcgen05 path (dflow_tc.cu)
   // the tensor-core kernels cover the reference's default conditioner only: Dense(in,h,relu), Dense(h,h,relu), Dense(h,a)
   bool tc_eligible = true;
   int has_coupling = 0;
@@ -492,22 +359,12 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
   c->must_wide = wide ? 1 : 0;
   c->hidden_max = hidden_max;
   if (tc_eligible) {
-    int rc = build_wide_plan(c);
-    if (!rc) rc = tc_build_plan(c);
+    int rc = tc_build_plan(c);
     if (rc && wide) {
       dflow_chain_destroy(c);
       return rc;
     }
-    if (rc) {  // a narrow chain simply stays on the CUDA-core path
-      tc_free_plan(c);
-      if (c->wide) {
-        if (c->wide->d_layers) cudaFree(c->wide->d_layers);
-        if (c->wide->d_img) cudaFree(c->wide->d_img);
-        if (c->wide->d_scratch) cudaFree(c->wide->d_scratch);
-        delete c->wide;
-        c->wide = nullptr;
-      }
-    }
+    if (rc) tc_free_plan(c);  // a narrow chain simply stays on the CUDA-core path
   }
   *out = c;
   return DFLOW_OK;
@@ -518,12 +375,6 @@ int dflow_chain_destroy(dflow_chain* c) {
   if (c->d_chain) cudaFree(c->d_chain);
   if (c->d_staged) cudaFree(c->d_staged);
   tc_free_plan(c);
-  if (c->wide) {
-    if (c->wide->d_layers) cudaFree(c->wide->d_layers);
-    if (c->wide->d_img) cudaFree(c->wide->d_img);
-    if (c->wide->d_scratch) cudaFree(c->wide->d_scratch);
-    delete c->wide;
-  }
   if (c->pipe) pipe_free((HostPipe*)c->pipe);
   delete c;
   return DFLOW_OK;
@@ -1027,18 +878,16 @@ int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
     c->ctas_per_sm = value;
   else if (!strcmp(key, "tc_fuse"))
     c->tc_fuse = value < 0 ? 0 : value > 2 ? 2 : value;
-  else if (!strcmp(key, "tc_ns_max"))
-    c->tc_ns_max = value;
   else if (!strcmp(key, "tc_ws_budget_mb"))
     c->tc_ws_budget_mb = value;
-  else if (!strcmp(key, "tc_cluster"))
-    c->tc_cluster = value < 0 ? 0 : value > 2 ? 2 : value;
+#ifdef DFLOW_TC_EXPERIMENTS  // timing experiments (wrong results by construction): never part of a release build
   else if (!strcmp(key, "tc_debug"))
     c->tc_debug = value;
-  else if (!strcmp(key, "wide_gen"))
-    c->wide_gen = value == 1 ? 1 : 2;
+  else if (!strcmp(key, "tc_cluster"))
+    c->tc_debug_cluster = value < 0 ? 0 : value > 2 ? 2 : value;
+#endif
   else if (!strcmp(key, "tc_mode")) {
-    if (value > 0 && !(c->wide && c->tcp)) {
+    if (value > 0 && !c->tcp) {
       set_error("tc_mode: this chain is not eligible for the tensor-core path (needs Dense(in,h,relu)->Dense(h,h,relu)->"
                 "Dense(h,a) conditioners with bias, h a multiple of 32)");
       return DFLOW_E_UNSUPPORTED;

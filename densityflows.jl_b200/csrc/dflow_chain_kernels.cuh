@@ -248,12 +248,7 @@ __device__ __forceinline__ void run_net(const DevNet& net, const float* __restri
   }
 }
 
-// ---- register-resident variant (hidden <= 32) ---------------------------------------------------------------
-// Measured on B200 (scripts/ubench.cu): a broadcast LDS.128 costs 2 clk/SM and 3-register FFMA issues at
-// ~115-128 /clk/SM, so every staged weight has to feed >= 4 FFMA per thread or the kernel is shared-memory bound.
-// Here the hidden activations of the S samples stay in REGISTERS between the Dense layers (fully unrolled over the
-// padded width HP, zero-padded weight rows), so the only shared-memory traffic of a hidden Dense is HP*HP/4
-// broadcast LDS.128 for HP*HP*S FFMA.
+// ---- register-resident activations (constant-bank kernels) ------------------------------------------------------
 template <int HP, int S>
 __device__ __forceinline__ void act_regs(float (&h)[HP][S], int act) {
   if (act == DFLOW_ACT_RELU) {
@@ -263,121 +258,6 @@ __device__ __forceinline__ void act_regs(float (&h)[HP][S], int act) {
       for (int s = 0; s < S; ++s) h[o][s] = fmaxf(h[o][s], 0.0f);
   }
   // tanh / sigmoid chains never reach the register-resident kernels (DevChainHdr::relu_only, launch_fwd)
-}
-
-template <int HP, int S>
-__device__ __forceinline__ void bias_regs(float (&h)[HP][S], const float* __restrict__ bst) {
-#pragma unroll
-  for (int g = 0; g < HP / 4; ++g) {
-    const float4 b = *reinterpret_cast<const float4*>(bst + 4 * g);
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      h[4 * g + 0][s] = b.x;
-      h[4 * g + 1][s] = b.y;
-      h[4 * g + 2][s] = b.z;
-      h[4 * g + 3][s] = b.w;
-    }
-  }
-}
-
-// out[NG*4 outputs starting at o0] of the LAST Dense from register-resident inputs; stored to outcol rows o0...
-template <int HP, int S, int NG>
-__device__ __forceinline__ void last_dense_regs(const float (&h)[HP][S], const float* __restrict__ Wst, int ld,
-                                                const float* __restrict__ bst, int act, float* outcol, int CS,
-                                                int slot0, int NT) {
-  float acc[NG * 4][S];
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    const float4 b = *reinterpret_cast<const float4*>(bst + 4 * g);
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      acc[4 * g + 0][s] = b.x;
-      acc[4 * g + 1][s] = b.y;
-      acc[4 * g + 2][s] = b.z;
-      acc[4 * g + 3][s] = b.w;
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < HP; ++k) {
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      const float4 w = *reinterpret_cast<const float4*>(Wst + k * ld + 4 * g);
-      fma_samples<S>(acc[4 * g + 0], h[k], w.x);
-      fma_samples<S>(acc[4 * g + 1], h[k], w.y);
-      fma_samples<S>(acc[4 * g + 2], h[k], w.z);
-      fma_samples<S>(acc[4 * g + 3], h[k], w.w);
-    }
-  }
-#pragma unroll
-  for (int o = 0; o < NG * 4; ++o) st_samples<S>(outcol + o * CS + slot0 * S, acc[o]);
-  if (act != DFLOW_ACT_IDENTITY) {
-#pragma unroll 1
-    for (int o = 0; o < NG * 4; ++o)
-#pragma unroll 1
-      for (int s = 0; s < S; ++s) {
-        float* p = outcol + o * CS + slot0 * S + s;
-        *p = act_apply(act, *p);
-      }
-  }
-}
-
-template <int HP, int S>
-__device__ __forceinline__ void run_net_reg(const DevNet& net, const float* __restrict__ wblk, const InSel& in,
-                                            float* outcol, int CS, int slot0, int NT) {
-  const int D = net.depth;
-  if (D == 1) {  // a single Dense straight from the inputs: use the column form
-    InSel in0 = in;
-    in0.first = true;
-    const int op = net.op[0];
-    for (int o0 = 0; o0 < op; o0 += 4)
-      dense_to_col<1, S>(in0, net.w[0], wblk + net.s_w[0] + o0, op, wblk + net.s_b[0] + o0, net.act[0],
-                         outcol + o0 * CS, CS, slot0, NT);
-    return;
-  }
-  float h[HP][S];
-  // first Dense: inputs are the gathered θ / x columns (runtime width), outputs in registers
-  bias_regs<HP, S>(h, wblk + net.s_b[0]);
-  {
-    const float* W0 = wblk + net.s_w[0];
-    const int n = in.n, K = net.w[0];
-    for (int k = 0; k < n; ++k) dense_row<HP / 4, S>(in.th + k * CS, W0 + k * HP, slot0, NT, h);
-    for (int k = n; k < K; ++k) dense_row<HP / 4, S>(in.xs + (int)in.id[k - n] * CS, W0 + k * HP, slot0, NT, h);
-  }
-  act_regs<HP, S>(h, net.act[0]);
-  // hidden Dense layers: registers -> registers, fully unrolled (weight rows are zero-padded to HP)
-  for (int j = 1; j < D - 1; ++j) {
-    float o[HP][S];
-    bias_regs<HP, S>(o, wblk + net.s_b[j]);
-    const float* Wj = wblk + net.s_w[j];
-#pragma unroll
-    for (int k = 0; k < HP; ++k) {
-#pragma unroll
-      for (int g = 0; g < HP / 4; ++g) {
-        const float4 w = *reinterpret_cast<const float4*>(Wj + k * HP + 4 * g);
-        fma_samples<S>(o[4 * g + 0], h[k], w.x);
-        fma_samples<S>(o[4 * g + 1], h[k], w.y);
-        fma_samples<S>(o[4 * g + 2], h[k], w.z);
-        fma_samples<S>(o[4 * g + 3], h[k], w.w);
-      }
-    }
-    act_regs<HP, S>(o, net.act[j]);
-#pragma unroll
-    for (int k = 0; k < HP; ++k)
-#pragma unroll
-      for (int s = 0; s < S; ++s) h[k][s] = o[k][s];
-  }
-  // last Dense: padded width op in {4, 8, 16, 32, 64}, groups of <= 8 outputs at a time
-  {
-    const int jl = D - 1, op = net.op[jl], act = net.act[jl];
-    const float* Wl = wblk + net.s_w[jl];
-    const float* bl = wblk + net.s_b[jl];
-    if (op == 4) {
-      last_dense_regs<HP, S, 1>(h, Wl, 4, bl, act, outcol, CS, slot0, NT);
-    } else {
-      for (int o0 = 0; o0 < op; o0 += 8)
-        last_dense_regs<HP, S, 2>(h, Wl + o0, op, bl + o0, act, outcol + o0 * CS, CS, slot0, NT);
-    }
-  }
 }
 
 // ---- constant-bank variant (weights never touch shared memory or vector registers) ----------------------------
@@ -540,10 +420,7 @@ __device__ __forceinline__ void elem_apply(const DevChainHdr& H, const DevElem& 
       continue;
     }
 #endif
-    if constexpr (REG)
-      run_net_reg<HP, S>(ni == 0 ? E.s : E.t, wblk, in, ni == 0 ? sb : tb, CS, slot0, NT);
-    else
-      run_net<HP, S>(ni == 0 ? E.s : E.t, wblk, in, hc, hstride, ni == 0 ? sb : tb, CS, slot0, NT);
+    run_net<HP, S>(ni == 0 ? E.s : E.t, wblk, in, hc, hstride, ni == 0 ? sb : tb, CS, slot0, NT);
   }
   float lsum[S];
 #pragma unroll
@@ -948,312 +825,8 @@ __global__ void __launch_bounds__((fwd_max_threads<HP, S, true>()), DFLOW_CB_MIN
 }
 #endif
 
-// ------------------------------------------------------------------------------------------------------------
-// K3: adjoint.  Forward normalising sweep, then a chain-order reverse sweep that RECOMPUTES each layer's
-// activations from its output (u_id = z_id, u_af = z_af*exp(s)+t), back-propagates through both conditioners and
-// accumulates the weight gradients warp-cooperatively (lane owns entries, loops over the warp's 32 samples).
-// ------------------------------------------------------------------------------------------------------------
-
-// dW[o][k] += sum_samples delta[o][s] * in_k[s] ; db[o] += sum_samples delta[o][s]
-__device__ __forceinline__ void dw_phase(const float* __restrict__ dcol, const InSel& in, int O, int K, int has_bias,
-                                         int p_w, int p_b, float* __restrict__ gsm, float* __restrict__ ggl, int CS,
-                                         int wbase, int lane) {
-  const int E = O * (K + (has_bias ? 1 : 0));
-  int o = lane % O, k = lane / O;
-  for (int e = lane; e < E; e += 32) {
-    const float4* dp = reinterpret_cast<const float4*>(dcol + o * CS + wbase);
-    float acc0 = 0.0f, acc1 = 0.0f;
-    int gi;
-    if (k < K) {
-      const float4* hp = reinterpret_cast<const float4*>(in(k) + wbase);
-#pragma unroll
-      for (int q = 0; q < 8; q += 2) {
-        const float4 x0 = dp[q], y0 = hp[q], x1 = dp[q + 1], y1 = hp[q + 1];
-        acc0 = fmaf(x0.x, y0.x, acc0);
-        acc0 = fmaf(x0.y, y0.y, acc0);
-        acc0 = fmaf(x0.z, y0.z, acc0);
-        acc0 = fmaf(x0.w, y0.w, acc0);
-        acc1 = fmaf(x1.x, y1.x, acc1);
-        acc1 = fmaf(x1.y, y1.y, acc1);
-        acc1 = fmaf(x1.z, y1.z, acc1);
-        acc1 = fmaf(x1.w, y1.w, acc1);
-      }
-      gi = p_w + o + O * k;
-    } else {
-#pragma unroll
-      for (int q = 0; q < 8; q += 2) {
-        const float4 x0 = dp[q], x1 = dp[q + 1];
-        acc0 += (x0.x + x0.y) + (x0.z + x0.w);
-        acc1 += (x1.x + x1.y) + (x1.z + x1.w);
-      }
-      gi = p_b + o;
-    }
-    if (gsm)
-      atomicAdd(gsm + gi, acc0 + acc1);
-    else
-      atomicAdd(ggl + gi, acc0 + acc1);
-    o += 32;
-    while (o >= O) {
-      o -= O;
-      ++k;
-    }
-  }
-}
-
-// g_in[k] = sum_o W[k][o] * delta[o] for k in [k0, K); `first` selects what happens to the result:
-// hidden: dlc[k] = g_in[k] * act'(hprev[k]);  first Dense: gx[axis_id[k-n]] += g_in[k].
-template <int NG>
-__device__ __forceinline__ void dense_T(const float* dcol, int CS, int sl, const float* __restrict__ Wst, int k0,
-                                        int K, bool first, float* dlc, const float* hprev, int actp, float* gx,
-                                        const unsigned char* id, int n) {
-  float dl[NG * 4];
-#pragma unroll
-  for (int o = 0; o < NG * 4; ++o) dl[o] = dcol[o * CS + sl];
-  for (int k = k0; k < K; ++k) {
-    const float4* wr = reinterpret_cast<const float4*>(Wst + k * (NG * 4));
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      const float4 w = wr[g];
-      a0 = fmaf(w.x, dl[4 * g + 0], a0);
-      a1 = fmaf(w.y, dl[4 * g + 1], a1);
-      a2 = fmaf(w.z, dl[4 * g + 2], a2);
-      a3 = fmaf(w.w, dl[4 * g + 3], a3);
-    }
-    const float v = (a0 + a1) + (a2 + a3);
-    if (first)
-      gx[(int)id[k - n] * CS + sl] += v;
-    else
-      dlc[k * CS + sl] = v * act_grad(actp, hprev[k * CS + sl]);
-  }
-}
-
-// Back-propagate through one conditioner.  gb holds the output cotangent (padded rows zero); hidden activations
-// are in hc + j*hstride; dlc is the delta column; input cotangent rows >= n are accumulated into gx[axis_id].
-template <int HP>
-__device__ __forceinline__ void net_backward(const DevChainHdr& H, const DevElem& E, const DevNet& net,
-                                             const float* __restrict__ wblk, float* xs, float* gx, float* th,
-                                             float* hc, int hstride, float* dlc, float* gb, const float* outvals,
-                                             float* gsm, float* ggl, int CS, int sl, int wbase, int lane) {
-  const int D = net.depth;
-  // delta of the last Dense: gout * act'(out)
-  {
-    const int actL = net.act[D - 1];
-    if (actL != DFLOW_ACT_IDENTITY) {
-      const int O = net.w[D];
-      for (int o = 0; o < O; ++o) gb[o * CS + sl] *= act_grad(actL, outvals[o * CS + sl]);
-    }
-  }
-  for (int j = D - 1; j >= 0; --j) {
-    const float* dcol = (j == D - 1) ? gb : dlc;
-    InSel in{th, xs, hc + (j > 0 ? (j - 1) * hstride : 0), E.id, H.n, CS, j == 0};
-    const int O = net.w[j + 1], K = net.w[j];
-    __syncwarp();
-    dw_phase(dcol, in, O, K, net.has_bias, net.p_w[j], net.p_b[j], gsm, ggl, CS, wbase, lane);
-    __syncwarp();
-    const float* Wst = wblk + net.s_w[j];
-    const bool first = (j == 0);
-    const float* hprev = hc + (j > 0 ? (j - 1) * hstride : 0);
-    const int actp = j > 0 ? net.act[j - 1] : 0;
-    const int k0 = first ? H.n : 0;  // θ rows (k < n) of the first Dense are discarded
-    // note: dcol may alias dlc (hidden layers): dense_T loads all of delta into registers before its first store
-    switch (net.op[j] >> 2) {
-      case 1: dense_T<1>(dcol, CS, sl, Wst, k0, K, first, dlc, hprev, actp, gx, E.id, H.n); break;
-      case 2: dense_T<2>(dcol, CS, sl, Wst, k0, K, first, dlc, hprev, actp, gx, E.id, H.n); break;
-      case 4: dense_T<4>(dcol, CS, sl, Wst, k0, K, first, dlc, hprev, actp, gx, E.id, H.n); break;
-      case 8: dense_T<8>(dcol, CS, sl, Wst, k0, K, first, dlc, hprev, actp, gx, E.id, H.n); break;
-      default: dense_T<16>(dcol, CS, sl, Wst, k0, K, first, dlc, hprev, actp, gx, E.id, H.n); break;
-    }
-    if (!first)
-      for (int k = K; k < HP; ++k) dlc[k * CS + sl] = 0.0f;  // padded units carry no gradient
-  }
-}
-
-template <int HP>
-__global__ void __launch_bounds__(256) chain_grad_kernel(const GradArgs a) {
-  extern __shared__ float4 smem4[];
-  float* smem = reinterpret_cast<float*>(smem4);
-  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, wbase = tid & ~31;
-  copy_f4(smem, reinterpret_cast<const float*>(a.chain), (a.chain_bytes + 15) / 16, tid, NT);
-  __syncthreads();
-  const DevChain* C = reinterpret_cast<const DevChain*>(smem);
-  const DevChainHdr& H = C->h;
-  const SmemPlan P = plan_grad(H, a.chain_bytes, NT, a.smem_grad);
-  float* wsm = smem + P.chain_f;
-  float* cols = wsm + P.w_f;
-  float* gsm = cols + P.cols_f;
-  const int CS = P.cs;
-  const int d = H.d, n = H.n, L = H.L;
-  const int hd = H.max_depth > 1 ? H.max_depth - 1 : 1;
-  const int hstride = H.hp * CS;
-  float* xs = cols;
-  float* gx = xs + d * CS;
-  float* th = gx + d * CS;
-  float* hc = th + n * CS;
-  float* dlc = hc + hd * hstride;
-  float* ob = dlc + H.hp * CS;    // s values
-  float* tb = ob + H.amax4 * CS;  // t values
-  float* eb = tb + H.amax4 * CS;  // exp(-s)
-  float* gb = eb + H.amax4 * CS;  // output cotangent
-
-  if (H.resident) copy_f4(wsm, a.staged, H.stage_total / 4, tid, NT);
-  if (a.smem_grad)
-    for (int i = tid; i < P.grad_f; i += NT) gsm[i] = 0.0f;
-  __syncthreads();
-  float* gacc = a.smem_grad ? gsm : nullptr;
-
-  const long long ntiles = (a.B + NT - 1) / NT;
-  float lsum_thread = 0.0f, nonfinite = 0.0f;
-  const int sl = tid;
-  float* ckb = a.ws + (size_t)blockIdx.x * H.ck_total * NT + tid;  // this thread's checkpoint column
-
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long gi = tile * NT + tid;
-    const bool valid = gi < a.B;
-    const long long src = (valid && a.idx) ? (long long)a.idx[gi] : gi;
-    {
-      const float* xp = a.x_in + src * d;
-      for (int k = 0; k < d; ++k) xs[k * CS + sl] = valid ? __ldg(xp + k) : 0.0f;
-      for (int k = 0; k < n; ++k) {
-        float v = (valid && a.theta) ? __ldg(a.theta + src * n + k) : 0.0f;
-        if (a.flags & DFLOW_THETA_NORMALIZE) v = (H.theta_rng[k] == 0.0f) ? 0.0f : (v - H.theta_min[k]) / H.theta_rng[k];
-        th[k * CS + sl] = v;
-      }
-    }
-    // ---- forward (normalising) sweep: last element first ----
-    float ldj[1] = {0.0f};
-    for (int step = 0; step < L; ++step) {
-      const DevElem& E = C->e[L - 1 - step];
-      const float* wblk;
-      if (H.resident) {
-        wblk = wsm + E.stage_off;
-      } else {
-        __syncthreads();
-        copy_f4(wsm, a.staged + E.stage_off, E.stage_len / 4, tid, NT);
-        __syncthreads();
-        wblk = wsm;
-      }
-      // checkpoint the coordinates this element is about to change (restored bit-exactly in the reverse sweep)
-      if (E.ck_len > 0) {
-        float* ck = ckb + (size_t)E.ck_off * NT;
-        if (E.kind == DFLOW_ELEM_NORM)
-          for (int k = 0; k < d; ++k) ck[k * NT] = xs[k * CS + sl];
-        else
-          for (int j = 0; j < E.a; ++j) ck[j * NT] = xs[(int)E.af[j] * CS + sl];
-      }
-      elem_apply<HP, 1>(H, E, wblk, false, xs, th, hc, 0, ob, tb, CS, sl, NT, ldj);
-    }
-    // ---- loss and seeds: z̄ = z * inv_btot, j̄ = -inv_btot (src/Flows.jl:352-359) ----
-    float q = 0.0f;
-    for (int k = 0; k < d; ++k) {
-      const float v = xs[k * CS + sl];
-      q = fmaf(v, v, q);
-    }
-    const float lp = H.logpdf_c0 - 0.5f * q + ldj[0];
-    if (valid) {
-      if (isfinite(lp))
-        lsum_thread += lp;
-      else
-        nonfinite += 1.0f;
-    }
-    const float ib = valid ? a.inv_btot : 0.0f;
-    for (int k = 0; k < d; ++k) gx[k * CS + sl] = xs[k * CS + sl] * ib;
-    const float jb = -ib;
-
-    // ---- reverse sweep in chain order ----
-    for (int ei = 0; ei < L; ++ei) {
-      const DevElem& E = C->e[ei];
-      const float* wblk;
-      if (H.resident) {
-        wblk = wsm + E.stage_off;
-      } else {
-        __syncthreads();
-        copy_f4(wsm, a.staged + E.stage_off, E.stage_len / 4, tid, NT);
-        __syncthreads();
-        wblk = wsm;
-      }
-      if (E.kind == DFLOW_ELEM_NORM) {
-        const float alpha = wblk[2 * d], beta = wblk[2 * d + 1];
-        for (int k = 0; k < d; ++k) {
-          const float xmin = wblk[k], xmax = wblk[d + k];
-          gx[k * CS + sl] *= (beta - alpha) / (xmax - xmin);
-          if (E.ck_len > 0) xs[k * CS + sl] = ckb[(size_t)(E.ck_off + k) * NT];
-        }
-        continue;
-      }
-      const bool rnvp = (E.kind == DFLOW_ELEM_RNVP);
-      InSel in{th, xs, hc, E.id, n, CS, true};
-      const int a4 = H.amax4;
-      if (!rnvp)
-        for (int j = 0; j < a4; ++j) eb[j * CS + sl] = 1.0f;
-      for (int ni = rnvp ? 0 : 1; ni < 2; ++ni) {
-        const DevNet& net = ni == 0 ? E.s : E.t;
-        float* outc = ni == 0 ? ob : tb;
-        run_net<HP, 1>(net, wblk, in, hc, hstride, outc, CS, sl, NT);  // recompute, keep hidden activations
-        for (int j = 0; j < a4; ++j) {
-          float gout = 0.0f;
-          if (j < E.a) {
-            const int k = E.af[j];
-            if (ni == 0) {
-              const float em = expf(-ob[j * CS + sl]);
-              eb[j * CS + sl] = em;
-              gout = -gx[k * CS + sl] * xs[k * CS + sl] - jb;  // s̄, RNVP.jl:134 with z_af = (u_af - t) exp(-s)
-            } else {
-              gout = -gx[k * CS + sl] * eb[j * CS + sl];  // t̄, RNVP.jl:135
-            }
-          } else if (ni == 0) {
-            eb[j * CS + sl] = 1.0f;
-          }
-          gb[j * CS + sl] = gout;
-        }
-        net_backward<HP>(H, E, net, wblk, xs, gx, th, hc, hstride, dlc, gb, outc, gacc, a.grad_out, CS, sl, wbase,
-                         lane);
-      }
-      // restore the layer input from its checkpoint and finish ū (RNVP.jl:137-139)
-      for (int j = 0; j < E.a; ++j) {
-        const int k = E.af[j];
-        xs[k * CS + sl] = ckb[(size_t)(E.ck_off + j) * NT];
-        gx[k * CS + sl] *= eb[j * CS + sl];
-      }
-    }
-    __syncwarp();
-  }
-
-  // ---- flush ----
-  __syncthreads();
-  if (a.smem_grad)
-    for (int i = tid; i < H.P; i += NT) {
-      const float v = gsm[i];
-      if (v != 0.0f) atomicAdd(a.grad_out + i, v);
-    }
-  float v0 = lsum_thread, v1 = nonfinite;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-    v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-  }
-  float* red = cols;
-  if (lane == 0) {
-    red[(tid >> 5) * 2] = v0;
-    red[(tid >> 5) * 2 + 1] = v1;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    float t0 = 0.0f, t1 = 0.0f;
-    for (int w = 0; w < (NT + 31) / 32; ++w) {
-      t0 += red[2 * w];
-      t1 += red[2 * w + 1];
-    }
-    atomicAdd(a.loss_out, t0);
-    if (t1 != 0.0f) atomicAdd(a.loss_out + 1, t1);
-  }
-}
-
-// per-instantiation launch shims (defined in the inst_*.cu units)
 template <int HP, int S, bool REG>
 cudaError_t launch_fwd_inst(const FwdArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st);
-template <int HP>
-cudaError_t launch_grad_inst(const GradArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st);
 // constant-bank forward kernel: uploads [DevChain | staged weights] into the instantiation's bank, then launches
 template <int HP, int S>
 cudaError_t launch_fwd_const_inst(const FwdArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st, int stage_floats);

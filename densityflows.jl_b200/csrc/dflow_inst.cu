@@ -1,5 +1,5 @@
 // One (HP, S[, REG]) instantiation of the chain kernels per object file: compile with
-//   -DDFLOW_INST_FWD -DDFLOW_HP=16 -DDFLOW_S=2 -DDFLOW_REG=0|1      or      -DDFLOW_INST_GRAD -DDFLOW_HP=16
+//   -DDFLOW_INST_FWD -DDFLOW_HP=16 -DDFLOW_S=2 -DDFLOW_REG=0      or      -DDFLOW_INST_GRAD2 -DDFLOW_HP=16 -DDFLOW_S=2
 #include "dflow_chain_kernels.cuh"
 #include "dflow_grad_kernel.cuh"
 
@@ -53,17 +53,6 @@ cudaError_t launch_fwd_const_inst<DFLOW_HP, DFLOW_S>(const FwdArgs& a, unsigned 
   kern<<<grid, nt, smem, st>>>(a);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   return cudaEventRecord(g_cb_ev[dev], st);
-}
-#endif
-
-#ifdef DFLOW_INST_GRAD
-template <>
-cudaError_t launch_grad_inst<DFLOW_HP>(const GradArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st) {
-  auto kern = chain_grad_kernel<DFLOW_HP>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, nt, smem, st>>>(a);
-  return cudaGetLastError();
 }
 #endif
 

@@ -111,7 +111,6 @@ struct GradArgs {
   int smem_grad;  // 1: accumulate the whole gradient in shared memory, flush once per CTA
 };
 
-struct WidePlan;
 struct TcPlan;
 
 struct PrepackArgs {
@@ -139,21 +138,16 @@ struct dflow_chain {
   long long launches = 0;
   // host pipeline scratch (dflow_*_host)
   void* pipe = nullptr;
-  // wide-conditioner (tcgen05) plan; non-null when some hidden width exceeds the narrow path's 64
-  dflow::WidePlan* wide = nullptr;
-  // generation-2 tensor-core plan (dflow_tc.cu): warp-specialised forward + adjoint; built for every eligible chain
+  // tensor-core plan (dflow_tc.cu): warp-specialised tcgen05 forward + adjoint; built for every eligible chain
   dflow::TcPlan* tcp = nullptr;
-  int wide_gen = 2;    // 1: dflow_wide.cu kernels, 2: dflow_tc.cu kernels
   int must_wide = 0;   // some hidden width > 64: the CUDA-core kernels cannot run this chain
-  int tc_cluster = 0;  // streamed conditioners: 0 independent CTAs (default, fastest measured), 1 CTA pairs sharing the
-                       // weight stream by bulk-copy multicast, 2 cta_group::2 pairs (one issuer, M = 256)
   int tc_ws_budget_mb = 0;  // adjoint workspace cap in MiB (0: 24 GiB); larger batches are processed in macro-batches
   int tc_fuse = 1;     // hidden <= 128 RealNVP layers run their s and t conditioners as one block-diagonal conditioner:
                        // 0 never, 1 in the train step (default), 2 in forward-type calls as well
-  int tc_ns_max = 0;   // cap on the weight-ring depth (experiments)
-  int tc_debug = 0;    // timing experiments (dflow_tc.cu)
+  int tc_debug = 0;    // timing experiments (dflow_tc.cu, only with -DDFLOW_TC_EXPERIMENTS)
+  int tc_debug_cluster = 0;  // CTA-pair variants (experiment builds only): 1 multicast weight stream, 2 cta_group::2
   int tc_mode = 0;     // 0: automatic (tensor cores iff must_wide), 1: force tensor cores, -1: force CUDA cores
-  bool use_tc() const { return wide && tcp && (must_wide || tc_mode > 0); }
+  bool use_tc() const { return tcp && (must_wide || tc_mode > 0); }
   // adjoint: at hidden 64 the tensor-core kernels beat the CUDA-core adjoint (3.8e7 vs 2.1e7 samples/s on C3) once the
   // batch fills the machine; narrower or smaller stays on CUDA cores
   int hidden_max = 0;
@@ -162,12 +156,12 @@ struct dflow_chain {
   bool use_tc_fwd(long long B) const {
     if (use_tc()) return true;
     // crossover measured with scripts/c3_fwd_threshold.py: 0.36 / 0.36 ms at 65536, 0.69 / 0.54 ms at 131072 (CUDA / tensor)
-    return wide && tcp && tc_mode == 0 && hidden_max == 64 && B >= 131072;
+    return tcp && tc_mode == 0 && hidden_max == 64 && B >= 131072;
   }
   bool use_tc_grad(long long B) const {
     if (use_tc()) return true;
     // hidden 32 (d = 10, 4 blocks, 2 Mi samples): 1.94e8 samples/s on the tensor-core kernels against 1.41e8 on CUDA cores
-    return wide && tcp && tc_mode == 0 && ((hidden_max == 64 && B >= 32768) || (hidden_max == 32 && B >= 65536));
+    return tcp && tc_mode == 0 && ((hidden_max == 64 && B >= 32768) || (hidden_max == 32 && B >= 65536));
   }
   const dflow::DevChain* hc() const { return reinterpret_cast<const dflow::DevChain*>(host_chain.data()); }
   dflow::DevChain* hc() { return reinterpret_cast<dflow::DevChain*>(host_chain.data()); }

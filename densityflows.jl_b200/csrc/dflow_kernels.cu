@@ -183,7 +183,7 @@ static int launch_fwd_const_t(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
   return DFLOW_OK;
 }
 
-// Kernel selection (fwd_spt tuning: 0 = automatic; negative = force the shared-memory-column variant with |spt|)
+// Kernel selection (fwd_spt tuning: 0 = automatic, else samples per thread of the shared-memory-column kernels)
 int launch_fwd(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
   const DevChainHdr& h = c->hc()->h;
   a.chain = c->d_chain;
@@ -195,23 +195,19 @@ int launch_fwd(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
     if (h.hp == 16) return launch_fwd_const_t<16, 4>(c, a, st);
     if (h.hp == 32) return launch_fwd_const_t<32, 2>(c, a, st);
   }
-  if (!h.relu_only && spt < 0) spt = -spt;  // tanh / sigmoid: shared-memory-column kernels only
+  if (spt < 0) spt = -spt;
   int nt = c->fwd_threads > 0 ? c->fwd_threads : 256;  // clamped to the instantiation's fixed block size
   if (nt > 256) nt = 256;
   nt = (nt + 31) & ~31;
-  // spt > 0: shared-memory-column kernels with spt samples per thread; spt < 0: register-resident kernels with
-  // |spt| samples per thread (relu chains only); 0: automatic
+  // spt > 0: samples per thread of the shared-memory-column kernels; 0: automatic
   switch (h.hp) {
     case 16:
       if (spt == 0 || spt == 4) return launch_fwd_t<16, 4, false>(c, a, st, nt);
       if (spt == 2) return launch_fwd_t<16, 2, false>(c, a, st, nt);
-      if (spt == -4) return launch_fwd_t<16, 4, true>(c, a, st, nt);
-      if (spt == -2) return launch_fwd_t<16, 2, true>(c, a, st, nt);
       return launch_fwd_t<16, 1, false>(c, a, st, nt);
     case 32:
       if (spt == 0 || spt == 4) return launch_fwd_t<32, 4, false>(c, a, st, nt);
       if (spt == 2) return launch_fwd_t<32, 2, false>(c, a, st, nt);
-      if (spt == -2) return launch_fwd_t<32, 2, true>(c, a, st, nt);
       return launch_fwd_t<32, 1, false>(c, a, st, nt);
     case 64:
       if (spt == 0 || spt == 2) return launch_fwd_t<64, 2, false>(c, a, st, nt);
@@ -219,36 +215,6 @@ int launch_fwd(dflow_chain* c, FwdArgs& a, cudaStream_t st) {
   }
   set_error("hidden width template %d not built", h.hp);
   return DFLOW_E_UNSUPPORTED;
-}
-
-template <int HP>
-static int launch_grad_t(dflow_chain* c, GradArgs& a, cudaStream_t st, int nt) {
-  const DevChainHdr& h = c->hc()->h;
-  a.smem_grad = (h.P * 4 <= 64 * 1024) ? 1 : 0;
-  SmemPlan p = plan_grad(h, c->chain_bytes, nt, a.smem_grad);
-  while (p.bytes() > (size_t)c->max_smem_optin && nt > 32) {
-    nt >>= 1;
-    p = plan_grad(h, c->chain_bytes, nt, a.smem_grad);
-  }
-  if (p.bytes() > (size_t)c->max_smem_optin) {
-    set_error("adjoint needs %zu bytes of shared memory (> %d)", p.bytes(), c->max_smem_optin);
-    return DFLOW_E_UNSUPPORTED;
-  }
-  const long long ntiles = (a.B + nt - 1) / nt;
-  int per_sm = c->ctas_per_sm;
-  if (per_sm <= 0) {
-    per_sm = (int)((size_t)c->max_smem_optin / (p.bytes() + 1024));
-    const int by_threads = 2048 / nt;
-    if (per_sm > by_threads) per_sm = by_threads;
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm < 1) per_sm = 1;
-  }
-  long long grid = (long long)c->sm_count * per_sm;
-  if (grid > ntiles) grid = ntiles;
-  if (grid < 1) grid = 1;
-  CK(launch_grad_inst<HP>(a, (unsigned)grid, nt, p.bytes(), st));
-  c->launches++;
-  return DFLOW_OK;
 }
 
 template <int HP, int S>
@@ -286,33 +252,23 @@ int launch_grad(dflow_chain* c, GradArgs& a, cudaStream_t st) {
   a.chain = c->d_chain;
   a.staged = c->d_staged;
   a.chain_bytes = c->chain_bytes;
-  if (c->grad_spt >= 0) {  // v2 adjoint (register-tiled dW); grad_spt < 0 selects the first-generation kernel
-    int nt2 = c->grad_threads > 0 ? c->grad_threads : 1024;  // clamped to the instantiation's fixed block size
-    nt2 = (nt2 + 31) & ~31;
-    int s = c->grad_spt;
-    // automatic: a minibatch that fits one wave of 256-thread CTAs runs one sample per thread -- a tile's latency is what
-    // such a step costs (85 us against 134 us for the S = 2 / 384-thread configuration at the reference's batchsize 64)
-    if (s == 0 && h.hp == 16 && a.B <= (long long)c->sm_count * 256) s = 1;
-    switch (h.hp) {
-      case 16:
-        if (s == 1) return launch_grad2_t<16, 1>(c, a, st, nt2);
-        if (s == 4) return launch_grad2_t<16, 4>(c, a, st, nt2);
-        return launch_grad2_t<16, 2>(c, a, st, nt2);
-      case 32:
-        if (s == 1) return launch_grad2_t<32, 1>(c, a, st, nt2);
-        return launch_grad2_t<32, 2>(c, a, st, nt2);
-      case 64:
-        if (s == 2) return launch_grad2_t<64, 2>(c, a, st, nt2);
-        return launch_grad2_t<64, 1>(c, a, st, nt2);
-    }
-  }
-  int nt = c->grad_threads > 0 ? c->grad_threads : (h.hp >= 64 ? 128 : 256);
-  if (nt > 256) nt = 256;
-  nt = (nt + 31) & ~31;
+  int nt2 = c->grad_threads > 0 ? c->grad_threads : 1024;  // clamped to the instantiation's fixed block size
+  nt2 = (nt2 + 31) & ~31;
+  int s = c->grad_spt;
+  // automatic: a minibatch that fits one wave of 256-thread CTAs runs one sample per thread -- a tile's latency is what
+  // such a step costs (85 us against 134 us for the S = 2 / 384-thread configuration at the reference's batchsize 64)
+  if (s == 0 && h.hp == 16 && a.B <= (long long)c->sm_count * 256) s = 1;
   switch (h.hp) {
-    case 16: return launch_grad_t<16>(c, a, st, nt);
-    case 32: return launch_grad_t<32>(c, a, st, nt);
-    case 64: return launch_grad_t<64>(c, a, st, nt);
+    case 16:
+      if (s == 1) return launch_grad2_t<16, 1>(c, a, st, nt2);
+      if (s == 4) return launch_grad2_t<16, 4>(c, a, st, nt2);
+      return launch_grad2_t<16, 2>(c, a, st, nt2);
+    case 32:
+      if (s == 1) return launch_grad2_t<32, 1>(c, a, st, nt2);
+      return launch_grad2_t<32, 2>(c, a, st, nt2);
+    case 64:
+      if (s == 2) return launch_grad2_t<64, 2>(c, a, st, nt2);
+      return launch_grad2_t<64, 1>(c, a, st, nt2);
   }
   set_error("hidden width template %d not built", h.hp);
   return DFLOW_E_UNSUPPORTED;

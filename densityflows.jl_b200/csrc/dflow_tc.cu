@@ -54,6 +54,16 @@ constexpr int NSMAX = TC_NSMAX;
 
 enum { TC_FWD = 0, TC_FWD_STORE = 1, TC_BWD = 2 };
 
+// Release builds compile the timing-experiment switches and the CTA-pair variants out (both measured, both slower or
+// wrong by construction: profiles/r01_tc_summary.md); -DDFLOW_TC_EXPERIMENTS brings them back.
+#ifdef DFLOW_TC_EXPERIMENTS
+#define TC_DBG(a) ((a).debug)
+#define TC_CLUSTER(a) ((a).cluster)
+#else
+#define TC_DBG(a) 0
+#define TC_CLUSTER(a) 0
+#endif
+
 // TMEM column map of the net kernel (per launch, TcArgs): D1 ring of NG groups x GW columns at 0, then D3 (<= 64
 // columns) and D2 (NH <= 256 columns)
 
@@ -222,7 +232,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
   constexpr bool pair2 = PAIR2;                             // cta_group::2: rank 0 of the pair issues for both CTAs
-  const uint32_t crank = a.cluster ? cluster_ctarank() : 0u;
+  const uint32_t crank = TC_CLUSTER(a) ? cluster_ctarank() : 0u;
   const TcNetImg& im = pair2 ? a.im2[crank] : a.im;         // (logical sizes are the same in all three images)
   const int hv = pair2 ? 2 : 1;                             // weight-block rows held by this CTA = logical rows / hv
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -247,7 +257,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
   if (tid == 0) {
     for (int i = 0; i < NSMAX; ++i) {
       mbar_init(bars + BAR_W_FULL + i, 1);
-      mbar_init(bars + BAR_W_EMPTY + i, a.cluster == 1 ? 2 : 1);  // multicast pair: released by both CTAs' MMA warps
+      mbar_init(bars + BAR_W_EMPTY + i, TC_CLUSTER(a) == 1 ? 2 : 1);  // multicast pair: released by both CTAs' MMA warps
       mbar_init(bars + BAR_W_PEER + i, 1);
     }
     const uint32_t two = pair2 ? 2u : 1u;  // cta_group::2: both CTAs' threads arrive on the leader's barriers
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
   for (int i = tid; i < nbias; i += NTHREADS) biasS[i] = i < 2 * H + N3p ? __ldg(gimg + im.bias_off + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
-  if (a.cluster) cluster_sync_all();  // the peer's barriers exist before any multicast copy / commit can reach them
+  if (TC_CLUSTER(a)) cluster_sync_all();  // the peer's barriers exist before any multicast copy / commit can reach them
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
   const long long ntiles = (a.B + 127) / 128;
@@ -309,7 +319,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
       float* a2h = A2 + slot * 2 * 128 * WKA;
       float* a2l = a2h + 128 * WKA;
       mbar_wait(bars + BAR_A2_EMPTY + slot, par ^ 1u);
-      if (!(a.debug & 16)) {
+      if (!(TC_DBG(a) & 16)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 hi, lo;
@@ -339,7 +349,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
     };
     for (long long it = 0; it < iters; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
-      const bool live = tile < ntiles && !(a.debug & (128 | 512));  // dummy tiles touch no global memory (512: timing
+      const bool live = tile < ntiles && !(TC_DBG(a) & (128 | 512));  // dummy tiles touch no global memory (512: timing
                                                                     // experiment without the training stores)
       for (int p = 0; p < passes; ++p) {
         // relu masks of the adjoint chain are fetched one chunk ahead (the global-load latency would otherwise sit
@@ -458,9 +468,9 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     auto build_a1 = [&](long long it, uint32_t tc) {
       const long long tile = blockIdx.x + it * gridDim.x;
-      const bool live = tile < ntiles && !(a.debug & 128);
+      const bool live = tile < ntiles && !(TC_DBG(a) & 128);
       const long long gi = tile * 128 + row;
-      const bool valid = gi < a.B && !(a.debug & 128);
+      const bool valid = gi < a.B && !(TC_DBG(a) & 128);
       (void)live;
         mbar_wait(bars + BAR_A1_EMPTY, (tc & 1) ^ 1);
         // ---- A1: this sample's GEMM-1 input row ----
@@ -584,9 +594,9 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
     };
     auto final_out = [&](long long it, uint32_t tc) {
       const long long tile = blockIdx.x + it * gridDim.x;
-      const bool live = tile < ntiles && !(a.debug & 128);
+      const bool live = tile < ntiles && !(TC_DBG(a) & 128);
       const long long gi = tile * 128 + row;
-      const bool valid = gi < a.B && !(a.debug & 128);
+      const bool valid = gi < a.B && !(TC_DBG(a) & 128);
       (void)live;
       mbar_wait(bars + BAR_D3_FULL, tc & 1);
       tc_fence_after();
@@ -684,11 +694,11 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
         const int cpg16 = GW / WKC;  // weight blocks per D1 group
         const uint32_t g1b = (uint32_t)im.g1_floats * 4u, s2b = (uint32_t)im.s2_floats * 4u, s3b = (uint32_t)im.s3_floats * 4u;
         auto put = [&](const float* src, uint32_t bytes) {
-          if (a.debug & 64) bytes = (bytes >> 3) & ~31u;  // timing experiment: an eighth of the weight stream
+          if (TC_DBG(a) & 64) bytes = (bytes >> 3) & ~31u;  // timing experiment: an eighth of the weight stream
           mbar_wait(bars + BAR_W_EMPTY + rW.slot, rW.par ^ 1);
           mbar_expect_tx(bars + BAR_W_FULL + rW.slot, bytes);
           char* dst = reinterpret_cast<char*>(ring + (size_t)rW.slot * im.slot_floats);
-          if (a.cluster == 1) {
+          if (TC_CLUSTER(a) == 1) {
             // each CTA of the pair fetches one half of the block and delivers it to both
             const uint32_t half = bytes >> 1;
             bulk_g2s_multicast(dst + crank * half, reinterpret_cast<const char*>(src) + crank * half, half,
@@ -744,7 +754,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
                    bA2_FULL = bars_u32 + BAR_A2_FULL * 8, bA2_EMPTY = bars_u32 + BAR_A2_EMPTY * 8,
                    bW_PEER = bars_u32 + BAR_W_PEER * 8;
     const uint32_t tD1 = tbase + TM_D1, tD2 = tbase + TM_D2, tD3 = tbase + TM_D3;
-    const bool resident = a.resident != 0, pair = a.cluster == 1;
+    const bool resident = a.resident != 0, pair = TC_CLUSTER(a) == 1;
     // issue / commit variants: one CTA, or the cta_group::2 pair (commits are multicast to both CTAs' barriers)
     auto MMA = [&](uint32_t dt, uint64_t da_, uint64_t db_, uint32_t id_, uint32_t acc_) {
       if constexpr (pair2) mma_tf32_2(dt, da_, db_, id_, acc_);
@@ -764,7 +774,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
       mbar_wait_a(bW_FULL + slot_ * 8, par_);
       if (pair2) mbar_wait_a(bW_PEER + slot_ * 8, par_);
     };
-    const bool skip1 = (a.debug & 2) != 0, skip2 = (a.debug & 8) != 0, skip3 = (a.debug & 4) != 0;
+    const bool skip1 = (TC_DBG(a) & 2) != 0, skip2 = (TC_DBG(a) & 8) != 0, skip3 = (TC_DBG(a) & 4) != 0;
     Ring rW{0, 0, (uint32_t)(resident ? 1 : a.NS)}, rD1{0, 0, (uint32_t)NG};
     uint32_t npass = 0, tcount = 0;
     if (pair2 && crank != 0) {
@@ -937,7 +947,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
     if constexpr (pair2) tmem_dealloc2(tbase, (uint32_t)a.tmem_cols);
     else tmem_dealloc(tbase, (uint32_t)a.tmem_cols);
   }
-  if (a.cluster) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
+  if (TC_CLUSTER(a)) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
 }
 
 // ---- weight gradients: K = samples GEMMs ------------------------------------------------------------------------
@@ -1083,7 +1093,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
 #pragma unroll
       for (int i = 0; i < DW_MAXRB; ++i) {
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (((okmask >> i) & 1u) && !(a.debug & 2))
+        if (((okmask >> i) & 1u) && !(TC_DBG(a) & 2))
           v[i] = __ldg(reinterpret_cast<const float4*>(my_ptr[i] + blk * (size_t)pick(ts_by, (codes >> (2 * i)) & 3u)));
       }
     };
@@ -1093,7 +1103,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       float* st = smem + (size_t)sl * stage_fl;
 #pragma unroll
       for (int i = 0; i < DW_MAXRB; ++i) {
-        if (((segmask >> i) & 1u) && !(a.debug & 4)) {
+        if (((segmask >> i) & 1u) && !(TC_DBG(a) & 4)) {
           float4 hi, lo;
           hi.x = to_tf32(v[i].x); lo.x = v[i].x - hi.x;
           hi.y = to_tf32(v[i].y); lo.y = v[i].y - hi.y;
@@ -1208,7 +1218,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
         const uint64_t b = d0 + slot * stage_step;
         const uint32_t acc = s > 0 ? 1u : 0u;
         // dW2 += delta2 * h1^T ; dW1 += delta1 * in^T ; dW3^T += h2 * delta3^T   (each: lo*hi + hi*lo + hi*hi, 2 K steps)
-        if (!(a.debug & 1)) {
+        if (!(TC_DBG(a) & 1)) {
           gemm3_desc(tbase + DWT_W2, b + so[0], b + so[0] + sl[0], b + so[3], b + so[3] + sl[3], DW_KS / 8, idW2, acc);
           gemm3_desc(tbase + DWT_W1, b + so[1], b + so[1] + sl[1], b + so[4], b + so[4] + sl[4], DW_KS / 8, idW1, acc);
           gemm3_desc(tbase + DWT_W3, b + so[2], b + so[2] + sl[2], b + so[5], b + so[5] + sl[5], DW_KS / 8, idW3, acc);
@@ -1467,7 +1477,6 @@ static bool tc_launch_cfg(const dflow_chain* c, const TcNetImg& im, TcLaunchCfg&
       const size_t room = cap > b ? cap - b : 0;
       int ns = (int)(room / ((size_t)im.slot_floats * 4));
       if (ns > 8) ns = 8;
-      if (c->tc_ns_max > 0 && ns > c->tc_ns_max) ns = c->tc_ns_max;
       if (ns >= (na == 4 ? 4 : 3)) {
         ok = true;
         cfg.NA = na;
@@ -1538,11 +1547,13 @@ int tc_build_plan(dflow_chain* c) {
       J.pb1 = net.p_b[0]; J.pb2 = net.p_b[1]; J.pb3 = net.p_b[2]; J.nb3 = a;
       tp->jobs_fwd.push_back(J);
       tp->k0pmax = std::max(tp->k0pmax, Ld.fwd[ni].K0p);
+#ifdef DFLOW_TC_EXPERIMENTS
       for (int r = 0; r < 2; ++r) {  // half-row images of the two CTAs of a cta_group::2 pair
         fill_img(Ld.fwd2[ni][r], Ld.nin, h, a, off, 8, 2, r);
         J.im = Ld.fwd2[ni][r];
         tp->jobs_fwd.push_back(J);
       }
+#endif
       if (h <= 256) {
         // adjoint orientation: M1[u][o] = W3[o][u], M2[i][o] = W2[o][i], M3[k][u] = W1[u][k]
         fill_img(Ld.bwd[ni], a, h, Ld.nin, off, 16);  // K0p = a16: delta3 rows double as the dW3 operand
@@ -1553,11 +1564,13 @@ int tc_build_plan(dflow_chain* c) {
         J.base3 = net.p_w[0]; J.sn3 = h; J.sk3 = 1; J.vn3 = Ld.nin; J.vk3 = h;
         J.pb1 = J.pb2 = J.pb3 = -1;
         tp->jobs_bwd.push_back(J);
+#ifdef DFLOW_TC_EXPERIMENTS
         for (int r = 0; r < 2; ++r) {
           fill_img(Ld.bwd2[ni][r], a, h, Ld.nin, off, 16, 2, r);
           J.im = Ld.bwd2[ni][r];
           tp->jobs_bwd.push_back(J);
         }
+#endif
       }
     }
     tp->hu = std::max(tp->hu, h);
@@ -1673,7 +1686,8 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st, const TcNetImg
   // streamed weights, CTA pairs: tc_cluster = 2 -> cta_group::2 (one issuer for two SMs, half of the weight rows per
   // CTA), tc_cluster = 1 -> independent CTAs that share the weight stream by bulk-copy multicast
   a.cluster = 0;
-  if (!cfg.resident && grid >= 2 && c->tc_cluster == 2 && half) {
+#ifdef DFLOW_TC_EXPERIMENTS
+  if (!cfg.resident && grid >= 2 && c->tc_debug_cluster == 2 && half) {
     TcLaunchCfg c2;
     if (tc_launch_cfg(c, half[0], c2, false)) {
       cfg = c2;
@@ -1682,7 +1696,10 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st, const TcNetImg
       a.im2[1] = half[1];
     }
   }
-  if (!a.cluster && !cfg.resident && grid >= 2 && c->tc_cluster == 1) a.cluster = 1;
+  if (!a.cluster && !cfg.resident && grid >= 2 && c->tc_debug_cluster == 1) a.cluster = 1;
+#else
+  (void)half;
+#endif
   a.resident = cfg.resident;
   a.NS = cfg.NS;
   a.NA = cfg.NA;
@@ -1693,9 +1710,13 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st, const TcNetImg
   a.s3ps = std::max(2, (imu.slot_floats / imu.s3_floats) & ~1);  // an even number of 16-unit blocks
   a.debug = c->tc_debug;
   a.tmem_cols = cfg.tmem_cols;
+#ifdef DFLOW_TC_EXPERIMENTS
   void (*kern)(TcArgs) = a.cluster == 2 ? tc_net_kernel<MODE, true, 2>
                          : cfg.nwg == 1 ? tc_net_kernel<MODE, false, 1>
                                         : tc_net_kernel<MODE, false, 2>;
+#else
+  void (*kern)(TcArgs) = cfg.nwg == 1 ? tc_net_kernel<MODE, false, 1> : tc_net_kernel<MODE, false, 2>;
+#endif
   const unsigned nthreads = (unsigned)(4 * cfg.nwg + 6) * 32u;
   CKT(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
   const long long cap = (long long)c->sm_count * cfg.ctas_per_sm;
@@ -2048,7 +2069,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       }
       w.inbuf = inbuf_of(ei);
       w.grad = grad_out;
-      w.debug = (c->tc_debug >> 12) & 7;  // bits 12-14 of tc_debug: weight-gradient kernel timing experiments
+      w.debug = (c->tc_debug >> 12) & 7;  // bits 12-14 of tc_debug: weight-gradient kernel timing experiments (experiment builds)
       const int RA = std::min(128, w.H);  // rows of the A segments (a multiple of 8: H % 32 == 0)
       const size_t stage_bytes = 2 * (size_t)(3 * RA + w.H + w.K0p + w.a16) * DW_KS * 4;
       // the M = 128 MMAs read 128 rows of every A segment: keep that overrun inside the allocation

@@ -34,7 +34,6 @@ def setup(name, B, seed=11):
     pc = chain.packed(DEV)
     if force:
         pc.tune(tc_mode=1)
-    pc.tune(tc_cluster=int(os.environ.get("DFLOW_TC_CLUSTER", "0")))
     return ochain, chain, pc, x, th
 
 

@@ -16,7 +16,6 @@ if h <= 64:
 g = torch.Generator(device="cuda").manual_seed(0)
 x = df.jl_empty((d, B), "cuda:0"); x.normal_(generator=g)
 th = df.jl_empty((n, B), "cuda:0"); th.uniform_(0, 1, generator=g)
-pc.tune(tc_debug=int(os.environ.get("DFLOW_TC_DEBUG", "0")))
 grad = torch.zeros(pc.P, device="cuda:0"); l2 = torch.zeros(2, device="cuda:0")
 pc.loss_grad(x, th, grad, l2)
 torch.cuda.synchronize()
