@@ -13,7 +13,7 @@ from .arrays import jl_empty, jl_full, jl_zeros, to_jl, to_numpy
 from .data import (DataArrays, DataPartition, MetaData, dflt_theta, dflt_θ, maximum_θ, minimum_θ, normalize_input,
                    normalized_training_data, normalized_validation_data, number_conditions, number_dimensions,
                    resize_output, testing_data, training_data, validation_data)
-from .flows import (Adam, Flow, OptimiserState, PeerTrainStep, TrainStep, make_train_step, logpdf, pdf, predict, sample, sample_with_rejection, setup, train_, training_loss,
+from .flows import (Adam, Flow, LocalDataParallel, OptimiserState, PeerTrainStep, TrainStep, make_train_step, logpdf, pdf, predict, sample, sample_with_rejection, setup, train_, training_loss,
                     validation_loss)
 from .model import (Chain, CouplingAxes, CouplingBlock, CouplingLayer, CouplingLayerBase, Dense, FlowChain,
                     FlowElement, NICECouplingLayer, NormalizationElement, NormalizationLayer, PackedChain,

@@ -48,6 +48,13 @@ class ChainDesc(C.Structure):
     ]
 
 
+class DpShard(C.Structure):
+    """dflow_dp_shard (include/dflow.h): one rank's share of a minibatch for dflow_dp_train_step."""
+    _fields_ = [("chain", C.c_void_p), ("W", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("x", C.c_void_p),
+                ("theta", C.c_void_p), ("B", C.c_int64), ("idx", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t),
+                ("loss2_out", C.c_void_p), ("stream", C.c_void_p)]
+
+
 class DflowError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libdflow error {code}: {msg}")
@@ -81,6 +88,7 @@ SYMBOLS = [
     ("dflow_sample_rng", C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint64, vp, vp, C.c_int64, C.c_int32, vp, vp]),
     ("dflow_workspace_bytes", C.c_size_t, [vp, C.c_int64]),
     ("dflow_loss_grad", C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_float, C.c_int32, vp, vp, vp, C.c_size_t, vp]),
+    ("dflow_vjp", C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
     ("dflow_adam_step", C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp]),
     ("dflow_train_epoch", C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float,
                                     C.c_float, C.POINTER(C.c_int64), C.c_int32, vp, vp, vp, C.c_size_t, vp]),
@@ -92,7 +100,12 @@ SYMBOLS = [
     ("dflow_dp_grad_buffer", vp, [vp]),
     ("dflow_dp_allreduce_adam", C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp, vp]),
     ("dflow_dp_status", C.c_int, [vp, vp]),
+    ("dflow_dp_set_timeout_ms", C.c_int, [vp, C.c_int64]),
     ("dflow_dp_destroy", C.c_int, [vp]),
+    ("dflow_dp_create_local", C.c_int, [C.c_int32, c_i32p, C.c_int64, C.POINTER(vp)]),
+    ("dflow_dp_train_step", C.c_int, [C.POINTER(vp), C.c_int32, vp, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, C.c_int64]),
+    ("dflow_dp_sync", C.c_int, [C.POINTER(vp), C.c_int32, vp]),
     ("dflow_set_tuning", C.c_int, [vp, C.c_char_p, C.c_int32]),
     ("dflow_launch_count", C.c_int64, [vp]),
 ]

@@ -600,8 +600,9 @@ int dflow_sample_rng(dflow_chain* c, const float* W, uint64_t seed, uint32_t off
 size_t dflow_workspace_bytes(const dflow_chain* c, int64_t B) {
   if (!c) return 0;
   if (c->use_tc_grad(B)) return tc_workspace_bytes(c, B);
-  // one checkpoint slab per resident CTA (not per sample): grid <= sm_count * 4 CTAs of <= 256 threads
-  return (size_t)c->sm_count * 4 * 512 * (size_t)c->hc()->h.ck_total * sizeof(float) + 256;
+  // one checkpoint slab per resident CTA (not per sample): the launcher caps the grid at sm_count * 4 CTAs, and the
+  // largest tile of any instantiation is 768 sample slots (384 threads x 2, 192 threads x 4)
+  return (size_t)c->sm_count * 4 * 768 * (size_t)c->hc()->h.ck_total * sizeof(float) + 256;
 }
 
 int dflow_loss_grad(dflow_chain* c, const float* W, const float* x, const float* theta, int64_t B, const int32_t* idx,
@@ -633,6 +634,51 @@ int dflow_loss_grad(dflow_chain* c, const float* W, const float* x, const float*
   a.B = B;
   a.inv_btot = inv_btot;
   a.flags = flags;
+  return launch_grad(c, a, st);
+}
+
+// Vector-Jacobian product of backward(chain, x, θ) -> (z, ln_det_jac) with caller cotangents (z̄, j̄): the pullback of
+// ChainRulesCore.rrule(::typeof(backward), chain, x, θ), i.e. the rrule of src/affine/RNVP.jl:99-147 composed through the
+// chain (src/Chains.jl:149-164) with the Dense pullbacks.
+int dflow_vjp(dflow_chain* c, const float* W, const float* x, const float* theta, int64_t B, int32_t flags,
+              const float* zbar, const float* jbar, float* grad_out, float* xbar_out, float* thetabar_out, void* ws,
+              size_t ws_bytes, void* stream) {
+  int rc = check_common(c, W, theta, nullptr, B, flags);
+  if (rc) return rc;
+  if (B > 0 && (!x || !grad_out || !zbar)) {
+    set_error("null pointer (x, zbar and grad_out are required; jbar = NULL means a zero cotangent of ln_det_jac)");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (B > 0 && (!ws || ws_bytes < dflow_workspace_bytes(c, B))) {
+    set_error("workspace too small: need %zu bytes (dflow_workspace_bytes), got %zu", dflow_workspace_bytes(c, B),
+              ws_bytes);
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (B == 0) return DFLOW_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->use_tc_grad(B)) {
+    TcVjp v{};
+    v.zbar = zbar;
+    v.jbar = jbar;
+    v.xbar_out = xbar_out;
+    v.thbar_out = thetabar_out;
+    // jbar == NULL: inv_btot = 0 is the (constant) minus-cotangent of ln_det_jac
+    return tc_loss_grad(c, W, x, theta, B, nullptr, 0.0f, flags, nullptr, grad_out, ws, ws_bytes, st, &v);
+  }
+  rc = launch_prepack(c, W, st);
+  if (rc) return rc;
+  GradArgs a{};
+  a.x_in = x;
+  a.theta = theta;
+  a.grad_out = grad_out;
+  a.ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  a.B = B;
+  a.inv_btot = 0.0f;
+  a.flags = flags;
+  a.zbar = zbar;
+  a.jbar = jbar;
+  a.xbar_out = xbar_out;
+  a.thbar_out = thetabar_out;
   return launch_grad(c, a, st);
 }
 

@@ -35,6 +35,7 @@ struct DpArgs {
   float lr, b1, b2, eps, c1, c2;
   float* loss2_out;   // [2] reduced sum logp / #non-finite, or null
   int* status;        // device int: set to 1 if the barrier timed out
+  long long timeout_clk;  // barrier time-out in SM clocks
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -58,7 +59,8 @@ __device__ __forceinline__ float ld_peer(const float* p) {  // bypass L1: peer d
 
 __global__ void __launch_bounds__(256) dp_allreduce_adam_kernel(const DpArgs a) {
   uint32_t* my_flags = reinterpret_cast<uint32_t*>(const_cast<char*>(a.bufs[a.rank]));
-  uint32_t* go = my_flags + 64;
+  uint32_t* go = my_flags + 64;    // epoch released by CTA 0 once every peer has published it
+  uint32_t* bad = my_flags + 65;   // epoch whose barrier timed out on this rank (poison: nobody reduces or updates)
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     __threadfence_system();  // the adjoint kernels' gradient (earlier launches on this stream) before the flag
     for (int j = 0; j < a.nranks; ++j)
@@ -67,22 +69,29 @@ __global__ void __launch_bounds__(256) dp_allreduce_adam_kernel(const DpArgs a) 
     bool ok = true;
     for (int j = 0; j < a.nranks && ok; ++j) {
       while ((int32_t)(ld_acquire_sys(my_flags + j) - a.epoch) < 0) {
-        if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer is gone
+        if (clock64() - t0 > a.timeout_clk) {  // ~10 s by default: a peer is gone
           ok = false;
           break;
         }
       }
     }
-    if (!ok && a.status) *a.status = 1;
+    if (!ok) {
+      // the peers' halves may be stale or half written: skip the reduction AND the update on this rank, and say so
+      if (a.status) *a.status = 1;
+      *bad = a.epoch;
+    }
     __threadfence();
     atomicExch(go, a.epoch);
   }
-  // all CTAs are co-resident (grid <= SM count): wait for the release by CTA 0
+  // all CTAs are co-resident (cooperative launch, grid <= SM count): wait for the release by CTA 0
+  __shared__ uint32_t poisoned;
   if (threadIdx.x == 0) {
     while ((int32_t)(ld_acquire_gpu(go) - a.epoch) < 0) {
     }
+    poisoned = (ld_acquire_gpu(bad) == a.epoch) ? 1u : 0u;
   }
   __syncthreads();
+  if (poisoned) return;
   const size_t half_off = DP_HDR_BYTES / sizeof(float) + (size_t)(a.epoch & 1u) * a.half_floats;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.P + 2; i += (long long)gridDim.x * blockDim.x) {
     float g = 0.0f;
@@ -111,15 +120,41 @@ using namespace dflow;
 
 struct dflow_dp {
   int rank = 0, nranks = 1;
+  int device = 0;
   long long P = 0;
   size_t half_floats = 0, bytes = 0;
   char* own = nullptr;
   char* peers[DP_MAX_RANKS] = {nullptr};
-  bool opened[DP_MAX_RANKS] = {false};
+  bool opened[DP_MAX_RANKS] = {false};  // peer buffers mapped through CUDA IPC (closed in dflow_dp_destroy)
+  bool local_group = false;             // created by dflow_dp_create_local: peers are plain device pointers
   int* d_status = nullptr;
   uint32_t epoch = 0;
   int sm_count = 148;
+  long long timeout_clk = 20000000000LL;  // ~10 s at 2 GHz
+  cudaStream_t own_stream = nullptr;      // dflow_dp_train_step uses it when the shard gives no stream
 };
+
+static int dp_alloc(dflow_dp* d, int device) {
+  d->device = device;
+  d->half_floats = (size_t)((d->P + 2 + 63) & ~63LL);
+  d->bytes = DP_HDR_BYTES + 2 * d->half_floats * sizeof(float);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    set_error("no CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+    return DFLOW_E_CUDA;
+  }
+  d->sm_count = prop.multiProcessorCount;
+  if (cudaMalloc(&d->own, d->bytes) != cudaSuccess || cudaMalloc(&d->d_status, sizeof(int)) != cudaSuccess ||
+      cudaMemset(d->own, 0, d->bytes) != cudaSuccess || cudaMemset(d->d_status, 0, sizeof(int)) != cudaSuccess) {
+    set_error("communication buffer setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (d->own) cudaFree(d->own);
+    if (d->d_status) cudaFree(d->d_status);
+    d->own = nullptr;
+    d->d_status = nullptr;
+    return DFLOW_E_NOMEM;
+  }
+  return DFLOW_OK;
+}
 
 extern "C" {
 
@@ -128,28 +163,28 @@ int dflow_dp_create(int32_t rank, int32_t nranks, int64_t P, dflow_dp** out, voi
     set_error("bad dflow_dp_create arguments (at most %d ranks)", DP_MAX_RANKS);
     return DFLOW_E_INVALID_ARG;
   }
+  *out = nullptr;
   dflow_dp* d = new (std::nothrow) dflow_dp();
   if (!d) return DFLOW_E_NOMEM;
   d->rank = rank;
   d->nranks = nranks;
   d->P = P;
-  d->half_floats = (size_t)((P + 2 + 63) & ~63LL);
-  d->bytes = DP_HDR_BYTES + 2 * d->half_floats * sizeof(float);
   int dev = 0;
-  cudaDeviceProp prop;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+  if (cudaGetDevice(&dev) != cudaSuccess) {
     set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
     delete d;
     return DFLOW_E_CUDA;
   }
-  d->sm_count = prop.multiProcessorCount;
+  int rc = dp_alloc(d, dev);
+  if (rc) {
+    delete d;
+    return rc;
+  }
   cudaIpcMemHandle_t h;
-  if (cudaMalloc(&d->own, d->bytes) != cudaSuccess || cudaMalloc(&d->d_status, sizeof(int)) != cudaSuccess ||
-      cudaMemset(d->own, 0, d->bytes) != cudaSuccess || cudaMemset(d->d_status, 0, sizeof(int)) != cudaSuccess ||
-      cudaIpcGetMemHandle(&h, d->own) != cudaSuccess) {
-    set_error("communication buffer setup failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (d->own) cudaFree(d->own);
-    if (d->d_status) cudaFree(d->d_status);
+  if (cudaIpcGetMemHandle(&h, d->own) != cudaSuccess) {
+    set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d->own);
+    cudaFree(d->d_status);
     delete d;
     return DFLOW_E_CUDA;
   }
@@ -181,11 +216,93 @@ int dflow_dp_connect(dflow_dp* d, const void* handles) {
   return DFLOW_OK;
 }
 
+/* Single-process variant (the reference's train! is one host process, src/Flows.jl:380-445): one context per device
+ * of `devs`, connected through cudaDeviceEnablePeerAccess instead of IPC handles.  out: ndev handles, out[r] lives on
+ * devs[r] and plays rank r.  The same device may appear more than once (replicas sharing a GPU). */
+int dflow_dp_create_local(int32_t ndev, const int32_t* devs, int64_t P, dflow_dp** out) {
+  if (!out || !devs || ndev < 1 || ndev > DP_MAX_RANKS || P < 0) {
+    set_error("bad dflow_dp_create_local arguments (1..%d devices)", DP_MAX_RANKS);
+    return DFLOW_E_INVALID_ARG;
+  }
+  int prev = 0, count = 0;
+  if (cudaGetDevice(&prev) != cudaSuccess || cudaGetDeviceCount(&count) != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    return DFLOW_E_CUDA;
+  }
+  for (int r = 0; r < ndev; ++r) {
+    out[r] = nullptr;
+    if (devs[r] < 0 || devs[r] >= count) {
+      set_error("device %d does not exist (%d visible)", devs[r], count);
+      return DFLOW_E_INVALID_ARG;
+    }
+  }
+  int rc = DFLOW_OK;
+  for (int r = 0; r < ndev && !rc; ++r) {
+    dflow_dp* d = new (std::nothrow) dflow_dp();
+    if (!d) {
+      rc = DFLOW_E_NOMEM;
+      break;
+    }
+    out[r] = d;
+    d->rank = r;
+    d->nranks = ndev;
+    d->P = P;
+    d->local_group = true;
+    if (cudaSetDevice(devs[r]) != cudaSuccess) {
+      set_error("cudaSetDevice(%d) failed: %s", devs[r], cudaGetErrorString(cudaGetLastError()));
+      rc = DFLOW_E_CUDA;
+      break;
+    }
+    rc = dp_alloc(d, devs[r]);
+    if (!rc && cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = DFLOW_E_CUDA;
+    }
+    for (int j = 0; j < ndev && !rc; ++j) {
+      if (devs[j] == devs[r]) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devs[r], devs[j]);
+      if (!can) {
+        set_error("device %d cannot access device %d (no NVLink / PCIe peer path)", devs[r], devs[j]);
+        rc = DFLOW_E_UNSUPPORTED;
+        break;
+      }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        set_error("cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", devs[r], devs[j], cudaGetErrorString(e));
+        rc = DFLOW_E_CUDA;
+      }
+      cudaGetLastError();  // clear "already enabled"
+    }
+  }
+  if (!rc)
+    for (int r = 0; r < ndev; ++r)
+      for (int j = 0; j < ndev; ++j) out[r]->peers[j] = out[j]->own;
+  cudaSetDevice(prev);
+  if (rc)
+    for (int r = 0; r < ndev; ++r) {
+      dflow_dp_destroy(out[r]);
+      out[r] = nullptr;
+    }
+  return rc;
+}
+
 /* device pointer of the [grad (P) | sum logp | #non-finite] accumulation area of the NEXT step; the caller zeroes it and
  * passes grad / loss2 pointers into it to dflow_loss_grad */
 float* dflow_dp_grad_buffer(dflow_dp* d) {
   if (!d) return nullptr;
   return reinterpret_cast<float*>(d->own + DP_HDR_BYTES) + (size_t)((d->epoch + 1) & 1u) * d->half_floats;
+}
+
+/* barrier time-out of the fused kernel in milliseconds (default ~10 s); a rank whose peers do not show up in time skips
+ * the reduction and the update and raises its status flag */
+int dflow_dp_set_timeout_ms(dflow_dp* d, int64_t ms) {
+  if (!d || ms < 1) {
+    set_error("bad time-out");
+    return DFLOW_E_INVALID_ARG;
+  }
+  d->timeout_clk = ms * 2000000LL;  // SM clock ~2 GHz
+  return DFLOW_OK;
 }
 
 int dflow_dp_allreduce_adam(dflow_dp* d, float* W, float* m, float* v, float lr, float beta1, float beta2, float eps,
@@ -215,27 +332,38 @@ int dflow_dp_allreduce_adam(dflow_dp* d, float* W, float* m, float* v, float lr,
   a.b1 = beta1;
   a.b2 = beta2;
   a.eps = eps;
-  float b1t = 1.0f, b2t = 1.0f;  // Float32 running products like Optimisers.jl (launch_adam)
-  for (long long i = 0; i < t; ++i) {
-    b1t *= beta1;
-    b2t *= beta2;
-  }
+  float b1t, b2t;  // Float32 running products like Optimisers.jl (launch_adam)
+  adam_beta_powers(beta1, beta2, t, &b1t, &b2t);
   a.c1 = 1.0f - b1t;
   a.c2 = 1.0f - b2t;
   a.loss2_out = loss2_out;
   a.status = d->d_status;
+  a.timeout_clk = d->timeout_clk;
   long long blocks = (d->P + 2 + 1023) / 1024;
-  if (blocks > d->sm_count) blocks = d->sm_count;  // co-resident: CTAs wait for CTA 0
+  if (blocks > d->sm_count) blocks = d->sm_count;
   if (blocks < 1) blocks = 1;
-  dp_allreduce_adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
-  if (cudaGetLastError() != cudaSuccess) {
-    set_error("dp_allreduce_adam launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  // cooperative launch: every CTA of the grid is resident at once (they wait for CTA 0), or the launch fails
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3((unsigned)blocks);
+  lc.blockDim = dim3(256);
+  lc.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&lc, dp_allreduce_adam_kernel, a);
+  if (e != cudaSuccess) {
+    set_error("dp_allreduce_adam launch failed: %s", cudaGetErrorString(e));
+    d->epoch -= 1;
     return DFLOW_E_CUDA;
   }
   return DFLOW_OK;
 }
 
-/* 0 = fine, 1 = a peer did not reach the barrier within ~10 s (synchronises the stream) */
+/* 0 = fine, 1 = a peer did not reach the barrier in time: that step's reduction and update were skipped on this rank
+ * (synchronises the stream) */
 int dflow_dp_status(dflow_dp* d, void* stream) {
   if (!d) return DFLOW_E_INVALID_ARG;
   int s = 0;
@@ -247,12 +375,78 @@ int dflow_dp_status(dflow_dp* d, void* stream) {
   return s;
 }
 
+/* ---- single-process fan-out: one minibatch step on every device of a local group ----------------------------------
+ * For every rank r (its device made current): zero the step's accumulation buffer, dflow_loss_grad on the shard with the
+ * GLOBAL seed inv_btot = 1 / B_global, then the fused all-reduce + Adam kernel -- all enqueued asynchronously on the
+ * shard's stream (NULL: the context's own non-blocking stream), so the host returns while the devices work; the kernels
+ * of different devices meet in the peer barrier.  dflow_dp_sync waits for all of them and returns the status. */
+int dflow_dp_train_step(dflow_dp* const* dps, int32_t ndev, const dflow_dp_shard* shards, float inv_btot, int32_t flags,
+                        float lr, float beta1, float beta2, float eps, int64_t t) {
+  if (!dps || !shards || ndev < 1 || t < 1) {
+    set_error("bad dflow_dp_train_step arguments");
+    return DFLOW_E_INVALID_ARG;
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int rc = DFLOW_OK;
+  for (int r = 0; r < ndev && !rc; ++r) {
+    dflow_dp* d = dps[r];
+    const dflow_dp_shard& s = shards[r];
+    if (!d || d->nranks != ndev || d->rank != r || !s.chain || dflow_param_count(s.chain) != d->P) {
+      set_error("shard %d does not match its data-parallel context", r);
+      rc = DFLOW_E_INVALID_ARG;
+      break;
+    }
+    if (cudaSetDevice(d->device) != cudaSuccess) {
+      set_error("cudaSetDevice(%d) failed: %s", d->device, cudaGetErrorString(cudaGetLastError()));
+      rc = DFLOW_E_CUDA;
+      break;
+    }
+    cudaStream_t st = s.stream ? (cudaStream_t)s.stream : d->own_stream;
+    float* buf = dflow_dp_grad_buffer(d);
+    if (cudaMemsetAsync(buf, 0, sizeof(float) * (size_t)(d->P + 2), st) != cudaSuccess) {
+      set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = DFLOW_E_CUDA;
+      break;
+    }
+    if (s.B > 0)
+      rc = dflow_loss_grad(s.chain, s.W, s.x, s.theta, s.B, s.idx, inv_btot, flags, buf + d->P, buf, s.ws, s.ws_bytes, st);
+    if (!rc) rc = dflow_dp_allreduce_adam(d, s.W, s.m, s.v, lr, beta1, beta2, eps, t, s.loss2_out, st);
+  }
+  cudaSetDevice(prev);
+  return rc;
+}
+
+int dflow_dp_sync(dflow_dp* const* dps, int32_t ndev, const dflow_dp_shard* shards) {
+  if (!dps || ndev < 1) {
+    set_error("bad dflow_dp_sync arguments");
+    return DFLOW_E_INVALID_ARG;
+  }
+  int prev = 0, worst = 0;
+  cudaGetDevice(&prev);
+  for (int r = 0; r < ndev; ++r) {
+    if (!dps[r]) continue;
+    cudaSetDevice(dps[r]->device);
+    cudaStream_t st = (shards && shards[r].stream) ? (cudaStream_t)shards[r].stream : dps[r]->own_stream;
+    const int s = dflow_dp_status(dps[r], st);
+    if (s < 0) worst = s;
+    else if (s > 0 && worst == 0) worst = s;
+  }
+  cudaSetDevice(prev);
+  return worst;
+}
+
 int dflow_dp_destroy(dflow_dp* d) {
   if (!d) return DFLOW_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (d->local_group) cudaSetDevice(d->device);
   for (int j = 0; j < d->nranks; ++j)
     if (d->opened[j] && d->peers[j]) cudaIpcCloseMemHandle(d->peers[j]);
+  if (d->own_stream) cudaStreamDestroy(d->own_stream);
   if (d->own) cudaFree(d->own);
   if (d->d_status) cudaFree(d->d_status);
+  if (d->local_group) cudaSetDevice(prev);
   delete d;
   return DFLOW_OK;
 }

@@ -12,13 +12,15 @@
 
 namespace dflow {
 
-__host__ __device__ inline SmemPlan plan_grad2(const DevChainHdr& h, int chain_bytes, int nts, int smem_grad) {
+__host__ __device__ inline SmemPlan plan_grad2(const DevChainHdr& h, int chain_bytes, int nts, int smem_grad,
+                                               int want_thbar = 0) {
   SmemPlan p;
   p.chain_f = ((chain_bytes + 15) / 16) * 4;
   p.w_f = h.resident ? h.stage_total : h.stage_max;
   p.cs = nts + 4;  // +4: consecutive rows start 4 banks apart (conflict-free multi-row LDS.128 in the dW phase)
   const int hd = h.max_depth > 1 ? h.max_depth - 1 : 1;
-  const int rows = 2 * h.d + h.n + hd * h.hp + 3 * h.amax4;  // x, xbar, theta, hidden activations, s, t, output cotangent
+  // x, xbar, theta (+ its cotangent for dflow_vjp), hidden activations, s, t, output cotangent
+  const int rows = 2 * h.d + h.n * (want_thbar ? 2 : 1) + hd * h.hp + 3 * h.amax4;
   p.cols_f = rows * p.cs;
   p.grad_f = smem_grad ? ((h.P + 3) / 4) * 4 : 0;
   return p;
@@ -151,7 +153,7 @@ __device__ __forceinline__ void dw_phase2(const float* __restrict__ dcol, const 
 template <int NG, int S>
 __device__ __forceinline__ void dense_T2(const float* dcol, int CS, int sb, const float* __restrict__ Wst, int k0,
                                          int K, bool first, float* hprev, int actp, float* gx,
-                                         const unsigned char* id, int n) {
+                                         const unsigned char* id, int n, float* gth = nullptr) {
   float dl[NG * 4][S];
 #pragma unroll
   for (int o = 0; o < NG * 4; ++o) ld_samples<S>(dcol + o * CS + sb, dl[o]);
@@ -168,7 +170,7 @@ __device__ __forceinline__ void dense_T2(const float* dcol, int CS, int sb, cons
       fma_samples<S>(a0, dl[4 * g + 2], w.z);
       fma_samples<S>(a1, dl[4 * g + 3], w.w);
     }
-    float* dst = first ? gx + (int)id[k - n] * CS + sb : hprev + k * CS + sb;
+    float* dst = first ? (k < n ? gth + k * CS + sb : gx + (int)id[k - n] * CS + sb) : hprev + k * CS + sb;
     float cur[S];
     ld_samples<S>(dst, cur);
 #pragma unroll
@@ -186,7 +188,8 @@ template <int HP, int S>
 __device__ __forceinline__ void net_backward2(const DevChainHdr& H, const DevElem& E, const DevNet& net,
                                               const float* __restrict__ wblk, float* xs, float* gx, float* th,
                                               float* hc, int hstride, float* gb, const float* outvals, float* gsm,
-                                              float* ggl, int CS, int sb, int wbase, int nq, int lane) {
+                                              float* ggl, int CS, int sb, int wbase, int nq, int lane,
+                                              float* gth = nullptr) {
   const int D = net.depth;
   {
     const int actL = net.act[D - 1];
@@ -208,13 +211,13 @@ __device__ __forceinline__ void net_backward2(const DevChainHdr& H, const DevEle
     const float* Wst = wblk + net.s_w[j];
     const bool first = (j == 0);
     const int actp = j > 0 ? net.act[j - 1] : 0;
-    const int k0 = first ? H.n : 0;  // θ rows (k < n) of the first Dense are discarded
+    const int k0 = (first && !gth) ? H.n : 0;  // θ rows (k < n) of the first Dense are dropped unless θ̄ is wanted
     switch (net.op[j] >> 2) {
-      case 1: dense_T2<1, S>(dcol, CS, sb, Wst, k0, K, first, hprev, actp, gx, E.id, H.n); break;
-      case 2: dense_T2<2, S>(dcol, CS, sb, Wst, k0, K, first, hprev, actp, gx, E.id, H.n); break;
-      case 4: dense_T2<4, S>(dcol, CS, sb, Wst, k0, K, first, hprev, actp, gx, E.id, H.n); break;
-      case 8: dense_T2<8, S>(dcol, CS, sb, Wst, k0, K, first, hprev, actp, gx, E.id, H.n); break;
-      default: dense_T2<16, S>(dcol, CS, sb, Wst, k0, K, first, hprev, actp, gx, E.id, H.n); break;
+      case 1: dense_T2<1, S>(dcol, CS, sb, Wst, k0, K, first, hprev, actp, gx, E.id, H.n, gth); break;
+      case 2: dense_T2<2, S>(dcol, CS, sb, Wst, k0, K, first, hprev, actp, gx, E.id, H.n, gth); break;
+      case 4: dense_T2<4, S>(dcol, CS, sb, Wst, k0, K, first, hprev, actp, gx, E.id, H.n, gth); break;
+      case 8: dense_T2<8, S>(dcol, CS, sb, Wst, k0, K, first, hprev, actp, gx, E.id, H.n, gth); break;
+      default: dense_T2<16, S>(dcol, CS, sb, Wst, k0, K, first, hprev, actp, gx, E.id, H.n, gth); break;
     }
   }
 }
@@ -242,7 +245,8 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
   __syncthreads();
   const DevChain* C = reinterpret_cast<const DevChain*>(smem);
   const DevChainHdr& H = C->h;
-  const SmemPlan P = plan_grad2(H, a.chain_bytes, NTS, a.smem_grad);
+  const bool want_th = a.thbar_out != nullptr && H.n > 0;
+  const SmemPlan P = plan_grad2(H, a.chain_bytes, NTS, a.smem_grad, want_th ? 1 : 0);
   float* wsm = smem + P.chain_f;
   float* cols = wsm + P.w_f;
   float* gsm = cols + P.cols_f;
@@ -253,7 +257,8 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
   float* xs = cols;
   float* gx = xs + d * CS;
   float* th = gx + d * CS;
-  float* hc = th + n * CS;
+  float* gth = want_th ? th + n * CS : nullptr;  // cotangent of the (normalised) conditions
+  float* hc = th + (want_th ? 2 : 1) * n * CS;
   float* ob = hc + hd * hstride;  // s values
   float* tb = ob + H.amax4 * CS;  // t values
   float* gb = tb + H.amax4 * CS;  // output cotangent  (exp(-s) is recomputed from the kept s values: 4 fewer column
@@ -284,7 +289,10 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
         if (a.flags & DFLOW_THETA_NORMALIZE) v = (H.theta_rng[k] == 0.0f) ? 0.0f : (v - H.theta_min[k]) / H.theta_rng[k];
         th[k * CS + sb + s] = v;
       }
-      ib[s] = valid ? a.inv_btot : 0.0f;
+      // ib = -j̄ of this sample: the loss seed 1/B_tot (src/Flows.jl:352-359), or minus the caller's cotangent of ln_det_jac
+      ib[s] = valid ? (a.jbar ? -__ldg(a.jbar + gi) : a.inv_btot) : 0.0f;
+      if (want_th)
+        for (int k = 0; k < n; ++k) gth[k * CS + sb + s] = 0.0f;
     }
     // ---- forward (normalising) sweep: last element first; checkpoint what each element changes ----
     float ldj[S];
@@ -317,17 +325,18 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
       }
       elem_apply<HP, S, false>(H, E, wblk, false, xs, th, hc, 0, ob, tb, CS, tid, NT, ldj);
     }
-    // ---- loss and seeds: z̄ = z * inv_btot, j̄ = -inv_btot (src/Flows.jl:352-359) ----
+    // ---- loss and seeds: z̄ = z * inv_btot, j̄ = -inv_btot (src/Flows.jl:352-359), or the caller's cotangents ----
 #pragma unroll
     for (int s = 0; s < S; ++s) {
+      const long long gi = base + sb + s;
       float q = 0.0f;
       for (int k = 0; k < d; ++k) {
         const float v = xs[k * CS + sb + s];
         q = fmaf(v, v, q);
-        gx[k * CS + sb + s] = v * ib[s];
+        gx[k * CS + sb + s] = a.zbar ? (gi < a.B ? __ldg(a.zbar + gi * d + k) : 0.0f) : v * ib[s];
       }
       const float lp = H.logpdf_c0 - 0.5f * q + ldj[s];
-      if (ib[s] != 0.0f || (base + sb + s) < a.B) {
+      if (gi < a.B) {
         if (isfinite(lp))
           lsum_thread += lp;
         else
@@ -384,7 +393,7 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
           }
         }
         net_backward2<HP, S>(H, E, net, wblk, xs, gx, th, hc, hstride, gb, outc, gacc, a.grad_out, CS, sb, wbase, NQ,
-                             lane);
+                             lane, gth);
       }
       // restore the layer input from its checkpoint and finish ū (RNVP.jl:137-139)
       for (int j = 0; j < E.a; ++j) {
@@ -394,6 +403,23 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
           xs[k * CS + sb + s] = ckb[(size_t)(E.ck_off + j) * NTS + s];
           if (rnvp) gx[k * CS + sb + s] *= expf(-ob[j * CS + sb + s]);
         }
+      }
+    }
+    // ---- cotangents of the inputs (dflow_vjp) ----
+    if (a.xbar_out || want_th) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const long long gi = base + sb + s;
+        if (gi >= a.B) continue;
+        if (a.xbar_out)
+          for (int k = 0; k < d; ++k) a.xbar_out[gi * d + k] = gx[k * CS + sb + s];
+        if (want_th)
+          for (int k = 0; k < n; ++k) {
+            float v = gth[k * CS + sb + s];
+            // chain rule through normalize_input (src/Data.jl:213-218): d θ̂ / d θ = 1 / (θ_max - θ_min), 0 for a zero range
+            if (a.flags & DFLOW_THETA_NORMALIZE) v = (H.theta_rng[k] == 0.0f) ? 0.0f : v / H.theta_rng[k];
+            a.thbar_out[gi * n + k] = v;
+          }
       }
     }
     __syncwarp();
@@ -424,8 +450,10 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
       t0 += red[2 * w];
       t1 += red[2 * w + 1];
     }
-    atomicAdd(a.loss_out, t0);
-    if (t1 != 0.0f) atomicAdd(a.loss_out + 1, t1);
+    if (a.loss_out) {
+      atomicAdd(a.loss_out, t0);
+      if (t1 != 0.0f) atomicAdd(a.loss_out + 1, t1);
+    }
   }
 }
 

@@ -109,6 +109,11 @@ struct GradArgs {
   int flags;
   int chain_bytes;
   int smem_grad;  // 1: accumulate the whole gradient in shared memory, flush once per CTA
+  // vector-Jacobian product with caller cotangents (dflow_vjp; rrule of src/affine/RNVP.jl:99-147 through the chain):
+  const float* zbar;   // (d, B) cotangent of z, or null: loss seeds z * inv_btot
+  const float* jbar;   // (B) cotangent of ln_det_jac, or null: -inv_btot
+  float* xbar_out;     // (d, B) cotangent of x, or null
+  float* thbar_out;    // (n, B) cotangent of theta, or null (then the theta rows of the first Dense are dropped)
 };
 
 struct TcPlan;

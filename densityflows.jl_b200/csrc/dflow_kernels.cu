@@ -222,10 +222,11 @@ static int launch_grad2_t(dflow_chain* c, GradArgs& a, cudaStream_t st, int nt) 
   const DevChainHdr& h = c->hc()->h;
   if (nt > grad2_max_threads<HP, S>()) nt = grad2_max_threads<HP, S>();
   a.smem_grad = (h.P * 4 <= 64 * 1024 && c->grad_smem >= 0) ? 1 : 0;
-  SmemPlan p = plan_grad2(h, c->chain_bytes, nt * S, a.smem_grad);
+  const int want_th = (a.thbar_out != nullptr && h.n > 0) ? 1 : 0;
+  SmemPlan p = plan_grad2(h, c->chain_bytes, nt * S, a.smem_grad, want_th);
   while (p.bytes() > (size_t)c->max_smem_optin && nt > 32) {
     nt = (nt > 256) ? (nt > 384 ? 384 : 256) : nt >> 1;  // 448 -> 384 -> 256 -> 128 -> ...
-    p = plan_grad2(h, c->chain_bytes, nt * S, a.smem_grad);
+    p = plan_grad2(h, c->chain_bytes, nt * S, a.smem_grad, want_th);
   }
   if (p.bytes() > (size_t)c->max_smem_optin) {
     set_error("adjoint needs %zu bytes of shared memory (> %d)", p.bytes(), c->max_smem_optin);

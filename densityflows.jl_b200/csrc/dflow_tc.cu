@@ -12,7 +12,9 @@
 //   MMA warp                     runs uniformly, one elected lane issues tcgen05.mma kind::tf32 (accumulators in TMEM)
 //
 // Float32 parity on a TF32 tensor core: every operand is split into hi = cvt.rna.tf32(x), lo = x - hi and each
-// product is issued as lo*hi + hi*lo + hi*hi (the dropped lo*lo term is ~2^-22 relative).
+// product is issued as lo*hi + hi*lo + hi*hi (the dropped lo*lo term is ~2^-22 relative).  (Rounding lo to TF32 with
+// cvt.rna as well was measured in round 2: no change of the chain-level error, which is ~10x the Float32 oracle's at
+// 12-16 layers -- profiles/r02_parity.md -- and it would break hi + lo == x, which the training stores rely on.)
 //
 // Pipeline per tile and conditioner (hidden width H, NH = min(H, 256) output columns per pass):
 //   D1 group (128 x GW)   = A1 (128 x K0) * M1_g^T        GW = 64 hidden units per group, NG-deep ring in TMEM,
@@ -119,6 +121,8 @@ struct TcArgs {
   float* zbar;        // (d, B) cotangent of the layer output, updated in place to the cotangent of its input
   const float* zout;  // (d, B) layer output (normalising direction)
   float inv_btot;
+  const float* jbar;  // per-sample cotangent of ln_det_jac (dflow_vjp), or null: -inv_btot for every sample
+  float* thbar;       // [tiles][n][128] cotangent of the conditions (dflow_vjp), or null: theta rows are dropped
   float* grad;
   int p_b3;
 };
@@ -477,6 +481,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
         if constexpr (MODE == TC_BWD) {
           // delta3 of this conditioner (src/affine/RNVP.jl:118-127): s: -zbar_af * z_af - jbar, t: -zbar_af * exp(-s)
           // (loads of a group of 8 are issued back to back before any store: one memory round trip per group)
+          const float njbar = (a.jbar && valid) ? -__ldg(a.jbar + gi) : a.inv_btot;  // -jbar of this sample
           for (int k0 = 0; k0 < K0p; k0 += 8) {
             float zb[8], zo[8], sv[8], v[8];
 #pragma unroll
@@ -501,7 +506,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
               const bool s_form = a.net_id == 0 || (a.net_id == 2 && j < a.a16);
               const int jj = (a.net_id == 2 && j >= a.a16) ? j - a.a16 : j;
               float val = 0.0f;
-              if (valid && jj < a.a) val = s_form ? -zb[qq] * zo[qq] + a.inv_btot : -zb[qq] * expf(-sv[qq]);
+              if (valid && jj < a.a) val = s_form ? -zb[qq] * zo[qq] + njbar : -zb[qq] * expf(-sv[qq]);
               v[qq] = val;
             }
 #pragma unroll
@@ -621,6 +626,16 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             for (int j = 0; j < 16; ++j) {
               const int k = o0 + j;
               if (k >= n && k < a.nin) a.zbar[tidx(tile, d, a.id[k - n], row)] = zb[j] + v[j];
+            }
+            if (a.thbar) {  // rows 0..n-1: cotangent of the (normalised) conditions, summed over layers and conditioners
+              for (int j = 0; j < 16; ++j) {
+                const int k = o0 + j;
+                if (k < n) {
+                  // chain rule through normalize_input (src/Data.jl:213-218)
+                  const float sc = (a.flags & DFLOW_THETA_NORMALIZE) ? (a.theta_rng[k] == 0.0f ? 0.0f : 1.0f / a.theta_rng[k]) : 1.0f;
+                  a.thbar[tidx(tile, n, k, row)] += v[j] * sc;
+                }
+              }
             }
           }
         } else if (a.net_id == 0 || (a.net_id == 2 && o0 < a.a16)) {
@@ -1886,7 +1901,7 @@ static void train_layout(const dflow_chain* c, long long B, TcTrainLayout& T) {
   const DevChainHdr& Hd = c->hc()->h;
   const long long L = (long long)tp->layers.size();
   // per-sample floats of everything that scales with the macro-batch
-  const long long per = (L + 1) * Hd.d + 1 + Hd.d + Hd.n + L * tp->a16max + L * tp->k0pmax + L * 4 * tp->hu +
+  const long long per = (L + 1) * Hd.d + 1 + Hd.d + 2 * Hd.n + L * tp->a16max + L * tp->k0pmax + L * 4 * tp->hu +
                         L * 4 * (tp->hu / 32) + 4 * tp->hu + 2 * tp->a16max;
   long long MB = ((B + 127) / 128) * 128;
   const long long budget = c->tc_ws_budget_mb > 0 ? (long long)c->tc_ws_budget_mb << 20 : (long long)24 << 30;  // bytes
@@ -1910,6 +1925,7 @@ static void train_layout(const dflow_chain* c, long long B, TcTrainLayout& T) {
   T.mbuf = take(L * 4 * (tp->hu / 32) * MB);
   T.dbuf = take(4LL * tp->hu * MB);
   T.d3buf = take(2LL * tp->a16max * MB);
+  T.thbar = take((long long)Hd.n * MB);
   T.total = o;
 }
 
@@ -1921,7 +1937,7 @@ size_t tc_workspace_bytes(const dflow_chain* c, long long B) {
 
 int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* theta, long long B, const int32_t* idx,
                  float inv_btot, int flags, float* loss_out, float* grad_out, void* ws, size_t ws_bytes,
-                 cudaStream_t st) {
+                 cudaStream_t st, const TcVjp* vjp) {
   TcPlan* tp = c->tcp;
   const DevChainHdr& Hd = c->hc()->h;
   if (!tp->train_ok) {
@@ -1999,14 +2015,34 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         if (rc) return rc;
       }
     }
-    // ---- loss and seeds ----
-    tc_logpdf_kernel<<<ew_blocks(mb), 256, 0, st>>>(slot(0), ldj, mb, d, Hd.logpdf_c0, inv_btot, zbar, nullptr, loss_out);
-    CKT(cudaGetLastError());
-    c->launches++;
+    // ---- loss and seeds (or the caller's cotangents: dflow_vjp) ----
+    const bool ext = vjp && vjp->zbar;
+    if (loss_out || !ext) {
+      tc_logpdf_kernel<<<ew_blocks(mb), 256, 0, st>>>(slot(0), ldj, mb, d, Hd.logpdf_c0, inv_btot, ext ? nullptr : zbar,
+                                                     nullptr, loss_out);
+      CKT(cudaGetLastError());
+      c->launches++;
+    }
+    if (ext) {
+      rc = gather_t(c, vjp->zbar, nullptr, first, mb, d, zbar, st);
+      if (rc) return rc;
+    }
+    if (vjp && vjp->z_out) {
+      tc_scatter_t_kernel<<<tile_blocks(mb), 256, tsm_bytes(d), st>>>(slot(0), mb, d, vjp->z_out + (size_t)first * d);
+      CKT(cudaGetLastError());
+      c->launches++;
+    }
+    if (vjp && vjp->ldj_out) CKT(cudaMemcpyAsync(vjp->ldj_out + first, ldj, sizeof(float) * mb, cudaMemcpyDeviceToDevice, st));
+    float* thbar = nullptr;
+    if (vjp && vjp->thbar_out && n > 0) {
+      thbar = wsf + T.thbar;
+      CKT(cudaMemsetAsync(thbar, 0, sizeof(float) * (size_t)n * ntiles * 128, st));
+    }
     // ---- reverse sweep in chain order ----
     int last_coupling = -1;
     for (int ei = 0; ei < L; ++ei)
       if (tp->layers[ei].is_coupling) last_coupling = ei;
+    if (vjp && vjp->xbar_out) last_coupling = L - 1;  // the cotangent of x also crosses a trailing NormalizationLayer
     for (int ei = 0; ei <= last_coupling; ++ei) {
       const TcLayer& Ld = tp->layers[ei];
       if (!Ld.is_coupling) {
@@ -2033,6 +2069,8 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         a.zbar = zbar;
         a.zout = slot(ei);
         a.inv_btot = inv_btot;
+        a.jbar = (vjp && vjp->jbar) ? vjp->jbar + first : nullptr;
+        a.thbar = thbar;
         a.grad = grad_out;
         a.p_b3 = Ld.p_b[fz ? 0 : ni][2];
         rc = launch_net<TC_BWD>(c, a, st, fz ? nullptr : Ld.bwd2[ni]);
@@ -2084,6 +2122,16 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       const size_t smem = nst * stage_bytes + overrun + 128;
       CKT(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       tc_dw_kernel<<<(unsigned)(w.units * w.ksplit), DW_THREADS, smem, st>>>(w);
+      CKT(cudaGetLastError());
+      c->launches++;
+    }
+    if (vjp && vjp->xbar_out) {
+      tc_scatter_t_kernel<<<tile_blocks(mb), 256, tsm_bytes(d), st>>>(zbar, mb, d, vjp->xbar_out + (size_t)first * d);
+      CKT(cudaGetLastError());
+      c->launches++;
+    }
+    if (thbar) {
+      tc_scatter_t_kernel<<<tile_blocks(mb), 256, tsm_bytes(n), st>>>(thbar, mb, n, vjp->thbar_out + (size_t)first * n);
       CKT(cudaGetLastError());
       c->launches++;
     }

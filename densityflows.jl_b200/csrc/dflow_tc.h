@@ -81,6 +81,7 @@ struct TcTrainLayout {
   size_t mbuf;         // [L][2 nets][2][(hmax/32) * MB]  relu masks (uint16 per 16-unit chunk)
   size_t dbuf;         // [2 nets][2][hmax * MB]      delta1, delta2 of the current layer
   size_t d3buf;        // [2 nets][a16max * MB]
+  size_t thbar;        // [n * MB] cotangent of the conditions (dflow_vjp)
   size_t total;        // floats
 };
 
@@ -107,8 +108,17 @@ int tc_fwd(dflow_chain* c, const float* W, FwdArgs& a, cudaStream_t st);
 int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* theta_const, float* ldj, long long B,
                  int sampling, int flags, cudaStream_t st);
 size_t tc_workspace_bytes(const dflow_chain* c, long long B);
+// caller cotangents / extra outputs of dflow_vjp (all sample-major device arrays; any pointer may be null)
+struct TcVjp {
+  const float* zbar;  // (d, B)
+  const float* jbar;  // (B)
+  float* xbar_out;    // (d, B)
+  float* thbar_out;   // (n, B)
+  float* z_out;       // (d, B) primal outputs of the normalising sweep
+  float* ldj_out;     // (B)
+};
 int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* theta, long long B, const int32_t* idx,
                  float inv_btot, int flags, float* loss_out, float* grad_out, void* ws, size_t ws_bytes,
-                 cudaStream_t st);
+                 cudaStream_t st, const TcVjp* vjp = nullptr);
 
 }  // namespace dflow

@@ -304,6 +304,10 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
 
 
+class PeerUnavailable(RuntimeError):
+    """Raised on EVERY rank when some rank could not set up the NVLink peer all-reduce."""
+
+
 class PeerTrainStep:
     """The same step with the collective fused into the optimiser kernel: every rank publishes its gradient buffer
     over CUDA IPC, and ONE kernel per rank waits for the peers' buffers of this step, sums them over NVLink peer
@@ -322,15 +326,40 @@ class PeerTrainStep:
         self.P = max(pc.P, 1)
         handle = C.create_string_buffer(64)
         self.dp = C.c_void_p()
+        self._views = {}
+        self.loss2 = torch.zeros(2, device=pc.device, dtype=torch.float32)
+
+        # Every rank runs the SAME collective sequence whatever fails locally: phase result -> all_reduce(MIN) -> next
+        # phase.  A failure on any rank makes every rank drop its partial context and raise together, so that
+        # make_train_step can fall back to the NCCL step on all ranks without mismatched collectives.
+        def agree(ok_local: bool, what: str) -> None:
+            flag = torch.tensor([1.0 if ok_local else 0.0], device=pc.device)
+            d.all_reduce(flag, op=d.ReduceOp.MIN)
+            if flag.item() < 1:
+                self._destroy()
+                raise PeerUnavailable(f"peer all-reduce unavailable ({what} failed on some rank)")
+
+        ok = True
         with torch.cuda.device(pc.device):
-            L.check(L.lib().dflow_dp_create(self.rank, self.world, self.P, C.byref(self.dp), handle))
+            try:
+                L.check(L.lib().dflow_dp_create(self.rank, self.world, self.P, C.byref(self.dp), handle))
+            except Exception:
+                ok = False
+            agree(ok, "dflow_dp_create")
             handles: list = [None] * self.world
             d.all_gather_object(handles, handle.raw)
             self._handles = b"".join(handles)
-            L.check(L.lib().dflow_dp_connect(self.dp, self._handles))
-        self._views = {}
-        self.loss2 = torch.zeros(2, device=pc.device, dtype=torch.float32)
+            try:
+                L.check(L.lib().dflow_dp_connect(self.dp, self._handles))
+            except Exception:
+                ok = False
+            agree(ok, "dflow_dp_connect")
         d.barrier()
+
+    def _destroy(self) -> None:
+        if getattr(self, "dp", None):
+            L.lib().dflow_dp_destroy(self.dp)
+            self.dp = None
 
     def _next_buffer(self) -> torch.Tensor:
         ptr = int(L.lib().dflow_dp_grad_buffer(self.dp))
@@ -363,9 +392,98 @@ class PeerTrainStep:
 
     def __del__(self):
         try:
-            if getattr(self, "dp", None):
-                L.lib().dflow_dp_destroy(self.dp)
-                self.dp = None
+            self._destroy()
+        except Exception:
+            pass
+
+
+class LocalDataParallel:
+    """Data-parallel training driven by ONE host process (the reference's train! is a single Julia process,
+    src/Flows.jl:380-445): one replica per device -- libdflow handle, packed parameters, Adam moments, resident data
+    shard -- and `dflow_dp_train_step` fanning a minibatch out over the devices' streams; the replicas meet in the
+    fused NVLink peer all-reduce + Adam kernel (csrc/dflow_dp.cu) and stay bit-identical.
+
+    `devices` may name the same GPU more than once (replicas sharing a device), which is how the single-GPU tests
+    exercise the multi-rank protocol."""
+
+    def __init__(self, chain: FlowChain, devices: Sequence[int], rule: Optional[Adam] = None, theta_min=None,
+                 theta_max=None):
+        import ctypes as C
+
+        self.devices = [int(v) for v in devices]
+        self.rule = rule or Adam()
+        leaves = chain._leaves()
+        dev0 = torch.device("cuda", self.devices[0])
+        primary = chain._packed
+        if primary is None or primary.device != dev0:
+            primary = PackedChain(leaves, dev0, theta_min, theta_max)
+            chain._packed = primary
+        elif theta_min is not None:
+            primary.set_theta_range(theta_min, theta_max)
+        primary.refresh()
+        self.replicas: List[PackedChain] = [primary]
+        for dv in self.devices[1:]:
+            self.replicas.append(PackedChain(leaves, torch.device("cuda", dv), theta_min, theta_max, replica_of=primary))
+        self.P = max(primary.P, 1)
+        self.m = [torch.zeros(self.P, device=r.device) for r in self.replicas]
+        self.v = [torch.zeros(self.P, device=r.device) for r in self.replicas]
+        self.loss2 = [torch.zeros(2, device=r.device) for r in self.replicas]
+        self.t = 0
+        n = len(self.devices)
+        self._dps = (C.c_void_p * n)()
+        devs = (C.c_int32 * n)(*self.devices)
+        L.check(L.lib().dflow_dp_create_local(n, devs, self.P, self._dps))
+        self._shards = (L.DpShard * n)()
+        self.x: List[Optional[torch.Tensor]] = [None] * n
+        self.θ: List[Optional[torch.Tensor]] = [None] * n
+        self._keep: list = []
+
+    def set_data(self, xs: Sequence, θs: Optional[Sequence] = None) -> None:
+        """Resident shard of every rank: xs[r] of size (d, N_r), θs[r] of size (n, N_r) (moved to rank r's device)."""
+        for r, rep in enumerate(self.replicas):
+            self.x[r] = to_jl(xs[r], rep.device)
+            self.θ[r] = to_jl(θs[r], rep.device) if (θs is not None and rep.n > 0) else None
+
+    def step(self, idxs: Sequence[Optional[torch.Tensor]], B_global: int, flags: int = 0) -> None:
+        """One minibatch: idxs[r] = int32 column indices into rank r's shard (None: all of its columns); the seed of
+        every rank's adjoint is 1 / B_global so that the peer all-reduce is a pure sum."""
+        self.t += 1
+        self._keep = []
+        for r, rep in enumerate(self.replicas):
+            sh = self._shards[r]
+            idx = idxs[r]
+            if idx is not None:
+                idx = idx.to(device=rep.device, dtype=torch.int32).contiguous()
+                self._keep.append(idx)
+            B = n_samples(self.x[r]) if idx is None else int(idx.numel())
+            ws = rep._workspace(max(B, 1))
+            sh.chain = rep.handle.value
+            sh.W, sh.m, sh.v = rep.W.data_ptr(), self.m[r].data_ptr(), self.v[r].data_ptr()
+            sh.x = flat_view(self.x[r]).data_ptr()
+            sh.theta = flat_view(self.θ[r]).data_ptr() if self.θ[r] is not None else None
+            sh.B = B
+            sh.idx = idx.data_ptr() if idx is not None else None
+            sh.ws, sh.ws_bytes = ws.data_ptr(), ws.numel()
+            sh.loss2_out = self.loss2[r].data_ptr()
+            sh.stream = None
+        ru = self.rule
+        L.check(L.lib().dflow_dp_train_step(self._dps, len(self.replicas), self._shards, 1.0 / B_global, flags, ru.eta,
+                                            ru.beta[0], ru.beta[1], ru.epsilon, self.t))
+
+    def sync(self) -> None:
+        """Waits for every device; raises if a rank missed the peer barrier (its update was skipped)."""
+        s = L.lib().dflow_dp_sync(self._dps, len(self.replicas), self._shards)
+        if s > 0:
+            raise RuntimeError("data-parallel step: a peer did not publish its gradient in time; the step was skipped")
+        if s < 0:
+            L.check(s)
+
+    def __del__(self):
+        try:
+            for i in range(len(self.replicas)):
+                if self._dps[i]:
+                    L.lib().dflow_dp_destroy(self._dps[i])
+                    self._dps[i] = None
         except Exception:
             pass
 
@@ -378,16 +496,11 @@ def make_train_step(pc: PackedChain, state: OptimiserState):
     d = _dist()
     if d is None or pc.device.type != "cuda" or os.environ.get("DFLOW_DP", "peer") == "nccl":
         return TrainStep(pc, state)
-    ok = torch.ones(1, device=pc.device)
-    step = None
     try:
-        step = PeerTrainStep(pc, state)
-    except Exception:
-        ok.zero_()
-    d.all_reduce(ok, op=d.ReduceOp.MIN)
-    if ok.item() < 1:  # some rank could not map its peers (no P2P): every rank falls back to the NCCL collective
-        return TrainStep(pc, state)
-    return step
+        # PeerTrainStep agrees on success or failure across ranks internally (same collectives on every rank)
+        return PeerTrainStep(pc, state)
+    except PeerUnavailable:
+        return TrainStep(pc, state)  # no P2P mapping on some rank: every rank uses the NCCL collective
 
 
 def _full_loss(pc: PackedChain, x, θ, idx: torch.Tensor, n_global: int, flags: int, tmp: torch.Tensor) -> float:
@@ -413,11 +526,29 @@ def train_(flow: Flow, data: DataArrays, optimiser_state: OptimiserState, epochs
         raise NotImplementedError("train! partitions along dim 2; only (d, N) arrays are supported (src/Data.jl:167)")
     tr = data.partition.training.to(pc.device)
     va = data.partition.validation.to(pc.device)
-    step = make_train_step(pc, optimiser_state)
     d = _dist()
     rank, world = (d.get_rank(), d.get_world_size()) if d is not None else (0, 1)
-    n_tr, n_va = int(tr.numel()), int(va.numel())
     gen = rng or _gen()
+    if d is not None:
+        # Ranks build their FlowChain / DataArrays independently (different RNG streams): make rank 0 authoritative for
+        # the initial parameters, the optimiser state, the train / validation split and the shuffle stream, so that the
+        # replicas really are replicas (they then stay bit-identical without any further broadcast).
+        optimiser_state._ensure(pc)
+        sizes = torch.tensor([tr.numel(), va.numel(), optimiser_state.t], device=pc.device, dtype=torch.int64)
+        d.broadcast(sizes, src=0)
+        n_tr0, n_va0, t0 = (int(v) for v in sizes.tolist())
+        if (int(tr.numel()), int(va.numel())) != (n_tr0, n_va0):
+            raise ValueError("ranks disagree on the size of the training / validation partitions")
+        optimiser_state.t = t0
+        tr, va = tr.contiguous(), va.contiguous()
+        for buf in (pc.W, optimiser_state.m, optimiser_state.v, tr, va):
+            d.broadcast(buf, src=0)
+        seed_t = torch.randint(0, 2**62, (1,), generator=gen).to(pc.device)
+        d.broadcast(seed_t, src=0)
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(int(seed_t.item()))
+    step = make_train_step(pc, optimiser_state)
+    n_tr, n_va = int(tr.numel()), int(va.numel())
     tmp = torch.zeros(2, device=pc.device, dtype=torch.float32)
 
     def shard(v: torch.Tensor) -> torch.Tensor:
@@ -447,6 +578,8 @@ def train_(flow: Flow, data: DataArrays, optimiser_state: OptimiserState, epochs
                 s, bad = step.loss2.tolist()
                 if bad > 0 or not math.isfinite(s):
                     raise ValueError(f"non-finite minibatch loss (Σlogp={s}, non-finite samples={bad})")  # Flows.jl:405-409
+        if isinstance(step, PeerTrainStep):
+            step.check()  # a rank that missed the peer barrier skipped its update: stop instead of training on
         train_loss = _full_loss(pc, x, θ, shard(tr), n_tr, flags, tmp)
         flow.train_loss.append(train_loss)
         if debug and not math.isfinite(train_loss):

@@ -107,7 +107,9 @@ def _gen() -> torch.Generator:
     global _default_gen
     if _default_gen is None:
         _default_gen = torch.Generator(device="cpu")
-        _default_gen.manual_seed(torch.seed() & 0x7FFFFFFF)
+        # torch.initial_seed() only READS the global generator's seed (torch.seed() would re-seed it, clobbering the
+        # user's RNG stream and giving every torchrun rank a different stream)
+        _default_gen.manual_seed(torch.initial_seed() & 0x7FFFFFFF)
     return _default_gen
 
 
@@ -501,7 +503,8 @@ class PackedChain:
     After packing, every Dense.weight / Dense.bias of the chain is a VIEW into `W` (column-major vec(weight) then
     bias, chain order, s_net before t_net), so the Flux-like structs stay authoritative and `unpack!` is free."""
 
-    def __init__(self, leaves: Sequence[FlowElement], device=None, theta_min=None, theta_max=None):
+    def __init__(self, leaves: Sequence[FlowElement], device=None, theta_min=None, theta_max=None,
+                 replica_of: Optional["PackedChain"] = None):
         if device is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("densityflows.jl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -516,7 +519,13 @@ class PackedChain:
         self.has_theta_range = theta_min is not None
         self.W = torch.zeros(max(self.P, 1), device=self.device, dtype=torch.float32)
         self._ws: Optional[torch.Tensor] = None  # adjoint workspace (dflow_workspace_bytes)
-        self._bind_views()
+        if replica_of is not None:
+            # a data-parallel replica on another device: same descriptor, its own copy of the parameters; the Dense
+            # tensors of the chain stay views into the primary's buffer
+            self.W.copy_(replica_of.W)
+            self._epoch = None
+        else:
+            self._bind_views()
 
     def _bind_views(self) -> None:
         global _bind_epoch
@@ -540,7 +549,7 @@ class PackedChain:
 
     def refresh(self) -> None:
         """Re-adopt the Dense tensors if another PackedChain has re-bound them since (shared layers)."""
-        if self._epoch != _bind_epoch:
+        if self._epoch is not None and self._epoch != _bind_epoch:
             self._bind_views()
 
     def set_theta_range(self, theta_min, theta_max) -> None:
@@ -685,6 +694,39 @@ class PackedChain:
                                             None if idx is None else idx.data_ptr(), ib, flags, loss2.data_ptr(),
                                             grad.data_ptr(), self._ws.data_ptr(), self._ws.numel(), self._stream()))
         return B
+
+    def _workspace(self, B: int) -> torch.Tensor:
+        need = int(L.lib().dflow_workspace_bytes(self.handle, B))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        return self._ws
+
+    def vjp(self, x, θ, z̄, j̄=None, flags: int = 0, grad: Optional[torch.Tensor] = None, want_x̄: bool = True,
+            want_θ̄: bool = False):
+        """Pullback of `backward(chain, x, θ) -> (z, ln_det_jac)` for caller cotangents (z̄, j̄): what
+        ChainRulesCore.rrule(::typeof(backward), chain, x, θ) returns (src/affine/RNVP.jl:99-147 through the chain).
+        Returns (grad, x̄, θ̄): grad is the packed-layout parameter cotangent (accumulated into `grad` if given)."""
+        x, θ = self._prep(x, θ)
+        B = n_samples(x)
+        z̄ = to_jl(z̄, self.device)
+        if tuple(z̄.shape) != tuple(x.shape):
+            raise ValueError(f"z̄ must have the size of x: {tuple(z̄.shape)} vs {tuple(x.shape)}")
+        if j̄ is not None:
+            j̄ = to_jl(j̄, self.device)
+            if int(j̄.numel()) != B:
+                raise ValueError("j̄ must have one entry per sample (size(x)[2:N])")
+        if grad is None:
+            grad = torch.zeros(max(self.P, 1), device=self.device, dtype=torch.float32)
+        x̄ = jl_empty(x.shape, self.device) if want_x̄ else None
+        θ̄ = jl_empty(θ.shape, self.device) if (want_θ̄ and θ is not None) else None
+        if B == 0:
+            return grad, x̄, θ̄
+        ws = self._workspace(B)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().dflow_vjp(self.handle, self.W.data_ptr(), self._ptr(x), self._ptr(θ), B, flags, self._ptr(z̄),
+                                      self._ptr(j̄), grad.data_ptr(), self._ptr(x̄), self._ptr(θ̄), ws.data_ptr(),
+                                      ws.numel(), self._stream()))
+        return grad, x̄, θ̄
 
     def adam_step(self, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, t: int, lr=1e-3, β=(0.9, 0.999),
                   ϵ=1e-8) -> None:

@@ -144,6 +144,18 @@ int dflow_loss_grad(dflow_chain* chain, const float* W, const float* x, const fl
                     const int32_t* idx, float inv_btot, int32_t flags, float* loss_out, float* grad_out, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* ---- pullback with caller cotangents: the ChainRulesCore.rrule of backward(chain, x, θ) -> (z, ln_det_jac) --------
+ * Replaces rrule(RNVP_backward) (src/affine/RNVP.jl:99-147) composed through the chain (src/Chains.jl:149-164) with the
+ * Dense pullbacks Zygote would add: given z̄ = zbar (d x B) and j̄ = jbar (B; NULL = zeros) it ACCUMULATES the parameter
+ * cotangent into grad_out (P floats, packed layout = a Tangent of the Flux structs) and writes the input cotangents
+ * x̄ (d x B, xbar_out, may be NULL) and θ̄ (n x B, thetabar_out, may be NULL; with DFLOW_THETA_NORMALIZE it is the
+ * cotangent of the RAW θ).  The forward values are recomputed inside (no tape): call dflow_normalize for (z, ldj).
+ * Any loss that is a function of (z, ln_det_jac) can therefore train on the GPU path; dflow_loss_grad is the special case
+ * z̄ = z / B_tot, j̄ = -1 / B_tot with the loss reduction fused in. */
+int dflow_vjp(dflow_chain* chain, const float* W, const float* x, const float* theta, int64_t B, int32_t flags,
+              const float* zbar, const float* jbar, float* grad_out, float* xbar_out, float* thetabar_out, void* ws,
+              size_t ws_bytes, void* stream);
+
 /* ---- Optimisers.Adam update (call site src/Flows.jl:415), in place on packed buffers; t = step count >= 1 ---- */
 int dflow_adam_step(float* W, const float* g, float* m, float* v, int64_t P, float lr, float beta1, float beta2,
                     float eps, int64_t t, void* stream);
@@ -175,8 +187,40 @@ int dflow_dp_connect(dflow_dp* dp, const void* handles);
 float* dflow_dp_grad_buffer(dflow_dp* dp);
 int dflow_dp_allreduce_adam(dflow_dp* dp, float* W, float* m, float* v, float lr, float beta1, float beta2, float eps,
                             int64_t t, float* loss2_out, void* stream);
+/* 0 = fine; 1 = a peer did not publish its gradient within the time-out: the reduction AND the Adam update of that step
+ * were skipped on this rank (stale peer buffers are never summed), the replicas are no longer in step and the caller
+ * must stop.  Synchronises `stream`. */
 int dflow_dp_status(dflow_dp* dp, void* stream);
+int dflow_dp_set_timeout_ms(dflow_dp* dp, int64_t ms); /* barrier time-out of the fused kernel, default ~10 s */
 int dflow_dp_destroy(dflow_dp* dp);
+
+/* ---- the same, driven by ONE host process (the reference's train! is a single Julia process, src/Flows.jl:380-445) ---
+ * dflow_dp_create_local builds one context per entry of `devs` (out: ndev handles; out[r] lives on devs[r] and is rank r)
+ * and connects them with cudaDeviceEnablePeerAccess -- no IPC handles.  The per-rank calls above work on these handles
+ * unchanged (with devs[r] current).  dflow_dp_train_step is the fan-out a train! loop calls once per minibatch: for every
+ * rank it zeroes the step's accumulation buffer, runs dflow_loss_grad on the shard with the global seed
+ * inv_btot = 1 / B_global and launches the fused all-reduce + Adam kernel, all asynchronously on shard.stream (NULL: the
+ * context's own non-blocking stream); the devices' kernels meet in the peer barrier.  Every rank holds its own replica
+ * (chain handle created on its device, W / m / v, resident data shard); replicas stay bit-identical.
+ * dflow_dp_sync waits for every rank's stream and returns the worst dflow_dp_status. */
+typedef struct dflow_dp_shard {
+  dflow_chain* chain;      /* handle created on this rank's device */
+  float* W;                /* this replica's packed parameters and Adam moments (device) */
+  float* m;
+  float* v;
+  const float* x;          /* resident data of this rank: (d, *), (n, *) */
+  const float* theta;
+  int64_t B;               /* samples of this rank's share of the minibatch (0 allowed) */
+  const int32_t* idx;      /* B column indices into x / theta, or NULL for the first B columns */
+  void* ws;                /* dflow_workspace_bytes(chain, B) */
+  size_t ws_bytes;
+  float* loss2_out;        /* device float[2] or NULL: reduced [sum logp, #non-finite] of the minibatch */
+  void* stream;            /* cudaStream_t on this rank's device, or NULL */
+} dflow_dp_shard;
+int dflow_dp_create_local(int32_t ndev, const int32_t* devs, int64_t P, dflow_dp** out);
+int dflow_dp_train_step(dflow_dp* const* dps, int32_t ndev, const dflow_dp_shard* shards, float inv_btot, int32_t flags,
+                        float lr, float beta1, float beta2, float eps, int64_t t);
+int dflow_dp_sync(dflow_dp* const* dps, int32_t ndev, const dflow_dp_shard* shards);
 
 /* ---- per-row min / max over B samples (NormalizationLayer ctor src/norm/Normalization.jl:52-53; minimum_θ /
  * maximum_θ src/Data.jl:182-183).  min_out / max_out: device float[rows]. */

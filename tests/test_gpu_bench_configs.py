@@ -7,7 +7,9 @@
 Batches span several 128-sample tiles per CTA and end in a ragged tail.  The Float64 oracle is evaluated on a subset
 of columns (head, strided middle, the whole ragged tail), which keeps it to seconds.  Gradients use the linearity of
 the loss in the samples: the batch is a gather (idx) with repetitions of Nd distinct columns, so that the oracle's
-count-weighted gradient over the Nd columns IS the gradient of the whole batch.
+count-weighted gradient over the Nd columns IS the gradient of the whole batch.  (Nd must not be small: a hidden unit
+within the kernels' rounding distance of its ReLU kink flips its mask, and a repeated column carries that flip with
+its whole weight count/B -- 320 distinct columns at C4 inflated the error to 3e-4 of the max-norm.)
 
 Also here: the committed golden vectors (tests/golden/*.npz, fixture included) against the CUDA path, and the
 host-buffer entry points dflow_logpdf_host / dflow_sample_host.
@@ -142,7 +144,7 @@ def _weighted_oracle_grad(oc, x, th, counts, inv_btot, dtype):
     return float(loss), tc.flat_grad().numpy().astype(np.float64), float((w * lp).sum())
 
 
-@pytest.mark.parametrize("name,B,Nd", [("c3", 32768 + 4 * 148 * 128 + 77, 1536), ("c4", 148 * 128 + 2 * 128 + 77, 320)])
+@pytest.mark.parametrize("name,B,Nd", [("c3", 32768 + 4 * 148 * 128 + 77, 1536), ("c4", 148 * 128 + 2 * 128 + 77, 4096)])
 def test_loss_grad_default_route_full_depth(name, B, Nd):
     d, n, L, h, _ = CFG[name]
     oc, chain = _bench_chain(name)
@@ -173,7 +175,9 @@ def test_loss_grad_default_route_full_depth(name, B, Nd):
                 k = dl.W.size + (dl.b.size if dl.b is not None else 0)
                 ref = go[off:off + k]
                 err = np.abs(g[off:off + k] - ref).max()
-                assert err <= 2e-4 * np.abs(ref).max() + 2e-6 * np.abs(go).max() + slack, (name, off, err, np.abs(ref).max())
+                # per Dense: 2e-4 of the block's own max-norm, on top of a floor of 2e-5 of the whole gradient's max-norm: the
+                # Float32 accumulation over ~1e5 samples (in TMEM here, in the sgemm of the reference's Dense pullback alike)
+                assert err <= 2e-4 * np.abs(ref).max() + 2e-5 * np.abs(go).max() + slack, (name, off, err, np.abs(ref).max())
                 off += k
 
 
