@@ -10,7 +10,7 @@ src/Data.jl:25-30); Julia's `f!` becomes `f_` (`train_`, `forward_`).
 from . import _lib
 from ._lib import DflowError, DflowInvalidArg, DflowUnsupported
 from .arrays import jl_empty, jl_full, jl_zeros, to_jl, to_numpy
-from .data import (DataArrays, DataPartition, MetaData, dflt_theta, dflt_θ, maximum_θ, minimum_θ, normalize_input,
+from .data import (DataArrays, DataPartition, MetaData, device_permutation, dflt_theta, dflt_θ, maximum_θ, minimum_θ, normalize_input,
                    normalized_training_data, normalized_validation_data, number_conditions, number_dimensions,
                    resize_output, testing_data, training_data, validation_data)
 from .flows import (Adam, Flow, LocalDataParallel, OptimiserState, PeerTrainStep, TrainStep, make_train_step, logpdf, pdf, predict, sample, sample_with_rejection, setup, train_, training_loss,

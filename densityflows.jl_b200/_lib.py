@@ -80,8 +80,11 @@ SYMBOLS = [
     ("dflow_chain_axes", C.c_int, [vp, C.c_int32, c_i32p, c_i32p, c_i32p, c_i32p]),
     ("dflow_param_offset", C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("dflow_chain_set_theta_range", C.c_int, [vp, c_f32p, c_f32p]),
+    ("dflow_scratch_bytes", C.c_size_t, [vp, C.c_int64]),
+    ("dflow_chain_set_scratch", C.c_int, [vp, vp, C.c_size_t]),
     ("dflow_normalize", C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int32, vp, vp, vp]),
     ("dflow_logpdf", C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_int32, vp, vp]),
+    ("dflow_logpdf_grid", C.c_int, [vp, vp, vp, C.POINTER(C.c_int64), vp, C.c_int32, vp, vp]),
     ("dflow_logpdf_sum", C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_int32, vp, vp]),
     ("dflow_sample_inplace", C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_int32, vp]),
     ("dflow_forward_ldj", C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int32, vp, vp, vp]),
@@ -93,6 +96,7 @@ SYMBOLS = [
     ("dflow_train_epoch", C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float,
                                     C.c_float, C.POINTER(C.c_int64), C.c_int32, vp, vp, vp, C.c_size_t, vp]),
     ("dflow_minmax", C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, vp]),
+    ("dflow_shuffle_indices", C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp]),
     ("dflow_logpdf_host", C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int32, vp, C.c_int64]),
     ("dflow_sample_host", C.c_int, [vp, vp, C.c_uint64, vp, C.c_int64, C.c_int32, vp, C.c_int64]),
     ("dflow_dp_create", C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(vp), vp]),

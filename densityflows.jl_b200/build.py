@@ -45,6 +45,7 @@ def _units():
         units.append((f"inst_grad2_{hp}_{s}.o", "dflow_inst.cu", ["-DDFLOW_INST_GRAD2", f"-DDFLOW_HP={hp}", f"-DDFLOW_S={s}"]))
     if os.path.exists(os.path.join(CSRC, "dflow_tc.cu")):
         units.append(("dflow_tc.o", "dflow_tc.cu", []))
+    units.append(("dflow_small.o", "dflow_small.cu", []))
     if os.path.exists(os.path.join(CSRC, "dflow_dp.cu")):
         units.append(("dflow_dp.o", "dflow_dp.cu", []))
     return units

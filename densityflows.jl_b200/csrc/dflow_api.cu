@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "dflow_internal.h"
+#include "dflow_small.h"
 #include "dflow_tc.h"
 
 namespace dflow {
@@ -327,6 +328,7 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
 
   cudaError_t e1 = cudaMalloc(&c->d_chain, c->chain_bytes);
   cudaError_t e2 = cudaMalloc(&c->d_staged, std::max(total, 4) * sizeof(float));
+  if (e1 == cudaSuccess) e1 = cudaMalloc(&c->d_gridmeta, sizeof(long long) * 3 * DMAX);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     set_error("cudaMalloc failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     dflow_chain_destroy(c);
@@ -366,6 +368,7 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
     }
     if (rc) tc_free_plan(c);  // a narrow chain simply stays on the CUDA-core path
   }
+  if (!wide && small_build_plan(c) != DFLOW_OK) small_free_plan(c);  // optional fast path of dflow_train_epoch
   *out = c;
   return DFLOW_OK;
 }
@@ -374,7 +377,9 @@ int dflow_chain_destroy(dflow_chain* c) {
   if (!c) return DFLOW_OK;
   if (c->d_chain) cudaFree(c->d_chain);
   if (c->d_staged) cudaFree(c->d_staged);
+  if (c->d_gridmeta) cudaFree(c->d_gridmeta);
   tc_free_plan(c);
+  small_free_plan(c);
   if (c->pipe) pipe_free((HostPipe*)c->pipe);
   delete c;
   return DFLOW_OK;
@@ -518,6 +523,48 @@ int dflow_logpdf(dflow_chain* c, const float* W, const float* x, const float* th
   return run_fwd(c, W, a, stream);
 }
 
+// logpdf(flow, x::NTuple{d, Vector}, θ::NTuple) on the tensor-product grid of the d coordinate vectors
+// (src/Flows.jl:287-331): the reference materialises the (d, prod(lens)) array with Iterators.product and a (n, prod(lens))
+// broadcast of θ; here the kernel derives every point's coordinates from its flat index and reads one constant θ.
+int dflow_logpdf_grid(dflow_chain* c, const float* W, const float* grid_vals, const int64_t* lens, const float* theta_const,
+                      int32_t flags, float* logp_out, void* stream) {
+  if (!c || !lens) {
+    set_error("null argument");
+    return DFLOW_E_INVALID_ARG;
+  }
+  const DevChainHdr& H = c->hc()->h;
+  long long B = 1, off = 0;
+  for (int k = 0; k < H.d; ++k) {
+    if (lens[k] < 0 || (lens[k] > 0 && B > (1LL << 40) / lens[k])) {
+      set_error("bad grid length %lld for dimension %d", (long long)lens[k], k);
+      return DFLOW_E_INVALID_ARG;
+    }
+    c->h_gridmeta[3 * k] = lens[k];
+    c->h_gridmeta[3 * k + 1] = B;
+    c->h_gridmeta[3 * k + 2] = off;
+    B *= lens[k];
+    off += lens[k];
+  }
+  int rc = check_common(c, W, nullptr, theta_const, B, flags);
+  if (rc) return rc;
+  if (B == 0) return DFLOW_OK;
+  if (!grid_vals || !logp_out) {
+    set_error("null data pointer");
+    return DFLOW_E_INVALID_ARG;
+  }
+  CKA(cudaMemcpyAsync(c->d_gridmeta, c->h_gridmeta, sizeof(long long) * 3 * H.d, cudaMemcpyHostToDevice,
+                      (cudaStream_t)stream));
+  FwdArgs a{};
+  a.theta_const = theta_const;
+  a.aux_out = logp_out;
+  a.B = B;
+  a.mode = MODE_LOGPDF;
+  a.flags = flags;
+  a.grid_vals = grid_vals;
+  a.grid_meta = c->d_gridmeta;
+  return run_fwd(c, W, a, stream);
+}
+
 int dflow_logpdf_sum(dflow_chain* c, const float* W, const float* x, const float* theta, int64_t B, const int32_t* idx,
                      int32_t flags, float* loss_out, void* stream) {
   int rc = check_common(c, W, theta, nullptr, B, flags);
@@ -595,6 +642,24 @@ int dflow_sample_rng(dflow_chain* c, const float* W, uint64_t seed, uint32_t off
   a.rng_offset = offset;
   a.first_sample = first_sample;
   return run_fwd(c, W, a, stream);
+}
+
+// Scratch of the forward-type calls (normalize / logpdf / logpdf_sum / sample_* / forward_ldj) for a batch of B samples:
+// 0 for chains that run on the CUDA-core kernels (whole chain in registers / shared memory), the tile-blocked working state
+// for the tensor-core kernels.  The caller owns the buffer and attaches it to the handle; hot calls never allocate.
+size_t dflow_scratch_bytes(const dflow_chain* c, int64_t B) {
+  if (!c || B <= 0 || !c->tcp || !(c->use_tc_fwd(B))) return 0;
+  return tc_scratch_bytes(c, B);
+}
+
+int dflow_chain_set_scratch(dflow_chain* c, void* scratch, size_t bytes) {
+  if (!c || (bytes > 0 && !scratch)) {
+    set_error("null argument");
+    return DFLOW_E_INVALID_ARG;
+  }
+  c->scratch = scratch;
+  c->scratch_bytes = scratch ? bytes : 0;
+  return DFLOW_OK;
 }
 
 size_t dflow_workspace_bytes(const dflow_chain* c, int64_t B) {
@@ -706,6 +771,15 @@ int dflow_train_epoch(dflow_chain* c, float* W, float* m, float* v, const float*
     return DFLOW_E_INVALID_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // Minibatches of up to 512 samples (the reference default is 64): the whole epoch runs inside one persistent CTA with the
+  // parameters, Adam moments and the minibatch's activations in shared memory (dflow_small.cu) -- one launch per epoch.
+  // Larger minibatches fill the machine and go through the per-minibatch launches below.
+  if (c->small && c->epoch_kernel >= 0 && batchsize <= 512 && !c->use_tc_grad(bmax)) {
+    rc = small_train_epoch(c, W, m, v, x, theta, order, n, batchsize, lr, beta1, beta2, eps, *t_io, flags, loss2_out, st);
+    if (rc) return rc;
+    *t_io += (n + batchsize - 1) / batchsize;
+    return DFLOW_OK;
+  }
   float b1t, b2t;
   adam_beta_powers(beta1, beta2, *t_io, &b1t, &b2t);
   float* loss2 = grad_scratch + P;  // [grad (P) | sum logp, #non-finite] of the current minibatch
@@ -748,8 +822,22 @@ int dflow_minmax(const float* x, int32_t rows, int64_t B, float* min_out, float*
   return launch_minmax(x, rows, B, min_out, max_out, (cudaStream_t)stream);
 }
 
+// out[j] = base[perm(first + j)] (base == NULL: perm itself) for j in [0, count): perm = the seed's pseudo-random permutation of
+// [0, n).  Stateless, so a data-parallel rank draws only its own slice of the epoch's order.
+int dflow_shuffle_indices(uint64_t seed, int64_t n, int64_t first, int64_t count, const int32_t* base, int32_t* out,
+                          void* stream) {
+  if (n < 0 || first < 0 || count < 0 || first + count > n || n > 0x7FFFFFFFLL || (count > 0 && !out)) {
+    set_error("bad dflow_shuffle_indices arguments (need 0 <= first, first + count <= n <= 2^31 - 1)");
+    return DFLOW_E_INVALID_ARG;
+  }
+  if (count == 0) return DFLOW_OK;
+  return launch_shuffle(seed, n, first, count, base, out, (cudaStream_t)stream);
+}
+
 // ---- host-buffer pipelines: chunked H2D -> kernel -> D2H on two streams ---------------------------------------
 struct HostPipe {
+  void* tc_scratch = nullptr;  // working state of the tensor-core kernels for one chunk (the _host entry points own their
+  size_t tc_scratch_bytes = 0; // device staging: the caller only has host buffers)
   cudaStream_t st[2] = {nullptr, nullptr};
   float* dx[2] = {nullptr, nullptr};
   float* dt[2] = {nullptr, nullptr};
@@ -760,6 +848,7 @@ struct HostPipe {
 
 static void pipe_free(HostPipe* p) {
   if (!p) return;
+  if (p->tc_scratch) cudaFree(p->tc_scratch);
   for (int i = 0; i < 2; ++i) {
     if (p->dx[i]) cudaFree(p->dx[i]);
     if (p->dt[i]) cudaFree(p->dt[i]);
@@ -794,10 +883,35 @@ static int pipe_get(dflow_chain* c, int64_t chunk, HostPipe** out) {
       return DFLOW_E_NOMEM;
     }
   }
+  if (c->use_tc()) {
+    p->tc_scratch_bytes = tc_scratch_bytes(c, chunk);
+    if (cudaMalloc(&p->tc_scratch, p->tc_scratch_bytes) != cudaSuccess) {
+      set_error("host pipeline allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      pipe_free(p);
+      return DFLOW_E_NOMEM;
+    }
+  }
   c->pipe = p;
   *out = p;
   return DFLOW_OK;
 }
+
+// the tensor-core kernels of a _host call work in the pipeline's own scratch, whatever the caller attached to the handle
+struct ScratchSwap {
+  dflow_chain* c;
+  void* old;
+  size_t old_bytes;
+  ScratchSwap(dflow_chain* c_, HostPipe* p) : c(c_), old(c_->scratch), old_bytes(c_->scratch_bytes) {
+    if (p->tc_scratch) {
+      c->scratch = p->tc_scratch;
+      c->scratch_bytes = p->tc_scratch_bytes;
+    }
+  }
+  ~ScratchSwap() {
+    c->scratch = old;
+    c->scratch_bytes = old_bytes;
+  }
+};
 
 int dflow_logpdf_host(dflow_chain* c, const float* W, const float* x_host, const float* theta_host, int64_t B,
                       int32_t flags, float* logp_host, int64_t chunk) {
@@ -814,6 +928,7 @@ int dflow_logpdf_host(dflow_chain* c, const float* W, const float* x_host, const
   HostPipe* p;
   rc = pipe_get(c, chunk, &p);
   if (rc) return rc;
+  ScratchSwap swap(c, p);
   // the staged image is shared by both streams: prepack once, make both streams wait for it
   cudaEvent_t ev;
   CKA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -869,6 +984,7 @@ int dflow_sample_host(dflow_chain* c, const float* W, uint64_t seed, const float
   HostPipe* p;
   int rc = pipe_get(c, chunk, &p);
   if (rc) return rc;
+  ScratchSwap swap(c, p);
   if (H.n > 0) {
     CKA(cudaMemcpyAsync(p->dt[0], theta_const_host, sizeof(float) * H.n, cudaMemcpyHostToDevice, p->st[0]));
   }
@@ -922,6 +1038,8 @@ int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
     c->grad_spt = value;
   else if (!strcmp(key, "ctas_per_sm"))
     c->ctas_per_sm = value;
+  else if (!strcmp(key, "epoch_kernel"))
+    c->epoch_kernel = value;
   else if (!strcmp(key, "tc_fuse"))
     c->tc_fuse = value < 0 ? 0 : value > 2 ? 2 : value;
   else if (!strcmp(key, "tc_ws_budget_mb"))

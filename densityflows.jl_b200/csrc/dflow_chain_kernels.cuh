@@ -538,7 +538,7 @@ template <int HP, int S>
 __device__ __forceinline__ void fwd_load_tile(const FwdArgs& a, const DevChainHdr& H, float* xs, float* th, int CS, int tid,
                                               long long base, int NTS, bool io_aligned) {
   const int d = H.d, n = H.n;
-    const bool vec_io = (S == 4) && a.idx == nullptr && (base + NTS <= a.B) && io_aligned;
+    const bool vec_io = (S == 4) && a.idx == nullptr && a.grid_vals == nullptr && (base + NTS <= a.B) && io_aligned;
     if (vec_io && a.mode != MODE_SAMPLE_RNG) {
       const float4* xp4 = reinterpret_cast<const float4*>(a.x_in + (base + (long long)tid * S) * d);
       int s = 0, k = 0;
@@ -591,6 +591,12 @@ __device__ __forceinline__ void fwd_load_tile(const FwdArgs& a, const DevChainHd
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             if (4 * g + q < d) xs[(4 * g + q) * CS + sl] = z[q];
+        }
+      } else if (a.grid_vals) {
+        // point gi of the tensor-product grid, first vector fastest (Iterators.product order, src/Flows.jl:301)
+        for (int k = 0; k < d; ++k) {
+          const long long len = a.grid_meta[3 * k], stride = a.grid_meta[3 * k + 1], off = a.grid_meta[3 * k + 2];
+          xs[k * CS + sl] = valid ? __ldg(a.grid_vals + off + (gi / stride) % len) : 0.0f;
         }
       } else if (!vec_io) {
         const float* xp = a.x_in + src * d;

@@ -93,6 +93,9 @@ struct FwdArgs {
   unsigned int rng_offset;
   unsigned long long first_sample;
   int cb_wofs;  // constant-bank kernels: float offset of the staged weights inside the bank
+  // tensor-product grid input (dflow_logpdf_grid, src/Flows.jl:287-331): sample b has x_k = grid_vals[off_k + (b / stride_k) % len_k]
+  const float* grid_vals;       // device: the d coordinate vectors back to back
+  const long long* grid_meta;   // device: per dimension [len_k, stride_k, off_k]
 };
 
 struct GradArgs {
@@ -117,6 +120,7 @@ struct GradArgs {
 };
 
 struct TcPlan;
+struct SmallPlan;
 
 struct PrepackArgs {
   const DevChain* chain;
@@ -143,9 +147,17 @@ struct dflow_chain {
   long long launches = 0;
   // host pipeline scratch (dflow_*_host)
   void* pipe = nullptr;
+  // caller-owned scratch of the forward-type calls on the tensor-core kernels (dflow_chain_set_scratch)
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  long long* d_gridmeta = nullptr;          // [DMAX][3] grid description of the current dflow_logpdf_grid call
+  long long h_gridmeta[3 * dflow::DMAX] = {0};
   // tensor-core plan (dflow_tc.cu): warp-specialised tcgen05 forward + adjoint; built for every eligible chain
   dflow::TcPlan* tcp = nullptr;
   int must_wide = 0;   // some hidden width > 64: the CUDA-core kernels cannot run this chain
+  // small-minibatch epoch kernel (dflow_small.cu): non-null when the chain fits it (every Dense output <= 32)
+  dflow::SmallPlan* small = nullptr;
+  int epoch_kernel = 0;  // tuning: -1 keeps dflow_train_epoch on the per-minibatch (loss_grad + Adam) launches
   int tc_ws_budget_mb = 0;  // adjoint workspace cap in MiB (0: 24 GiB); larger batches are processed in macro-batches
   int tc_fuse = 1;     // hidden <= 128 RealNVP layers run their s and t conditioners as one block-diagonal conditioner:
                        // 0 never, 1 in the train step (default), 2 in forward-type calls as well
@@ -184,4 +196,6 @@ void adam_beta_powers(float b1, float b2, long long t, float* b1t, float* b2t);
 int launch_adam_pw(float* W, const float* g, float* m, float* v, long long P, float lr, float b1, float b2, float eps,
                    float b1t, float b2t, cudaStream_t st);
 int launch_minmax(const float* x, int rows, long long B, float* mn, float* mx, cudaStream_t st);
+int launch_shuffle(unsigned long long seed, long long n, long long first, long long count, const int32_t* base, int32_t* out,
+                   cudaStream_t st);
 }  // namespace dflow

@@ -117,6 +117,83 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K7: stateless pseudo-random permutation (DataPartition randperm src/Data.jl:112-128, DataLoader shuffle
+// src/Flows.jl:394).  perm_i = cycle-walked balanced Feistel network over 2*hb >= log2(n) bits: a bijection of [0, n)
+// that any thread (and any rank, for its own slice) evaluates independently from (seed, i) -- no sort, no state.
+// Specification shared with the oracle: oracle/shuffle.py.
+// ------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t feistel_mix(uint32_t x) {  // murmur3 finaliser
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ inline uint64_t feistel_perm(uint64_t i, uint64_t n, int hb, const uint32_t* key) {
+  const uint32_t mask = hb >= 32 ? 0xFFFFFFFFu : ((1u << hb) - 1u);
+  uint64_t x = i;
+  do {
+    uint32_t l = (uint32_t)(x >> hb) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const uint32_t t = l ^ (feistel_mix(r ^ key[q]) & mask);
+      l = r;
+      r = t;
+    }
+    x = ((uint64_t)l << hb) | r;
+  } while (x >= n);
+  return x;
+}
+
+struct ShuffleArgs {
+  uint32_t key[6];
+  long long n, first, count;
+  int hb;
+  const int32_t* base;
+  int32_t* out;
+};
+
+__global__ void shuffle_kernel(const ShuffleArgs a) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < a.count; j += (long long)gridDim.x * blockDim.x) {
+    const long long p = (long long)feistel_perm((uint64_t)(a.first + j), (uint64_t)a.n, a.hb, a.key);
+    a.out[j] = a.base ? a.base[p] : (int32_t)p;
+  }
+}
+
+int launch_shuffle(unsigned long long seed, long long n, long long first, long long count, const int32_t* base, int32_t* out,
+                   cudaStream_t st) {
+  ShuffleArgs a;
+  uint64_t z = seed;
+  for (int q = 0; q < 6; ++q) {  // splitmix64 key schedule
+    z += 0x9E3779B97F4A7C15ull;
+    uint64_t y = z;
+    y = (y ^ (y >> 30)) * 0xBF58476D1CE4E5B9ull;
+    y = (y ^ (y >> 27)) * 0x94D049BB133111EBull;
+    y ^= y >> 31;
+    a.key[q] = (uint32_t)(y >> 32);
+  }
+  int bits = 1;
+  while (bits < 62 && (1ull << bits) < (unsigned long long)n) ++bits;
+  a.hb = (bits + 1) / 2;
+  if (a.hb < 1) a.hb = 1;
+  a.n = n;
+  a.first = first;
+  a.count = count;
+  a.base = base;
+  a.out = out;
+  long long blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  shuffle_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  if (cudaGetLastError() != cudaSuccess) {
+    set_error("shuffle_kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return DFLOW_E_CUDA;
+  }
+  return DFLOW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------------------
 #define CK(call)                                                                          \

@@ -1360,6 +1360,17 @@ __global__ void __launch_bounds__(256) tc_scatter_t_kernel(const float* __restri
   }
 }
 
+// tensor-product grid points in the tile-blocked layout (dflow_logpdf_grid): x_k(b) = vals[off_k + (b / stride_k) % len_k]
+__global__ void tc_grid_kernel(float* x, long long B, int d, const float* __restrict__ vals, const long long* __restrict__ meta) {
+  const long long total = ((B + 127) / 128) * 128;
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < total; b += (long long)gridDim.x * blockDim.x) {
+    const long long tile = b >> 7;
+    const int r = (int)(b & 127);
+    for (int k = 0; k < d; ++k)
+      x[tidx(tile, d, k, r)] = b < B ? __ldg(vals + meta[3 * k + 2] + (b / meta[3 * k + 1]) % meta[3 * k]) : 0.0f;
+  }
+}
+
 // base draw z ~ N(0, I) in the tile-blocked layout: Philox4x32-10 + Box-Muller, counter = global sample index
 __global__ void tc_philox_kernel(float* z, long long B, int d, unsigned long long seed, unsigned int offset,
                                  unsigned long long first) {
@@ -1652,8 +1663,6 @@ void tc_free_plan(dflow_chain* c) {
   if (tp->d_img) cudaFree(tp->d_img);
   if (tp->d_jobs_fwd) cudaFree(tp->d_jobs_fwd);
   if (tp->d_jobs_bwd) cudaFree(tp->d_jobs_bwd);
-  if (tp->d_sbuf) cudaFree(tp->d_sbuf);
-  if (tp->d_work) cudaFree(tp->d_work);
   delete tp;
   c->tcp = nullptr;
 }
@@ -1760,19 +1769,6 @@ static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st, const TcNetImg
   return DFLOW_OK;
 }
 
-static int grow_sbuf(TcPlan* tp, size_t floats) {
-  if (tp->sbuf_floats >= floats) return DFLOW_OK;
-  if (tp->d_sbuf) cudaFree(tp->d_sbuf);
-  tp->d_sbuf = nullptr;
-  tp->sbuf_floats = 0;
-  if (cudaMalloc(&tp->d_sbuf, floats * sizeof(float)) != cudaSuccess) {
-    set_error("cudaMalloc failed for %zu floats of conditioner-output scratch", floats);
-    return DFLOW_E_NOMEM;
-  }
-  tp->sbuf_floats = floats;
-  return DFLOW_OK;
-}
-
 static unsigned ew_blocks(long long work) {
   long long blocks = (work + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -1792,14 +1788,13 @@ static int gather_t(dflow_chain* c, const float* src, const int32_t* idx, long l
 }
 
 // Runs the whole chain on the tile-blocked state `x` in place (x already holds the input), accumulating ldj (per sample).
-int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* theta_const, float* ldj, long long B,
-                 int sampling, int flags, cudaStream_t st) {
+int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* theta_const, float* ldj, float* sbuf,
+                 long long B, int sampling, int flags, cudaStream_t st) {
   TcPlan* tp = c->tcp;
   const DevChainHdr& Hd = c->hc()->h;
   const int L = (int)tp->layers.size();
   const long long Bp = ((B + 127) / 128) * 128;
-  int rc = grow_sbuf(tp, (size_t)tp->a16max * Bp + 16);
-  if (rc) return rc;
+  int rc = DFLOW_OK;
   for (int step = 0; step < L; ++step) {
     const int ei = sampling ? step : (L - 1 - step);  // src/Chains.jl:155-161 vs :174-180
     const TcLayer& Ld = tp->layers[ei];
@@ -1827,7 +1822,7 @@ int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* thet
       a.theta = theta;
       a.theta_const = theta_const;
       a.ldj = ldj;
-      a.sbuf = tp->d_sbuf;
+      a.sbuf = sbuf;
       rc = launch_net<TC_FWD>(c, a, st, fz ? nullptr : Ld.fwd2[ni]);
       if (rc) return rc;
     }
@@ -1850,22 +1845,23 @@ int tc_fwd(dflow_chain* c, const float* W, FwdArgs& a, cudaStream_t st) {
   const bool own_ldj = (a.mode == MODE_LOGPDF || a.mode == MODE_LOGPDF_SUM);
   const bool want_ldj = !(a.mode == MODE_SAMPLE || a.mode == MODE_SAMPLE_RNG);
   const bool per_sample_theta = n > 0 && a.theta && !a.theta_const;
-  const size_t need = (size_t)(d + 1 + n) * Bp + 64;
-  if (tp->work_floats < need) {
-    if (tp->d_work) cudaFree(tp->d_work);
-    tp->d_work = nullptr;
-    tp->work_floats = 0;
-    if (cudaMalloc(&tp->d_work, need * sizeof(float)) != cudaSuccess) {
-      set_error("cudaMalloc failed for %zu floats of tensor-core working state", need);
-      return DFLOW_E_NOMEM;
-    }
-    tp->work_floats = need;
+  // working state in the caller's scratch (dflow_scratch_bytes / dflow_chain_set_scratch): [x (d Bp) | ldj (Bp) | theta (n Bp) |
+  // s values of the current layer (a16max Bp)] -- nothing is allocated here
+  if (c->scratch_bytes < tc_scratch_bytes(c, B) || !c->scratch) {
+    set_error("scratch too small for B = %lld: need %zu bytes (dflow_scratch_bytes), the handle has %zu "
+              "(dflow_chain_set_scratch)", B, tc_scratch_bytes(c, B), c->scratch_bytes);
+    return DFLOW_E_INVALID_ARG;
   }
-  float* xw = tp->d_work;
+  float* xw = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c->scratch) + 255) & ~(uintptr_t)255);
   float* ldj = xw + (size_t)d * Bp;
   float* thw = ldj + Bp;
+  float* sbuf = thw + (size_t)n * Bp;
   if (a.mode == MODE_SAMPLE_RNG) {
     tc_philox_kernel<<<ew_blocks(B), 256, 0, st>>>(xw, B, d, a.seed, a.rng_offset, a.first_sample);
+    CKT(cudaGetLastError());
+    c->launches++;
+  } else if (a.grid_vals) {
+    tc_grid_kernel<<<ew_blocks(B), 256, 0, st>>>(xw, B, d, a.grid_vals, a.grid_meta);
     CKT(cudaGetLastError());
     c->launches++;
   } else {
@@ -1881,7 +1877,7 @@ int tc_fwd(dflow_chain* c, const float* W, FwdArgs& a, cudaStream_t st) {
     ldj_dst = own_ldj ? ldj : a.aux_out;
     CKT(cudaMemsetAsync(ldj_dst, 0, sizeof(float) * B, st));
   }
-  rc = tc_run_chain(c, xw, per_sample_theta ? thw : nullptr, a.theta_const, ldj_dst, B, sampling ? 1 : 0, a.flags, st);
+  rc = tc_run_chain(c, xw, per_sample_theta ? thw : nullptr, a.theta_const, ldj_dst, sbuf, B, sampling ? 1 : 0, a.flags, st);
   if (rc) return rc;
   if (own_ldj) {
     tc_logpdf_kernel<<<ew_blocks(B), 256, 0, st>>>(xw, ldj, B, d, Hd.logpdf_c0, 0.0f, nullptr,
@@ -1893,6 +1889,13 @@ int tc_fwd(dflow_chain* c, const float* W, FwdArgs& a, cudaStream_t st) {
   CKT(cudaGetLastError());
   c->launches++;
   return DFLOW_OK;
+}
+
+size_t tc_scratch_bytes(const dflow_chain* c, long long B) {
+  const TcPlan* tp = c->tcp;
+  const DevChainHdr& Hd = c->hc()->h;
+  const size_t Bp = (size_t)((B + 127) / 128) * 128;
+  return ((size_t)(Hd.d + 1 + Hd.n + tp->a16max) * Bp + 128) * sizeof(float) + 256;
 }
 
 // ---- training -------------------------------------------------------------------------------------------------

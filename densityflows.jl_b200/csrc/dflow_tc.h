@@ -92,10 +92,6 @@ struct TcPlan {
   TcPackJob* d_jobs_bwd = nullptr;
   float* d_img = nullptr;
   size_t img_floats = 0;
-  float* d_sbuf = nullptr;  // s values of the current layer (forward-type calls), grow-only
-  size_t sbuf_floats = 0;
-  float* d_work = nullptr;  // tile-blocked working state of the forward-type calls [x | ldj | theta], grow-only
-  size_t work_floats = 0;
   int hmax = 0, a16max = 0, k0pmax = 0;
   int hu = 0;  // widest single conditioner (training buffers hold 2 nets x 2 activations x hu per layer and sample)
   bool train_ok = false;  // adjoint supported (h <= 256)
@@ -105,8 +101,9 @@ int tc_build_plan(dflow_chain* c);
 void tc_free_plan(dflow_chain* c);
 int tc_prepack(dflow_chain* c, const float* W, bool with_bwd, cudaStream_t st);
 int tc_fwd(dflow_chain* c, const float* W, FwdArgs& a, cudaStream_t st);
-int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* theta_const, float* ldj, long long B,
-                 int sampling, int flags, cudaStream_t st);
+int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* theta_const, float* ldj, float* sbuf,
+                 long long B, int sampling, int flags, cudaStream_t st);
+size_t tc_scratch_bytes(const dflow_chain* c, long long B);  // working state of a forward-type call on B samples
 size_t tc_workspace_bytes(const dflow_chain* c, long long B);
 // caller cotangents / extra outputs of dflow_vjp (all sample-major device arrays; any pointer may be null)
 struct TcVjp {

@@ -10,8 +10,29 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from . import _lib as L
 from .arrays import jl_empty, n_samples, to_jl
 from .model import _gen, minmax_rows
+
+
+def device_permutation(n: int, seed: int, device, first: int = 0, count: Optional[int] = None,
+                       base: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int32 device tensor out[j] = base[perm(first + j)] (perm itself without `base`), perm = the seed's pseudo-random
+    permutation of 0..n-1, drawn ON the device by dflow_shuffle_indices (stateless Feistel bijection, oracle/shuffle.py):
+    replaces randperm (src/Data.jl:112-128) and the DataLoader shuffle (src/Flows.jl:394) without a host round trip."""
+    device = torch.device(device)
+    count = n - first if count is None else int(count)
+    out = torch.empty(count, device=device, dtype=torch.int32)
+    if count == 0:
+        return out
+    if base is not None:
+        base = base.to(device=device, dtype=torch.int32).contiguous()
+        assert int(base.numel()) >= n
+    with torch.cuda.device(device):
+        L.check(L.lib().dflow_shuffle_indices(int(seed) & 0xFFFFFFFFFFFFFFFF, int(n), int(first), count,
+                                              None if base is None else base.data_ptr(), out.data_ptr(),
+                                              torch.cuda.current_stream(device).cuda_stream))
+    return out
 
 
 def dflt_θ(*args) -> torch.Tensor:
@@ -47,11 +68,16 @@ class DataPartition:
             self.training, self.validation, self.testing = n_or_training, validation, testing
             return
         n = int(n_or_training)
-        p = torch.randperm(n, generator=rng or _gen(), dtype=torch.int64).to(torch.int32)
         i1 = int(round(n * f_training))
         i2 = i1 + int(round(n * f_validation))
-        if device is not None:
-            p = p.to(device)
+        if device is not None and torch.device(device).type == "cuda":
+            # the permutation is drawn on the device (only its seed comes from the host generator)
+            self.seed = int(torch.randint(0, 2**62, (1,), generator=rng or _gen()).item())
+            p = device_permutation(n, self.seed, device)
+        else:
+            p = torch.randperm(n, generator=rng or _gen(), dtype=torch.int64).to(torch.int32)
+            if device is not None:
+                p = p.to(device)
         self.training, self.validation, self.testing = p[:i1].contiguous(), p[i1:i2].contiguous(), p[i2:n].contiguous()
 
 
@@ -72,6 +98,39 @@ class DataArrays:
         self.x, self.θ = x, θ
         self.partition = DataPartition(int(x.shape[1]), f_training, f_validation, rng, device=device)
         self._θ_range: Optional[Tuple[np.ndarray, np.ndarray]] = None
+        # data-parallel sharding (shard_): this rank's share of the GLOBAL training / validation sets
+        self.is_shard = False
+        self.n_training_global = int(self.partition.training.numel())
+        self.n_validation_global = int(self.partition.validation.numel())
+
+    def shard_(self, rank: int, world: int) -> "DataArrays":
+        """Keep only this rank's contiguous share of the training / validation / testing index lists RESIDENT (SURVEY §8e:
+        dataset sharded once; weights replicated).  Call it on every rank after the Flow / NormalizationLayer have been
+        built from the full data (x_min / x_max / θ range are global statistics), with the same partition on every rank
+        (train_ checks the global counts).  train_ then shuffles shard-locally: minibatch k is the union of every rank's
+        k-th local slice -- sampling without replacement stratified by shard."""
+        from .flows import shard_range
+
+        _θ_range(self)  # global θ range before the columns go away
+        parts = []
+        for v in (self.partition.training, self.partition.validation, self.partition.testing):
+            lo, hi = shard_range(int(v.numel()), rank, world)
+            parts.append(v[lo:hi])
+        self.n_training_global = int(self.partition.training.numel())
+        self.n_validation_global = int(self.partition.validation.numel())
+        cols = torch.cat(parts).to(torch.int64)
+        self.x = to_jl(self.x.index_select(1, cols))
+        self.θ = to_jl(self.θ.index_select(1, cols))
+        o = 0
+        new = []
+        for v in parts:
+            k = int(v.numel())
+            new.append(torch.arange(o, o + k, device=self.x.device, dtype=torch.int32))
+            o += k
+        self.partition = DataPartition(new[0], validation=new[1], testing=new[2])
+        self.is_shard = True
+        self.shard_rank, self.shard_world = int(rank), int(world)
+        return self
 
     theta = property(lambda self: self.θ)
 

@@ -14,7 +14,8 @@ import torch
 
 from . import _lib as L
 from .arrays import flat_view, jl_empty, n_samples, to_jl
-from .data import DataArrays, MetaData, maximum_θ, minimum_θ, number_conditions, number_dimensions
+from .data import (DataArrays, MetaData, device_permutation, maximum_θ, minimum_θ, number_conditions,
+                   number_dimensions)
 from .model import FlowChain, PackedChain, _gen
 
 # ------------------------------------------------------------------------------------------------------------
@@ -228,14 +229,13 @@ def logpdf(flow: Flow, x, θ=None):
             raise ValueError(f"grid logpdf needs {flow.d} coordinate vectors")
         vs = [torch.as_tensor(np.asarray(v, np.float32) if not isinstance(v, torch.Tensor) else v, dtype=torch.float32,
                               device=pc.device).reshape(-1) for v in x]
-        lens = tuple(int(v.numel()) for v in vs)
-        # Iterators.product(x...): first vector varies fastest == Julia column-major grid (src/Flows.jl:301)
-        grids = torch.meshgrid(*vs, indexing="ij")
-        y = jl_empty((flow.d,) + lens, pc.device)
-        for k, g in enumerate(grids):
-            y[k] = g
-        θa = _θ_broadcast(flow, tuple(θ) if θ is not None else (), lens, pc.device)
-        return pc.logpdf(y, θa, flags)
+        # Iterators.product(x...): first vector varies fastest == Julia column-major grid (src/Flows.jl:301).  The kernel
+        # derives every point from its flat index (dflow_logpdf_grid): neither the (d, prod(lens)) point array nor the
+        # (n, prod(lens)) broadcast of θ is materialised.
+        θt = tuple(θ) if θ is not None else ()
+        if len(θt) != flow.n:
+            raise ValueError(f"θ must be an NTuple of length n={flow.n}")
+        return pc.logpdf_grid(vs, θt, flags)
     x = to_jl(x, pc.device)
     if isinstance(θ, tuple):
         θ = _θ_broadcast(flow, θ, tuple(x.shape[1:]), pc.device)
@@ -513,71 +513,111 @@ def _full_loss(pc: PackedChain, x, θ, idx: torch.Tensor, n_global: int, flags: 
     return float("nan") if bad > 0 else -s / max(n_global, 1)
 
 
+def _shard_schedule(n_total: int, batchsize: int, world: int, n_local: Sequence[int]) -> List[List[int]]:
+    """Per minibatch step, how many samples every rank contributes from its resident shard: the minibatch of nb samples is
+    split like shard_range(nb, r, world), clipped to what the rank still has this epoch.  Pure arithmetic, identical on every
+    rank, so the global minibatch size of a step (the 1 / B_global seed) needs no communication."""
+    left = list(n_local)
+    steps = []
+    for b0 in range(0, n_total, batchsize):
+        nb = min(batchsize, n_total - b0)
+        row = []
+        for r in range(world):
+            lo, hi = shard_range(nb, r, world)
+            k = min(hi - lo, left[r])
+            left[r] -= k
+            row.append(k)
+        steps.append(row)
+    # anything a rank has left (uneven shards) joins the last step so that every sample is visited once per epoch
+    if steps:
+        for r in range(world):
+            steps[-1][r] += left[r]
+    return steps
+
+
 def train_(flow: Flow, data: DataArrays, optimiser_state: OptimiserState, epochs: int = 100, batchsize: int = 64,
            shuffle: bool = True, verbose: bool = True, debug: bool = False, rng: Optional[torch.Generator] = None):
     """train!(flow, data, state; epochs=100, batchsize=64, shuffle=true, verbose=true, debug=false),
     src/Flows.jl:380-445.  Per epoch: reshuffled minibatches (partial last batch kept, like Flux.DataLoader),
-    gradient + Adam per batch, then the full-set training and validation losses are pushed to the flow."""
+    gradient + Adam per batch, then the full-set training and validation losses are pushed to the flow.
+
+    The epoch's order is drawn on the device (dflow_shuffle_indices).  Under torch.distributed every rank either holds the
+    whole dataset and takes its slice of every (globally shuffled) minibatch, or -- after `data.shard_(rank, world)` --
+    holds only its shard and shuffles shard-locally."""
     pc = flow.packed()
     flags = L.THETA_NORMALIZE if flow.n > 0 else 0  # θ is normalised in-kernel (src/Data.jl:189-199)
     x = to_jl(data.x, pc.device)
     θ = to_jl(data.θ, pc.device) if flow.n > 0 else None
     if x.dim() != 2:
         raise NotImplementedError("train! partitions along dim 2; only (d, N) arrays are supported (src/Data.jl:167)")
-    tr = data.partition.training.to(pc.device)
-    va = data.partition.validation.to(pc.device)
+    tr = data.partition.training.to(pc.device).contiguous()
+    va = data.partition.validation.to(pc.device).contiguous()
     d = _dist()
     rank, world = (d.get_rank(), d.get_world_size()) if d is not None else (0, 1)
+    sharded = bool(getattr(data, "is_shard", False)) and world > 1
     gen = rng or _gen()
+    seed0 = int(torch.randint(0, 2**62, (1,), generator=gen).item())
     if d is not None:
         # Ranks build their FlowChain / DataArrays independently (different RNG streams): make rank 0 authoritative for
         # the initial parameters, the optimiser state, the train / validation split and the shuffle stream, so that the
         # replicas really are replicas (they then stay bit-identical without any further broadcast).
         optimiser_state._ensure(pc)
-        sizes = torch.tensor([tr.numel(), va.numel(), optimiser_state.t], device=pc.device, dtype=torch.int64)
+        n_tr_g = data.n_training_global if sharded else int(tr.numel())
+        n_va_g = data.n_validation_global if sharded else int(va.numel())
+        sizes = torch.tensor([n_tr_g, n_va_g, optimiser_state.t, seed0], device=pc.device, dtype=torch.int64)
+        mine = sizes.clone()
         d.broadcast(sizes, src=0)
-        n_tr0, n_va0, t0 = (int(v) for v in sizes.tolist())
-        if (int(tr.numel()), int(va.numel())) != (n_tr0, n_va0):
+        if mine[:2].tolist() != sizes[:2].tolist():
             raise ValueError("ranks disagree on the size of the training / validation partitions")
-        optimiser_state.t = t0
-        tr, va = tr.contiguous(), va.contiguous()
-        for buf in (pc.W, optimiser_state.m, optimiser_state.v, tr, va):
+        optimiser_state.t, seed0 = int(sizes[2].item()), int(sizes[3].item())
+        bufs = [pc.W, optimiser_state.m, optimiser_state.v] + ([] if sharded else [tr, va])
+        for buf in bufs:
             d.broadcast(buf, src=0)
-        seed_t = torch.randint(0, 2**62, (1,), generator=gen).to(pc.device)
-        d.broadcast(seed_t, src=0)
-        gen = torch.Generator(device="cpu")
-        gen.manual_seed(int(seed_t.item()))
     step = make_train_step(pc, optimiser_state)
-    n_tr, n_va = int(tr.numel()), int(va.numel())
+    n_tr = data.n_training_global if sharded else int(tr.numel())
+    n_va = data.n_validation_global if sharded else int(va.numel())
     tmp = torch.zeros(2, device=pc.device, dtype=torch.float32)
+    schedule = None
+    if sharded:
+        n_local = [shard_range(n_tr, r, world)[1] - shard_range(n_tr, r, world)[0] for r in range(world)]
+        if n_local[rank] != int(tr.numel()):
+            raise ValueError("this rank's resident training shard does not match shard_range(n_training_global, rank, world)")
+        schedule = _shard_schedule(n_tr, batchsize, world, n_local)
 
     def shard(v: torch.Tensor) -> torch.Tensor:
-        if world == 1:
+        if world == 1 or sharded:
             return v
         lo, hi = shard_range(int(v.numel()), rank, world)
         return v[lo:hi]
 
-    for _ in range(epochs):
+    for ep in range(epochs):
         if shuffle:
-            # every rank draws the same permutation (same generator state) -> global shuffle, per-rank slices
-            perm = torch.randperm(n_tr, generator=gen).to(pc.device)
-            order = tr[perm]
+            # drawn on the device; every rank evaluates the same bijection (global shuffle), or -- sharded -- its own
+            # permutation of its resident shard
+            eseed = seed0 + ep + (1000003 * (rank + 1) if sharded else 0)
+            order = device_permutation(int(tr.numel()), eseed, pc.device, base=tr)
         else:
             order = tr
         if world == 1 and not debug and isinstance(step, TrainStep):
             # single GPU: the whole epoch is enqueued from C (dflow_train_epoch) -- with the reference's default
             # batchsize = 64 a step is launch-bound, and a Python round trip per minibatch would dominate it
             st_ = optimiser_state
-            st_.t = pc.train_epoch(x, θ, order.to(torch.int32).contiguous(), batchsize, st_.m, st_.v, st_.t, st_.rule.eta,
-                                   st_.rule.beta, st_.rule.epsilon, flags, step.buf)
-            order = order[:0]
-        for b0 in range(0, int(order.numel()), batchsize):
-            batch = order[b0: b0 + batchsize]
-            step(x, θ, shard(batch), int(batch.numel()), flags)
-            if debug:
-                s, bad = step.loss2.tolist()
-                if bad > 0 or not math.isfinite(s):
-                    raise ValueError(f"non-finite minibatch loss (Σlogp={s}, non-finite samples={bad})")  # Flows.jl:405-409
+            st_.t = pc.train_epoch(x, θ, order, batchsize, st_.m, st_.v, st_.t, st_.rule.eta, st_.rule.beta,
+                                   st_.rule.epsilon, flags, step.buf)
+        elif sharded:
+            cur = 0
+            for row in schedule:
+                k = row[rank]
+                step(x, θ, order[cur: cur + k], sum(row), flags)
+                cur += k
+        else:
+            for b0 in range(0, int(order.numel()), batchsize):
+                batch = order[b0: b0 + batchsize]
+                step(x, θ, shard(batch), int(batch.numel()), flags)
+                if debug:
+                    s_, bad = step.loss2.tolist()
+                    if bad > 0 or not math.isfinite(s_):
+                        raise ValueError(f"non-finite minibatch loss (Σlogp={s_}, non-finite samples={bad})")  # Flows.jl:405-409
         if isinstance(step, PeerTrainStep):
             step.check()  # a rank that missed the peer barrier skipped its update: stop instead of training on
         train_loss = _full_loss(pc, x, θ, shard(tr), n_tr, flags, tmp)

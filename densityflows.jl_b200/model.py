@@ -519,6 +519,7 @@ class PackedChain:
         self.has_theta_range = theta_min is not None
         self.W = torch.zeros(max(self.P, 1), device=self.device, dtype=torch.float32)
         self._ws: Optional[torch.Tensor] = None  # adjoint workspace (dflow_workspace_bytes)
+        self._scratch_buf: Optional[torch.Tensor] = None  # forward-call scratch (dflow_scratch_bytes), caller owned
         if replica_of is not None:
             # a data-parallel replica on another device: same descriptor, its own copy of the parameters; the Dense
             # tensors of the chain stay views into the primary's buffer
@@ -609,6 +610,7 @@ class PackedChain:
         B = n_samples(x)
         z = jl_empty(x.shape, self.device)
         ldj = jl_empty(tail_shape(x) or (1,), self.device)
+        self.ensure_scratch(B)
         with torch.cuda.device(self.device):
             L.check(L.lib().dflow_normalize(self.handle, self.W.data_ptr(), self._ptr(x), self._ptr(θ), B, flags,
                                             self._ptr(z), self._ptr(ldj), self._stream()))
@@ -619,6 +621,7 @@ class PackedChain:
         B = n_samples(z)
         x = jl_empty(z.shape, self.device)
         ldj = jl_empty(tail_shape(z) or (1,), self.device)
+        self.ensure_scratch(B)
         with torch.cuda.device(self.device):
             L.check(L.lib().dflow_forward_ldj(self.handle, self.W.data_ptr(), self._ptr(z), self._ptr(θ), B, flags,
                                               self._ptr(x), self._ptr(ldj), self._stream()))
@@ -636,6 +639,7 @@ class PackedChain:
                 raise ValueError("θ must have size (n, dims...) matching z")
         else:
             θ = None
+        self.ensure_scratch(n_samples(z))
         with torch.cuda.device(self.device):
             L.check(L.lib().dflow_sample_inplace(self.handle, self.W.data_ptr(), self._ptr(z), self._ptr(θ),
                                                  None if θ_const is None else θ_const.data_ptr(), n_samples(z), flags,
@@ -649,14 +653,35 @@ class PackedChain:
         else:
             B = int(idx.numel()) if B is None else B
             out = torch.empty(B, device=self.device, dtype=torch.float32)
+        self.ensure_scratch(B)
         with torch.cuda.device(self.device):
             L.check(L.lib().dflow_logpdf(self.handle, self.W.data_ptr(), self._ptr(x), self._ptr(θ), B,
                                          None if idx is None else idx.data_ptr(), flags, self._ptr(out), self._stream()))
         return out
 
+    def logpdf_grid(self, vectors: Sequence[torch.Tensor], θ: Sequence[float] = (), flags: int = 0) -> torch.Tensor:
+        """log-density on the tensor-product grid of d coordinate vectors with one fixed condition (src/Flows.jl:287-331);
+        result of size (len_1, ..., len_d), column-major."""
+        self.refresh()
+        if len(vectors) != self.d:
+            raise ValueError(f"grid logpdf needs {self.d} coordinate vectors")
+        lens = [int(v.numel()) for v in vectors]
+        B = int(np.prod(lens)) if lens else 0
+        vals = torch.cat([v.to(device=self.device, dtype=torch.float32).reshape(-1) for v in vectors])
+        θc = torch.tensor([float(v) for v in θ], device=self.device, dtype=torch.float32) if self.n > 0 else None
+        out = jl_empty(tuple(lens), self.device)
+        self.ensure_scratch(B)
+        lens_c = (C.c_int64 * self.d)(*lens)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().dflow_logpdf_grid(self.handle, self.W.data_ptr(), vals.data_ptr() if vals.numel() else None,
+                                              lens_c, None if θc is None else θc.data_ptr(), flags, self._ptr(out),
+                                              self._stream()))
+        return out
+
     def logpdf_sum(self, x, θ, out2: torch.Tensor, flags: int = 0, idx: Optional[torch.Tensor] = None) -> int:
         x, θ = self._prep(x, θ)
         B = n_samples(x) if idx is None else int(idx.numel())
+        self.ensure_scratch(B)
         with torch.cuda.device(self.device):
             L.check(L.lib().dflow_logpdf_sum(self.handle, self.W.data_ptr(), self._ptr(x), self._ptr(θ), B,
                                              None if idx is None else idx.data_ptr(), flags, out2.data_ptr(),
@@ -672,6 +697,7 @@ class PackedChain:
             θ = to_jl(θ, self.device)
         else:
             θ = None
+        self.ensure_scratch(B)
         with torch.cuda.device(self.device):
             L.check(L.lib().dflow_sample_rng(self.handle, self.W.data_ptr(), seed_, offset, first_sample, self._ptr(θ),
                                              None if θ_const is None else θ_const.data_ptr(), B, flags, self._ptr(out),
@@ -694,6 +720,15 @@ class PackedChain:
                                             None if idx is None else idx.data_ptr(), ib, flags, loss2.data_ptr(),
                                             grad.data_ptr(), self._ws.data_ptr(), self._ws.numel(), self._stream()))
         return B
+
+    def ensure_scratch(self, B: int) -> None:
+        """Attach dflow_scratch_bytes(B) of caller-owned scratch to the handle (grow-only; a no-op for chains on the
+        CUDA-core kernels).  Raw ABI users call this once for their largest batch; the library never allocates."""
+        need = int(L.lib().dflow_scratch_bytes(self.handle, int(B)))
+        if need and (self._scratch_buf is None or self._scratch_buf.numel() < need):
+            torch.cuda.synchronize(self.device)  # earlier calls may still work in the old buffer
+            self._scratch_buf = torch.empty(need, device=self.device, dtype=torch.uint8)
+            L.check(L.lib().dflow_chain_set_scratch(self.handle, self._scratch_buf.data_ptr(), need))
 
     def _workspace(self, B: int) -> torch.Tensor:
         need = int(L.lib().dflow_workspace_bytes(self.handle, B))

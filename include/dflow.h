@@ -105,6 +105,15 @@ int dflow_param_offset(const dflow_chain* chain, int32_t elem, int32_t net, int3
 /* replace θ_min / θ_max (host pointers, n entries each) */
 int dflow_chain_set_theta_range(dflow_chain* chain, const float* theta_min, const float* theta_max);
 
+/* ---- scratch of the forward-type calls below ---------------------------------------------------------------------
+ * Chains on the CUDA-core kernels need none (dflow_scratch_bytes returns 0: the whole chain runs in registers / shared
+ * memory).  Chains routed to the tensor-core kernels (hidden > 64 always; hidden 64 from B >= 131072) work on a
+ * tile-blocked copy of the state: the caller allocates dflow_scratch_bytes(chain, B_max) bytes once, attaches them with
+ * dflow_chain_set_scratch and keeps them alive; a forward-type call whose batch needs more returns DFLOW_E_INVALID_ARG.
+ * No entry point that takes device pointers allocates device memory (the *_host entry points own their staging buffers). */
+size_t dflow_scratch_bytes(const dflow_chain* chain, int64_t B);
+int dflow_chain_set_scratch(dflow_chain* chain, void* scratch, size_t bytes);
+
 /* ---- normalising direction: backward(chain, x, θ) -> (z, ln_det_jac)  (src/Chains.jl:149-164) -------------- */
 int dflow_normalize(dflow_chain* chain, const float* W, const float* x, const float* theta, int64_t B, int32_t flags,
                     float* z_out, float* ldj_out, void* stream);
@@ -112,6 +121,12 @@ int dflow_normalize(dflow_chain* chain, const float* W, const float* x, const fl
  * NULL) gathers sample b from column idx[b] of x and θ (selectdim views of src/Data.jl:185-187 / DataLoader batches). */
 int dflow_logpdf(dflow_chain* chain, const float* W, const float* x, const float* theta, int64_t B, const int32_t* idx,
                  int32_t flags, float* logp_out, void* stream);
+/* logpdf(flow, x::NTuple{d,Vector}, θ::NTuple{n}) on the tensor-product grid (src/Flows.jl:287-331).  grid_vals (device):
+ * the d coordinate vectors back to back; lens (host, d entries): their lengths.  logp_out (device, prod(lens) floats) is in
+ * Julia's column-major order of the (lens...) array: the first vector varies fastest (Iterators.product).  theta_const:
+ * device, n floats (NULL when n = 0).  The (d, prod(lens)) point array is never materialised. */
+int dflow_logpdf_grid(dflow_chain* chain, const float* W, const float* grid_vals, const int64_t* lens,
+                      const float* theta_const, int32_t flags, float* logp_out, void* stream);
 /* Σ_b logpdf_b accumulated into loss_out[0] (device float[2], caller zeroes it); loss_out[1] counts non-finite
  * samples.  loss = -loss_out[0]/B (src/Flows.jl:352-359; epoch-end passes src/Flows.jl:419-430). */
 int dflow_logpdf_sum(dflow_chain* chain, const float* W, const float* x, const float* theta, int64_t B,
@@ -226,6 +241,13 @@ int dflow_dp_sync(dflow_dp* const* dps, int32_t ndev, const dflow_dp_shard* shar
  * maximum_θ src/Data.jl:182-183).  min_out / max_out: device float[rows]. */
 int dflow_minmax(const float* x, int32_t rows, int64_t B, float* min_out, float* max_out, void* stream);
 
+/* ---- pseudo-random permutations on the device (DataPartition's randperm src/Data.jl:112-128; the per-epoch shuffle of
+ * Flux.DataLoader, src/Flows.jl:394).  perm = cycle-walked 6-round Feistel bijection of [0, n) keyed by `seed` (specification:
+ * oracle/shuffle.py, bit-exact test).  out[j] = base[perm(first + j)], or perm(first + j) when base == NULL, for j < count:
+ * stateless, so every data-parallel rank evaluates exactly its own slice of the epoch's order. */
+int dflow_shuffle_indices(uint64_t seed, int64_t n, int64_t first, int64_t count, const int32_t* base, int32_t* out,
+                          void* stream);
+
 /* ---- host-buffer entry points (pinned or pageable host memory; chunked H2D -> kernel -> D2H pipeline) -------- */
 int dflow_logpdf_host(dflow_chain* chain, const float* W, const float* x_host, const float* theta_host, int64_t B,
                       int32_t flags, float* logp_host, int64_t chunk);
@@ -233,13 +255,12 @@ int dflow_sample_host(dflow_chain* chain, const float* W, uint64_t seed, const f
                       int32_t flags, float* x_host, int64_t chunk);
 
 /* ---- tuning / introspection ------------------------------------------------------------------------------ */
-/* keys: "fwd_spt", "grad_spt" (samples per thread; negative selects the alternative kernel generation),
- * "fwd_threads", "grad_threads", "ctas_per_sm"; value 0 = automatic.
+/* keys: "fwd_spt", "grad_spt" (samples per thread), "fwd_threads", "grad_threads", "ctas_per_sm"; value 0 = automatic.
  * "fwd_const" (-1: keep small relu chains off the constant-bank forward kernel), "grad_smem" (-1: weight gradients of the
  * narrow adjoint go straight to global memory), "tc_mode" (1 / 0 / -1: force eligible hidden <= 64 chains onto / automatic
  * / off the tensor-core kernels), "tc_fuse" (0 / 1 / 2: s and t conditioners of a layer as one block-diagonal conditioner
- * never / in the train step / everywhere), "tc_ws_budget_mb" (adjoint workspace cap), "tc_cluster", "tc_ns_max",
- * "tc_debug", "wide_gen" (experiments). */
+ * never / in the train step / everywhere), "tc_ws_budget_mb" (adjoint workspace cap), "epoch_kernel" (-1: dflow_train_epoch
+ * never uses the persistent small-minibatch kernel).  Unknown keys return DFLOW_E_INVALID_ARG. */
 int dflow_set_tuning(dflow_chain* chain, const char* key, int32_t value);
 /* number of kernels the library has launched on behalf of this handle since creation */
 int64_t dflow_launch_count(const dflow_chain* chain);

@@ -269,8 +269,12 @@ def test_train_matches_oracle_trajectory():
     # replay on the oracle with the same partition and permutations
     tr = data.partition.training.cpu().numpy()
     va = data.partition.validation.cpu().numpy()
+    # train_ draws one seed from the generator and shuffles epoch e on the device with seed + e (oracle/shuffle.py)
+    from oracle import shuffle as SH
+
     gen2 = torch.Generator().manual_seed(77)
-    perms = [torch.randperm(len(tr), generator=gen2).numpy() for _ in range(3)]
+    seed0 = int(torch.randint(0, 2**62, (1,), generator=gen2).item())
+    perms = [SH.permutation(seed0 + e, len(tr)) for e in range(3)]
     tmin, tmax = th.min(axis=1), th.max(axis=1)
     thn = O.normalize_input(th, tmin, tmax)
     tl, vl = O.train(ochain, x[:, tr], thn[:, tr], x[:, va], thn[:, va], epochs=3, batchsize=64, perms=perms,
@@ -430,6 +434,7 @@ def test_train_epoch_from_c_equals_step_by_step():
     ochain, chain_a, x, th = _setup("readme_n2", 1000, seed=5)
     _, chain_b, _, _ = _setup("readme_n2", 1000, seed=5)
     pa, pb = chain_a.packed(), chain_b.packed()
+    pa.tune(epoch_kernel=-1)  # the per-minibatch launches (the persistent epoch kernel is compared below, to tolerance)
     assert torch.equal(pa.W, pb.W)
     xj, tj = df.to_jl(x, DEV), df.to_jl(th, DEV)
     order = torch.randperm(900, generator=torch.Generator().manual_seed(3)).to(torch.int32).to(DEV)
@@ -454,3 +459,55 @@ def test_train_epoch_from_c_equals_step_by_step():
     assert torch.equal(pa.W, pb.W) and torch.equal(ma, mb) and torch.equal(va, vb)
     assert torch.equal(loss2, acc)
     assert float((pa.W - chain_from_oracle(ochain).packed().W).abs().max()) > 0  # the weights did move
+
+
+@pytest.mark.parametrize("name,bs", [("readme_n2", 64), ("readme_n1", 100), ("hetero_d6_n0", 37), ("blocks_d10_h32", 64),
+                                     ("ref_chain_d7", 512)])
+def test_persistent_epoch_kernel_matches_step_by_step(name, bs):
+    """dflow_train_epoch with minibatches <= 512 runs the whole epoch inside one persistent CTA (csrc/dflow_small.cu:
+    parameters + Adam moments + the minibatch's activations in shared memory, a sample spread over 16 / 32 lanes, fixed-
+    order weight-gradient reduction).  Same mathematics as loss_grad + adam_step per minibatch -- different summation
+    order, so equal to Float32 tolerance, and bitwise reproducible run to run (no atomics)."""
+    ochain, chain_a, x, th = _setup(name, 1000, seed=5)
+    _, chain_b, _, _ = _setup(name, 1000, seed=5)
+    _, chain_c, _, _ = _setup(name, 1000, seed=5)
+    pa, pb, pcc = chain_a.packed(), chain_b.packed(), chain_c.packed()
+    n = th.shape[0]
+    xj = df.to_jl(x, DEV)
+    tj = df.to_jl(th, DEV) if n else None
+    N = 900
+    order = torch.randperm(N, generator=torch.Generator().manual_seed(3)).to(torch.int32).to(DEV)
+    P = pa.P
+    out = {}
+    for tag, pc in (("a", pa), ("c", pcc)):
+        m_, v_ = torch.zeros(P, device=DEV), torch.zeros(P, device=DEV)
+        loss2 = torch.zeros(2, device=DEV)
+        before = pc.launch_count()
+        t = 0
+        for _ in range(2):
+            t = pc.train_epoch(xj, tj, order, bs, m_, v_, t, 1e-3, (0.9, 0.999), 1e-8, 0, None, loss2)
+        if name in ("readme_n2", "readme_n1", "hetero_d6_n0"):
+            assert pc.launch_count() - before == 2, "one launch per epoch"
+        # (chains whose parameters + Adam moments + tape exceed one SM's shared memory stay on the per-minibatch launches)
+        assert t == 2 * ((N + bs - 1) // bs)
+        out[tag] = (pc.W.clone(), m_, v_, loss2)
+    if name in ("readme_n2", "readme_n1", "hetero_d6_n0"):  # the generic path reduces with float atomics
+        for i in range(4):
+            assert torch.equal(out["a"][i], out["c"][i]), "run-to-run reproducible"
+    mb, vb = torch.zeros(P, device=DEV), torch.zeros(P, device=DEV)
+    buf = torch.zeros(P + 2, device=DEV)
+    tb, acc = 0, torch.zeros(2, device=DEV)
+    for _ in range(2):
+        for b0 in range(0, N, bs):
+            idx = order[b0:b0 + bs]
+            buf.zero_()
+            pb.loss_grad(xj, tj, buf[:P], buf[P:], 1.0 / int(idx.numel()), 0, idx)
+            acc += buf[P:]
+            tb += 1
+            pb.adam_step(buf[:P], mb, vb, tb, 1e-3, (0.9, 0.999), 1e-8)
+    wa, ma, va, l2 = out["a"]
+    assert float((wa - pb.W).abs().max()) <= 2e-5, float((wa - pb.W).abs().max())
+    assert torch.allclose(ma, mb, rtol=1e-3, atol=1e-6 * float(mb.abs().max()) + 1e-9)
+    assert torch.allclose(va, vb, rtol=2e-3, atol=1e-6 * float(vb.abs().max()) + 1e-12)
+    assert abs(float(l2[0] - acc[0])) <= 1e-5 * abs(float(acc[0])) and float(l2[1]) == 0
+    assert float((wa - chain_from_oracle(ochain).packed().W).abs().max()) > 1e-3  # the weights did move
