@@ -105,6 +105,7 @@ SYMBOLS = [
     ("dflow_dp_allreduce_adam", C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, vp, vp]),
     ("dflow_dp_status", C.c_int, [vp, vp]),
     ("dflow_dp_set_timeout_ms", C.c_int, [vp, C.c_int64]),
+    ("dflow_dp_wait_stats", C.c_int, [vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("dflow_dp_destroy", C.c_int, [vp]),
     ("dflow_dp_create_local", C.c_int, [C.c_int32, c_i32p, C.c_int64, C.POINTER(vp)]),
     ("dflow_dp_train_step", C.c_int, [C.POINTER(vp), C.c_int32, vp, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float,

@@ -2,7 +2,7 @@
 // (src/Flows.jl:413-415: gradient -> Optimisers.update!).  One process per GPU; every rank owns one communication
 // buffer (cudaMalloc + CUDA IPC handle, opened by its peers):
 //
-//   [ flags: uint32[64] | go: uint32 | pad to 512 B ] [ half 0: P + 2 floats, padded ] [ half 1: P + 2 floats, padded ]
+//   [ flags: uint32[64] | go | bad | pad | wait statistics: uint64[2] at word 68 | pad to 512 B ] [ half 0: P + 2 floats, padded ] [ half 1: P + 2 floats, padded ]
 //
 // Step e writes its local gradient sum [grad | sum logp | #non-finite] into half e & 1 (the adjoint kernels accumulate
 // there directly), then ONE kernel per rank: (1) thread 0 of CTA 0 publishes flags[rank] = e in every peer's buffer
@@ -74,6 +74,12 @@ __global__ void __launch_bounds__(256) dp_allreduce_adam_kernel(const DpArgs a) 
           break;
         }
       }
+    }
+    // accumulated barrier wait (SM clocks) and step count: the measurement behind the scaling split in bench.py
+    {
+      unsigned long long* stats = reinterpret_cast<unsigned long long*>(my_flags + 68);
+      stats[0] += (unsigned long long)(clock64() - t0);
+      stats[1] += 1ull;
     }
     if (!ok) {
       // the peers' halves may be stale or half written: skip the reduction AND the update on this rank, and say so
@@ -434,6 +440,25 @@ int dflow_dp_sync(dflow_dp* const* dps, int32_t ndev, const dflow_dp_shard* shar
   }
   cudaSetDevice(prev);
   return worst;
+}
+
+/* total SM clocks rank-local CTA 0 spent waiting for its peers' gradients, and the number of steps, since creation
+ * (synchronises the stream) */
+int dflow_dp_wait_stats(dflow_dp* d, void* stream, int64_t* wait_clk, int64_t* steps) {
+  if (!d || !wait_clk || !steps) {
+    set_error("null argument");
+    return DFLOW_E_INVALID_ARG;
+  }
+  unsigned long long h[2] = {0, 0};
+  if (cudaMemcpyAsync(h, d->own + 68 * sizeof(uint32_t), sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream) !=
+          cudaSuccess ||
+      cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+    set_error("stats read failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return DFLOW_E_CUDA;
+  }
+  *wait_clk = (int64_t)h[0];
+  *steps = (int64_t)h[1];
+  return DFLOW_OK;
 }
 
 int dflow_dp_destroy(dflow_dp* d) {

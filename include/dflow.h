@@ -206,6 +206,8 @@ int dflow_dp_allreduce_adam(dflow_dp* dp, float* W, float* m, float* v, float lr
  * were skipped on this rank (stale peer buffers are never summed), the replicas are no longer in step and the caller
  * must stop.  Synchronises `stream`. */
 int dflow_dp_status(dflow_dp* dp, void* stream);
+/* measurement: SM clocks this rank's kernels have spent waiting in the peer barrier, and the number of steps, since creation */
+int dflow_dp_wait_stats(dflow_dp* dp, void* stream, int64_t* wait_clk, int64_t* steps);
 int dflow_dp_set_timeout_ms(dflow_dp* dp, int64_t ms); /* barrier time-out of the fused kernel, default ~10 s */
 int dflow_dp_destroy(dflow_dp* dp);
 
