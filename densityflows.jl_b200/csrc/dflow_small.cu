@@ -38,8 +38,9 @@ struct SmNet {
   int w[MAX_DENSE + 1];
   int act[MAX_DENSE];
   int pw[MAX_DENSE], pb[MAX_DENSE];   // packed offsets (global W / m / v)
-  int sw[MAX_DENSE], sb[MAX_DENSE];   // offsets in the padded shared-memory parameter image; row pitch op[j]
-  int op[MAX_DENSE];                  // odd row pitch >= w[j+1]
+  int sw[MAX_DENSE], sb[MAX_DENSE];   // offsets in the padded shared-memory parameter image: W[o + op k]; bias
+  int op[MAX_DENSE];                  // row pitch of the image (multiple of 4, op / 4 odd): row k = the O outputs of input k
+  int tw[MAX_DENSE], kp[MAX_DENSE];   // transposed copy for the forward pass: WT[k + kp u], row u = the K inputs of output u
   int ta[MAX_DENSE + 1];              // tape offsets: ta[0] = conditioner input (nin), ta[j] = output of Dense j-1
   int dl[MAX_DENSE];                  // delta offsets (per-sample delta row): dl[j] = cotangent of Dense j's pre-activation
 };
@@ -63,8 +64,9 @@ struct SmallPlanDev {
   int d, n, L, lps;
   int P;          // packed parameter count
   int PS;         // padded parameter image size (floats, multiple of 4)
-  int TP;         // tape pitch per sample (odd)
-  int DP;         // delta-row pitch per sample (odd)
+  int PT;         // size of the transposed weight copy (floats)
+  int TP;         // tape pitch per sample (= 8 mod 32: float4 rows of neighbouring samples / sample quarters hit distinct banks)
+  int DP;         // delta-row pitch per sample (= 8 mod 32)
   int t_x, t_th, t_gx;  // tape offsets of the state, the conditions, the state cotangent
   int nconst;     // floats of normalisation constants
   int has_theta_range;
@@ -89,22 +91,34 @@ struct SmallArgs {
   float* loss2_out;
 };
 
-__device__ __forceinline__ float sm_act(int code, float v) { return act_apply(code, v); }
+__device__ __forceinline__ float sm_act(int code, float v) {
+  if (code == DFLOW_ACT_RELU) return fmaxf(v, 0.0f);
+  if (code == DFLOW_ACT_IDENTITY) return v;
+  return act_apply(code, v);
+}
+__device__ __forceinline__ float sm_act_grad(int code, float y) {
+  if (code == DFLOW_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
+  return act_grad(code, y);
+}
 
-// y_u = act(b_u + sum_k W[u + op k] a_k) for the NG sample groups of this CTA; lane u < O stores to the tape
-__device__ __forceinline__ void sm_dense_fwd(const float* __restrict__ Wsm, const SmNet& net, int j, const float* in,
-                                             float* out, int u) {
-  const int K = net.w[j], O = net.w[j + 1], op = net.op[j];
+// y_u = act(b_u + sum_k W[u, k] a_k): lane u < O walks row u of the transposed copy and the sample's input vector with
+// 128-bit shared-memory loads (rows and vectors are zero-padded to a multiple of 4)
+__device__ __forceinline__ void sm_dense_fwd(const float* __restrict__ Wsm, const float* __restrict__ WT, const SmNet& net,
+                                             int j, const float* in, float* out, int u) {
+  const int K4 = (net.w[j] + 3) >> 2, O = net.w[j + 1];
   if (u < O) {
-    const float* wr = Wsm + net.sw[j] + u;
-    float acc0 = net.has_bias ? Wsm[net.sb[j] + u] : 0.0f, acc1 = 0.0f;
-    int k = 0;
-    for (; k + 1 < K; k += 2) {
-      acc0 = fmaf(wr[op * k], in[k], acc0);
-      acc1 = fmaf(wr[op * (k + 1)], in[k + 1], acc1);
+    const float4* wr = reinterpret_cast<const float4*>(WT + net.tw[j] + net.kp[j] * u);
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    float acc0 = net.has_bias ? Wsm[net.sb[j] + u] : 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+#pragma unroll 4
+    for (int k = 0; k < K4; ++k) {
+      const float4 w = wr[k], x = in4[k];
+      acc0 = fmaf(w.x, x.x, acc0);
+      acc1 = fmaf(w.y, x.y, acc1);
+      acc2 = fmaf(w.z, x.z, acc2);
+      acc3 = fmaf(w.w, x.w, acc3);
     }
-    if (k < K) acc0 = fmaf(wr[op * k], in[k], acc0);
-    out[u] = sm_act(net.act[j], acc0 + acc1);
+    out[u] = sm_act(net.act[j], (acc0 + acc1) + (acc2 + acc3));
   }
   __syncwarp();
 }
@@ -131,12 +145,17 @@ __global__ void __launch_bounds__(SM_THREADS, 1) epoch_small_kernel(const SmallA
   float* Msm = Wsm + PS;
   float* Vsm = Msm + PS;
   float* Gsm = Vsm + PS;
-  float* tape = Gsm + PS;
+  float* WT = Gsm + PS;  // transposed copy of the weights (forward pass), refreshed after every Adam update
+  int* tmap = reinterpret_cast<int*>(WT + Pn.PT);  // image index -> index in the transposed copy (-1: bias / padding)
+  float* tape = reinterpret_cast<float*>(tmap + PS);
   float* drow = tape + NG * TP;
   float* red = drow + NG * DP;  // [NG] logp values + 2 accumulators
 
   for (int i = tid; i < Pn.nconst; i += SM_THREADS) cst[i] = a.consts[i];
-  for (int i = tid; i < 4 * PS; i += SM_THREADS) Wsm[i] = 0.0f;
+  // everything zero: image padding, tape / delta-row padding slots (read by the 128-bit loops, never written)
+  for (int i = tid; i < 4 * PS + Pn.PT; i += SM_THREADS) Wsm[i] = 0.0f;
+  for (int i = tid; i < NG * (TP + DP); i += SM_THREADS) tape[i] = 0.0f;
+  for (int i = tid; i < PS; i += SM_THREADS) tmap[i] = -1;
   __syncthreads();
   // packed -> padded image of W, m, v
   for (int ei = 0; ei < L; ++ei) {
@@ -149,7 +168,10 @@ __global__ void __launch_bounds__(SM_THREADS, 1) epoch_small_kernel(const SmallA
         for (int i = tid; i < O * K; i += SM_THREADS) {
           const int k = i / O, o = i - k * O;
           const int si = net.sw[j] + o + op * k, gi = net.pw[j] + i;
-          Wsm[si] = a.W[gi];
+          const float wv = a.W[gi];
+          Wsm[si] = wv;
+          WT[net.tw[j] + k + net.kp[j] * o] = wv;
+          tmap[si] = net.tw[j] + k + net.kp[j] * o;
           Msm[si] = a.m[gi];
           Vsm[si] = a.v[gi];
         }
@@ -175,7 +197,6 @@ __global__ void __launch_bounds__(SM_THREADS, 1) epoch_small_kernel(const SmallA
   for (long long b0 = 0; b0 < a.n; b0 += a.batchsize) {
     const long long nb = min(a.batchsize, a.n - b0);
     const float ib = (float)(1.0 / (double)nb);  // seed 1 / |minibatch| (mean over its true size, src/Flows.jl:358)
-    for (int i = tid; i < PS; i += SM_THREADS) Gsm[i] = 0.0f;
     for (long long p0 = 0; p0 < nb; p0 += NG) {
       const bool valid = p0 + grp < nb;
       // ---- gather the sample (src/Flows.jl:394 DataLoader batch through the index) ----
@@ -210,7 +231,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) epoch_small_kernel(const SmallA
         __syncwarp();
         for (int ni = rnvp ? 0 : 1; ni < 2; ++ni) {
           const SmNet& net = ni == 0 ? E.s : E.t;
-          for (int j = 0; j < net.depth; ++j) sm_dense_fwd(Wsm, net, j, T + net.ta[j], T + net.ta[j + 1], u);
+          for (int j = 0; j < net.depth; ++j) sm_dense_fwd(Wsm, WT, net, j, T + net.ta[j], T + net.ta[j + 1], u);
         }
         const float* sv = T + E.s.ta[E.s.depth];
         const float* tv = T + E.t.ta[E.t.depth];
@@ -275,21 +296,23 @@ __global__ void __launch_bounds__(SM_THREADS, 1) epoch_small_kernel(const SmallA
             __syncwarp();
           }
           for (int j = D - 1; j >= 0; --j) {
-            const int K = net.w[j], O = net.w[j + 1], op = net.op[j];
-            const float* dl = Dr + net.dl[j];
-            // g_in[k] = sum_o W[o + op k] delta_j[o]: lane k walks row k (odd pitch: conflict free)
+            const int K = net.w[j], O4 = (net.w[j + 1] + 3) >> 2, op = net.op[j];
+            const float4* dl4 = reinterpret_cast<const float4*>(Dr + net.dl[j]);
+            // g_in[k] = sum_o W[o + op k] delta_j[o]: lane k walks row k of the image (128-bit loads, zero padded)
             for (int k = u; k < K; k += LPS) {
-              const float* wr = Wsm + net.sw[j] + op * k;
-              float acc0 = 0.0f, acc1 = 0.0f;
-              int o = 0;
-              for (; o + 1 < O; o += 2) {
-                acc0 = fmaf(wr[o], dl[o], acc0);
-                acc1 = fmaf(wr[o + 1], dl[o + 1], acc1);
+              const float4* wr = reinterpret_cast<const float4*>(Wsm + net.sw[j] + op * k);
+              float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+#pragma unroll 4
+              for (int o = 0; o < O4; ++o) {
+                const float4 w = wr[o], dv = dl4[o];
+                acc0 = fmaf(w.x, dv.x, acc0);
+                acc1 = fmaf(w.y, dv.y, acc1);
+                acc2 = fmaf(w.z, dv.z, acc2);
+                acc3 = fmaf(w.w, dv.w, acc3);
               }
-              if (o < O) acc0 = fmaf(wr[o], dl[o], acc0);
-              const float g = acc0 + acc1;
+              const float g = (acc0 + acc1) + (acc2 + acc3);
               if (j > 0) {
-                Dr[net.dl[j - 1] + k] = g * act_grad(net.act[j - 1], T[net.ta[j] + k]);
+                Dr[net.dl[j - 1] + k] = g * sm_act_grad(net.act[j - 1], T[net.ta[j] + k]);
               } else if (k >= n) {
                 gx[E.id[k - n]] += g;  // identity coordinates; the theta rows are dropped
               }
@@ -304,34 +327,60 @@ __global__ void __launch_bounds__(SM_THREADS, 1) epoch_small_kernel(const SmallA
           xs[k] = T[E.t_ck + u];
         }
         __syncthreads();
-        // ---- weight gradients of this element: entry e is owned by 4 adjacent lanes, 1/4 of the samples each ----
+        // ---- weight gradients of this element.  A task = (output o, four consecutive inputs k) of one Dense, or one bias
+        // entry; 8 tasks per warp iteration, each summed by 4 lanes over a quarter of the samples (lane = task + 8 quarter):
+        // per sample one scalar delta load and one 128-bit activation load feed four fmas; the quarters meet in two shuffles
+        // and one lane owns the entry -- fixed order, no atomics.
         {
           const int total = E.dw_start[E.n_dense];
-          for (int base = 0; base < 4 * total; base += SM_THREADS) {  // warp-uniform trip count (shuffles below)
-            const int task = base + tid;
-            const bool live = task < 4 * total;
-            const int e = live ? task >> 2 : 0, q = task & 3;
+          const int lane = tid & 31, warp = tid >> 5, q = lane >> 3;
+          for (int base = 0; base < total; base += 8 * (SM_THREADS / 32)) {  // warp-uniform trip count
+            const int e_raw = base + warp * 8 + (lane & 7);
+            const bool live = e_raw < total;
+            const int e = live ? e_raw : 0;
             int di = 0;
             while (e >= E.dw_start[di + 1]) ++di;
             const int r = e - E.dw_start[di];
-            const int O = E.dw_O[di], K = E.dw_K[di];
-            float acc = 0.0f;
-            int gidx;
-            if (r < O * K) {
-              const int k = r / O, o = r - k * O;
-              const float* dp = drow + E.dw_dl[di] + o;
-              const float* ap = tape + E.dw_in[di] + k;
-              for (int s = q; s < NG; s += 4) acc = fmaf(dp[s * DP], ap[s * TP], acc);
-              gidx = E.dw_g[di] + o + E.dw_op[di] * k;
+            const int O = E.dw_O[di], K = E.dw_K[di], KQ = (K + 3) >> 2;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            const bool is_w = r < O * KQ;
+            const int kq = is_w ? r / O : 0, o = is_w ? r - kq * O : r - O * KQ;
+            const float* dp = drow + E.dw_dl[di] + o + q * DP;
+            if (is_w) {
+              const float* ap = tape + E.dw_in[di] + 4 * kq + q * TP;
+#pragma unroll
+              for (int i = 0; i < NG / 4; ++i) {
+                const float dv = dp[4 * i * DP];
+                const float4 av = *reinterpret_cast<const float4*>(ap + 4 * i * TP);
+                a0 = fmaf(dv, av.x, a0);
+                a1 = fmaf(dv, av.y, a1);
+                a2 = fmaf(dv, av.z, a2);
+                a3 = fmaf(dv, av.w, a3);
+              }
             } else {
-              const int o = r - O * K;
-              const float* dp = drow + E.dw_dl[di] + o;
-              for (int s = q; s < NG; s += 4) acc += dp[s * DP];
-              gidx = E.dw_gb[di] + o;
+#pragma unroll
+              for (int i = 0; i < NG / 4; ++i) a0 += dp[4 * i * DP];
             }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if (live && q == 0) Gsm[gidx] += acc;
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 8);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, 8);
+            a3 += __shfl_xor_sync(0xffffffffu, a3, 8);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+            a3 += __shfl_xor_sync(0xffffffffu, a3, 16);
+            if (live && q == 0) {
+              if (is_w) {
+                float* g = Gsm + E.dw_g[di] + o + E.dw_op[di] * 4 * kq;
+                const int op = E.dw_op[di];
+                g[0] += a0;
+                if (4 * kq + 1 < K) g[op] += a1;
+                if (4 * kq + 2 < K) g[2 * op] += a2;
+                if (4 * kq + 3 < K) g[3 * op] += a3;
+              } else {
+                Gsm[E.dw_gb[di] + o] += a0;
+              }
+            }
           }
         }
         __syncthreads();
@@ -360,7 +409,11 @@ __global__ void __launch_bounds__(SM_THREADS, 1) epoch_small_kernel(const SmallA
         Msm[i] = mi;
         Vsm[i] = vi;
         const float den = __fadd_rn(__fsqrt_rn(__fdiv_rn(vi, c2)), a.eps);
-        Wsm[i] = __fsub_rn(Wsm[i], __fmul_rn(__fdiv_rn(__fdiv_rn(mi, c1), den), a.lr));
+        const float wn = __fsub_rn(Wsm[i], __fmul_rn(__fdiv_rn(__fdiv_rn(mi, c1), den), a.lr));
+        Wsm[i] = wn;
+        Gsm[i] = 0.0f;  // consumed: the next minibatch accumulates from zero
+        const int ti = tmap[i];
+        if (ti >= 0) WT[ti] = wn;  // transposed copy for the next step's forward pass
       }
     }
     __syncthreads();
@@ -405,7 +458,18 @@ struct SmallPlan {
   size_t smem = 0;
 };
 
-static void layout_small_net(const DevNet& src, SmNet& dst, int& ps, int& tp, int& dp, int in_tape) {
+static int pitch4(int w) {  // multiple of 4 with pitch / 4 odd: 128-bit rows, consecutive rows 4 (mod 8) banks apart
+  int p = (w + 3) & ~3;
+  if (((p >> 2) & 1) == 0) p += 4;
+  return p;
+}
+static int pitch_mod32_8(int w) {  // smallest p >= w with p = 8 (mod 32)
+  int p = (w + 7) & ~7;
+  while ((p & 31) != 8) p += 8;
+  return p;
+}
+
+static void layout_small_net(const DevNet& src, SmNet& dst, int& ps, int& pt, int& tp, int& dp, int in_tape) {
   memset(&dst, 0, sizeof(dst));
   dst.depth = src.depth;
   dst.has_bias = src.has_bias;
@@ -415,15 +479,18 @@ static void layout_small_net(const DevNet& src, SmNet& dst, int& ps, int& tp, in
     dst.act[j] = src.act[j];
     dst.pw[j] = src.p_w[j];
     dst.pb[j] = src.p_b[j];
-    dst.op[j] = src.w[j + 1] | 1;
+    dst.op[j] = pitch4(src.w[j + 1]);
     dst.sw[j] = ps;
     ps += dst.op[j] * src.w[j];
     dst.sb[j] = ps;
-    ps += src.w[j + 1];
+    ps += (src.w[j + 1] + 3) & ~3;
+    dst.kp[j] = pitch4(src.w[j]);
+    dst.tw[j] = pt;
+    pt += dst.kp[j] * src.w[j + 1];
     dst.ta[j + 1] = tp;
-    tp += src.w[j + 1];
+    tp += (src.w[j + 1] + 3) & ~3;
     dst.dl[j] = dp;
-    dp += src.w[j + 1];
+    dp += (src.w[j + 1] + 3) & ~3;
   }
 }
 
@@ -463,10 +530,11 @@ int small_build_plan(dflow_chain* c) {
   P->P = H.P;
   P->has_theta_range = H.has_theta_range;
   P->logpdf_c0 = H.logpdf_c0;
-  int ps = 0, tp = 0, dp = 0, nconst = 0;
-  P->t_x = tp; tp += H.d;
-  P->t_th = tp; tp += H.n;
-  P->t_gx = tp; tp += H.d;
+  int ps = 0, pt = 0, tp = 0, dp = 0, nconst = 0;
+  auto r4 = [](int v) { return (v + 3) & ~3; };
+  P->t_x = tp; tp += r4(H.d);
+  P->t_th = tp; tp += r4(H.n);
+  P->t_gx = tp; tp += r4(H.d);
   std::vector<float> consts;
   for (int ei = 0; ei < H.L; ++ei) {
     const DevElem& E = C->e[ei];
@@ -481,22 +549,22 @@ int small_build_plan(dflow_chain* c) {
       S.nstage = nconst;
       nconst += 2 * H.d + 4;
       S.t_ck = (ei == H.L - 1) ? -1 : tp;  // a trailing normalisation acts on the data itself: nothing to restore
-      if (S.t_ck >= 0) tp += H.d;
+      if (S.t_ck >= 0) tp += r4(H.d);
       continue;
     }
     const int in_tape = tp;
-    tp += E.nin;
+    tp += r4(E.nin);
     int dpe = 0;  // the delta rows are reused element after element (their weight-gradient phase ends before the next one)
     S.t_ck = tp;
-    tp += E.a;
+    tp += r4(E.a);
     S.t_em = tp;
-    tp += E.a;
+    tp += r4(E.a);
     S.n_dense = 0;
     S.dw_start[0] = 0;
     for (int ni = (E.kind == DFLOW_ELEM_RNVP ? 0 : 1); ni < 2; ++ni) {
       const DevNet& net = ni == 0 ? E.s : E.t;
       SmNet& sn = ni == 0 ? S.s : S.t;
-      layout_small_net(net, sn, ps, tp, dpe, in_tape);
+      layout_small_net(net, sn, ps, pt, tp, dpe, in_tape);
       for (int j = 0; j < net.depth; ++j) {
         const int di = S.n_dense++;
         S.dw_O[di] = net.w[j + 1];
@@ -506,18 +574,20 @@ int small_build_plan(dflow_chain* c) {
         S.dw_dl[di] = sn.dl[j];
         S.dw_g[di] = sn.sw[j];
         S.dw_gb[di] = sn.sb[j];
-        S.dw_start[di + 1] = S.dw_start[di] + net.w[j + 1] * net.w[j] + (net.has_bias ? net.w[j + 1] : 0);
+        // tasks: (output, quad of inputs) pairs, then the bias entries
+        S.dw_start[di + 1] = S.dw_start[di] + net.w[j + 1] * ((net.w[j] + 3) / 4) + (net.has_bias ? net.w[j + 1] : 0);
       }
     }
     dp = std::max(dp, dpe);
   }
   P->PS = (ps + 3) & ~3;
-  P->TP = tp | 1;
-  P->DP = std::max(dp, 1) | 1;
+  P->PT = (pt + 3) & ~3;
+  P->TP = pitch_mod32_8(tp);
+  P->DP = pitch_mod32_8(std::max(dp, 4));
   P->nconst = nconst;
   const int ng = SM_THREADS / lps;
   const size_t smem = img.size() + 4 * (size_t)((nconst + 3) & ~3) +
-                      4 * ((size_t)4 * P->PS + (size_t)ng * P->TP + (size_t)ng * P->DP + ng + 8);
+                      4 * ((size_t)5 * P->PS + (size_t)P->PT + (size_t)ng * P->TP + (size_t)ng * P->DP + ng + 8);
   if (smem > (size_t)c->max_smem_optin) return DFLOW_E_UNSUPPORTED;
   SmallPlan* sp = new (std::nothrow) SmallPlan();
   if (!sp) return DFLOW_E_NOMEM;

@@ -12,7 +12,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 N = 100000
 x = df.jl_empty((d, N), "cuda:0"); x.normal_(generator=g)
 th = df.jl_empty((n, N), "cuda:0"); th.uniform_(0, 1, generator=g)
-order = torch.randperm(640, generator=torch.Generator().manual_seed(5)).to(torch.int32).to("cuda:0")
+order = torch.randperm(6400, generator=torch.Generator().manual_seed(5)).to(torch.int32).to("cuda:0")
 m = torch.zeros(pc.P, device="cuda:0"); v = torch.zeros(pc.P, device="cuda:0")
 t = pc.train_epoch(x, th, order, 64, m, v, 0)
 torch.cuda.synchronize()
