@@ -375,6 +375,8 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         Be = B
+        if dist is not None:
+            dist.barrier()  # every rank copies at the same time: the ceiling is the one the ranks see TOGETHER
         ceiling = host_copy_ceiling(dev)
         xh = torch.empty(Be * D, dtype=torch.float32).pin_memory()
         thh = torch.empty(Be * N_COND, dtype=torch.float32).pin_memory()

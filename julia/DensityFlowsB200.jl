@@ -1,22 +1,27 @@
 # DensityFlowsB200.jl -- thin `ccall` layer that lets DensityFlows.jl run its coupling-chain hot path on libdflow.so
 # (hand-written sm_100a kernels, include/dflow.h).  Load AFTER `using DensityFlows, CUDA`.
 #
-# NOTE: Julia is not installed in the build environment of this repository, so this file has never been executed;
-# every call below mirrors, argument for argument, the ctypes binding in densityflows.jl_b200/_lib.py + model.py,
-# which IS exercised by tests/ on a B200.  Treat it as the reference-side stub a maintainer adapts (INTEGRATION.md).
+# STATUS: Julia is not installed in the build environment of this repository (no `julia` binary, no network), so this file
+# has NEVER been executed.  Every ccall below mirrors, argument for argument, the ctypes binding in
+# densityflows.jl_b200/_lib.py + model.py + flows.py, which IS exercised by tests/ on a B200 through the same C ABI.
+# Treat it as the reference-side stub a maintainer adapts (INTEGRATION.md).
 #
-# What it adds (no method of the reference is overwritten for CPU arrays):
-#   backward(chain, x::CuArray, Î¸::CuArray)        -> dflow_normalize          (src/Chains.jl:149-164)
-#   forward(chain, z::CuArray, Î¸::CuArray)         -> dflow_forward_ldj        (src/Chains.jl:167-183)
-#   forward!(chain, z::CuArray, Î¸::CuArray)        -> dflow_sample_inplace     (src/Chains.jl:187-197)
-#   logpdf(flow, x::CuArray, Î¸::CuArray)           -> dflow_logpdf             (src/Flows.jl:272-281)
-#   sample(flow, dims, Î¸::NTuple; device=true)     -> dflow_sample_rng         (src/Flows.jl:157-192)
-#   train!(flow, data::CuDataArrays, state; ...)   -> dflow_loss_grad + dflow_adam_step (src/Flows.jl:380-445)
-#   ChainRulesCore.rrule(backward, chain, x, Î¸)    -> dflow_loss_grad-style pullback for Zygote users
+# It only ADDS methods, all on the reference's own types, selected by dispatch on device arrays (no CPU method of the
+# reference is overwritten):
+#   backward / forward / forward!(::FlowChain | ::Flow, ::CuArray, ::CuArray)   src/Chains.jl:149-197, src/Macros.jl:104-112
+#   logpdf(::Flow, x::CuArray, Î¸::CuArray | ::NTuple)                           src/Flows.jl:272-284
+#   logpdf(DeviceGrid(), ::Flow, x::NTuple{D,Vector}, Î¸::NTuple)                src/Flows.jl:287-331 (in-kernel grid)
+#   sample(rng::DeviceRNG, ::Flow, dims, Î¸::NTuple | ::CuArray)                 src/Flows.jl:157-192
+#   train!(::Flow, ::DataArrays{Float32,2,<:CuArray,...}, state; kws...)         src/Flows.jl:380-445
+#   ChainRulesCore.rrule(::typeof(backward), ::FlowChain, ::CuArray, ::CuArray)  src/affine/RNVP.jl:99-147 through the chain
+#   train_local!(flow, shards, state; devices, kws...)                          one process, several GPUs (dflow_dp_*_local)
 module DensityFlowsB200
 
 using DensityFlows
 using CUDA
+using Random
+import ChainRulesCore
+import ChainRulesCore: Tangent, NoTangent
 import DensityFlows: backward, forward, forward!, logpdf, sample, train!
 import DensityFlows: FlowChain, CouplingBlock, RNVPCouplingLayer, NICECouplingLayer, NormalizationLayer, Flow, DataArrays
 import Flux
@@ -54,6 +59,22 @@ struct ChainDesc
     theta_max::Ptr{Float32}
 end
 
+# dflow_dp_shard: one rank's share of a minibatch for dflow_dp_train_step
+struct DpShard
+    chain::Ptr{Cvoid}
+    W::CuPtr{Float32}
+    m::CuPtr{Float32}
+    v::CuPtr{Float32}
+    x::CuPtr{Float32}
+    theta::CuPtr{Float32}
+    B::Int64
+    idx::CuPtr{Int32}
+    ws::CuPtr{Cvoid}
+    ws_bytes::Csize_t
+    loss2_out::CuPtr{Float32}
+    stream::Ptr{Cvoid}
+end
+
 const ELEM_RNVP, ELEM_NICE, ELEM_NORM = Int32(0), Int32(1), Int32(2)
 const THETA_NORMALIZE = Int32(1)
 
@@ -85,7 +106,8 @@ mutable struct PackedChain
     n::Int
     P::Int
     W::CuVector{Float32}            # packed parameters: chain order, s_net then t_net, vec(weight) then bias
-    ws::CuVector{UInt8}             # adjoint workspace (dflow_workspace_bytes)
+    ws::CuVector{UInt8}             # adjoint workspace (dflow_workspace_bytes), caller owned
+    scratch::CuVector{UInt8}        # forward-call scratch (dflow_scratch_bytes), caller owned
     leaves::Vector{Any}
 end
 
@@ -130,7 +152,7 @@ function PackedChain(chain::FlowChain; Î¸_min = nothing, Î¸_max = nothing)
         check(ccall((:dflow_chain_create, libdflow), Cint, (Ref{ChainDesc}, Ref{Ptr{Cvoid}}), desc, handle))
     end
     P = Int(ccall((:dflow_param_count, libdflow), Int64, (Ptr{Cvoid},), handle[]))
-    pc = PackedChain(handle[], d, n, P, CUDA.zeros(Float32, max(P, 1)), CuVector{UInt8}(undef, 0), ls)
+    pc = PackedChain(handle[], d, n, P, CUDA.zeros(Float32, max(P, 1)), CuVector{UInt8}(undef, 0), CuVector{UInt8}(undef, 0), ls)
     finalizer(p -> ccall((:dflow_chain_destroy, libdflow), Cint, (Ptr{Cvoid},), p.handle), pc)
     pack!(pc)
     return pc
@@ -168,181 +190,313 @@ packed(flow::Flow) = get!(() -> PackedChain(flow.model; Î¸_min = flow.metadata.Î
 nsamples(x) = prod(size(x)[2:end])
 stream() = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)
 Î¸ptr(Î¸::CuArray) = size(Î¸, 1) == 0 ? CU_NULL : pointer(Î¸)
+flagsof(flow::Flow) = flow.metadata.n > 0 ? THETA_NORMALIZE : Int32(0)   # @flow_wrapper: Î¸ normalised with the flow's range
+
+"Caller-owned scratch of the forward-type calls (0 bytes on the CUDA-core kernels); the library never allocates."
+function ensure_scratch!(pc::PackedChain, B::Integer)
+    need = ccall((:dflow_scratch_bytes, libdflow), Csize_t, (Ptr{Cvoid}, Int64), pc.handle, B)
+    if need > length(pc.scratch)
+        CUDA.synchronize()
+        pc.scratch = CuVector{UInt8}(undef, need)
+        check(ccall((:dflow_chain_set_scratch, libdflow), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, Csize_t), pc.handle, pc.scratch, need))
+    end
+end
+function workspace!(pc::PackedChain, B::Integer)
+    need = ccall((:dflow_workspace_bytes, libdflow), Csize_t, (Ptr{Cvoid}, Int64), pc.handle, B)
+    length(pc.ws) < need && (pc.ws = CuVector{UInt8}(undef, need))
+    return pc.ws
+end
 
 # ---- element protocol on device arrays (src/Chains.jl:33-72) --------------------------------------------------
 function _normalize(pc, x::CuArray{Float32}, Î¸::CuArray{Float32}, flags)
     z = similar(x); ldj = CuArray{Float32}(undef, size(x)[2:end]...)
+    ensure_scratch!(pc, nsamples(x))
     check(ccall((:dflow_normalize, libdflow), Cint,
                 (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, Int32, CuPtr{Float32}, CuPtr{Float32}, Ptr{Cvoid}),
                 pc.handle, pc.W, x, Î¸ptr(Î¸), nsamples(x), flags, z, ldj, stream()))
     return z, ldj
 end
 backward(chain::FlowChain, x::CuArray{Float32,N}, Î¸::CuArray{Float32,N}) where {N} = _normalize(packed(chain), x, Î¸, Int32(0))
-backward(flow::Flow{Float32}, x::CuArray{Float32,N}, Î¸::CuArray{Float32,N}) where {N} =
-    _normalize(packed(flow), x, Î¸, flow.metadata.n > 0 ? THETA_NORMALIZE : Int32(0))   # @flow_wrapper, src/Macros.jl:104-112
+backward(flow::Flow{Float32}, x::CuArray{Float32,N}, Î¸::CuArray{Float32,N}) where {N} = _normalize(packed(flow), x, Î¸, flagsof(flow))
 
 function _forward(pc, z::CuArray{Float32}, Î¸::CuArray{Float32}, flags)
     x = similar(z); ldj = CuArray{Float32}(undef, size(z)[2:end]...)
+    ensure_scratch!(pc, nsamples(z))
     check(ccall((:dflow_forward_ldj, libdflow), Cint,
                 (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, Int32, CuPtr{Float32}, CuPtr{Float32}, Ptr{Cvoid}),
                 pc.handle, pc.W, z, Î¸ptr(Î¸), nsamples(z), flags, x, ldj, stream()))
     return x, ldj
 end
 forward(chain::FlowChain, z::CuArray{Float32,N}, Î¸::CuArray{Float32,N}) where {N} = _forward(packed(chain), z, Î¸, Int32(0))
-forward(flow::Flow{Float32}, z::CuArray{Float32,N}, Î¸::CuArray{Float32,N}) where {N} =
-    _forward(packed(flow), z, Î¸, flow.metadata.n > 0 ? THETA_NORMALIZE : Int32(0))
+forward(flow::Flow{Float32}, z::CuArray{Float32,N}, Î¸::CuArray{Float32,N}) where {N} = _forward(packed(flow), z, Î¸, flagsof(flow))
 
 function _forward!(pc, z::CuArray{Float32}, Î¸::CuArray{Float32}, flags)
+    ensure_scratch!(pc, nsamples(z))
     check(ccall((:dflow_sample_inplace, libdflow), Cint,
                 (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, Int32, Ptr{Cvoid}),
                 pc.handle, pc.W, z, Î¸ptr(Î¸), CU_NULL, nsamples(z), flags, stream()))
     return nothing
 end
 forward!(chain::FlowChain, z::CuArray{Float32}, Î¸::CuArray{Float32}) = _forward!(packed(chain), z, Î¸, Int32(0))
-forward!(flow::Flow{Float32}, z::CuArray{Float32}, Î¸::CuArray{Float32}) =
-    _forward!(packed(flow), z, Î¸, flow.metadata.n > 0 ? THETA_NORMALIZE : Int32(0))
+forward!(flow::Flow{Float32}, z::CuArray{Float32}, Î¸::CuArray{Float32}) = _forward!(packed(flow), z, Î¸, flagsof(flow))
 
-# ---- logpdf / sample (src/Flows.jl:157-192, 272-281) ----------------------------------------------------------
+# ---- logpdf (src/Flows.jl:272-331) ------------------------------------------------------------------------------
 function logpdf(flow::Flow{Float32}, x::CuArray{Float32,N}, Î¸::CuArray{Float32,N}) where {N}
     pc = packed(flow); out = CuArray{Float32}(undef, size(x)[2:end]...)
+    ensure_scratch!(pc, nsamples(x))
     check(ccall((:dflow_logpdf, libdflow), Cint,
                 (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, CuPtr{Int32}, Int32, CuPtr{Float32}, Ptr{Cvoid}),
-                pc.handle, pc.W, x, Î¸ptr(Î¸), nsamples(x), CU_NULL, flow.metadata.n > 0 ? THETA_NORMALIZE : Int32(0), out, stream()))
+                pc.handle, pc.W, x, Î¸ptr(Î¸), nsamples(x), CU_NULL, flagsof(flow), out, stream()))
+    return out
+end
+# fixed condition for every column: the reference collects Î¸ and broadcasts it (src/Flows.jl:284)
+logpdf(flow::Flow{Float32,D,NÎ¸}, x::CuArray{Float32}, Î¸::NTuple{NÎ¸,Float32}) where {D,NÎ¸} =
+    logpdf(flow, x, CuArray(repeat(collect(Î¸), 1, size(x)[2:end]...)))
+
+"Dispatch tag: evaluate the grid methods of logpdf on the device."
+struct DeviceGrid end
+
+"""
+    logpdf(DeviceGrid(), flow, x::NTuple{D,Vector}, Î¸::NTuple)
+
+src/Flows.jl:287-331 on the device: values on the tensor-product grid of the d coordinate vectors (first vector fastest,
+like Iterators.product); the (d, prod(lens)) point array and the broadcast Î¸ are never materialised (dflow_logpdf_grid).
+"""
+function logpdf(::DeviceGrid, flow::Flow{Float32,D,NÎ¸}, x::NTuple{D,AbstractVector{Float32}}, Î¸::NTuple{NÎ¸,Float32} = ()) where {D,NÎ¸}
+    pc = packed(flow)
+    lens = Int64[length(v) for v in x]
+    vals = CuArray(reduce(vcat, collect.(x)))
+    Î¸c = CuArray(Float32[Î¸...])
+    out = CuArray{Float32}(undef, lens...)
+    ensure_scratch!(pc, prod(lens))
+    check(ccall((:dflow_logpdf_grid, libdflow), Cint,
+                (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, Ptr{Int64}, CuPtr{Float32}, Int32, CuPtr{Float32}, Ptr{Cvoid}),
+                pc.handle, pc.W, vals, lens, NÎ¸ > 0 ? pointer(Î¸c) : CU_NULL, flagsof(flow), out, stream()))
     return out
 end
 
-"sample(flow, dims, Î¸::NTuple; seed) on the device: base draw (Philox4x32-10) + forward! fused in one kernel."
-function sample_device(flow::Flow{Float32,D}, dims::Tuple{Vararg{Integer}}, Î¸::NTuple{NÎ¸,Float32};
-                       seed::UInt64 = rand(UInt64)) where {D,NÎ¸}
+# ---- sample (src/Flows.jl:157-192) ------------------------------------------------------------------------------
+"""
+    DeviceRNG(seed)
+
+RNG tag for `sample(rng, flow, dims, Î¸)`: the base draw r ~ N(0, I) happens inside the sampling kernel
+(Philox4x32-10 + Box-Muller, counter = sample index: dflow_sample_rng) instead of `rand(rng, flow.base, n)` + `forward!`.
+Every call advances `offset`, so successive calls draw fresh points.
+"""
+mutable struct DeviceRNG <: Random.AbstractRNG
+    seed::UInt64
+    offset::UInt32
+end
+DeviceRNG(seed::Integer = rand(UInt64)) = DeviceRNG(UInt64(seed), UInt32(0))
+
+function _sample_rng(flow::Flow{Float32,D}, rng::DeviceRNG, dims, Î¸, Î¸c; first::Integer = 0) where {D}
     pc = packed(flow); B = prod(dims); out = CuArray{Float32}(undef, D, dims...)
-    Î¸c = CuArray(collect(Î¸))
+    ensure_scratch!(pc, B)
     check(ccall((:dflow_sample_rng, libdflow), Cint,
                 (Ptr{Cvoid}, CuPtr{Float32}, UInt64, UInt32, UInt64, CuPtr{Float32}, CuPtr{Float32}, Int64, Int32, CuPtr{Float32}, Ptr{Cvoid}),
-                pc.handle, pc.W, seed, UInt32(0), UInt64(0), CU_NULL, NÎ¸ > 0 ? pointer(Î¸c) : CU_NULL, B,
-                NÎ¸ > 0 ? THETA_NORMALIZE : Int32(0), out, stream()))
+                pc.handle, pc.W, rng.seed, rng.offset, UInt64(first), Î¸, Î¸c, B, flagsof(flow), out, stream()))
     return out
 end
 
+function sample(rng::DeviceRNG, flow::Flow{Float32,D,NÎ¸}, dims::Tuple{Vararg{Integer}}, Î¸::NTuple{NÎ¸,Float32}) where {D,NÎ¸}
+    Î¸c = CuArray(Float32[Î¸...])
+    out = _sample_rng(flow, rng, dims, CU_NULL, NÎ¸ > 0 ? pointer(Î¸c) : CU_NULL)
+    rng.offset += UInt32(1)
+    return out
+end
+function sample(rng::DeviceRNG, flow::Flow{Float32,D}, dims::NTuple{M,Integer}, Î¸::CuArray{Float32,K}) where {D,M,K}
+    @assert K == M + 1 "dimensions Î¸ must match (n, dims...) with n number of trained parameters"   # src/Flows.jl:165
+    out = _sample_rng(flow, rng, dims, Î¸ptr(Î¸), CU_NULL)
+    rng.offset += UInt32(1)
+    return out
+end
+sample(rng::DeviceRNG, flow::Flow{Float32}, dims::Integer, Î¸) = sample(rng, flow, (dims,), Î¸)
+
 """
-sample_with_rejection(condition, flow, dims, Î¸::NTuple, m = 100) on the device (src/Flows.jl:196-229): the same stream
-of points as `sample_device` with that seed (Philox counter = draw index), drawn in batches; `condition(points, Î¸)`
-gets a `(D, nb)` CuArray and returns a Bool vector over the batch; accepted points are compacted in draw order.
+sample_with_rejection(rng::DeviceRNG, condition, flow, dims, Î¸::NTuple, m = 100) (src/Flows.jl:196-229): the same stream of
+points as `sample(rng, ...)` (Philox counter = draw index), drawn in batches; `condition(points, Î¸)` gets a `(D, nb)`
+CuArray and returns a Bool vector over the batch; accepted points are compacted in draw order.
 """
-function sample_with_rejection_device(condition::Function, flow::Flow{Float32,D}, dims::Tuple{Vararg{Integer}},
-                                      Î¸::NTuple{NÎ¸,Float32}, m::Int = 100; seed::UInt64 = rand(UInt64)) where {D,NÎ¸}
-    pc = packed(flow); n = prod(dims); out = CuArray{Float32}(undef, D, n)
-    Î¸c = CuArray(collect(Î¸))
+function DensityFlows.sample_with_rejection(rng::DeviceRNG, condition::Function, flow::Flow{Float32,D,NÎ¸},
+                                            dims::Tuple{Vararg{Integer}}, Î¸::NTuple{NÎ¸,Float32}, m::Int = 100) where {D,NÎ¸}
+    n = prod(dims); out = CuArray{Float32}(undef, D, n)
+    Î¸c = CuArray(Float32[Î¸...])
     have = 0; drawn = 0; nb = max(1024, 2n)
     while have < n && drawn < m * n
         cur = min(nb, m * n - drawn)
-        pts = CuArray{Float32}(undef, D, cur)
-        check(ccall((:dflow_sample_rng, libdflow), Cint,
-                    (Ptr{Cvoid}, CuPtr{Float32}, UInt64, UInt32, UInt64, CuPtr{Float32}, CuPtr{Float32}, Int64, Int32, CuPtr{Float32}, Ptr{Cvoid}),
-                    pc.handle, pc.W, seed, UInt32(0), UInt64(drawn), CU_NULL, NÎ¸ > 0 ? pointer(Î¸c) : CU_NULL, cur,
-                    NÎ¸ > 0 ? THETA_NORMALIZE : Int32(0), pts, stream()))
+        pts = _sample_rng(flow, rng, (cur,), CU_NULL, NÎ¸ > 0 ? pointer(Î¸c) : CU_NULL; first = drawn)
         keep = pts[:, findall(Array(condition(pts, Î¸)))]
         take = min(size(keep, 2), n - have)
         out[:, have+1:have+take] .= keep[:, 1:take]
         have += take; drawn += cur; nb = min(2nb, 1 << 24)
     end
-    have < n && throw(ArgumentError("Impossible to reach convergence of rejection sampling"))
+    rng.offset += UInt32(1)
+    have < n && throw(ArgumentError("Impossible to reach convergence of rejection sampling"))   # src/Flows.jl:221-224
     return reshape(out, D, dims...)
 end
 
+# ---- the adjoint: rrule of backward(chain, x, Î¸) (src/affine/RNVP.jl:99-147 composed through src/Chains.jl:149-164) ----
+"Parameter cotangent in the packed layout -> Tangent mirroring the Flux.@layer structure of the chain."
+function tangent_of(chain::FlowChain, g::Vector{Float32})
+    off = Ref(0)
+    take(dims...) = (k = prod(dims); r = reshape(g[off[]+1:off[]+k], dims...); off[] += k; r)
+    dense(l) = Tangent{typeof(l)}(weight = take(size(l.weight)...), bias = l.bias === false ? NoTangent() : take(length(l.bias)))
+    net(c::Flux.Chain) = Tangent{typeof(c)}(layers = map(dense, c.layers))
+    elem(e::RNVPCouplingLayer) = Tangent{typeof(e)}(s_net = net(e.s_net), t_net = net(e.t_net))
+    elem(e::NICECouplingLayer) = Tangent{typeof(e)}(t_net = net(e.t_net))
+    elem(::NormalizationLayer) = NoTangent()                      # not trainable (src/norm/Normalization.jl:61)
+    elem(b::CouplingBlock) = (t1 = elem(b.layer_1); t2 = elem(b.layer_2); Tangent{typeof(b)}(layer_1 = t1, layer_2 = t2))
+    elem(c::FlowChain) = Tangent{typeof(c)}(layers = map(elem, c.layers))
+    return elem(chain)
+end
+
+function ChainRulesCore.rrule(::typeof(backward), chain::FlowChain, x::CuArray{Float32,N}, Î¸::CuArray{Float32,N}) where {N}
+    pc = packed(chain)
+    pack!(pc)                                        # Zygote differentiates the CURRENT Flux parameters
+    z, ldj = _normalize(pc, x, Î¸, Int32(0))
+    function backward_pullback(È³)
+        zÌ„, jÌ„ = È³
+        B = nsamples(x)
+        zÌ„d = zÌ„ isa ChainRulesCore.AbstractZero ? CUDA.zeros(Float32, size(x)) : CuArray{Float32}(ChainRulesCore.unthunk(zÌ„))
+        jÌ„p = jÌ„ isa ChainRulesCore.AbstractZero ? CU_NULL : pointer(CuArray{Float32}(ChainRulesCore.unthunk(jÌ„)))
+        grad = CUDA.zeros(Float32, max(pc.P, 1)); xÌ„ = similar(x); Î¸Ì„ = similar(Î¸)
+        ws = workspace!(pc, B)
+        check(ccall((:dflow_vjp, libdflow), Cint,
+                    (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, Int32, CuPtr{Float32}, CuPtr{Float32},
+                     CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                    pc.handle, pc.W, x, Î¸ptr(Î¸), B, Int32(0), zÌ„d, jÌ„p, grad, xÌ„, size(Î¸, 1) == 0 ? CU_NULL : pointer(Î¸Ì„),
+                    ws, length(ws), stream()))
+        return NoTangent(), tangent_of(chain, Array(grad)[1:pc.P]), xÌ„, Î¸Ì„
+    end
+    return (z, ldj), backward_pullback
+end
+
 # ---- train! on device-resident data (src/Flows.jl:380-445) -----------------------------------------------------
-"Device-resident DataArrays: x, Î¸ on the GPU and the partition as 0-based Int32 index vectors."
-struct CuDataArrays
-    x::CuMatrix{Float32}
-    Î¸::CuMatrix{Float32}
-    training::CuVector{Int32}
-    validation::CuVector{Int32}
+"Î·, Î², Ïµ of the Optimisers.Adam rule inside `Optimisers.setup(Optimisers.Adam(Î·), flow.model)`: first Leaf of the tree."
+function adam_hyper(state)
+    leaf = nothing
+    walk(t) = t isa NamedTuple || t isa Tuple ? foreach(walk, t) : (hasproperty(t, :rule) && leaf === nothing && (leaf = t))
+    walk(state)
+    leaf === nothing && throw(ArgumentError("no Optimisers.Leaf found in the optimiser state"))
+    r = leaf.rule
+    return Float32(r.eta), (Float32(r.beta[1]), Float32(r.beta[2])), Float32(r.epsilon)
 end
-CuDataArrays(data::DataArrays) = CuDataArrays(CuArray(data.x), CuArray(data.Î¸),
-                                              CuArray(Int32.(data.partition.training .- 1)),
-                                              CuArray(Int32.(data.partition.validation .- 1)))
 
-mutable struct AdamState
-    m::CuVector{Float32}; v::CuVector{Float32}; t::Int; Î·::Float32; Î²::NTuple{2,Float32}; Ïµ::Float32
+# packed Adam moments + step count, kept per optimiser-state object (the Leaf tree's own moments are left untouched)
+mutable struct PackedAdam
+    m::CuVector{Float32}; v::CuVector{Float32}; t::Int64
 end
-AdamState(pc::PackedChain; Î· = 1f-3, Î² = (0.9f0, 0.999f0), Ïµ = 1f-8) =
-    AdamState(CUDA.zeros(Float32, max(pc.P, 1)), CUDA.zeros(Float32, max(pc.P, 1)), 0, Î·, Î², Ïµ)
+const _adam = IdDict{Any,PackedAdam}()
+packed_adam(state, P) = get!(() -> PackedAdam(CUDA.zeros(Float32, P), CUDA.zeros(Float32, P), 0), _adam, state)
 
-function _full_loss(pc, data, idx, flags)
+function _full_loss(pc, x, Î¸, idx, flags)
     acc = CUDA.zeros(Float32, 2)
+    ensure_scratch!(pc, length(idx))
     check(ccall((:dflow_logpdf_sum, libdflow), Cint,
                 (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, CuPtr{Int32}, Int32, CuPtr{Float32}, Ptr{Cvoid}),
-                pc.handle, pc.W, data.x, Î¸ptr(data.Î¸), length(idx), idx, flags, acc, stream()))
+                pc.handle, pc.W, x, Î¸ptr(Î¸), length(idx), idx, flags, acc, stream()))
     s, bad = Array(acc)
     return bad > 0 ? NaN32 : -s / length(idx)       # loss = -mean(logpdf + ldj), src/Flows.jl:352-359
 end
 
-function train!(flow::Flow{Float32}, data::CuDataArrays, st::AdamState; epochs::Int = 100, batchsize::Int = 64,
-                shuffle::Bool = true, verbose::Bool = true)
-    pc = packed(flow); flags = flow.metadata.n > 0 ? THETA_NORMALIZE : Int32(0)
-    need = ccall((:dflow_workspace_bytes, libdflow), Csize_t, (Ptr{Cvoid}, Int64), pc.handle, batchsize)
-    length(pc.ws) < need && (pc.ws = CuVector{UInt8}(undef, need))
-    buf = CUDA.zeros(Float32, max(pc.P, 1) + 2); grad = view(buf, 1:max(pc.P, 1)); loss2 = view(buf, max(pc.P, 1)+1:max(pc.P, 1)+2)
-    ntr = length(data.training)
-    for _ in 1:epochs
-        order = shuffle ? data.training[CuArray(Int32.(Random.randperm(ntr)))] : data.training
-        for b0 in 1:batchsize:ntr                    # Flux.DataLoader: partial last batch kept
-            idx = view(order, b0:min(b0 + batchsize - 1, ntr)); nb = length(idx)
-            fill!(buf, 0f0)
-            check(ccall((:dflow_loss_grad, libdflow), Cint,
-                        (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, CuPtr{Int32}, Float32, Int32,
-                         CuPtr{Float32}, CuPtr{Float32}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
-                        pc.handle, pc.W, data.x, Î¸ptr(data.Î¸), nb, idx, 1f0 / nb, flags, loss2, grad, pc.ws, length(pc.ws), stream()))
-            st.t += 1
-            check(ccall((:dflow_adam_step, libdflow), Cint,
-                        (CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, Float32, Float32, Float32, Float32, Int64, Ptr{Cvoid}),
-                        pc.W, grad, st.m, st.v, pc.P, st.Î·, st.Î²[1], st.Î²[2], st.Ïµ, st.t, stream()))
-        end
-        push!(flow.train_loss, _full_loss(pc, data, data.training, flags))       # src/Flows.jl:419-421
-        push!(flow.valid_loss, _full_loss(pc, data, data.validation, flags))     # src/Flows.jl:428-430
+"Epoch order drawn on the device: out[j] = base[perm(j)] (dflow_shuffle_indices, stateless Feistel bijection)."
+function device_shuffle(seed::Integer, base::CuVector{Int32})
+    n = length(base); out = similar(base)
+    check(ccall((:dflow_shuffle_indices, libdflow), Cint, (UInt64, Int64, Int64, Int64, CuPtr{Int32}, CuPtr{Int32}, Ptr{Cvoid}),
+                UInt64(seed), n, 0, n, base, out, stream()))
+    return out
+end
+
+"""
+    train!(flow, data::DataArrays{Float32,2,<:CuArray,<:CuArray}, optimiser_state; epochs, batchsize, shuffle, verbose)
+
+Same signature and epoch structure as src/Flows.jl:380-445 for data that lives on the GPU: Î¸ is normalised in-kernel,
+minibatches are gathered through the (0-based) partition indices inside the adjoint kernel, the whole epoch is enqueued by
+ONE call (dflow_train_epoch: a persistent on-chip kernel for minibatches <= 512, else loss+gradient and Adam kernels per
+minibatch), and the epoch-end full-set losses are dflow_logpdf_sum reductions.
+"""
+function train!(flow::Flow{Float32}, data::DataArrays{Float32,2,<:CuArray,<:CuArray}, optimiser_state;
+                epochs::Int = 100, batchsize::Int = 64, shuffle::Bool = true, verbose::Bool = true, debug::Bool = false)
+    pc = packed(flow); pack!(pc); flags = flagsof(flow)
+    Î·, Î², Ïµ = adam_hyper(optimiser_state)
+    st = packed_adam(optimiser_state, max(pc.P, 1))
+    tr = CuArray(Int32.(collect(data.partition.training) .- 1))
+    va = CuArray(Int32.(collect(data.partition.validation) .- 1))
+    ws = workspace!(pc, min(batchsize, length(tr)))
+    scratch = CUDA.zeros(Float32, max(pc.P, 1) + 2)
+    seed0 = rand(UInt64) >> 2
+    for ep in 1:epochs
+        order = shuffle ? device_shuffle(seed0 + ep, tr) : tr
+        t = Ref{Int64}(st.t)
+        check(ccall((:dflow_train_epoch, libdflow), Cint,
+                    (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Int32},
+                     Int64, Int64, Float32, Float32, Float32, Float32, Ref{Int64}, Int32, CuPtr{Float32}, CuPtr{Float32},
+                     CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                    pc.handle, pc.W, st.m, st.v, data.x, Î¸ptr(data.Î¸), order, length(order), batchsize, Î·, Î²[1], Î²[2], Ïµ, t,
+                    flags, scratch, CU_NULL, ws, length(ws), stream()))
+        st.t = t[]
+        push!(flow.train_loss, _full_loss(pc, data.x, data.Î¸, tr, flags))       # src/Flows.jl:419-421
+        push!(flow.valid_loss, _full_loss(pc, data.x, data.Î¸, va, flags))       # src/Flows.jl:428-430
         verbose && println("epoch: $(length(flow.train_loss)) | train_loss = $(flow.train_loss[end]), valid_loss = $(flow.valid_loss[end])")
     end
-    unpack!(pc)                                       # Flux structs see the trained weights
-    return nothing
+    unpack!(pc)                                       # the Flux structs see the trained weights
+    return debug ? (nothing, nothing) : nothing
 end
 
-# ---- data-parallel step over NVLink peer memory (include/dflow.h: dflow_dp_*) -------------------------------------
-# One Julia process per GPU (e.g. MPI.jl).  `exchange(handle::Vector{UInt8})::Vector{UInt8}` must return the ranks'
-# 64-byte IPC handles concatenated in rank order (an MPI.Allgather of 64 bytes).  Every step accumulates the local
-# gradient straight into the communication buffer and ONE kernel per rank reduces the peers' buffers and applies Adam.
-mutable struct PeerStep
-    dp::Ptr{Cvoid}
-    P::Int
-end
+# ---- one Julia process, several GPUs: dflow_dp_create_local + dflow_dp_train_step -------------------------------------
+"""
+    train_local!(flow, shards::Vector{<:DataArrays}, optimiser_state; devices = 0:length(shards)-1, epochs, batchsize, ...)
 
-function PeerStep(pc, rank::Integer, nranks::Integer, exchange)
-    dp = Ref{Ptr{Cvoid}}(C_NULL); handle = zeros(UInt8, 64)
-    check(ccall((:dflow_dp_create, libdflow), Cint, (Int32, Int32, Int64, Ptr{Ptr{Cvoid}}, Ptr{UInt8}),
-                rank, nranks, max(pc.P, 1), dp, handle))
-    check(ccall((:dflow_dp_connect, libdflow), Cint, (Ptr{Cvoid}, Ptr{UInt8}), dp[], exchange(handle)))
-    return PeerStep(dp[], max(pc.P, 1))
-end
-
-function peer_train_step!(ps::PeerStep, pc, st::AdamState, x, Î¸, idx, B_global::Integer, flags::Int32, loss2)
-    buf = ccall((:dflow_dp_grad_buffer, libdflow), CuPtr{Float32}, (Ptr{Cvoid},), ps.dp)
-    CUDA.memset(buf, UInt32(0), ps.P + 2)              # [grad | Î£logp | #non-finite] of this step
-    nb = length(idx)
-    need = ccall((:dflow_workspace_bytes, libdflow), Csize_t, (Ptr{Cvoid}, Int64), pc.handle, nb)
-    length(pc.ws) < need && (pc.ws = CuVector{UInt8}(undef, need))
-    check(ccall((:dflow_loss_grad, libdflow), Cint,
-                (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, CuPtr{Int32}, Float32, Int32,
-                 CuPtr{Float32}, CuPtr{Float32}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
-                pc.handle, pc.W, x, Î¸ptr(Î¸), nb, idx, 1f0 / B_global, flags, buf + 4 * ps.P, buf, pc.ws, length(pc.ws), stream()))
-    st.t += 1
-    check(ccall((:dflow_dp_allreduce_adam, libdflow), Cint,
-                (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Float32, Float32, Float32, Float32, Int64,
-                 CuPtr{Float32}, Ptr{Cvoid}),
-                ps.dp, pc.W, st.m, st.v, st.Î·, st.Î²[1], st.Î²[2], st.Ïµ, st.t, loss2, stream()))
+Data-parallel train! driven by this one process: shards[r] is resident on devices[r] (its training partition is rank r's
+share of the training set).  Every minibatch is split like the shards; each device runs the adjoint on its share with the
+global seed 1 / B_global, and the replicas meet in ONE fused kernel per device that sums the gradients over NVLink peer
+memory and applies Adam (bit-identical replicas, no NCCL call, no host round trip per step).
+"""
+function train_local!(flow::Flow{Float32}, shards::Vector, optimiser_state; devices = collect(0:length(shards)-1),
+                      epochs::Int = 100, batchsize::Int = 64, shuffle::Bool = true, verbose::Bool = true)
+    R = length(shards); flags = flagsof(flow)
+    Î·, Î², Ïµ = adam_hyper(optimiser_state)
+    reps = PackedChain[]; ms = CuVector{Float32}[]; vs = CuVector{Float32}[]; l2 = CuVector{Float32}[]; trs = CuVector{Int32}[]
+    for r in 1:R
+        CUDA.device!(devices[r])
+        pc = PackedChain(flow.model; Î¸_min = flow.metadata.Î¸_min, Î¸_max = flow.metadata.Î¸_max)
+        push!(reps, pc); push!(ms, CUDA.zeros(Float32, max(pc.P, 1))); push!(vs, CUDA.zeros(Float32, max(pc.P, 1)))
+        push!(l2, CUDA.zeros(Float32, 2)); push!(trs, CuArray(Int32.(collect(shards[r].partition.training) .- 1)))
+    end
+    P = max(reps[1].P, 1)
+    dps = fill(C_NULL, R)
+    check(ccall((:dflow_dp_create_local, libdflow), Cint, (Int32, Ptr{Int32}, Int64, Ptr{Ptr{Cvoid}}), R, Int32.(devices), P, dps))
+    ntr = sum(length, trs); t = 0; seed0 = rand(UInt64) >> 2
+    share(nb, r) = (per = cld(nb, R); lo = min((r - 1) * per, nb); min(lo + per, nb) - lo)   # shard_range of flows.py
+    for ep in 1:epochs
+        orders = [(CUDA.device!(devices[r]); shuffle ? device_shuffle(seed0 + ep + 1000003r, trs[r]) : trs[r]) for r in 1:R]
+        cur = zeros(Int, R)
+        for b0 in 0:batchsize:ntr-1
+            nb = min(batchsize, ntr - b0)
+            ks = [min(share(nb, r), length(orders[r]) - cur[r]) for r in 1:R]
+            t += 1
+            sh = [begin
+                      CUDA.device!(devices[r]); ws = workspace!(reps[r], max(ks[r], 1))
+                      DpShard(reps[r].handle, pointer(reps[r].W), pointer(ms[r]), pointer(vs[r]), pointer(shards[r].x),
+                              Î¸ptr(shards[r].Î¸), ks[r], pointer(orders[r]) + 4 * cur[r], pointer(ws), length(ws), pointer(l2[r]), C_NULL)
+                  end for r in 1:R]
+            check(ccall((:dflow_dp_train_step, libdflow), Cint,
+                        (Ptr{Ptr{Cvoid}}, Int32, Ptr{DpShard}, Float32, Int32, Float32, Float32, Float32, Float32, Int64),
+                        dps, R, sh, 1f0 / sum(ks), flags, Î·, Î²[1], Î²[2], Ïµ, t))
+            cur .+= ks
+        end
+        rc = ccall((:dflow_dp_sync, libdflow), Cint, (Ptr{Ptr{Cvoid}}, Int32, Ptr{DpShard}), dps, R, C_NULL)
+        rc > 0 && error("data-parallel step: a device missed the peer barrier; its update was skipped")
+        check(min(rc, 0))
+        verbose && println("epoch: $ep done ($(t) steps)")
+    end
+    foreach(dp -> ccall((:dflow_dp_destroy, libdflow), Cint, (Ptr{Cvoid},), dp), dps)
+    CUDA.device!(devices[1]); unpack!(reps[1])
     return nothing
 end
 
 # tuning knobs (dflow_set_tuning): "tc_mode" 1 / 0 / -1 forces an eligible hidden <= 64 chain onto / off the tensor cores,
-# "tc_ws_budget_mb" caps the adjoint workspace, "tc_cluster" 0 / 1 / 2 selects independent CTAs / multicast pairs /
-# cta_group::2 pairs for streamed conditioners.
+# "tc_ws_budget_mb" caps the adjoint workspace, "epoch_kernel" -1 keeps train! on per-minibatch launches.
 tune!(pc, key::AbstractString, value::Integer) =
     check(ccall((:dflow_set_tuning, libdflow), Cint, (Ptr{Cvoid}, Cstring, Int32), pc.handle, key, value))
 

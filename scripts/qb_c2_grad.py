@@ -1,26 +1,28 @@
-"""C2 adjoint timing for tuning knobs (CUDA events)."""
-import sys, os, json
+"""C2 train-step timing: v3 register-resident adjoint (constant-bank weights) against the v2 shared-memory-column adjoint."""
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import densityflows.jl_b200 as df
-from oracle import dflow_oracle as O
-from tests.helpers import chain_from_oracle
-from scripts.quick_bench import timeit
-d, n, B = 5, 2, 1 << 23
-xs, ths = O.synthetic_data(d, n, 4096, seed=1)
-chain = chain_from_oracle(O.readme_chain(2, xs))
-pc = chain.packed("cuda:0")
-g = torch.Generator(device="cuda").manual_seed(0)
-x = df.jl_empty((d, B), "cuda:0"); x.normal_(generator=g)
-th = df.jl_empty((n, B), "cuda:0"); th.uniform_(0, 1, generator=g)
+from bench import packed, device_inputs
+dev = torch.device("cuda:0")
+B = 1 << 24
+x, th = device_inputs(5, 2, B, dev, 1)
+tmin, tmax = df.minmax_rows(th)
+chain, pc = packed("c2", dev, tmin, tmax)
 grads = {}
-for tune in [dict(grad_smem=0), dict(grad_smem=-1)]:
+for tune in [dict(grad_v3=0), dict(grad_v3=-1)]:
     pc.tune(**tune)
-    grad = torch.zeros(pc.P, device="cuda:0"); l2 = torch.zeros(2, device="cuda:0")
-    pc.loss_grad(x, th, grad, l2)
-    grads[str(tune)] = grad.clone()
-    g2 = torch.zeros(pc.P, device="cuda:0")
-    med, mn = timeit(lambda: pc.loss_grad(x, th, g2, l2), iters=3, warm=1)
+    grad = torch.zeros(pc.P, device=dev); l2 = torch.zeros(2, device=dev)
+    pc.loss_grad(x, th, grad, l2, None, 1)
+    grads[str(tune)] = (grad.clone(), l2.clone())
+    ts = []
+    for _ in range(5):
+        grad.zero_(); l2.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); pc.loss_grad(x, th, grad, l2, None, 1); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    med = float(np.median(ts))
     print(json.dumps({"tune": tune, "ms": med, "sps": B / med * 1e3}), flush=True)
-ks = list(grads)
-print("rel diff", float((grads[ks[0]] - grads[ks[1]]).abs().max() / grads[ks[0]].abs().max()))
+a, b = grads["{'grad_v3': 0}"], grads["{'grad_v3': -1}"]
+print("max |dg| / max|g| =", float((a[0] - b[0]).abs().max() / b[0].abs().max()), "loss", float(a[1][0]), float(b[1][0]))

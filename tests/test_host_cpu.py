@@ -179,3 +179,55 @@ def test_custom_elements_are_rejected_not_emulated():
 
     with pytest.raises(NotImplementedError):
         ChainDescriptor([NewLayer()])
+
+
+def _split_top_level(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_glue_matches_the_c_abi():
+    """julia/DensityFlowsB200.jl cannot be executed here (no Julia), so at least keep it ABI-consistent: every ccall names
+    an exported symbol, passes as many arguments as the ctypes binding (which the GPU tests exercise) declares, and uses
+    pointer / scalar classes in the same positions.  Also the oracle's permutation is a bijection (device shuffle spec)."""
+    src = open(os.path.join(ROOT, "julia", "DensityFlowsB200.jl")).read()
+    assert "using Random" in src
+    bound = {name: args for name, _, args in L.SYMBOLS}
+    calls = list(re.finditer(r"ccall\(\(:(dflow_[a-z_0-9]+), libdflow\),\s*([A-Za-z{}]+),\s*\(", src))
+    assert len(calls) >= 18
+    seen = set()
+    for m in calls:
+        name = m.group(1)
+        assert name in bound, f"{name} is not exported by libdflow.so"
+        seen.add(name)
+        i, depth = m.end(), 1
+        while depth:  # the argument-type tuple
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        types = _split_top_level(src[m.end():i - 1])
+        assert len(types) == len(bound[name]), (name, types, len(bound[name]))
+        for jt, ct in zip(types, bound[name]):
+            is_ptr_j = any(k in jt for k in ("Ptr", "Ref", "Cstring"))
+            is_ptr_c = ct in (L.vp, L.C.c_char_p) or hasattr(ct, "_type_") and not isinstance(ct._type_, str)
+            assert is_ptr_j == is_ptr_c, (name, jt, ct)
+    for must in ("dflow_vjp", "dflow_train_epoch", "dflow_dp_create_local", "dflow_dp_train_step", "dflow_logpdf_grid",
+                 "dflow_shuffle_indices", "dflow_chain_set_scratch", "dflow_sample_rng"):
+        assert must in seen, must
+    assert "ChainRulesCore.rrule(::typeof(backward)" in src
+    from oracle import shuffle as SH
+
+    for n in (1, 2, 3, 17, 4096, 12345):
+        assert sorted(SH.permutation(99, n).tolist()) == list(range(n))
+        np.testing.assert_array_equal(SH.permutation(99, n, 3 % n, max(0, n - 5)), SH.permutation(99, n)[3 % n: 3 % n + max(0, n - 5)])
