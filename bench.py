@@ -353,7 +353,8 @@ def run_ours(args):
         v1 = torch.zeros(pc.P, device=dev)
         tt = [0]
         nsteps = (n_tr + bs - 1) // bs
-        for tag, mode in (("train_epoch_c1", 0), ("train_epoch_c1_per_minibatch_launches", -1)):
+        modes = (("train_epoch_c1", 0),) if args.profile else (("train_epoch_c1", 0), ("train_epoch_c1_per_minibatch_launches", -1))
+        for tag, mode in modes:
             pc.tune(epoch_kernel=mode)
             pc.W.copy_(w_save)
             m1.zero_()
@@ -814,6 +815,8 @@ def main():
     ap.add_argument("--no-c3", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-wide", action="store_true", help="skip the tensor-core configs C4 / C5")
+    ap.add_argument("--profile", action="store_true",
+                    help="for ncu launch lists: skip the 5 600-launch comparison leg (C1 epoch on per-minibatch launches)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

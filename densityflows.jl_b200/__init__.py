@@ -20,6 +20,8 @@ from .model import (Chain, CouplingAxes, CouplingBlock, CouplingLayer, CouplingL
                     RNVPCouplingLayer, backward, concatenate, forward, forward_, identity, is_reverse, minmax_rows,
                     relu, reverse, seed, sigmoid, tanh)
 
+from .persist import load_flow, packed_parameters, save_flow
+
 train_bang = train_
 forward_bang = forward_
 __version__ = "0.1.0"

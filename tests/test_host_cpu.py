@@ -231,3 +231,38 @@ def test_julia_glue_matches_the_c_abi():
     for n in (1, 2, 3, 17, 4096, 12345):
         assert sorted(SH.permutation(99, n).tolist()) == list(range(n))
         np.testing.assert_array_equal(SH.permutation(99, n, 3 % n, max(0, n - 5)), SH.permutation(99, n)[3 % n: 3 % n + max(0, n - 5)])
+
+
+def test_save_and_load_flow_round_trip(tmp_path):
+    """Persistence of the mirror (counterpart of src/Loading.jl save_flow / load_flow): structure, axes (incl. un-sorted
+    masks and a block), activations, bias flags, the packed parameter vector, metadata and loss histories survive."""
+    df.seed(3)
+    x = np.random.default_rng(0).standard_normal((7, 50)).astype(np.float32)
+    th = np.random.default_rng(1).random((2, 50)).astype(np.float32)
+    data = df.DataArrays(x, th, device="cpu")
+    chain = df.FlowChain(df.CouplingLayer(data, [4, 2, 5, 1, 6], hidden_dim_s=8, hidden_dim_t=12, n_sublayers_t=3, σ_s="tanh"),
+                         df.CouplingBlock(data, [1, 3, 5, 7], hidden_dim_s=16, hidden_dim_t=16, bias=False),
+                         df.CouplingLayer(df.NICECouplingLayer, data, [2, 3], hidden_dim_t=8),
+                         df.NormalizationLayer(data.x, -1.0, 1.0))
+    flow = df.Flow(chain, data, train_loss=[3.0, 2.5], valid_loss=[3.1, 2.6])
+    p = str(tmp_path / "flow.npz")
+    df.save_flow(p, flow)
+    back = df.load_flow(p, device="cpu")
+    np.testing.assert_array_equal(df.packed_parameters(back.model), df.packed_parameters(flow.model))
+    assert df.packed_parameters(flow.model).size == O.pack_params(O.Chain([])).size + sum(
+        l.weight.numel() + (l.bias.numel() if l.bias is not None else 0)
+        for e in chain._leaves() for net in df.model._nets_of(e) for l in net.layers)
+    la, lb = flow.model._leaves(), back.model._leaves()
+    assert [type(e).__name__ for e in la] == [type(e).__name__ for e in lb]
+    for ea, eb in zip(la, lb):
+        if hasattr(ea, "axes"):
+            assert (ea.axes.axis_id, ea.axes.axis_af, ea.axes.axis_nn) == (eb.axes.axis_id, eb.axes.axis_af, eb.axes.axis_nn)
+            for na, nb in zip(df.model._nets_of(ea), df.model._nets_of(eb)):
+                assert na.widths() == nb.widths() and [l.act for l in na.layers] == [l.act for l in nb.layers]
+                assert [l.bias is None for l in na.layers] == [l.bias is None for l in nb.layers]
+        else:
+            np.testing.assert_array_equal(ea.x_min, eb.x_min)
+            assert (ea.α, ea.β) == (eb.α, eb.β)
+    assert back.train_loss == [3.0, 2.5] and back.valid_loss == [3.1, 2.6]
+    np.testing.assert_array_equal(back.metadata.θ_min, flow.metadata.θ_min)
+    assert (back.d, back.n) == (7, 2)
