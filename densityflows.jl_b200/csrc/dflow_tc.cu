@@ -982,6 +982,8 @@ constexpr uint32_t DWT_W2 = 0, DWT_W1 = 256, DWT_W3 = 320;
 
 struct DwArgs {
   int H, K0p, K0, a, a16, mtiles, units, ksplit, nstage;
+  int nsplit, NB;  // hidden 512: the H columns of dW2 are split over nsplit = 2 CTAs of NB = 256 columns each (TMEM holds 512);
+                   // the second one carries only dW2 (no dW1 / dW3 / bias sums)
   long long ntiles;
   const float* h1buf[2];
   const float* h2buf[2];
@@ -1009,10 +1011,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = a.H, K0p = a.K0p, a16 = a.a16;
   const int unit = blockIdx.x % a.units, ks = blockIdx.x / a.units;
-  const int net = a.first_net + unit / a.mtiles, mt = unit % a.mtiles;
+  const int nh = unit % a.nsplit, NB = a.NB;  // column half of dW2 handled here
+  const int net = a.first_net + unit / (a.mtiles * a.nsplit), mt = (unit / a.nsplit) % a.mtiles;
   const int rows_valid = min(128, H - mt * 128);
   const int RA = (rows_valid + 7) & ~7;
-  const int seg_rows[6] = {RA, RA, RA, H, K0p, a16};
+  // segments: delta2, delta1, h2 (A operands, this m-tile's rows) | h1 (this column half), in, delta3 (B operands)
+  const int seg_rows[6] = {RA, nh ? 0 : RA, nh ? 0 : RA, NB, nh ? 0 : K0p, nh ? 0 : a16};
   int seg_dst[6], seg_rb0[7];
   {
     int o = 0, rb = 0;
@@ -1024,7 +1028,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
     }
     seg_rb0[6] = rb;
   }
-  const int stage_fl = 2 * (3 * RA + H + K0p + a16) * DW_KS;
+  const int stage_fl = 2 * (seg_rows[0] + seg_rows[1] + seg_rows[2] + seg_rows[3] + seg_rows[4] + seg_rows[5]) * DW_KS;
   const int RB = seg_rb0[6];
   const int NST = a.nstage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NST * stage_fl);
@@ -1076,7 +1080,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       const int sgi = seg_of(rb, rb0);
       const int dst0 = sgi == 0 ? seg_dst[0] : sgi == 1 ? seg_dst[1] : sgi == 2 ? seg_dst[2] : sgi == 3 ? seg_dst[3]
                        : sgi == 4 ? seg_dst[4] : seg_dst[5];
-      const int srows = sgi < 3 ? RA : sgi == 3 ? H : sgi == 4 ? K0p : a16;          // rows of the segment in the stage
+      const int srows = sgi < 3 ? RA : sgi == 3 ? NB : sgi == 4 ? K0p : a16;         // rows of the segment in the stage
       const int valid = sgi < 3 ? rows_valid : srows;                                  // rows that exist in the source
       const float* base = sgi == 0 ? a.d2buf[net] : sgi == 1 ? a.d1buf[net] : sgi == 2 ? a.h2buf[net]
                           : sgi == 3 ? a.h1buf[net] : sgi == 4 ? a.inbuf : a.d3buf[net];
@@ -1085,14 +1089,14 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       if (rb < RB) segmask |= 1u << i;
       if (rb < RB && row < valid) okmask |= 1u << i;
       // bias gradients: sums over the samples of delta2 / delta1 (this m-tile's rows) and delta3 (m-tile 0 only)
-      if (rb < RB && (sgi < 2 || (sgi == 5 && mt == 0))) biasmask |= 1u << i;
+      if (rb < RB && nh == 0 && (sgi < 2 || (sgi == 5 && mt == 0))) biasmask |= 1u << i;
       codes |= (uint32_t)(sgi < 3 ? 0 : sgi - 2) << (2 * i);
       my_dst[i] = dst0 + (r0 >> 3) * 128 + lofs;
-      my_ptr[i] = base + (size_t)((sgi < 3 ? mt * 128 : 0) + row) * 16 + (lane >> 3) * 4;
+      my_ptr[i] = base + (size_t)((sgi < 3 ? mt * 128 : sgi == 3 ? nh * NB : 0) + row) * 16 + (lane >> 3) * 4;
     }
     // floats per [rows x 16 samples] block of the source buffer / offset of the lo half inside the stage, by code
     const int ts_by[4] = {H * 16, H * 16, K0p * 16, a16 * 16};
-    const int lo_by[4] = {RA * DW_KS, H * DW_KS, K0p * DW_KS, a16 * DW_KS};
+    const int lo_by[4] = {RA * DW_KS, NB * DW_KS, K0p * DW_KS, a16 * DW_KS};
     auto pick = [](const int (&t)[4], uint32_t c) { return c == 0 ? t[0] : c == 1 ? t[1] : c == 2 ? t[2] : t[3]; };
     // Stages are produced in PAIRS (register buffers vA / vB): both are loaded, split and stored, then ONE
     // fence.proxy.async + two barrier arrivals, then the loads of the next pair are issued.  The fence compiles to
@@ -1190,20 +1194,21 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       const int i_lo = a.fused ? fn * a.hblk : 0;           // columns of dW2 that belong to it (diagonal block)
       const int j_lo = a.fused ? fn * a.ablk : 0, j_n = a.fused ? a.ablk : a16;
       float w[16];
-      for (int i0 = 0; i0 < Hn; i0 += 16) {  // dW2[o][i] at p_w2 + o + Hn * i
+      const int ncol = a.nsplit > 1 ? NB : Hn;  // columns of dW2 accumulated by this CTA, global column = nh * NB + i0 + j
+      for (int i0 = 0; i0 < ncol; i0 += 16) {  // dW2[o][i] at p_w2 + o + Hn * i
         tmem_ld16(tbase + lane_off + DWT_W2 + i_lo + i0, w);
         if (ok && fn < 2)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(a.grad + a.p_w[fn][1] + o + (size_t)Hn * (i0 + j), w[j]);
+          for (int j = 0; j < 16; ++j) atomicAdd(a.grad + a.p_w[fn][1] + o + (size_t)Hn * (nh * NB + i0 + j), w[j]);
       }
-      for (int k0 = 0; k0 < K0p; k0 += 16) {  // dW1[o][k] at p_w1 + o + Hn * k
+      for (int k0 = 0; k0 < (nh ? 0 : K0p); k0 += 16) {  // dW1[o][k] at p_w1 + o + Hn * k
         tmem_ld16(tbase + lane_off + DWT_W1 + k0, w);
         if (ok && fn < 2)
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (k0 + j < a.K0) atomicAdd(a.grad + a.p_w[fn][0] + o + (size_t)Hn * (k0 + j), w[j]);
       }
-      for (int j0 = 0; j0 < j_n; j0 += 16) {  // dW3[j][i=o] at p_w3 + j + a * o
+      for (int j0 = 0; j0 < (nh ? 0 : j_n); j0 += 16) {  // dW3[j][i=o] at p_w3 + j + a * o
         tmem_ld16(tbase + lane_off + DWT_W3 + j_lo + j0, w);
         if (ok && fn < 2)
 #pragma unroll
@@ -1215,7 +1220,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
     // ---- MMA issuer: the warp runs the loop uniformly, one elected lane issues ----
     const int K0n = (K0p + 15) & ~15;  // N of the dW1 GEMM (M = 128 needs N % 16 == 0); extra rows read finite data
     const uint32_t hi = desc_hi(DW_KS);
-    const uint32_t idW2 = instr_desc_tf32(H), idW1 = instr_desc_tf32(K0n), idW3 = instr_desc_tf32(a16);
+    const uint32_t idW2 = instr_desc_tf32(NB), idW1 = instr_desc_tf32(K0n), idW3 = instr_desc_tf32(a16);
     const uint64_t d0 = desc_at(hi, smem_u32(smem));
     const uint32_t stage_step = ((uint32_t)stage_fl * 4u) >> 4;
     uint32_t so[6], sl[6];
@@ -1235,8 +1240,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
         // dW2 += delta2 * h1^T ; dW1 += delta1 * in^T ; dW3^T += h2 * delta3^T   (each: lo*hi + hi*lo + hi*hi, 2 K steps)
         if (!(TC_DBG(a) & 1)) {
           gemm3_desc(tbase + DWT_W2, b + so[0], b + so[0] + sl[0], b + so[3], b + so[3] + sl[3], DW_KS / 8, idW2, acc);
-          gemm3_desc(tbase + DWT_W1, b + so[1], b + so[1] + sl[1], b + so[4], b + so[4] + sl[4], DW_KS / 8, idW1, acc);
-          gemm3_desc(tbase + DWT_W3, b + so[2], b + so[2] + sl[2], b + so[5], b + so[5] + sl[5], DW_KS / 8, idW3, acc);
+          if (nh == 0) {
+            gemm3_desc(tbase + DWT_W1, b + so[1], b + so[1] + sl[1], b + so[4], b + so[4] + sl[4], DW_KS / 8, idW1, acc);
+            gemm3_desc(tbase + DWT_W3, b + so[2], b + so[2] + sl[2], b + so[5], b + so[5] + sl[5], DW_KS / 8, idW3, acc);
+          }
         }
         mma_commit_a(empty_u32 + slot * 8);
         if (s == nstages - 1) mma_commit(done);
@@ -1553,7 +1560,6 @@ int tc_build_plan(dflow_chain* c) {
     memcpy(Ld.af, E.af, sizeof(Ld.af));
     memcpy(Ld.id, E.id, sizeof(Ld.id));
     const int h = Ld.h, a = Ld.a;
-    if (h > 256) tp->train_ok = false;
     tp->hmax = std::max(tp->hmax, h);
     tp->a16max = std::max(tp->a16max, Ld.a16);
     for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
@@ -1580,7 +1586,7 @@ int tc_build_plan(dflow_chain* c) {
         tp->jobs_fwd.push_back(J);
       }
 #endif
-      if (h <= 256) {
+      {
         // adjoint orientation: M1[u][o] = W3[o][u], M2[i][o] = W2[o][i], M3[k][u] = W1[u][k]
         fill_img(Ld.bwd[ni], a, h, Ld.nin, off, 16);  // K0p = a16: delta3 rows double as the dW3 operand
         memset(&J, 0, sizeof(J));
@@ -1631,7 +1637,7 @@ int tc_build_plan(dflow_chain* c) {
     }
     TcLaunchCfg cfg;
     for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
-      if (!tc_launch_cfg(c, Ld.fwd[ni], cfg) || (h <= 256 && !tc_launch_cfg(c, Ld.bwd[ni], cfg))) {
+      if (!tc_launch_cfg(c, Ld.fwd[ni], cfg) || !tc_launch_cfg(c, Ld.bwd[ni], cfg)) {
         set_error("element %d: conditioner does not fit the tensor-core pipeline's shared memory", ei);
         return DFLOW_E_UNSUPPORTED;
       }
@@ -1943,10 +1949,6 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
                  cudaStream_t st, const TcVjp* vjp) {
   TcPlan* tp = c->tcp;
   const DevChainHdr& Hd = c->hc()->h;
-  if (!tp->train_ok) {
-    set_error("the adjoint of conditioners wider than 256 is not built (sampling / log-density only)");
-    return DFLOW_E_UNSUPPORTED;
-  }
   (void)ws_bytes;
   TcTrainLayout T;
   train_layout(c, B, T);
@@ -2092,8 +2094,10 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       w.hblk = Ld.h;
       w.ablk = Ld.a16;
       w.mtiles = (w.H + 127) / 128;
+      w.nsplit = w.H > 256 ? 2 : 1;
+      w.NB = w.H / w.nsplit;
       w.first_net = (fzw || Ld.has_s) ? 0 : 1;
-      w.units = (fzw ? 1 : Ld.has_s ? 2 : 1) * w.mtiles;
+      w.units = (fzw ? 1 : Ld.has_s ? 2 : 1) * w.mtiles * w.nsplit;
       w.ksplit = (int)std::max<long long>(1, std::min<long long>(ntiles, c->sm_count / w.units));
       w.ntiles = ntiles;
       for (int ni = 0; ni < 2; ++ni) {
@@ -2112,12 +2116,12 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       w.grad = grad_out;
       w.debug = (c->tc_debug >> 12) & 7;  // bits 12-14 of tc_debug: weight-gradient kernel timing experiments (experiment builds)
       const int RA = std::min(128, w.H);  // rows of the A segments (a multiple of 8: H % 32 == 0)
-      const size_t stage_bytes = 2 * (size_t)(3 * RA + w.H + w.K0p + w.a16) * DW_KS * 4;
+      const size_t stage_bytes = 2 * (size_t)(3 * RA + w.NB + w.K0p + w.a16) * DW_KS * 4;  // the fullest CTA (column half 0)
       // the M = 128 MMAs read 128 rows of every A segment: keep that overrun inside the allocation
       const size_t overrun = (size_t)(128 - RA) * DW_KS * 4 * 2;
       int nst = (int)(((size_t)c->max_smem_optin - 128 - overrun) / stage_bytes);
       if (nst > 4) nst = 4;
-      if (nst < 2 || (3 * RA + w.H + w.K0p + w.a16) / 8 > DW_MAXRB * DW_STAGE_WARPS) {
+      if (nst < 2 || (3 * RA + w.NB + w.K0p + w.a16) / 8 > DW_MAXRB * DW_STAGE_WARPS) {
         set_error("weight-gradient stage does not fit (%zu bytes per stage)", stage_bytes);
         return DFLOW_E_UNSUPPORTED;
       }

@@ -95,7 +95,7 @@ def _grad_slack(ochain, x, th, go):
     return s
 
 
-def _check_grad(name, ochain, pc, x, th, B):
+def _check_grad(name, ochain, pc, x, th, B, per_dense=2e-4):
     grad = torch.zeros(pc.P, device=DEV)
     loss2 = torch.zeros(2, device=DEV)
     pc.loss_grad(x, th if th.shape[0] else None, grad, loss2)
@@ -114,7 +114,7 @@ def _check_grad(name, ochain, pc, x, th, B):
                 k = dl.W.size + (dl.b.size if dl.b is not None else 0)
                 ref = go[off:off + k]
                 err = np.abs(g[off:off + k] - ref).max()
-                assert err <= 2e-4 * np.abs(ref).max() + 1e-7 * gmax + slack[off:off + k].max(), \
+                assert err <= per_dense * np.abs(ref).max() + 1e-7 * gmax + slack[off:off + k].max(), \
                     (name, off, err, np.abs(ref).max(), slack[off:off + k].max())
                 off += k
 
@@ -196,13 +196,19 @@ def test_wide_grad_idx_and_dp_seed():
     assert abs(l_acc[0].item() - l_full[0].item()) <= 1e-4 * abs(l_full[0].item())
 
 
-def test_wide_adjoint_h512_is_rejected_not_emulated():
-    ochain, chain, x, th = _setup("c5_like_h512", 64)
-    pc = chain.packed()
-    g = torch.zeros(pc.P, device=DEV)
-    l2 = torch.zeros(2, device=DEV)
-    with pytest.raises(df.DflowUnsupported):
-        pc.loss_grad(x, th, g, l2)
+@pytest.mark.parametrize("B", [5, 300, 2049])
+def test_wide_adjoint_h512(B):
+    """Hidden 512 (C5's conditioner) trains since round 2: the input-gradient chain runs its two 256-column passes on the
+    transposed matrices, and the weight-gradient kernel splits the 512 columns of dW2 over two CTAs per 128-row tile (TMEM
+    holds 512 columns; the second CTA carries only dW2)."""
+    d, n, L, h = CASES["c5_like_h512"]
+    xn = O.synthetic_data(d, n, 1000, seed=99)[0]
+    ochain = O.block_chain(d, n, L, h, xn, s_out_scale=0.3)
+    x, th = O.synthetic_data(d, n, B, seed=21)
+    chain = chain_from_oracle(ochain)
+    # whole gradient: 1e-4 of its max-norm like every other case; per Dense the 512 x 512 blocks sit at 2.6e-4 of their own
+    # max-norm at B = 2049 (3xTF32 products accumulated over 512-wide contractions and 2049 samples), hence 4e-4 here
+    _check_grad("c5_like_h512", ochain, chain.packed(), x, th, B, per_dense=4e-4)
 
 
 NARROW_ON_TC = {"h64_d16": (16, 4, 2, 64), "h32_d10": (10, 3, 4, 32)}
