@@ -235,14 +235,15 @@ int dflow_chain_create(const dflow_chain_desc* desc, dflow_chain** out) {
     for (int ni = (E.kind == DFLOW_ELEM_RNVP ? 0 : 1); ni < 2; ++ni) {
       const DevNet& net = ni == 0 ? E.s : E.t;
       const int h = net.w[1];
-      const bool ok = net.depth == 3 && net.has_bias && net.w[2] == h && net.act[0] == DFLOW_ACT_RELU &&
-                      net.act[1] == DFLOW_ACT_RELU && net.act[2] == DFLOW_ACT_IDENTITY && h % 32 == 0 && h >= 32 &&
+      // three Dense layers of equal hidden width, any of relu / tanh / sigmoid / identity on the hidden layers, identity on the
+      // output (src/Layers.jl:33-50 with n_sublayers = 2), with or without bias
+      const bool ok = net.depth == 3 && net.w[2] == h && net.act[2] == DFLOW_ACT_IDENTITY && h % 32 == 0 && h >= 32 &&
                       (h <= 256 || h == 512) && E.nin <= 64 && E.a <= 32 && h == E.t.w[1];
       if (!ok) {
         tc_eligible = false;
         if (wide) {
-          set_error("element %d: wide conditioners (hidden > 64) must be Dense(in,h,relu)->Dense(h,h,relu)->Dense(h,a) with "
-                    "bias, h a multiple of 32 up to 256 or 512, <= 64 inputs and <= 32 outputs", ei);
+          set_error("element %d: wide conditioners (hidden > 64) must be Dense(in,h,σ)->Dense(h,h,σ)->Dense(h,a) (n_sublayers = 2, "
+                    "identity output), h a multiple of 32 up to 256 or 512, <= 64 inputs and <= 32 outputs", ei);
           return DFLOW_E_UNSUPPORTED;
         }
       }

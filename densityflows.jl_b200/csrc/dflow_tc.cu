@@ -120,6 +120,7 @@ struct TcArgs {
   float* d3buf;
   float* zbar;        // (d, B) cotangent of the layer output, updated in place to the cotangent of its input
   const float* zout;  // (d, B) layer output (normalising direction)
+  int act1, act2;     // activations of the two hidden Dense layers (DFLOW_ACT_*; relu is the fast path)
   float inv_btot;
   const float* jbar;  // per-sample cotangent of ln_det_jac (dflow_vjp), or null: -inv_btot for every sample
   float* thbar;       // [tiles][n][128] cotangent of the conditions (dflow_vjp), or null: theta rows are dropped
@@ -381,11 +382,23 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             const int c = g * cpg + cg;  // 32-unit chunk index inside the hidden layer
             if constexpr (MODE == TC_BWD) {
               const uint32_t mword = mnext;
+              if (a.act2 == DFLOW_ACT_RELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
+                for (int j = 0; j < 32; ++j) v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
+              } else {
+                // non-relu hidden layer: derivative from the stored activation (output form: tanh 1 - y^2, sigmoid y (1 - y))
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j)
+                  v[j] = live ? v[j] * act_grad(a.act2, a.h2buf[tbuf_idx(tile, H, c * WKA + j, row)]) : 0.0f;
+              }
             } else {
+              if (a.act1 == DFLOW_ACT_RELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[c * WKA + j], 0.0f);
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[c * WKA + j], 0.0f);
+              } else {
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j) v[j] = act_apply(a.act1, v[j] + biasS[c * WKA + j]);
+              }
             }
             handoff(v);
             // The training stores come AFTER the hand-off: its fence.proxy.async is a MEMBAR.ALL.CTA that waits for every
@@ -436,11 +449,22 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
           }
           if constexpr (MODE == TC_BWD) {
             const uint32_t mword = mnext;
+            if (a.act1 == DFLOW_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
+              for (int j = 0; j < 32; ++j) v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
+            } else {
+#pragma unroll 4
+              for (int j = 0; j < 32; ++j)
+                v[j] = live ? v[j] * act_grad(a.act1, a.h1buf[tbuf_idx(tile, H, gc * WKA + j, row)]) : 0.0f;
+            }
           } else {
+            if (a.act2 == DFLOW_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[H + gc * WKA + j], 0.0f);
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[H + gc * WKA + j], 0.0f);
+            } else {
+#pragma unroll 4
+              for (int j = 0; j < 32; ++j) v[j] = act_apply(a.act2, v[j] + biasS[H + gc * WKA + j]);
+            }
           }
           handoff(v);
           if constexpr (MODE == TC_BWD) {  // (mask prefetch and stores after the hand-off's fence, see epilogue 1)
@@ -1174,11 +1198,11 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       if (seg_ok && sgi < 2 && lane < 8 && ok && nstages > 0) {
         const int hr = mt * 128 + row;
         const int bn = a.fused ? hr / a.hblk : net, hr2 = a.fused ? hr % a.hblk : hr;
-        atomicAdd(a.grad + a.p_b[bn][sgi == 0 ? 1 : 0] + hr2, r);
+        if (a.p_b[bn][sgi == 0 ? 1 : 0] >= 0) atomicAdd(a.grad + a.p_b[bn][sgi == 0 ? 1 : 0] + hr2, r);
       }
       if (seg_ok && sgi == 5 && mt == 0 && lane < 8 && nstages > 0) {
         const int bn = a.fused ? row / a.ablk : net, r2 = a.fused ? row % a.ablk : row;
-        if (row < a16 && r2 < a.a) atomicAdd(a.grad + a.p_b[bn][2] + r2, r);
+        if (row < a16 && r2 < a.a && a.p_b[bn][2] >= 0) atomicAdd(a.grad + a.p_b[bn][2] + r2, r);
       }
     }
     // ---- flush: warps 0-3 own TMEM lanes 32w..32w+31 = hidden unit rows of this m-tile ----
@@ -1568,6 +1592,8 @@ int tc_build_plan(dflow_chain* c) {
         Ld.p_w[ni][j] = net.p_w[j];
         Ld.p_b[ni][j] = net.p_b[j];
       }
+      Ld.act[ni][0] = net.act[0];
+      Ld.act[ni][1] = net.act[1];
       // forward orientation: M1 = W1 (h x nin), M2 = W2, M3 = W3 (a x h); Flux (out,in) column-major W[o + out*i]
       fill_img(Ld.fwd[ni], Ld.nin, h, a, off);
       TcPackJob J;
@@ -1607,7 +1633,8 @@ int tc_build_plan(dflow_chain* c) {
     }
     tp->hu = std::max(tp->hu, h);
     // fused s + t pair: same input, same widths, 2h within one 256-column pass
-    if (Ld.has_s && E.s.w[1] == h && E.s.w[2] == h && 2 * h <= 256) {
+    if (Ld.has_s && E.s.w[1] == h && E.s.w[2] == h && 2 * h <= 256 && E.s.act[0] == E.t.act[0] && E.s.act[1] == E.t.act[1] &&
+        E.s.has_bias == E.t.has_bias) {
       const int a16 = Ld.a16;
       TcPackJob J;
       // forward: M1 = [W1_s ; W1_t] (2h x nin), M2 = diag(W2_s, W2_t), M3 = diag(W3_s, W3_t) with the t rows at a16
@@ -1820,6 +1847,8 @@ int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* thet
       fill_common(c, Ld, a);
       a.im = fz ? Ld.ffwd : Ld.fwd[ni];
       a.net_id = ni;
+      a.act1 = Ld.act[ni == 0 ? 0 : 1][0];
+      a.act2 = Ld.act[ni == 0 ? 0 : 1][1];
       a.B = B;
       a.sampling = sampling;
       a.flags = flags;
@@ -2003,6 +2032,8 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         fill_common(c, Ld, a);
         a.im = fz ? Ld.ffwd : Ld.fwd[ni];
         a.net_id = ni;
+        a.act1 = Ld.act[ni == 0 ? 0 : 1][0];
+        a.act2 = Ld.act[ni == 0 ? 0 : 1][1];
         a.B = mb;
         a.sampling = 0;
         a.flags = flags;
@@ -2063,9 +2094,13 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         fill_common(c, Ld, a);
         a.im = fz ? Ld.fbwd : Ld.bwd[ni];
         a.net_id = ni;
+        a.act1 = Ld.act[ni == 0 ? 0 : 1][0];
+        a.act2 = Ld.act[ni == 0 ? 0 : 1][1];
         a.B = mb;
         a.flags = flags;
         a.sbuf = sbuf_of(ei);
+        a.h1buf = hbuf_of(ei, ni, 0);  // non-relu hidden layers take their derivative from the stored activations
+        a.h2buf = hbuf_of(ei, ni, 1);
         a.m1buf = mbuf_of(ei, ni, 0);
         a.m2buf = mbuf_of(ei, ni, 1);
         a.d1buf = dbuf_of(ni, 0);

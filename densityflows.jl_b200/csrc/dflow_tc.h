@@ -60,6 +60,7 @@ struct TcLayer {
   int norm_off;
   unsigned char af[DMAX], id[DMAX];
   int p_w[2][3], p_b[2][3];
+  int act[2][2];  // [net][hidden layer]: DFLOW_ACT_* of the two hidden Dense layers
   TcNetImg fwd[2], bwd[2];
   TcNetImg fwd2[2][2], bwd2[2][2];  // [net][rank of the CTA pair]: half-row images for cta_group::2
   // hidden <= 128 RealNVP layers: the s and t conditioners (same input, same widths) run as ONE conditioner of width 2h

@@ -331,3 +331,34 @@ def test_fused_conditioner_pair_matches_separate_conditioners(name):
     gmax = float(out[0][3].abs().max())
     assert float((out[2][3] - out[0][3]).abs().max()) <= 2e-5 * gmax
     assert abs(float(out[2][4][0] - out[0][4][0])) <= 1e-5 * abs(float(out[0][4][0]))
+
+
+def _nondefault_wide_chain(x, bias):
+    """hidden 128 conditioners with tanh (s) / sigmoid (t) hidden activations, with or without bias; a second block with
+    relu s-nets and identity-hidden t-nets.  Reference: CouplingLayer(...; σ_s, σ_t, bias) (src/Layers.jl:113-123)."""
+    rng = np.random.default_rng(17)
+    b1 = O.coupling_block(O.coupling_axes_cut(8, 4, n=2), hidden_dim_s=128, hidden_dim_t=128, act_s="tanh", act_t="sigmoid",
+                          bias=bias, rng=rng, bias_scale=0.1, s_out_scale=0.3)
+    b2 = O.coupling_block(O.coupling_axes_cut(8, 4, n=2), hidden_dim_s=128, hidden_dim_t=128, act_s="relu", act_t="identity",
+                          bias=bias, rng=rng, bias_scale=0.1, s_out_scale=0.3)
+    return O.Chain([b1, b2, O.norm_layer_from_data(x)])
+
+
+@pytest.mark.parametrize("bias", [True, False])
+def test_wide_nondefault_activations_and_bias(bias):
+    """Round 2: the tensor-core kernels take any of relu / tanh / sigmoid / identity on the two hidden layers and
+    bias = false (the non-relu derivative comes from the stored activations in the adjoint sweep)."""
+    xn = O.synthetic_data(8, 2, 1000, seed=99)[0]
+    ochain = _nondefault_wide_chain(xn, bias)
+    B = 700
+    x, th = O.synthetic_data(8, 2, B, seed=13)
+    chain = chain_from_oracle(ochain)
+    z, ldj = df.backward(chain, x, th)
+    zo, lo = O.chain_backward(ochain, x, th, np.float64)
+    zo32, lo32 = O.chain_backward(ochain, x, th)
+    slack = np.abs(zo32 - zo).max() + np.abs(lo32 - lo).max()
+    assert_close(df.to_numpy(z), zo, 1e-5, 1e-5 + slack, "nondefault z")
+    assert_close(df.to_numpy(ldj), lo, 1e-5, 1e-5 + slack, "nondefault ldj")
+    x2, _ = df.forward(chain, df.to_numpy(z), th)
+    assert_close(df.to_numpy(x2), x, 1e-4, 1e-4, "nondefault round trip")
+    _check_grad("nondefault_h128", ochain, chain.packed(), x, th, B)
