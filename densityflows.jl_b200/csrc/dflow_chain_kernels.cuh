@@ -538,7 +538,7 @@ template <int HP, int S>
 __device__ __forceinline__ void fwd_load_tile(const FwdArgs& a, const DevChainHdr& H, float* xs, float* th, int CS, int tid,
                                               long long base, int NTS, bool io_aligned) {
   const int d = H.d, n = H.n;
-    const bool vec_io = (S == 4) && a.idx == nullptr && a.grid_vals == nullptr && (base + NTS <= a.B) && io_aligned;
+    const bool vec_io = (S == 4) && a.idx == nullptr && (base + NTS <= a.B) && io_aligned;
     if (vec_io && a.mode != MODE_SAMPLE_RNG) {
       const float4* xp4 = reinterpret_cast<const float4*>(a.x_in + (base + (long long)tid * S) * d);
       int s = 0, k = 0;
@@ -592,12 +592,6 @@ __device__ __forceinline__ void fwd_load_tile(const FwdArgs& a, const DevChainHd
           for (int q = 0; q < 4; ++q)
             if (4 * g + q < d) xs[(4 * g + q) * CS + sl] = z[q];
         }
-      } else if (a.grid_vals) {
-        // point gi of the tensor-product grid, first vector fastest (Iterators.product order, src/Flows.jl:301)
-        for (int k = 0; k < d; ++k) {
-          const long long len = a.grid_meta[3 * k], stride = a.grid_meta[3 * k + 1], off = a.grid_meta[3 * k + 2];
-          xs[k * CS + sl] = valid ? __ldg(a.grid_vals + off + (gi / stride) % len) : 0.0f;
-        }
       } else if (!vec_io) {
         const float* xp = a.x_in + src * d;
         for (int k = 0; k < d; ++k) xs[k * CS + sl] = valid ? __ldg(xp + k) : 0.0f;
@@ -616,6 +610,29 @@ __device__ __forceinline__ void fwd_load_tile(const FwdArgs& a, const DevChainHd
         th[k * CS + sl] = v;
       }
     }
+}
+
+// Tile input of dflow_logpdf_grid: point gi of the tensor-product grid, first vector fastest (Iterators.product order,
+// src/Flows.jl:301), one fixed condition.  A separate real call: the hot tile loader above stays exactly as profiled.
+template <int S>
+__device__ __noinline__ void fwd_load_grid_tile(const FwdArgs& a, const DevChainHdr& H, float* xs, float* th, int CS, int tid,
+                                                long long base) {
+  const int d = H.d, n = H.n;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int sl = tid * S + s;
+    const long long gi = base + sl;
+    const bool valid = gi < a.B;
+    for (int k = 0; k < d; ++k) {
+      const long long len = a.grid_meta[3 * k], stride = a.grid_meta[3 * k + 1], off = a.grid_meta[3 * k + 2];
+      xs[k * CS + sl] = valid ? __ldg(a.grid_vals + off + (gi / stride) % len) : 0.0f;
+    }
+    for (int k = 0; k < n; ++k) {
+      float v = a.theta_const ? __ldg(a.theta_const + k) : 0.0f;
+      if (a.flags & DFLOW_THETA_NORMALIZE) v = (H.theta_rng[k] == 0.0f) ? 0.0f : (v - H.theta_min[k]) / H.theta_rng[k];
+      th[k * CS + sl] = v;
+    }
+  }
 }
 
 // Tile output: columns -> global (z / x, ldj or logp); returns this thread's (sum logp, #non-finite) contribution.
@@ -741,7 +758,9 @@ __device__ __forceinline__ void chain_fwd_body(const FwdArgs& a) {
     // ---- load ----
     // fast path (S == 4, full tile, no gather): the thread's 4 consecutive samples are 4*d contiguous floats =
     // d aligned float4 -> coalesced 128-bit global loads, transposed into the columns on the fly
-    if constexpr (CB)
+    if (a.grid_vals)
+      fwd_load_grid_tile<S>(a, H, xs, th, CS, tid, base);
+    else if constexpr (CB)
       fwd_load_tile_call<HP, S>(a, H, xs, th, CS, tid, base, NTS, io_aligned);
     else
       fwd_load_tile<HP, S>(a, H, xs, th, CS, tid, base, NTS, io_aligned);

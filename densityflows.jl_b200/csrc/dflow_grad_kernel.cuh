@@ -233,7 +233,9 @@ constexpr int grad2_min_ctas() {
   return grad2_max_threads<HP, S>() > 256 ? 1 : 2;
 }
 
-template <int HP, int S, bool FIXED>
+// VJP = false is the loss-seeded train step exactly as profiled in round 1 (no cotangent inputs / outputs compiled in);
+// VJP = true adds the caller's cotangents (zbar, jbar) and the input cotangents (xbar, thetabar) of dflow_vjp.
+template <int HP, int S, bool FIXED, bool VJP>
 __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
   extern __shared__ float4 smem4[];
   float* smem = reinterpret_cast<float*>(smem4);
@@ -245,7 +247,7 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
   __syncthreads();
   const DevChain* C = reinterpret_cast<const DevChain*>(smem);
   const DevChainHdr& H = C->h;
-  const bool want_th = a.thbar_out != nullptr && H.n > 0;
+  const bool want_th = VJP && a.thbar_out != nullptr && H.n > 0;
   const SmemPlan P = plan_grad2(H, a.chain_bytes, NTS, a.smem_grad, want_th ? 1 : 0);
   float* wsm = smem + P.chain_f;
   float* cols = wsm + P.w_f;
@@ -290,9 +292,13 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
         th[k * CS + sb + s] = v;
       }
       // ib = -j̄ of this sample: the loss seed 1/B_tot (src/Flows.jl:352-359), or minus the caller's cotangent of ln_det_jac
-      ib[s] = valid ? (a.jbar ? -__ldg(a.jbar + gi) : a.inv_btot) : 0.0f;
-      if (want_th)
-        for (int k = 0; k < n; ++k) gth[k * CS + sb + s] = 0.0f;
+      if constexpr (VJP) {
+        ib[s] = valid ? (a.jbar ? -__ldg(a.jbar + gi) : a.inv_btot) : 0.0f;
+        if (want_th)
+          for (int k = 0; k < n; ++k) gth[k * CS + sb + s] = 0.0f;
+      } else {
+        ib[s] = valid ? a.inv_btot : 0.0f;
+      }
     }
     // ---- forward (normalising) sweep: last element first; checkpoint what each element changes ----
     float ldj[S];
@@ -333,7 +339,10 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
       for (int k = 0; k < d; ++k) {
         const float v = xs[k * CS + sb + s];
         q = fmaf(v, v, q);
-        gx[k * CS + sb + s] = a.zbar ? (gi < a.B ? __ldg(a.zbar + gi * d + k) : 0.0f) : v * ib[s];
+        if constexpr (VJP)
+          gx[k * CS + sb + s] = a.zbar ? (gi < a.B ? __ldg(a.zbar + gi * d + k) : 0.0f) : v * ib[s];
+        else
+          gx[k * CS + sb + s] = v * ib[s];
       }
       const float lp = H.logpdf_c0 - 0.5f * q + ldj[s];
       if (gi < a.B) {
@@ -393,7 +402,7 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
           }
         }
         net_backward2<HP, S>(H, E, net, wblk, xs, gx, th, hc, hstride, gb, outc, gacc, a.grad_out, CS, sb, wbase, NQ,
-                             lane, gth);
+                             lane, VJP ? gth : nullptr);
       }
       // restore the layer input from its checkpoint and finish ū (RNVP.jl:137-139)
       for (int j = 0; j < E.a; ++j) {
@@ -406,7 +415,7 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
       }
     }
     // ---- cotangents of the inputs (dflow_vjp) ----
-    if (a.xbar_out || want_th) {
+    if (VJP && (a.xbar_out || want_th)) {
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         const long long gi = base + sb + s;
@@ -460,9 +469,19 @@ __device__ __forceinline__ void chain_grad2_body(const GradArgs& a) {
 template <int HP, int S>
 __global__ void __launch_bounds__((grad2_max_threads<HP, S>()), (grad2_min_ctas<HP, S>())) chain_grad2_kernel(const GradArgs a) {
   if (blockDim.x == grad2_max_threads<HP, S>())
-    chain_grad2_body<HP, S, true>(a);
+    chain_grad2_body<HP, S, true, false>(a);
   else
-    chain_grad2_body<HP, S, false>(a);
+    chain_grad2_body<HP, S, false, false>(a);
+}
+
+// the same sweep with caller cotangents and input-cotangent outputs (dflow_vjp): a kernel of its own, so that the train
+// step's register allocation is not shaped by the pullback's extra state
+template <int HP, int S>
+__global__ void __launch_bounds__((grad2_max_threads<HP, S>()), (grad2_min_ctas<HP, S>())) chain_vjp2_kernel(const GradArgs a) {
+  if (blockDim.x == grad2_max_threads<HP, S>())
+    chain_grad2_body<HP, S, true, true>(a);
+  else
+    chain_grad2_body<HP, S, false, true>(a);
 }
 
 template <int HP, int S>

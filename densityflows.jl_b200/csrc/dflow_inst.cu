@@ -69,7 +69,8 @@ cudaError_t launch_fwd_const_inst<DFLOW_HP, DFLOW_S>(const FwdArgs& a, unsigned 
 #ifdef DFLOW_INST_GRAD2
 template <>
 cudaError_t launch_grad2_inst<DFLOW_HP, DFLOW_S>(const GradArgs& a, unsigned grid, int nt, size_t smem, cudaStream_t st) {
-  auto kern = chain_grad2_kernel<DFLOW_HP, DFLOW_S>;
+  const bool vjp = a.zbar != nullptr || a.jbar != nullptr || a.xbar_out != nullptr || a.thbar_out != nullptr;
+  auto kern = vjp ? chain_vjp2_kernel<DFLOW_HP, DFLOW_S> : chain_grad2_kernel<DFLOW_HP, DFLOW_S>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, nt, smem, st>>>(a);
