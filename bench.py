@@ -439,12 +439,12 @@ def run_ours(args):
 
         ms3l = timed(step_c3_logpdf, 3, 2, dist)
         ops["logpdf_c3"] = {"samples_per_s": world * Bl / (ms3l * 1e-3), "ms_per_step": ms3l, "B_per_gpu": Bl,
-                            "path": "tcgen05 3xTF32 (automatic for hidden 64, B >= 131072)",
+                            "path": "tcgen05 3xTF32 (automatic for hidden 64, B >= 65536: TMEM-sourced four-chain kernel)",
                             "roofline": roofline_of("c3", "logpdf", Bl / (ms3l * 1e-3), "tf32x3")}
         # default routing: at hidden 64 and a batch this large the adjoint runs on the tensor cores (dflow_tc.cu)
         ops["train_step_c3"] = {"samples_per_s": Bg / (ms3 * 1e-3), "ms_per_step": ms3, "global_batch": Bg,
                                 "scaling": "strong", "allreduce_bytes": 4 * (pc3.P + 2), "collective": coll(ts3),
-                                "path": "tcgen05 3xTF32 adjoint (automatic for hidden 64, B >= 32768)",
+                                "path": "tcgen05 3xTF32 adjoint (automatic for hidden 64, B >= 8192)",
                                 "roofline": roofline_of("c3", "train", Bl / (ms3 * 1e-3), "tf32x3")}
         if world > 1 and isinstance(ts3, PeerTrainStep):
             ops["train_step_c3"]["split"] = dp_split(df, dist, lib, pc3, ts3, x3, th3, Bg, flags, ms3)

@@ -159,26 +159,27 @@ struct dflow_chain {
   dflow::SmallPlan* small = nullptr;
   int epoch_kernel = 0;  // tuning: -1 keeps dflow_train_epoch on the per-minibatch (loss_grad + Adam) launches
   int tc_ws_budget_mb = 0;  // adjoint workspace cap in MiB (0: 24 GiB); larger batches are processed in macro-batches
+  int tc_ts = 0;       // -1: hidden 32 / 64 conditioners stay on the warp-specialised pipeline (tc_net_kernel)
   int tc_fuse = 1;     // hidden <= 128 RealNVP layers run their s and t conditioners as one block-diagonal conditioner:
                        // 0 never, 1 in the train step (default), 2 in forward-type calls as well
   int tc_debug = 0;    // timing experiments (dflow_tc.cu, only with -DDFLOW_TC_EXPERIMENTS)
   int tc_debug_cluster = 0;  // CTA-pair variants (experiment builds only): 1 multicast weight stream, 2 cta_group::2
   int tc_mode = 0;     // 0: automatic (tensor cores iff must_wide), 1: force tensor cores, -1: force CUDA cores
   bool use_tc() const { return tcp && (must_wide || tc_mode > 0); }
-  // adjoint: at hidden 64 the tensor-core kernels beat the CUDA-core adjoint (3.8e7 vs 2.1e7 samples/s on C3) once the
-  // batch fills the machine; narrower or smaller stays on CUDA cores
+  // Hidden 32 / 64 chains are eligible for both paths; the automatic choice follows scripts/tc_thresholds.py (one B200,
+  // C3-like chain of 8 blocks at hidden 64, 4 blocks at hidden 32; CUDA-core / tensor-core ms per call):
+  //   hidden 64 log-density   32 768: 0.20 / 0.29    65 536: 0.38 / 0.29    1 Mi: 4.91 / 2.45
+  //   hidden 64 train step     8 192: 1.02 / 0.80    65 536: 4.00 / 1.28    1 Mi: 55.4 / 13.9
+  //   hidden 32 log-density   always the CUDA-core kernel (1 Mi: 0.65 / 0.83)
+  //   hidden 32 train step    32 768: 0.33 / 0.41    65 536: 0.63 / 0.51    1 Mi: 8.48 / 5.42
   int hidden_max = 0;
-  // forward-type calls: at hidden 64 the tensor-core kernels (two small CTAs per SM) reach 2.9e8 samples/s on C3
-  // against 1.95e8 for the CUDA-core chain kernel once the batch fills the machine
   bool use_tc_fwd(long long B) const {
     if (use_tc()) return true;
-    // crossover measured with scripts/c3_fwd_threshold.py: 0.36 / 0.36 ms at 65536, 0.69 / 0.54 ms at 131072 (CUDA / tensor)
-    return tcp && tc_mode == 0 && hidden_max == 64 && B >= 131072;
+    return tcp && tc_mode == 0 && hidden_max == 64 && B >= 65536;
   }
   bool use_tc_grad(long long B) const {
     if (use_tc()) return true;
-    // hidden 32 (d = 10, 4 blocks, 2 Mi samples): 1.94e8 samples/s on the tensor-core kernels against 1.41e8 on CUDA cores
-    return tcp && tc_mode == 0 && ((hidden_max == 64 && B >= 32768) || (hidden_max == 32 && B >= 65536));
+    return tcp && tc_mode == 0 && ((hidden_max == 64 && B >= 8192) || (hidden_max == 32 && B >= 65536));
   }
   const dflow::DevChain* hc() const { return reinterpret_cast<const dflow::DevChain*>(host_chain.data()); }
   dflow::DevChain* hc() { return reinterpret_cast<dflow::DevChain*>(host_chain.data()); }

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
                 for (int j = 0; j < 32; ++j) v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
               } else {
                 // non-relu hidden layer: derivative from the stored activation (output form: tanh 1 - y^2, sigmoid y (1 - y))
-#pragma unroll 4
+#pragma unroll
                 for (int j = 0; j < 32; ++j)
                   v[j] = live ? v[j] * act_grad(a.act2, a.h2buf[tbuf_idx(tile, H, c * WKA + j, row)]) : 0.0f;
               }
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[c * WKA + j], 0.0f);
               } else {
-#pragma unroll 4
+#pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = act_apply(a.act1, v[j] + biasS[c * WKA + j]);
               }
             }
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = ((mword >> j) & 1u) ? v[j] : 0.0f;
             } else {
-#pragma unroll 4
+#pragma unroll
               for (int j = 0; j < 32; ++j)
                 v[j] = live ? v[j] * act_grad(a.act1, a.h1buf[tbuf_idx(tile, H, gc * WKA + j, row)]) : 0.0f;
             }
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[H + gc * WKA + j], 0.0f);
             } else {
-#pragma unroll 4
+#pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = act_apply(a.act2, v[j] + biasS[H + gc * WKA + j]);
             }
           }
@@ -988,6 +988,10 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
   }
   if (TC_CLUSTER(a)) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
 }
+
+}  // namespace dflow
+#include "dflow_tcs.cuh"
+namespace dflow {
 
 // ---- weight gradients: K = samples GEMMs ------------------------------------------------------------------------
 // CTA = (conditioner, 128-row tile mt of the hidden units, a contiguous range of sample tiles).  Operands come from the
@@ -1663,6 +1667,11 @@ int tc_build_plan(dflow_chain* c) {
       Ld.fused = (tc_launch_cfg(c, Ld.ffwd, fc) && tc_launch_cfg(c, Ld.fbwd, fc)) ? 1 : 0;
     }
     TcLaunchCfg cfg;
+    Ld.tcs = 1;
+    for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni)
+      if (!tcs_image_ok(Ld.fwd[ni]) || !tcs_image_ok(Ld.bwd[ni]) || tcs_smem_bytes(Ld.fwd[ni]) > (size_t)c->max_smem_optin ||
+          tcs_smem_bytes(Ld.bwd[ni]) > (size_t)c->max_smem_optin)
+        Ld.tcs = 0;
     for (int ni = (Ld.has_s ? 0 : 1); ni < 2; ++ni) {
       if (!tc_launch_cfg(c, Ld.fwd[ni], cfg) || !tc_launch_cfg(c, Ld.bwd[ni], cfg)) {
         set_error("element %d: conditioner does not fit the tensor-core pipeline's shared memory", ei);
@@ -1732,8 +1741,33 @@ static void fill_common(const dflow_chain* c, const TcLayer& Ld, TcArgs& a) {
   }
 }
 
+// narrow conditioners (hidden 32 / 64): the TMEM-sourced kernel of dflow_tcs.cuh, unless tc_ts = -1
+static inline bool tcs_layer(const dflow_chain* c, const TcLayer& Ld) { return Ld.tcs && c->tc_ts >= 0; }
+
+template <int MODE>
+static int launch_tcs(dflow_chain* c, TcArgs& a, cudaStream_t st) {
+  const size_t smem = tcs_smem_bytes(a.im);  // one 512-thread CTA per SM (it owns the SM's 512 TMEM columns)
+  if (smem > (size_t)c->max_smem_optin) {
+    set_error("conditioner does not fit the narrow tensor-core kernel's shared memory");
+    return DFLOW_E_UNSUPPORTED;
+  }
+  a.tmem_cols = 512;
+  void (*kern)(TcArgs) = tcs_net_kernel<MODE>;
+  CKT(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long grid = ((a.B + 127) / 128 + TCS_CHAINS - 1) / TCS_CHAINS;
+  if (grid > c->sm_count) grid = c->sm_count;
+  // never two of these CTAs on one SM (the second would spin in tcgen05.alloc): request more than half of the shared memory
+  const size_t smem_req = std::max(smem, (size_t)(233472 / 2 + 1 - 1024));
+  CKT(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
+  kern<<<(unsigned)grid, TCS_THREADS, smem_req, st>>>(a);
+  CKT(cudaGetLastError());
+  c->launches++;
+  return DFLOW_OK;
+}
+
 template <int MODE>
 static int launch_net(dflow_chain* c, TcArgs& a, cudaStream_t st, const TcNetImg* half = nullptr) {
+  if (c->tc_ts >= 0 && tcs_image_ok(a.im) && tcs_smem_bytes(a.im) <= (size_t)c->max_smem_optin) return launch_tcs<MODE>(c, a, st);
   TcLaunchCfg cfg;
   if (!tc_launch_cfg(c, a.im, cfg)) {
     set_error("conditioner does not fit the tensor-core pipeline's shared memory");
@@ -1840,7 +1874,7 @@ int tc_run_chain(dflow_chain* c, float* x, const float* theta, const float* thet
     // s and t conditioners as one block-diagonal conditioner: forward-type calls only on request (tc_fuse = 2) -- the
     // zero blocks double the weight image, which costs the hidden-64 nets their resident weights and second CTA per SM
     // (C3 log-density 6.9 ms fused vs 6.2 ms separate); the train step (tc_loss_grad) fuses by default (31.6 vs 36.8 ms)
-    const bool fz = Ld.fused && c->tc_fuse >= 2;
+    const bool fz = Ld.fused && c->tc_fuse >= 2 && !tcs_layer(c, Ld);
     for (int ni = (fz ? 2 : Ld.has_s ? 0 : 1); ni < (fz ? 3 : 2); ++ni) {
       TcArgs a;
       memset(&a, 0, sizeof(a));
@@ -2025,7 +2059,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         c->launches++;
         continue;
       }
-      const bool fz = Ld.fused && c->tc_fuse > 0;
+      const bool fz = Ld.fused && c->tc_fuse > 0 && !tcs_layer(c, Ld);
       for (int ni = (fz ? 2 : Ld.has_s ? 0 : 1); ni < (fz ? 3 : 2); ++ni) {
         TcArgs a;
         memset(&a, 0, sizeof(a));
@@ -2087,7 +2121,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
         c->launches++;
         continue;
       }
-      const bool fz = Ld.fused && c->tc_fuse > 0;
+      const bool fz = Ld.fused && c->tc_fuse > 0 && !tcs_layer(c, Ld);
       for (int ni = (fz ? 2 : Ld.has_s ? 0 : 1); ni < (fz ? 3 : 2); ++ni) {
         TcArgs a;
         memset(&a, 0, sizeof(a));
@@ -2119,7 +2153,7 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       // weight gradients of this layer
       DwArgs w;
       memset(&w, 0, sizeof(w));
-      const bool fzw = Ld.fused && c->tc_fuse > 0;
+      const bool fzw = Ld.fused && c->tc_fuse > 0 && !tcs_layer(c, Ld);
       w.H = fzw ? 2 * Ld.h : Ld.h;
       w.K0p = Ld.fwd[1].K0p;
       w.K0 = Ld.nin;

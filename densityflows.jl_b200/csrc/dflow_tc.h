@@ -66,6 +66,7 @@ struct TcLayer {
   // hidden <= 128 RealNVP layers: the s and t conditioners (same input, same widths) run as ONE conditioner of width 2h
   // with block-diagonal W2 / W3 -- half the launches, MMA issues and pipeline hand-offs on an issue-bound shape
   int fused;
+  int tcs;  // every conditioner of the layer (both orientations) fits the narrow TMEM-sourced kernel (dflow_tcs.cuh)
   TcNetImg ffwd, fbwd;
 };
 

@@ -19,7 +19,7 @@ pc = chain.packed("cuda:0")
 g = torch.Generator(device="cuda").manual_seed(0)
 x = df.jl_empty((d, B), "cuda:0"); x.normal_(generator=g)
 th = df.jl_empty((n, B), "cuda:0"); th.uniform_(0, 1, generator=g)
-for mode in (-1, 1):
-    pc.tune(tc_mode=mode)
+for mode, ts in ((-1, 0), (1, -1), (1, 0)):
+    pc.tune(tc_mode=mode, tc_ts=ts)
     ms = timeit(lambda: pc.logpdf(x, th))
-    print(json.dumps({"tc_mode": mode, "logpdf_ms": ms, "sps": B / ms * 1e3}))
+    print(json.dumps({"tc_mode": mode, "tc_ts": ts, "logpdf_ms": ms, "sps": B / ms * 1e3}))

@@ -10,7 +10,7 @@ xs, _ = O.synthetic_data(d, n, 4096, seed=1)
 chain = chain_from_oracle(O.block_chain(d, n, L, h, xs))
 pc = chain.packed("cuda:0")
 g = torch.Generator(device="cuda").manual_seed(0)
-for B in (65536, 131072, 262144, 524288, 1048576):
+for B in (8192, 16384, 32768, 65536, 131072, 262144, 1048576):
     x = df.jl_empty((d, B), "cuda:0"); x.normal_(generator=g)
     th = df.jl_empty((n, B), "cuda:0"); th.uniform_(0, 1, generator=g)
     r = {}

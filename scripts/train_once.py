@@ -13,6 +13,8 @@ chain = chain_from_oracle(O.block_chain(d, n, L, h, xs))
 pc = chain.packed("cuda:0")
 if h <= 64:
     pc.tune(tc_mode=int(os.environ.get("DFLOW_TC_MODE", "1")))
+if "DFLOW_TC_TS" in os.environ:
+    pc.tune(tc_ts=int(os.environ["DFLOW_TC_TS"]))
 g = torch.Generator(device="cuda").manual_seed(0)
 x = df.jl_empty((d, B), "cuda:0"); x.normal_(generator=g)
 th = df.jl_empty((n, B), "cuda:0"); th.uniform_(0, 1, generator=g)

@@ -1,6 +1,6 @@
 """GPU parity at the BASELINE shapes, depths and batch sizes that bench.py times, on the DEFAULT-ROUTED kernels:
 
-  C3  d=16 n=4  L=8  h=64   -> tcgen05 3xTF32 forward from B >= 131072, tcgen05 adjoint from B >= 32768
+  C3  d=16 n=4  L=8  h=64   -> tcgen05 3xTF32 forward from B >= 65536, tcgen05 adjoint from B >= 8192
   C4  d=32 n=8  L=12 h=256  -> tcgen05 forward + adjoint
   C5  d=64 n=16 L=16 h=512  -> tcgen05 forward / sampling (two 256-column passes)
 

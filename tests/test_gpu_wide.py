@@ -214,10 +214,12 @@ def test_wide_adjoint_h512(B):
 NARROW_ON_TC = {"h64_d16": (16, 4, 2, 64), "h32_d10": (10, 3, 4, 32)}
 
 
+@pytest.mark.parametrize("tc_ts", [0, -1])
 @pytest.mark.parametrize("name", list(NARROW_ON_TC))
-def test_narrow_chain_on_tensor_cores(name):
+def test_narrow_chain_on_tensor_cores(name, tc_ts):
     """tc_mode=1 routes an eligible hidden <= 64 chain through the tensor-core kernels: same results as the oracle and
-    as the CUDA-core kernels."""
+    as the CUDA-core kernels.  tc_ts = 0 (default): the TMEM-sourced four-chain kernel (dflow_tcs.cuh); tc_ts = -1: the
+    warp-specialised pipeline that serves the wider nets."""
     d, n, L, h = NARROW_ON_TC[name]
     xn = O.synthetic_data(d, n, 1000, seed=99)[0]
     ochain = O.block_chain(d, n, L, h, xn, s_out_scale=0.3)
@@ -227,7 +229,7 @@ def test_narrow_chain_on_tensor_cores(name):
     pc = chain.packed()
     lp_cuda = pc.logpdf(x, th).clone()
     n0 = pc.launch_count()
-    pc.tune(tc_mode=1)
+    pc.tune(tc_mode=1, tc_ts=tc_ts)
     lp_tc = pc.logpdf(x, th)
     assert pc.launch_count() - n0 > 2 * L  # one launch per conditioner, not the single fused narrow kernel
     zo, lo = O.chain_backward(ochain, x, th, np.float64)
@@ -235,7 +237,11 @@ def test_narrow_chain_on_tensor_cores(name):
     assert_close(df.to_numpy(lp_tc), lpo, 1e-5, 1e-4, f"{name} logpdf on tensor cores")
     assert_close(df.to_numpy(lp_tc), df.to_numpy(lp_cuda), 1e-5, 1e-4, f"{name} tensor vs CUDA cores")
     _check_grad(name, ochain, pc, x, th, B)
-    pc.tune(tc_mode=0)
+    # sampling direction through the same kernels: the round trip returns x
+    z, _ = pc.normalize(df.to_jl(x, DEV), df.to_jl(th, DEV))
+    x2, _ = pc.forward_ldj(z, df.to_jl(th, DEV))
+    assert_close(df.to_numpy(x2), x, 1e-4, 1e-4, f"{name} round trip on tensor cores")
+    pc.tune(tc_mode=0, tc_ts=0)
 
 
 @pytest.mark.parametrize("name", ["c4_like_h256", "c5_like_h512", "h128_d8", "h64_forced"])
@@ -308,7 +314,7 @@ def test_fused_conditioner_pair_matches_separate_conditioners(name):
     chain = chain_from_oracle(ochain)
     pc = chain.packed()
     if narrow:
-        pc.tune(tc_mode=1)
+        pc.tune(tc_mode=1, tc_ts=-1)  # hidden <= 64 pairs fuse on the warp-specialised pipeline only
     xj = df.to_jl(x, DEV)
     tj = df.to_jl(th, DEV) if n else None
     out = {}
@@ -324,7 +330,7 @@ def test_fused_conditioner_pair_matches_separate_conditioners(name):
         out[fuse] = (lp, z.clone(), ldj.clone(), grad, l2, nl)
     pc.tune(tc_fuse=1)
     if narrow:
-        pc.tune(tc_mode=0)
+        pc.tune(tc_mode=0, tc_ts=0)
     assert out[2][5] < out[0][5], "fused pairs need fewer launches"
     for i in range(3):
         assert torch.equal(out[2][i], out[0][i])
@@ -333,26 +339,30 @@ def test_fused_conditioner_pair_matches_separate_conditioners(name):
     assert abs(float(out[2][4][0] - out[0][4][0])) <= 1e-5 * abs(float(out[0][4][0]))
 
 
-def _nondefault_wide_chain(x, bias):
-    """hidden 128 conditioners with tanh (s) / sigmoid (t) hidden activations, with or without bias; a second block with
-    relu s-nets and identity-hidden t-nets.  Reference: CouplingLayer(...; σ_s, σ_t, bias) (src/Layers.jl:113-123)."""
+def _nondefault_wide_chain(x, bias, hidden=128):
+    """hidden 128 (or 64) conditioners with tanh (s) / sigmoid (t) hidden activations, with or without bias; a second block
+    with relu s-nets and identity-hidden t-nets.  Reference: CouplingLayer(...; σ_s, σ_t, bias) (src/Layers.jl:113-123)."""
     rng = np.random.default_rng(17)
-    b1 = O.coupling_block(O.coupling_axes_cut(8, 4, n=2), hidden_dim_s=128, hidden_dim_t=128, act_s="tanh", act_t="sigmoid",
+    b1 = O.coupling_block(O.coupling_axes_cut(8, 4, n=2), hidden_dim_s=hidden, hidden_dim_t=hidden, act_s="tanh", act_t="sigmoid",
                           bias=bias, rng=rng, bias_scale=0.1, s_out_scale=0.3)
-    b2 = O.coupling_block(O.coupling_axes_cut(8, 4, n=2), hidden_dim_s=128, hidden_dim_t=128, act_s="relu", act_t="identity",
+    b2 = O.coupling_block(O.coupling_axes_cut(8, 4, n=2), hidden_dim_s=hidden, hidden_dim_t=hidden, act_s="relu", act_t="identity",
                           bias=bias, rng=rng, bias_scale=0.1, s_out_scale=0.3)
     return O.Chain([b1, b2, O.norm_layer_from_data(x)])
 
 
+@pytest.mark.parametrize("hidden", [128, 64])
 @pytest.mark.parametrize("bias", [True, False])
-def test_wide_nondefault_activations_and_bias(bias):
+def test_wide_nondefault_activations_and_bias(bias, hidden):
     """Round 2: the tensor-core kernels take any of relu / tanh / sigmoid / identity on the two hidden layers and
-    bias = false (the non-relu derivative comes from the stored activations in the adjoint sweep)."""
+    bias = false (the non-relu derivative comes from the stored activations in the adjoint sweep).  hidden = 64 runs the
+    narrow TMEM-sourced kernel (tc_mode = 1 forces the tensor cores at this small batch)."""
     xn = O.synthetic_data(8, 2, 1000, seed=99)[0]
-    ochain = _nondefault_wide_chain(xn, bias)
+    ochain = _nondefault_wide_chain(xn, bias, hidden)
     B = 700
     x, th = O.synthetic_data(8, 2, B, seed=13)
     chain = chain_from_oracle(ochain)
+    if hidden <= 64:
+        chain.packed().tune(tc_mode=1)
     z, ldj = df.backward(chain, x, th)
     zo, lo = O.chain_backward(ochain, x, th, np.float64)
     zo32, lo32 = O.chain_backward(ochain, x, th)
@@ -361,4 +371,4 @@ def test_wide_nondefault_activations_and_bias(bias):
     assert_close(df.to_numpy(ldj), lo, 1e-5, 1e-5 + slack, "nondefault ldj")
     x2, _ = df.forward(chain, df.to_numpy(z), th)
     assert_close(df.to_numpy(x2), x, 1e-4, 1e-4, "nondefault round trip")
-    _check_grad("nondefault_h128", ochain, chain.packed(), x, th, B)
+    _check_grad(f"nondefault_h{hidden}", ochain, chain.packed(), x, th, B)
