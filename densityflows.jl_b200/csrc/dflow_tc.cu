@@ -328,10 +328,10 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 hi, lo;
-          hi.x = to_tf32(v[4 * j + 0]); lo.x = v[4 * j + 0] - hi.x;
-          hi.y = to_tf32(v[4 * j + 1]); lo.y = v[4 * j + 1] - hi.y;
-          hi.z = to_tf32(v[4 * j + 2]); lo.z = v[4 * j + 2] - hi.z;
-          hi.w = to_tf32(v[4 * j + 3]); lo.w = v[4 * j + 3] - hi.w;
+          hi.x = tf32_hi(v[4 * j + 0]); lo.x = v[4 * j + 0] - hi.x;
+          hi.y = tf32_hi(v[4 * j + 1]); lo.y = v[4 * j + 1] - hi.y;
+          hi.z = tf32_hi(v[4 * j + 2]); lo.z = v[4 * j + 2] - hi.z;
+          hi.w = tf32_hi(v[4 * j + 3]); lo.w = v[4 * j + 3] - hi.w;
           const int idx = core_idx(row, 4 * j, WKA);
           *reinterpret_cast<float4*>(a2h + idx) = hi;
           *reinterpret_cast<float4*>(a2l + idx) = lo;
@@ -536,10 +536,10 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
 #pragma unroll
             for (int h4 = 0; h4 < 8; h4 += 4) {
               float4 hi, lo;
-              hi.x = to_tf32(v[h4 + 0]); lo.x = v[h4 + 0] - hi.x;
-              hi.y = to_tf32(v[h4 + 1]); lo.y = v[h4 + 1] - hi.y;
-              hi.z = to_tf32(v[h4 + 2]); lo.z = v[h4 + 2] - hi.z;
-              hi.w = to_tf32(v[h4 + 3]); lo.w = v[h4 + 3] - hi.w;
+              hi.x = tf32_hi(v[h4 + 0]); lo.x = v[h4 + 0] - hi.x;
+              hi.y = tf32_hi(v[h4 + 1]); lo.y = v[h4 + 1] - hi.y;
+              hi.z = tf32_hi(v[h4 + 2]); lo.z = v[h4 + 2] - hi.z;
+              hi.w = tf32_hi(v[h4 + 3]); lo.w = v[h4 + 3] - hi.w;
               const int idx = core_idx(row, k0 + h4, K0p);
               *reinterpret_cast<float4*>(A1h + idx) = hi;
               *reinterpret_cast<float4*>(A1l + idx) = lo;
@@ -571,10 +571,10 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
 #pragma unroll
             for (int h4 = 0; h4 < 8; h4 += 4) {
               float4 hi, lo;
-              hi.x = to_tf32(v[h4 + 0]); lo.x = v[h4 + 0] - hi.x;
-              hi.y = to_tf32(v[h4 + 1]); lo.y = v[h4 + 1] - hi.y;
-              hi.z = to_tf32(v[h4 + 2]); lo.z = v[h4 + 2] - hi.z;
-              hi.w = to_tf32(v[h4 + 3]); lo.w = v[h4 + 3] - hi.w;
+              hi.x = tf32_hi(v[h4 + 0]); lo.x = v[h4 + 0] - hi.x;
+              hi.y = tf32_hi(v[h4 + 1]); lo.y = v[h4 + 1] - hi.y;
+              hi.z = tf32_hi(v[h4 + 2]); lo.z = v[h4 + 2] - hi.z;
+              hi.w = tf32_hi(v[h4 + 3]); lo.w = v[h4 + 3] - hi.w;
               const int idx = core_idx(row, k0 + h4, K0p);
               *reinterpret_cast<float4*>(A1h + idx) = hi;
               *reinterpret_cast<float4*>(A1l + idx) = lo;
@@ -1152,10 +1152,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       for (int i = 0; i < DW_MAXRB; ++i) {
         if (((segmask >> i) & 1u) && !(TC_DBG(a) & 4)) {
           float4 hi, lo;
-          hi.x = to_tf32(v[i].x); lo.x = v[i].x - hi.x;
-          hi.y = to_tf32(v[i].y); lo.y = v[i].y - hi.y;
-          hi.z = to_tf32(v[i].z); lo.z = v[i].z - hi.z;
-          hi.w = to_tf32(v[i].w); lo.w = v[i].w - hi.w;
+          hi.x = tf32_hi(v[i].x); lo.x = v[i].x - hi.x;
+          hi.y = tf32_hi(v[i].y); lo.y = v[i].y - hi.y;
+          hi.z = tf32_hi(v[i].z); lo.z = v[i].z - hi.z;
+          hi.w = tf32_hi(v[i].w); lo.w = v[i].w - hi.w;
           *reinterpret_cast<float4*>(st + my_dst[i]) = hi;
           *reinterpret_cast<float4*>(st + my_dst[i] + pick(lo_by, (codes >> (2 * i)) & 3u)) = lo;
           if ((biasmask >> i) & 1u) bacc[i] += (v[i].x + v[i].y) + (v[i].z + v[i].w);

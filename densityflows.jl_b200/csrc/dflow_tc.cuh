@@ -20,6 +20,10 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// The same rounding (nearest, ties away from zero) for the hot epilogues: cvt.rna.tf32.f32 compiles to
+// FSETP |x| >= inf, VIADD 0x1000, SEL, LOP3 -- the inf / nan guard is not needed here (inf stays inf, a nan stays a nan,
+// a value that rounds past the largest float becomes inf as it should), so two of the four instructions go.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 // ---- mbarrier ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
       for (int q4 = 0; q4 < 4; ++q4) {
         float4 lo;
         float hi;
-        hi = to_tf32(v[16 * half + 4 * q4 + 0]); h[4 * q4 + 0] = __float_as_uint(hi); lo.x = v[16 * half + 4 * q4 + 0] - hi;
-        hi = to_tf32(v[16 * half + 4 * q4 + 1]); h[4 * q4 + 1] = __float_as_uint(hi); lo.y = v[16 * half + 4 * q4 + 1] - hi;
-        hi = to_tf32(v[16 * half + 4 * q4 + 2]); h[4 * q4 + 2] = __float_as_uint(hi); lo.z = v[16 * half + 4 * q4 + 2] - hi;
-        hi = to_tf32(v[16 * half + 4 * q4 + 3]); h[4 * q4 + 3] = __float_as_uint(hi); lo.w = v[16 * half + 4 * q4 + 3] - hi;
+        hi = tf32_hi(v[16 * half + 4 * q4 + 0]); h[4 * q4 + 0] = __float_as_uint(hi); lo.x = v[16 * half + 4 * q4 + 0] - hi;
+        hi = tf32_hi(v[16 * half + 4 * q4 + 1]); h[4 * q4 + 1] = __float_as_uint(hi); lo.y = v[16 * half + 4 * q4 + 1] - hi;
+        hi = tf32_hi(v[16 * half + 4 * q4 + 2]); h[4 * q4 + 2] = __float_as_uint(hi); lo.z = v[16 * half + 4 * q4 + 2] - hi;
+        hi = tf32_hi(v[16 * half + 4 * q4 + 3]); h[4 * q4 + 3] = __float_as_uint(hi); lo.w = v[16 * half + 4 * q4 + 3] - hi;
         *reinterpret_cast<float4*>(lobuf + core_idx(row, k0 + 16 * half + 4 * q4, H)) = lo;
       }
       tmem_st16(hi_col + lane_off + 16u * half, h);
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
       uint32_t h[8], l[8];
 #pragma unroll
       for (int qq = 0; qq < 8; ++qq) {
-        const float hi = to_tf32(v[qq]);
+        const float hi = tf32_hi(v[qq]);
         h[qq] = __float_as_uint(hi);
         l[qq] = __float_as_uint(v[qq] - hi);
       }
