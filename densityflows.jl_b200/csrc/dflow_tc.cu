@@ -1010,6 +1010,7 @@ constexpr uint32_t DWT_W2 = 0, DWT_W1 = 256, DWT_W3 = 320;
 
 struct DwArgs {
   int H, K0p, K0, a, a16, mtiles, units, ksplit, nstage;
+  int ngroups;  // staging-warp groups that alternate stage pairs (narrow nets: one group's loads fly while another stores)
   int nsplit, NB;  // hidden 512: the H columns of dW2 are split over nsplit = 2 CTAs of NB = 256 columns each (TMEM holds 512);
                    // the second one carries only dW2 (no dW1 / dW3 / bias sums)
   long long ntiles;
@@ -1067,7 +1068,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
-      mbar_init(full + i, DW_STAGE_THREADS);
+      mbar_init(full + i, (uint32_t)(DW_STAGE_WARPS / a.ngroups) * 32u);
       mbar_init(empty + i, 1);
     }
     mbar_init(done, 1);
@@ -1088,6 +1089,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
     // this warp's row-blocks: rb = warp + 8 i  (everything per row-block is resolved once, outside the stage loop)
     // Per row-block metadata is packed (bit masks + a 2-bit segment-shape code) so that two stages of loaded data fit
     // the 96-register budget next to it without spills.
+    // Narrow nets need only a few row-blocks per stage: the staging warps then split into ngroups groups that take stage
+    // pairs in turn (group g: pairs g, g + ngroups, ...), each warp covering more row-blocks of the pairs it handles.
+    // The groups run out of phase, so one group's global loads are in flight while another splits and stores -- the
+    // fence.proxy.async of a thread waits for that thread's own loads only.
+    const int G = a.ngroups, GW = DW_STAGE_WARPS / G, grp = warp / GW, gw = warp % GW;
+    const bool active = grp < G;
     const float* my_ptr[DW_MAXRB];
     int my_dst[DW_MAXRB];
     uint32_t okmask = 0, segmask = 0, biasmask = 0, codes = 0;  // code: 0 RA-row A segment, 1 h1, 2 in, 3 delta3
@@ -1103,7 +1110,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
     };
 #pragma unroll
     for (int i = 0; i < DW_MAXRB; ++i) {
-      const int rb = warp + DW_STAGE_WARPS * i;
+      const int rb = gw + GW * i;
       int rb0;
       const int sgi = seg_of(rb, rb0);
       const int dst0 = sgi == 0 ? seg_dst[0] : sgi == 1 ? seg_dst[1] : sgi == 2 ? seg_dst[2] : sgi == 3 ? seg_dst[3]
@@ -1144,7 +1151,6 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
           v[i] = __ldg(reinterpret_cast<const float4*>(my_ptr[i] + blk * (size_t)pick(ts_by, (codes >> (2 * i)) & 3u)));
       }
     };
-    uint32_t slot = 0, par = 0;
     auto put_stage = [&](float4 (&v)[DW_MAXRB], uint32_t sl, uint32_t pr) {
       mbar_wait(empty + sl, pr ^ 1);
       float* st = smem + (size_t)sl * stage_fl;
@@ -1162,30 +1168,22 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
         }
       }
     };
-    auto advance = [&]() {
-      if (++slot == (uint32_t)NST) {
-        slot = 0;
-        par ^= 1;
-      }
-    };
-    // nstages is a multiple of 128 / DW_KS = 8: the loop handles two stages per iteration
-    if (nstages > 0) {
-      load_stage(0, vA);
-      load_stage(1, vB);
+    // nstages is a multiple of 128 / DW_KS = 8 and NST is even: a pair occupies ring slots (s % NST, s % NST + 1)
+    const long long s_first = 2 * grp, s_step = 2 * G;
+    if (active && s_first < nstages) {
+      load_stage(s_first, vA);
+      load_stage(s_first + 1, vB);
     }
-    for (long long s = 0; s < nstages; s += 2) {
-      const uint32_t slA = slot, prA = par;
-      advance();
-      const uint32_t slB = slot, prB = par;
-      advance();
+    for (long long s = s_first; active && s < nstages; s += s_step) {
+      const uint32_t slA = (uint32_t)(s % NST), prA = (uint32_t)((s / NST) & 1);
       put_stage(vA, slA, prA);
-      put_stage(vB, slB, prB);
+      put_stage(vB, slA + 1, prA);
       fence_async_smem();
       mbar_arrive(full + slA);
-      mbar_arrive(full + slB);
-      if (s + 2 < nstages) {
-        load_stage(s + 2, vA);
-        load_stage(s + 3, vB);
+      mbar_arrive(full + slA + 1);
+      if (s + s_step < nstages) {
+        load_stage(s + s_step, vA);
+        load_stage(s + s_step + 1, vB);
       }
     }
     // bias gradients: reduce the four sample quads of a row, one atomic per row
@@ -1194,11 +1192,11 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       float r = bacc[i];
       r += __shfl_xor_sync(0xffffffffu, r, 8);
       r += __shfl_xor_sync(0xffffffffu, r, 16);
-      const int rb = warp + DW_STAGE_WARPS * i;
+      const int rb = gw + GW * i;
       int rb0;
       const int sgi = seg_of(rb, rb0);
       const int row = (rb - rb0) * 8 + (lane & 7);
-      const bool seg_ok = (segmask >> i) & 1u, ok = (okmask >> i) & 1u;
+      const bool seg_ok = active && ((segmask >> i) & 1u), ok = (okmask >> i) & 1u;
       if (seg_ok && sgi < 2 && lane < 8 && ok && nstages > 0) {
         const int hr = mt * 128 + row;
         const int bn = a.fused ? hr / a.hblk : net, hr2 = a.fused ? hr % a.hblk : hr;
@@ -2190,7 +2188,13 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       const size_t overrun = (size_t)(128 - RA) * DW_KS * 4 * 2;
       int nst = (int)(((size_t)c->max_smem_optin - 128 - overrun) / stage_bytes);
       if (nst > 4) nst = 4;
-      if (nst < 2 || (3 * RA + w.NB + w.K0p + w.a16) / 8 > DW_MAXRB * DW_STAGE_WARPS) {
+      nst &= ~1;  // stage pairs
+      const int nrb = (3 * RA + w.NB + w.K0p + w.a16) / 8;  // row-blocks per stage
+      w.ngroups = 1;
+      for (int g = 3; g >= 2; --g)
+        if (w.ngroups == 1 && nst >= 2 * g && nrb <= DW_MAXRB * (DW_STAGE_WARPS / g)) w.ngroups = g;
+      if (c->tc_dw_groups > 0 && c->tc_dw_groups <= w.ngroups) w.ngroups = c->tc_dw_groups;
+      if (nst < 2 || nrb > DW_MAXRB * DW_STAGE_WARPS) {
         set_error("weight-gradient stage does not fit (%zu bytes per stage)", stage_bytes);
         return DFLOW_E_UNSUPPORTED;
       }

@@ -36,6 +36,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[128 x n] (+)= A[128 x 8] (TMEM, one tf32 element per column) * B[n x 8]^T (shared memory descriptor)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -381,26 +388,33 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
     }
     wait_mma();
     // ---- 7. output: s values, coupling transform / log-det, or the cotangent of the conditioner input ----
+    // (8 columns at a time, only the columns that exist: predicated-off gathers would still cost their issue slots)
     float lsum = 0.0f;
-    for (int o0 = 0; o0 < N3p; o0 += 16) {
-      float v[16];
-      tmem_ld16(tA + lane_off + (uint32_t)o0, v);
+    const int nout = MODE == TC_BWD ? a.nin : a.a;
+    for (int o0 = 0; o0 < nout; o0 += 8) {
+      float v[8];
+      {
+        uint32_t r[8];
+        tmem_ld8(tA + lane_off + (uint32_t)o0, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+      }
       if constexpr (MODE == TC_BWD) {
         // rows n.. go to the identity coordinates; rows 0..n-1 are the cotangent of the (normalised) conditions
         if (valid) {
-          float zb[16];
+          float zb[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const int k = o0 + j;
             zb[j] = (k >= n && k < a.nin) ? a.zbar[tidx(tile, d, a.id[k - n], row)] : 0.0f;
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const int k = o0 + j;
             if (k >= n && k < a.nin) a.zbar[tidx(tile, d, a.id[k - n], row)] = zb[j] + v[j];
           }
           if (a.thbar) {
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const int k = o0 + j;
               if (k < n) {
                 // chain rule through normalize_input (src/Data.jl:213-218)
@@ -411,19 +425,21 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
           }
         }
       } else if (a.net_id == 0) {
+        float* srow = a.sbuf + ((size_t)tile * a.a16 + o0) * 128 + row;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) a.sbuf[((size_t)tile * a.a16 + o0 + j) * 128 + row] = v[j] + biasS[2 * H + o0 + j];
+        for (int j = 0; j < 8; ++j) srow[j * 128] = v[j] + biasS[2 * H + o0 + j];
       } else if (valid) {
         // coupling transform (src/affine/RNVP.jl:92,184; NICE: s = 0)
-        float sv[16], xv[16];
+        float sv[8], xv[8];
+        const float* srow = a.sbuf + ((size_t)tile * a.a16 + o0) * 128 + row;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const int jj = o0 + j;
-          sv[j] = (jj < a.a && a.has_s) ? a.sbuf[((size_t)tile * a.a16 + jj) * 128 + row] : 0.0f;
+          sv[j] = (jj < a.a && a.has_s) ? srow[j * 128] : 0.0f;
           xv[j] = (jj < a.a) ? a.x_in[tidx(tile, d, a.af[jj], row)] : 0.0f;
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const int jj = o0 + j;
           if (jj < a.a) {
             const float tv = v[j] + biasS[2 * H + o0 + j];

@@ -15,6 +15,8 @@ if h <= 64:
     pc.tune(tc_mode=int(os.environ.get("DFLOW_TC_MODE", "1")))
 if "DFLOW_TC_TS" in os.environ:
     pc.tune(tc_ts=int(os.environ["DFLOW_TC_TS"]))
+if "DFLOW_DW_GROUPS" in os.environ:
+    pc.tune(tc_dw_groups=int(os.environ["DFLOW_DW_GROUPS"]))
 g = torch.Generator(device="cuda").manual_seed(0)
 x = df.jl_empty((d, B), "cuda:0"); x.normal_(generator=g)
 th = df.jl_empty((n, B), "cuda:0"); th.uniform_(0, 1, generator=g)
