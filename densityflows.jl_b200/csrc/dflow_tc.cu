@@ -219,6 +219,16 @@ __device__ __forceinline__ size_t tidx(long long tile, int rows, int k, int r) {
   return ((size_t)tile * (size_t)rows + (size_t)k) * 128 + (size_t)r;
 }
 
+// bit j <-> v[j] > 0 for values that are >= +0 (relu outputs): bits + 0x7fffffff carries into bit 31 iff the value is not
+// zero, and a funnel shift collects that bit -- two instructions per value.  (Only read back when the activation is relu;
+// other activations take their derivative from the stored values.)
+__device__ __forceinline__ uint32_t positive_mask(const float (&v)[32]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 31; j >= 0; --j) m = __funnelshift_l(__float_as_uint(v[j]) + 0x7FFFFFFFu, m, 1);
+  return m;
+}
+
 // ring cursor: slot index + phase parity, advanced without divisions
 struct Ring {
   uint32_t slot, par, n;
@@ -412,13 +422,9 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
               }
             } else if constexpr (MODE == TC_FWD_STORE) {
               if (p == 0 && live) {
-                uint32_t mword = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  a.h1buf[tbuf_idx(tile, H, c * WKA + j, row)] = v[j];
-                  mword |= (v[j] > 0.0f ? 1u : 0u) << j;
-                }
-                a.m1buf[((size_t)tile * (H >> 5) + c) * 128 + row] = mword;
+                for (int j = 0; j < 32; ++j) a.h1buf[tbuf_idx(tile, H, c * WKA + j, row)] = v[j];
+                a.m1buf[((size_t)tile * (H >> 5) + c) * 128 + row] = positive_mask(v);
               }
             }
           }
@@ -475,13 +481,9 @@ __global__ void __launch_bounds__((4 * NWG + 6) * 32, NWG == 1 ? 2 : 1) tc_net_k
             }
           } else if constexpr (MODE == TC_FWD_STORE) {
             if (live) {
-              uint32_t mword = 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                a.h2buf[tbuf_idx(tile, H, gc * WKA + j, row)] = v[j];
-                mword |= (v[j] > 0.0f ? 1u : 0u) << j;
-              }
-              a.m2buf[((size_t)tile * (H >> 5) + gc) * 128 + row] = mword;
+              for (int j = 0; j < 32; ++j) a.h2buf[tbuf_idx(tile, H, gc * WKA + j, row)] = v[j];
+              a.m2buf[((size_t)tile * (H >> 5) + gc) * 128 + row] = positive_mask(v);
             }
           }
         }

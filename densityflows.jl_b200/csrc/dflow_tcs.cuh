@@ -140,6 +140,22 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
       tmem_st16(hi_col + lane_off + 16u * half, h);
     }
   };
+  // accumulator init: `ncols` (a multiple of 16) bias values from shared memory -> this thread's lane, columns col..
+  // (the MMAs then accumulate on top of the bias: no bias add in the epilogue)
+  auto bias_init = [&](uint32_t col, const float* b, int ncols) {
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 bv = *reinterpret_cast<const float4*>(b + c0 + 4 * q4);
+        r[4 * q4 + 0] = __float_as_uint(bv.x);
+        r[4 * q4 + 1] = __float_as_uint(bv.y);
+        r[4 * q4 + 2] = __float_as_uint(bv.z);
+        r[4 * q4 + 3] = __float_as_uint(bv.w);
+      }
+      tmem_st16(col + lane_off + (uint32_t)c0, r);
+    }
+  };
   auto ld32 = [&](uint32_t taddr, float (&v)[32]) {
     uint32_t r0[16], r1[16];
     tmem_ld16_nowait(taddr, r0);
@@ -166,7 +182,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
   // D (+)= A (K = 8 * ksteps: hi in TMEM at a_hi.., lo in the chain's shared-memory operand) * the 16-wide weight blocks
   // at b0, b0 + chunk_step, ... (lo part of a block lo_off further): lo*hi + hi*lo + hi*hi per K step of 8
   auto gemm_mixed = [&](uint32_t td, uint32_t a_hi, int ksteps, uint32_t idesc, uint64_t b0, uint32_t lo_off, uint32_t chunk_step) {
-    uint32_t acc = 0u;
+    uint32_t acc = MODE != TC_BWD ? 1u : 0u;  // forward modes: the accumulator was initialised with the bias
     for (int ks = 0; ks < ksteps; ++ks) {
       const uint64_t db = b0 + (uint64_t)((uint32_t)(ks >> 1) * chunk_step + (uint32_t)(ks & 1) * 16u);
       mma_tf32(td, dLo + (uint64_t)((uint32_t)ks * 16u), db, idesc, acc);
@@ -255,13 +271,14 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
       tmem_st8(tC + lane_off + (uint32_t)k0, h);
       tmem_st8(tC + lane_off + (uint32_t)(K0p + k0), l);
     }
+    if constexpr (MODE != TC_BWD) bias_init(tA, biasS, H);  // D1 starts from b1
     publish();
     // ---- 2. D1 (region A) = input row * M1^T ----
     if ((warp & 3) == 0) {
       if (!wready) mbar_wait(bars + TCS_BAR_W, 0);
       tc_fence_after();
       if (elect_one()) {
-        uint32_t acc = 0u;
+        uint32_t acc = MODE != TC_BWD ? 1u : 0u;
         for (int ks = 0; ks < (K0p >> 3); ++ks) {
           const uint64_t db = dW1 + (uint64_t)((uint32_t)ks * 16u);
           mma_tf32_ts(tA, tC + (uint32_t)(K0p + ks * 8), db, id12, acc);
@@ -304,10 +321,10 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
       } else {
         if (a.act1 == DFLOW_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[c * 32 + j], 0.0f);
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = act_apply(a.act1, v[j] + biasS[c * 32 + j]);
+          for (int j = 0; j < 32; ++j) v[j] = act_apply(a.act1, v[j]);
         }
       }
       split_store(v, tA + (uint32_t)(c * 32), c * 32);
@@ -317,15 +334,12 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
         for (int j = 0; j < 32; ++j) grow[j * 16] = v[j];
       } else if constexpr (MODE == TC_FWD_STORE) {
         float* grow = a.h1buf + tbuf_idx(tile, H, c * 32, row);
-        uint32_t mword = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          grow[j * 16] = v[j];
-          mword |= (v[j] > 0.0f ? 1u : 0u) << j;
-        }
-        a.m1buf[((size_t)tile * nchunk + c) * 128 + row] = mword;
+        for (int j = 0; j < 32; ++j) grow[j * 16] = v[j];
+        if (a.act1 == DFLOW_ACT_RELU) a.m1buf[((size_t)tile * nchunk + c) * 128 + row] = positive_mask(v);
       }
     }
+    if constexpr (MODE != TC_BWD) bias_init(tC, biasS + H, H);  // D2 starts from b2 (the input row in region C is dead)
     publish();
     // ---- 4. D2 (region C) = h1 * M2^T ----
     if ((warp & 3) == 0) {
@@ -354,10 +368,10 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
       } else {
         if (a.act2 == DFLOW_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + biasS[H + c * 32 + j], 0.0f);
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = act_apply(a.act2, v[j] + biasS[H + c * 32 + j]);
+          for (int j = 0; j < 32; ++j) v[j] = act_apply(a.act2, v[j]);
         }
       }
       split_store(v, tC + (uint32_t)(c * 32), c * 32);
@@ -367,15 +381,12 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
         for (int j = 0; j < 32; ++j) grow[j * 16] = v[j];
       } else if constexpr (MODE == TC_FWD_STORE) {
         float* grow = a.h2buf + tbuf_idx(tile, H, c * 32, row);
-        uint32_t mword = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          grow[j * 16] = v[j];
-          mword |= (v[j] > 0.0f ? 1u : 0u) << j;
-        }
-        a.m2buf[((size_t)tile * nchunk + c) * 128 + row] = mword;
+        for (int j = 0; j < 32; ++j) grow[j * 16] = v[j];
+        if (a.act2 == DFLOW_ACT_RELU) a.m2buf[((size_t)tile * nchunk + c) * 128 + row] = positive_mask(v);
       }
     }
+    if constexpr (MODE != TC_BWD) bias_init(tA, biasS + 2 * H, N3p);  // D3 starts from b3 (h1.hi in region A is dead)
     publish();
     // ---- 6. D3 (region A, over the dead h1.hi) = h2 * M3^T ----
     if ((warp & 3) == 0) {
@@ -427,7 +438,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
       } else if (a.net_id == 0) {
         float* srow = a.sbuf + ((size_t)tile * a.a16 + o0) * 128 + row;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) srow[j * 128] = v[j] + biasS[2 * H + o0 + j];
+        for (int j = 0; j < 8; ++j) srow[j * 128] = v[j];
       } else if (valid) {
         // coupling transform (src/affine/RNVP.jl:92,184; NICE: s = 0)
         float sv[8], xv[8];
@@ -442,7 +453,7 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
         for (int j = 0; j < 8; ++j) {
           const int jj = o0 + j;
           if (jj < a.a) {
-            const float tv = v[j] + biasS[2 * H + o0 + j];
+            const float tv = v[j];
             a.x_out[tidx(tile, d, a.af[jj], row)] = a.sampling ? xv[j] * expf(sv[j]) + tv : (xv[j] - tv) * expf(-sv[j]);
             lsum += sv[j];
           }

@@ -131,25 +131,29 @@ def test_wide_loss_grad(name, B):
     _check_grad(name, ochain, chain.packed(), x, th, B)
 
 
-def _mixed_wide_chain(x):
-    """RNVP + NICE coupling layers with a NormalizationLayer in the middle and one at the end, hidden 128."""
+def _mixed_wide_chain(x, hidden=128):
+    """RNVP + NICE coupling layers with a NormalizationLayer in the middle and one at the end, hidden 128 (or 64)."""
     rng = np.random.default_rng(7)
-    l1 = O.coupling_layer(O.coupling_axes(8, [1, 2, 3, 4], n=2), hidden_dim_s=128, hidden_dim_t=128, rng=rng,
+    l1 = O.coupling_layer(O.coupling_axes(8, [1, 2, 3, 4], n=2), hidden_dim_s=hidden, hidden_dim_t=hidden, rng=rng,
                           bias_scale=0.1, s_out_scale=0.3)
-    l2 = O.coupling_layer(O.coupling_axes(8, [8, 5, 6], n=2), kind="nice", hidden_dim_t=128, rng=rng, bias_scale=0.1)
-    l3 = O.coupling_layer(O.coupling_axes(8, [7, 2, 4, 6, 1], n=2), hidden_dim_s=128, hidden_dim_t=128, rng=rng,
+    l2 = O.coupling_layer(O.coupling_axes(8, [8, 5, 6], n=2), kind="nice", hidden_dim_t=hidden, rng=rng, bias_scale=0.1)
+    l3 = O.coupling_layer(O.coupling_axes(8, [7, 2, 4, 6, 1], n=2), hidden_dim_s=hidden, hidden_dim_t=hidden, rng=rng,
                           bias_scale=0.1, s_out_scale=0.3)
     return O.Chain([l1, O.norm_layer_from_data(x, -2.0, 3.0), l2, l3, O.norm_layer_from_data(x)])
 
 
-def test_wide_nice_layer_and_inner_normalization():
+@pytest.mark.parametrize("hidden", [128, 64])
+def test_wide_nice_layer_and_inner_normalization(hidden):
     """NICE (no s-net) layers and a NormalizationLayer inside the chain on the tensor-core kernels, both directions
-    and the adjoint (the cotangent is scaled through the inner NormalizationLayer)."""
+    and the adjoint (the cotangent is scaled through the inner NormalizationLayer).  hidden = 64: the narrow
+    TMEM-sourced kernel, forced onto the tensor cores at this small batch."""
     xn = O.synthetic_data(8, 2, 1000, seed=99)[0]
-    ochain = _mixed_wide_chain(xn)
+    ochain = _mixed_wide_chain(xn, hidden)
     B = 700
     x, th = O.synthetic_data(8, 2, B, seed=13)
     chain = chain_from_oracle(ochain)
+    if hidden <= 64:
+        chain.packed().tune(tc_mode=1)
     z, ldj = df.backward(chain, x, th)
     zo, lo = O.chain_backward(ochain, x, th, np.float64)
     zo32, lo32 = O.chain_backward(ochain, x, th)
@@ -158,7 +162,7 @@ def test_wide_nice_layer_and_inner_normalization():
     assert_close(df.to_numpy(ldj), lo, 1e-5, 1e-5 + slack, "mixed ldj")
     x2, ldj2 = df.forward(chain, df.to_numpy(z), th)
     assert_close(df.to_numpy(x2), x, 1e-4, 1e-4, "mixed round trip")
-    _check_grad("mixed_h128", ochain, chain.packed(), x, th, B)
+    _check_grad(f"mixed_h{hidden}", ochain, chain.packed(), x, th, B)
 
 
 def test_wide_adjoint_macro_batches():
