@@ -1,4 +1,5 @@
-"""C2 train-step timing: v3 register-resident adjoint (constant-bank weights) against the v2 shared-memory-column adjoint."""
+"""C2 train-step timing of the shipped narrow adjoint (chain_grad2_kernel) across samples-per-thread settings.
+(The register-resident v3 variant this script once compared against was measured and removed: profiles/r02_narrow_adjoint_v3.md.)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -10,7 +11,7 @@ x, th = device_inputs(5, 2, B, dev, 1)
 tmin, tmax = df.minmax_rows(th)
 chain, pc = packed("c2", dev, tmin, tmax)
 grads = {}
-for tune in [dict(grad_v3=0), dict(grad_v3=-1)]:
+for tune in [dict(grad_spt=0), dict(grad_spt=1), dict(grad_spt=2)]:
     pc.tune(**tune)
     grad = torch.zeros(pc.P, device=dev); l2 = torch.zeros(2, device=dev)
     pc.loss_grad(x, th, grad, l2, None, 1)
@@ -24,5 +25,6 @@ for tune in [dict(grad_v3=0), dict(grad_v3=-1)]:
         ts.append(e0.elapsed_time(e1))
     med = float(np.median(ts))
     print(json.dumps({"tune": tune, "ms": med, "sps": B / med * 1e3}), flush=True)
-a, b = grads["{'grad_v3': 0}"], grads["{'grad_v3': -1}"]
-print("max |dg| / max|g| =", float((a[0] - b[0]).abs().max() / b[0].abs().max()), "loss", float(a[1][0]), float(b[1][0]))
+ks = list(grads)
+a, b = grads[ks[0]], grads[ks[-1]]
+print("max |dg| / max|g| between the first and the last setting =", float((a[0] - b[0]).abs().max() / b[0].abs().max()), "loss", float(a[1][0]), float(b[1][0]))
