@@ -376,3 +376,62 @@ def test_wide_nondefault_activations_and_bias(bias, hidden):
     x2, _ = df.forward(chain, df.to_numpy(z), th)
     assert_close(df.to_numpy(x2), x, 1e-4, 1e-4, "nondefault round trip")
     _check_grad(f"nondefault_h{hidden}", ochain, chain.packed(), x, th, B)
+
+
+def _random_narrow_chain(seed):
+    """A random hidden 32 / 64 chain the narrow tensor-core kernel is eligible for: random d, n, masks (unsorted, ragged),
+    RealNVP / NICE layers, activations, bias on / off, a NormalizationLayer at a random position."""
+    rng = np.random.default_rng(seed)
+    h = int(rng.choice([32, 64]))
+    n = int(rng.integers(0, 5))
+    d = int(rng.integers(3, 14 if h == 32 else 20))
+    acts = ["relu", "relu", "tanh", "sigmoid", "identity"]
+    layers = []
+    nl = int(rng.integers(2, 5))
+    for li in range(nl):
+        na = int(rng.integers(1, min(d - 1, 12) + 1))
+        mask = [int(m) + 1 for m in rng.permutation(d)[:na]]
+        kind = "nice" if rng.random() < 0.25 else "rnvp"
+        layers.append(O.coupling_layer(O.coupling_axes(d, mask, n=n), kind=kind, hidden_dim_s=h, hidden_dim_t=h,
+                                       act_s=str(rng.choice(acts)), act_t=str(rng.choice(acts)), bias=bool(rng.random() < 0.7),
+                                       rng=rng, bias_scale=0.1, s_out_scale=0.3))
+    xn = O.synthetic_data(d, n, 500, seed=seed + 1000)[0]
+    layers.insert(int(rng.integers(0, len(layers) + 1)), O.norm_layer_from_data(xn, -1.0, 2.0))
+    return O.Chain(layers), d, n, h
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_narrow_tensor_core_kernel_random_chains(seed):
+    """Randomised structure sweep: the TMEM-sourced kernel (tc_mode = 1) against the CUDA-core kernels (tc_mode = -1, exact
+    Float32 FMA chains) on the same chain and batch -- log-density, the sampling direction and the gradient; batch sizes
+    with ragged tiles, fewer tiles than chains per CTA, and several tiles per chain."""
+    ochain, d, n, h = _random_narrow_chain(seed)
+    B = [1, 77, 129, 600, 1500, 5000, 700, 333, 2048, 4097][seed]
+    x, th = O.synthetic_data(d, n, B, seed=seed + 50)
+    chain = chain_from_oracle(ochain)
+    pc = chain.packed()
+    xj = df.to_jl(x, DEV)
+    tj = df.to_jl(th, DEV) if n else None
+    out = {}
+    launches = {}
+    for mode in (-1, 1):
+        pc.tune(tc_mode=mode)
+        n0 = pc.launch_count()
+        lp = pc.logpdf(xj, tj).clone()
+        launches[mode] = pc.launch_count() - n0
+        z, ldj = pc.normalize(xj, tj)
+        xb, ldjb = pc.forward_ldj(z.clone(), tj)
+        grad = torch.zeros(pc.P, device=DEV)
+        l2 = torch.zeros(2, device=DEV)
+        pc.loss_grad(xj, tj, grad, l2)
+        out[mode] = (lp, z.clone(), ldj.clone(), xb.clone(), grad, l2.clone())
+    pc.tune(tc_mode=0)
+    assert launches[1] > launches[-1] + 2, "the chain did not route to the tensor-core kernels"
+    ref, got = out[-1], out[1]
+    assert_close(df.to_numpy(got[0]), df.to_numpy(ref[0]), 2e-5, 2e-4, f"seed {seed} logpdf")
+    assert_close(df.to_numpy(got[1]), df.to_numpy(ref[1]), 2e-5, 2e-5, f"seed {seed} z")
+    assert_close(df.to_numpy(got[2]), df.to_numpy(ref[2]), 2e-5, 2e-5, f"seed {seed} ldj")
+    assert_close(df.to_numpy(got[3]), x, 2e-4, 2e-4, f"seed {seed} round trip")
+    gmax = float(ref[4].abs().max())
+    assert float((got[4] - ref[4]).abs().max()) <= 2e-4 * gmax + 1e-7, (seed, float((got[4] - ref[4]).abs().max()), gmax)
+    assert abs(float(got[5][0] - ref[5][0])) <= 1e-5 * abs(float(ref[5][0])) + 1e-3
