@@ -1084,7 +1084,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
 
   const long long per = (a.ntiles + a.ksplit - 1) / a.ksplit;
   const long long t0 = ks * per, t1 = min(a.ntiles, t0 + per);
-  const long long nstages = (t1 > t0) ? (t1 - t0) * (128 / DW_KS) : 0;
+  const int nstages = (t1 > t0) ? (int)((t1 - t0) * (128 / DW_KS)) : 0;  // (< 2^31: a CTA's share of the sample tiles)
 
   if (warp < DW_STAGE_WARPS) {
     // ---- staging warps: global (fp32) -> hi/lo split -> shared operand layout, loads issued one stage ahead ----
@@ -1144,7 +1144,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
     float bacc[DW_MAXRB];
 #pragma unroll
     for (int i = 0; i < DW_MAXRB; ++i) bacc[i] = 0.0f;
-    auto load_stage = [&](long long s, float4 (&v)[DW_MAXRB]) {
+    auto load_stage = [&](int s, float4 (&v)[DW_MAXRB]) {
       const size_t blk = (size_t)(t0 * (128 / DW_KS) + s);  // [tile][16-sample block] index (tbuf_idx)
 #pragma unroll
       for (int i = 0; i < DW_MAXRB; ++i) {
@@ -1171,12 +1171,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
       }
     };
     // nstages is a multiple of 128 / DW_KS = 8 and NST is even: a pair occupies ring slots (s % NST, s % NST + 1)
-    const long long s_first = 2 * grp, s_step = 2 * G;
+    const int s_first = 2 * grp, s_step = 2 * G;
     if (active && s_first < nstages) {
       load_stage(s_first, vA);
       load_stage(s_first + 1, vB);
     }
-    for (long long s = s_first; active && s < nstages; s += s_step) {
+    for (int s = s_first; active && s < nstages; s += s_step) {
       const uint32_t slA = (uint32_t)(s % NST), prA = (uint32_t)((s / NST) & 1);
       put_stage(vA, slA, prA);
       put_stage(vB, slA + 1, prA);
@@ -1259,7 +1259,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
     }
     const uint32_t full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
     uint32_t slot = 0, par = 0;
-    for (long long s = 0; s < nstages; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_wait_a(full_u32 + slot * 8, par);
       tc_fence_after();
       if (elect_one()) {
