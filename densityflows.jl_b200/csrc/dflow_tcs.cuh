@@ -195,6 +195,14 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
   for (long long tile = (long long)blockIdx.x * TCS_CHAINS + wg; tile < ntiles; tile += (long long)gridDim.x * TCS_CHAINS) {
     const long long gi = tile * 128 + row;
     const bool valid = gi < a.B;
+    // this sample's column in the tile-blocked state / theta arrays: element k at base[k * 128] (one 64-bit base per
+    // array and tile, 32-bit offsets per gathered coordinate)
+    const size_t sd = (size_t)tile * (size_t)d * 128 + (size_t)row, sn = (size_t)tile * (size_t)n * 128 + (size_t)row;
+    const float* const xin_t = a.x_in ? a.x_in + sd : nullptr;
+    float* const xout_t = a.x_out ? a.x_out + sd : nullptr;
+    float* const zbar_t = a.zbar ? a.zbar + sd : nullptr;
+    const float* const zout_t = a.zout ? a.zout + sd : nullptr;
+    const float* const th_t = a.theta ? a.theta + sn : nullptr;
     // relu masks of the adjoint chain, fetched before anything waits
     uint32_t mw2[2] = {0u, 0u}, mw1[2] = {0u, 0u};
     if constexpr (MODE == TC_BWD) {
@@ -217,9 +225,9 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
           zb[qq] = zo[qq] = sv[qq] = 0.0f;
           if (valid && j < a.a) {
             const int k = a.af[j];
-            zb[qq] = a.zbar[tidx(tile, d, k, row)];
+            zb[qq] = zbar_t[k * 128];
             if (a.net_id == 0)
-              zo[qq] = a.zout[tidx(tile, d, k, row)];
+              zo[qq] = zout_t[k * 128];
             else if (a.has_s)
               sv[qq] = a.sbuf[((size_t)tile * a.a16 + j) * 128 + row];
           }
@@ -241,9 +249,9 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
           float val = 0.0f;
           if (valid && k < a.nin) {
             if (k < n)
-              val = a.theta_const ? __ldg(a.theta_const + k) : __ldg(a.theta + tidx(tile, n, k, row));
+              val = a.theta_const ? __ldg(a.theta_const + k) : __ldg(th_t + k * 128);
             else
-              val = a.x_in[tidx(tile, d, a.id[k - n], row)];
+              val = xin_t[(int)a.id[k - n] * 128];
           }
           v[qq] = val;
         }
@@ -296,10 +304,10 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
         for (int k0 = 0; k0 < d; k0 += 8) {
           float v[8];
 #pragma unroll
-          for (int qq = 0; qq < 8; ++qq) v[qq] = (k0 + qq < d) ? a.x_in[tidx(tile, d, k0 + qq, row)] : 0.0f;
+          for (int qq = 0; qq < 8; ++qq) v[qq] = (k0 + qq < d) ? xin_t[(k0 + qq) * 128] : 0.0f;
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq)
-            if (k0 + qq < d) a.x_out[tidx(tile, d, k0 + qq, row)] = v[qq];
+            if (k0 + qq < d) xout_t[(k0 + qq) * 128] = v[qq];
         }
       }
     }
@@ -414,23 +422,23 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
         // rows n.. go to the identity coordinates; rows 0..n-1 are the cotangent of the (normalised) conditions
         if (valid) {
           float zb[8];
+          int off[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = o0 + j;
-            zb[j] = (k >= n && k < a.nin) ? a.zbar[tidx(tile, d, a.id[k - n], row)] : 0.0f;
+            off[j] = (k >= n && k < a.nin) ? (int)a.id[k - n] * 128 : -1;
+            zb[j] = off[j] >= 0 ? zbar_t[off[j]] : 0.0f;
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int k = o0 + j;
-            if (k >= n && k < a.nin) a.zbar[tidx(tile, d, a.id[k - n], row)] = zb[j] + v[j];
-          }
+          for (int j = 0; j < 8; ++j)
+            if (off[j] >= 0) zbar_t[off[j]] = zb[j] + v[j];
           if (a.thbar) {
             for (int j = 0; j < 8; ++j) {
               const int k = o0 + j;
               if (k < n) {
                 // chain rule through normalize_input (src/Data.jl:213-218)
                 const float sc = (a.flags & DFLOW_THETA_NORMALIZE) ? (a.theta_rng[k] == 0.0f ? 0.0f : 1.0f / a.theta_rng[k]) : 1.0f;
-                a.thbar[tidx(tile, n, k, row)] += v[j] * sc;
+                a.thbar[sn + (size_t)k * 128] += v[j] * sc;
               }
             }
           }
@@ -447,14 +455,14 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
         for (int j = 0; j < 8; ++j) {
           const int jj = o0 + j;
           sv[j] = (jj < a.a && a.has_s) ? srow[j * 128] : 0.0f;
-          xv[j] = (jj < a.a) ? a.x_in[tidx(tile, d, a.af[jj], row)] : 0.0f;
+          xv[j] = (jj < a.a) ? xin_t[(int)a.af[jj] * 128] : 0.0f;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int jj = o0 + j;
           if (jj < a.a) {
             const float tv = v[j];
-            a.x_out[tidx(tile, d, a.af[jj], row)] = a.sampling ? xv[j] * expf(sv[j]) + tv : (xv[j] - tv) * expf(-sv[j]);
+            xout_t[(int)a.af[jj] * 128] = a.sampling ? xv[j] * expf(sv[j]) + tv : (xv[j] - tv) * expf(-sv[j]);
             lsum += sv[j];
           }
         }
@@ -469,11 +477,11 @@ __global__ void __launch_bounds__(TCS_THREADS, 1) tcs_net_kernel(const __grid_co
           for (int qq = 0; qq < 8; ++qq) {
             const int j = j0 + qq;
             sv[qq] = j < a.a ? a.sbuf[((size_t)tile * a.a16 + j) * 128 + row] : 0.0f;
-            zb[qq] = j < a.a ? a.zbar[tidx(tile, d, a.af[j], row)] : 0.0f;
+            zb[qq] = j < a.a ? zbar_t[(int)a.af[j] * 128] : 0.0f;
           }
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq)
-            if (j0 + qq < a.a) a.zbar[tidx(tile, d, a.af[j0 + qq], row)] = zb[qq] * expf(-sv[qq]);
+            if (j0 + qq < a.a) zbar_t[(int)a.af[j0 + qq] * 128] = zb[qq] * expf(-sv[qq]);
         }
     } else {
       if (a.net_id >= 1 && a.ldj && valid) a.ldj[gi] += a.sampling ? lsum : -lsum;
