@@ -1047,6 +1047,8 @@ int dflow_set_tuning(dflow_chain* c, const char* key, int32_t value) {
     c->tc_ts = value < 0 ? -1 : 0;
   else if (!strcmp(key, "tc_dw_groups"))
     c->tc_dw_groups = value < 0 ? 0 : value;
+  else if (!strcmp(key, "tc_dw_ts"))
+    c->tc_dw_ts = value < 0 ? -1 : 0;
   else if (!strcmp(key, "tc_ws_budget_mb"))
     c->tc_ws_budget_mb = value;
 #ifdef DFLOW_TC_EXPERIMENTS  // timing experiments (wrong results by construction): never part of a release build

@@ -161,6 +161,7 @@ struct dflow_chain {
   int tc_ws_budget_mb = 0;  // adjoint workspace cap in MiB (0: 24 GiB); larger batches are processed in macro-batches
   int tc_ts = 0;       // -1: hidden 32 / 64 conditioners stay on the warp-specialised pipeline (tc_net_kernel)
   int tc_dw_groups = 0; // > 0: cap on the staging-warp groups of the weight-gradient kernel (1 = all warps on every stage)
+  int tc_dw_ts = 0;    // -1: weight gradients always through tc_dw_kernel (all operands staged in shared memory)
   int tc_fuse = 1;     // hidden <= 128 RealNVP layers run their s and t conditioners as one block-diagonal conditioner:
                        // 0 never, 1 in the train step (default), 2 in forward-type calls as well
   int tc_debug = 0;    // timing experiments (dflow_tc.cu, only with -DDFLOW_TC_EXPERIMENTS)

@@ -1291,6 +1291,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dw_kernel(const __grid_const
   }
 }
 
+}  // namespace dflow
+#include "dflow_tc_dwts.cuh"
+namespace dflow {
+
 // ---- small element-wise kernels ------------------------------------------------------------------------------
 // All element-wise kernels below work on the tile-blocked layout (tidx): element i of a [tiles][rows][128] array.
 __global__ void tc_norm_kernel(const float* x_in, float* x_out, float* ldj, long long B, int d,
@@ -2184,28 +2188,47 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       w.inbuf = inbuf_of(ei);
       w.grad = grad_out;
       w.debug = (c->tc_debug >> 12) & 7;  // bits 12-14 of tc_debug: weight-gradient kernel timing experiments (experiment builds)
-      const int RA = std::min(128, w.H);  // rows of the A segments (a multiple of 8: H % 32 == 0)
-      const size_t stage_bytes = 2 * (size_t)(3 * RA + w.NB + w.K0p + w.a16) * DW_KS * 4;  // the fullest CTA (column half 0)
-      // the M = 128 MMAs read 128 rows of every A segment: keep that overrun inside the allocation
-      const size_t overrun = (size_t)(128 - RA) * DW_KS * 4 * 2;
-      int nst = (int)(((size_t)c->max_smem_optin - 128 - overrun) / stage_bytes);
-      if (nst > 4) nst = 4;
-      nst &= ~1;  // stage pairs
-      const int nrb = (3 * RA + w.NB + w.K0p + w.a16) / 8;  // row-blocks per stage
-      w.ngroups = 1;
-      for (int g = 3; g >= 2; --g)
-        if (w.ngroups == 1 && nst >= 2 * g && nrb <= DW_MAXRB * (DW_STAGE_WARPS / g)) w.ngroups = g;
-      if (c->tc_dw_groups > 0 && c->tc_dw_groups <= w.ngroups) w.ngroups = c->tc_dw_groups;
-      if (nst < 2 || nrb > DW_MAXRB * DW_STAGE_WARPS) {
-        set_error("weight-gradient stage does not fit (%zu bytes per stage)", stage_bytes);
-        return DFLOW_E_UNSUPPORTED;
+      if (c->tc_dw_ts >= 0 && dwts_shape_ok(w.NB, w.K0p, w.a16)) {
+        // A operands through TMEM (dflow_tc_dwts.cuh): only the B segments are staged in shared memory
+        const size_t stage_bytes = 2 * (size_t)(w.NB + w.K0p + w.a16) * DW_KS * 4;
+        int nst = (int)(((size_t)c->max_smem_optin - 256) / stage_bytes);
+        if (nst > 4) nst = 4;
+        nst &= ~1;
+        if (nst < 2) {
+          set_error("weight-gradient stage does not fit (%zu bytes per stage)", stage_bytes);
+          return DFLOW_E_UNSUPPORTED;
+        }
+        w.nstage = nst;
+        w.ngroups = 1;
+        const size_t smem = nst * stage_bytes + 256;
+        CKT(cudaFuncSetAttribute(tc_dwts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_dwts_kernel<<<(unsigned)(w.units * w.ksplit), DW_THREADS, smem, st>>>(w);
+        CKT(cudaGetLastError());
+        c->launches++;
+      } else {
+        const int RA = std::min(128, w.H);  // rows of the A segments (a multiple of 8: H % 32 == 0)
+        const size_t stage_bytes = 2 * (size_t)(3 * RA + w.NB + w.K0p + w.a16) * DW_KS * 4;  // the fullest CTA (column half 0)
+        // the M = 128 MMAs read 128 rows of every A segment: keep that overrun inside the allocation
+        const size_t overrun = (size_t)(128 - RA) * DW_KS * 4 * 2;
+        int nst = (int)(((size_t)c->max_smem_optin - 128 - overrun) / stage_bytes);
+        if (nst > 4) nst = 4;
+        nst &= ~1;  // stage pairs
+        const int nrb = (3 * RA + w.NB + w.K0p + w.a16) / 8;  // row-blocks per stage
+        w.ngroups = 1;
+        for (int g = 3; g >= 2; --g)
+          if (w.ngroups == 1 && nst >= 2 * g && nrb <= DW_MAXRB * (DW_STAGE_WARPS / g)) w.ngroups = g;
+        if (c->tc_dw_groups > 0 && c->tc_dw_groups <= w.ngroups) w.ngroups = c->tc_dw_groups;
+        if (nst < 2 || nrb > DW_MAXRB * DW_STAGE_WARPS) {
+          set_error("weight-gradient stage does not fit (%zu bytes per stage)", stage_bytes);
+          return DFLOW_E_UNSUPPORTED;
+        }
+        w.nstage = nst;
+        const size_t smem = nst * stage_bytes + overrun + 128;
+        CKT(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_dw_kernel<<<(unsigned)(w.units * w.ksplit), DW_THREADS, smem, st>>>(w);
+        CKT(cudaGetLastError());
+        c->launches++;
       }
-      w.nstage = nst;
-      const size_t smem = nst * stage_bytes + overrun + 128;
-      CKT(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      tc_dw_kernel<<<(unsigned)(w.units * w.ksplit), DW_THREADS, smem, st>>>(w);
-      CKT(cudaGetLastError());
-      c->launches++;
     }
     if (vjp && vjp->xbar_out) {
       tc_scatter_t_kernel<<<tile_blocks(mb), 256, tsm_bytes(d), st>>>(zbar, mb, d, vjp->xbar_out + (size_t)first * d);

@@ -17,6 +17,8 @@ if "DFLOW_TC_TS" in os.environ:
     pc.tune(tc_ts=int(os.environ["DFLOW_TC_TS"]))
 if "DFLOW_DW_GROUPS" in os.environ:
     pc.tune(tc_dw_groups=int(os.environ["DFLOW_DW_GROUPS"]))
+if "DFLOW_DW_TS" in os.environ:
+    pc.tune(tc_dw_ts=int(os.environ["DFLOW_DW_TS"]))
 g = torch.Generator(device="cuda").manual_seed(0)
 x = df.jl_empty((d, B), "cuda:0"); x.normal_(generator=g)
 th = df.jl_empty((n, B), "cuda:0"); th.uniform_(0, 1, generator=g)
