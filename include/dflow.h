@@ -263,7 +263,8 @@ int dflow_sample_host(dflow_chain* chain, const float* W, uint64_t seed, const f
  * / off the tensor-core kernels), "tc_fuse" (0 / 1 / 2: s and t conditioners of a layer as one block-diagonal conditioner
  * never / in the train step / everywhere), "tc_ts" (-1: hidden 32 / 64 conditioners stay on the warp-specialised
  * tensor-core pipeline instead of the TMEM-sourced four-chain kernel), "tc_dw_groups" (1: the staging warps of the
- * weight-gradient kernel never split into alternating groups), "tc_ws_budget_mb" (adjoint workspace cap), "epoch_kernel" (-1: dflow_train_epoch
+ * weight-gradient kernel never split into alternating groups), "tc_dw_ts" (-1: weight gradients never take their A operands
+ * through TMEM), "tc_ws_budget_mb" (adjoint workspace cap), "epoch_kernel" (-1: dflow_train_epoch
  * never uses the persistent small-minibatch kernel).  Unknown keys return DFLOW_E_INVALID_ARG. */
 int dflow_set_tuning(dflow_chain* chain, const char* key, int32_t value);
 /* number of kernels the library has launched on behalf of this handle since creation */
