@@ -122,6 +122,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dwts_kernel(const __grid_con
       tc_fence_before();
       mbar_arrive(fullA + set);
       if (s + 2 < nstages) load(s + 2);  // in flight while the MMAs of this stage (and the other set's stage) run
+      if (rok && s + 4 < nstages) {
+        const size_t o4 = (blk0 + (size_t)(s + 4)) * bstride;
+#pragma unroll
+        for (int sg = 0; sg < 3; ++sg)
+          if (sg < nseg) asm volatile("prefetch.global.L2 [%0];" ::"l"(src[sg] + o4));
+      }
       par ^= 1u;
     }
     if (rok && nh == 0 && nstages > 0) {
@@ -200,6 +206,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dwts_kernel(const __grid_con
         if ((segmask >> i) & 1u) v[i] = __ldg(reinterpret_cast<const float4*>(ptr[i] + blk * (size_t)stride[i]));
       }
     };
+    auto prefetch_stage = [&](int s) {
+      const size_t blk = blk0 + (size_t)s;
+#pragma unroll
+      for (int i = 0; i < DWTS_MAXB; ++i)
+        if ((segmask >> i) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr[i] + blk * (size_t)stride[i]));
+    };
     auto put_stage = [&](float4 (&v)[DWTS_MAXB], uint32_t sl, uint32_t pr) {
       mbar_wait(emptyB + sl, pr ^ 1u);
       float* st = smem + (size_t)sl * stage_fl;
@@ -232,6 +244,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dwts_kernel(const __grid_con
       if (s + 2 < nstages) {
         load_stage(s + 2, vA);
         load_stage(s + 3, vB);
+      }
+      if (s + 4 < nstages) {  // the pair after next: pulled into L2 now, so that its loads above find it there
+        prefetch_stage(s + 4);
+        prefetch_stage(s + 5);
       }
       slA += 2;
       if (slA >= (uint32_t)NST) {
