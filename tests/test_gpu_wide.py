@@ -435,3 +435,38 @@ def test_narrow_tensor_core_kernel_random_chains(seed):
     gmax = float(ref[4].abs().max())
     assert float((got[4] - ref[4]).abs().max()) <= 2e-4 * gmax + 1e-7, (seed, float((got[4] - ref[4]).abs().max()), gmax)
     assert abs(float(got[5][0] - ref[5][0])) <= 1e-5 * abs(float(ref[5][0])) + 1e-3
+
+
+@pytest.mark.parametrize("name", ["h128_d8", "c4_like_h256", "h64_d16"])
+def test_weight_gradient_kernels_agree(name):
+    """The two weight-gradient kernels -- A operands through TMEM (default where the TMEM column budget allows) and all six
+    operand segments staged in shared memory (tc_dw_ts = -1; the only one for hidden 512 with many conditioner inputs) --
+    accumulate the same products: gradients agree to summation order, at a batch where every CTA walks several stages
+    and the last tile is ragged."""
+    narrow = name in NARROW_ON_TC
+    d, n, L, h = NARROW_ON_TC[name] if narrow else CASES[name]
+    B = 148 * 128 + 4 * 128 + 77
+    ochain = O.block_chain(d, n, L, h, O.synthetic_data(d, n, 1000, seed=99)[0], s_out_scale=0.3)
+    chain = chain_from_oracle(ochain)
+    pc = chain.packed()
+    if narrow:
+        pc.tune(tc_mode=1)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    x = df.jl_empty((d, B), DEV)
+    x.normal_(generator=g)
+    th = df.jl_empty((n, B), DEV)
+    th.uniform_(0, 1, generator=g)
+    grads = {}
+    for ts in (0, -1):
+        pc.tune(tc_dw_ts=ts)
+        grad = torch.zeros(pc.P, device=DEV)
+        l2 = torch.zeros(2, device=DEV)
+        pc.loss_grad(x, th, grad, l2)
+        grads[ts] = (grad, l2)
+    pc.tune(tc_dw_ts=0)
+    if narrow:
+        pc.tune(tc_mode=0)
+    gmax = float(grads[-1][0].abs().max())
+    assert float((grads[0][0] - grads[-1][0]).abs().max()) <= 2e-5 * gmax
+    # the loss does not depend on the weight-gradient kernel (its block sums are added atomically: summation order only)
+    assert abs(float(grads[0][1][0]) - float(grads[-1][1][0])) <= 2e-6 * abs(float(grads[-1][1][0]))
