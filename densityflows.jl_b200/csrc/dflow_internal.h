@@ -169,11 +169,11 @@ struct dflow_chain {
   int tc_mode = 0;     // 0: automatic (tensor cores iff must_wide), 1: force tensor cores, -1: force CUDA cores
   bool use_tc() const { return tcp && (must_wide || tc_mode > 0); }
   // Hidden 32 / 64 chains are eligible for both paths; the automatic choice follows scripts/tc_thresholds.py (one B200,
-  // C3-like chain of 8 blocks at hidden 64, 4 blocks at hidden 32; CUDA-core / tensor-core ms per call):
-  //   hidden 64 log-density   32 768: 0.20 / 0.29    65 536: 0.38 / 0.29    1 Mi: 4.91 / 2.45
-  //   hidden 64 train step     8 192: 1.02 / 0.80    65 536: 4.00 / 1.28    1 Mi: 55.4 / 13.9
-  //   hidden 32 log-density   always the CUDA-core kernel (1 Mi: 0.65 / 0.83)
-  //   hidden 32 train step    32 768: 0.33 / 0.41    65 536: 0.63 / 0.51    1 Mi: 8.48 / 5.42
+  // C3-like chain of 8 blocks at hidden 64, 4 blocks at hidden 32; CUDA-core / tensor-core ms per call, final round-2 kernels):
+  //   hidden 64 log-density   32 768: 0.20 / 0.25    65 536: 0.38 / 0.26    1 Mi: 4.90 / 2.00
+  //   hidden 64 train step     8 192: 1.02 / 0.70    65 536: 3.99 / 0.99    1 Mi: 55.3 / 10.3
+  //   hidden 32 log-density   always the CUDA-core kernel (131 072: 0.16 / 0.16, 1 Mi: 0.66 / 0.68)
+  //   hidden 32 train step     8 192: 0.33 / 0.26    32 768: 0.33 / 0.34    65 536: 0.63 / 0.41    1 Mi: 8.47 / 3.95
   int hidden_max = 0;
   bool use_tc_fwd(long long B) const {
     if (use_tc()) return true;
@@ -181,7 +181,7 @@ struct dflow_chain {
   }
   bool use_tc_grad(long long B) const {
     if (use_tc()) return true;
-    return tcp && tc_mode == 0 && ((hidden_max == 64 && B >= 8192) || (hidden_max == 32 && B >= 65536));
+    return tcp && tc_mode == 0 && ((hidden_max == 64 || hidden_max == 32) && B >= 8192);
   }
   const dflow::DevChain* hc() const { return reinterpret_cast<const dflow::DevChain*>(host_chain.data()); }
   dflow::DevChain* hc() { return reinterpret_cast<dflow::DevChain*>(host_chain.data()); }
