@@ -7,8 +7,9 @@
 // hand-offs and memory round trips, not by the tensor pipe (ncu, profiles/r02_c3_tc.md: 12-23 % tensor-pipe active), and its
 // TMEM / shared-memory footprint allows only two tiles in flight per SM.  Here a 512-thread CTA holds four warpgroups; each
 // walks its own tile through
-//   input row -> TMEM | D1 = in W1^T | bias, act, hi/lo split in registers | D2 = h1 W2^T | ... | D3 = h2 W3^T | output
-// with one commit / wait and one 128-thread named barrier per GEMM; the four chains hide each other's latencies.
+//   input row -> TMEM | D1 = b1 + in W1^T | act, hi/lo split in registers | D2 = b2 + h1 W2^T | ... | D3 = b3 + h2 W3^T | output
+// (every accumulator is initialised with its bias by tcgen05.st) with one commit / wait and one 128-thread named barrier per
+// GEMM; the four chains hide each other's latencies.
 //
 // Per chain, 128 TMEM columns (H = hidden width <= 64):
 //   A = [0, H)    D1, then h1.hi in place, finally D3 (h1 is dead by then)
