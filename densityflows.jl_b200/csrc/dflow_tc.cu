@@ -1669,6 +1669,15 @@ int tc_build_plan(dflow_chain* c) {
       tp->jobs_bwd.push_back(J);
       TcLaunchCfg fc;
       Ld.fused = (tc_launch_cfg(c, Ld.ffwd, fc) && tc_launch_cfg(c, Ld.fbwd, fc)) ? 1 : 0;
+      // the pair's weight-gradient launch (width 2h, 2 a16 delta3 rows) must fit one of the two kernels as well
+      {
+        const int H2 = 2 * h, RAf = std::min(128, H2), K0pf = Ld.ffwd.K0p, a16f = 2 * a16;
+        const bool ts_ok = dwts_shape_ok(H2, K0pf, a16f);
+        const int rows = 3 * RAf + H2 + K0pf + a16f;
+        const size_t sb = 2 * (size_t)rows * DW_KS * 4, ov = (size_t)(128 - RAf) * DW_KS * 4 * 2;
+        const bool smem_ok = rows / 8 <= DW_MAXRB * DW_STAGE_WARPS && (size_t)c->max_smem_optin >= 2 * sb + ov + 128;
+        if (!ts_ok && !smem_ok) Ld.fused = 0;
+      }
     }
     TcLaunchCfg cfg;
     Ld.tcs = 1;
