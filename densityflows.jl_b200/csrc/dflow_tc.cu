@@ -2177,6 +2177,11 @@ int tc_loss_grad(dflow_chain* c, const float* W, const float* x, const float* th
       w.ablk = Ld.a16;
       w.mtiles = (w.H + 127) / 128;
       w.nsplit = w.H > 256 ? 2 : 1;
+      // hidden 256 with many conditioner inputs and transformed coordinates: more row-blocks per stage than the staging
+      // warps of tc_dw_kernel cover -> split the dW2 columns over two CTAs as at hidden 512
+      if (w.nsplit == 1 && !fzw && !dwts_shape_ok(w.H, w.K0p, w.a16) &&
+          (3 * std::min(128, w.H) + w.H + w.K0p + w.a16) / 8 > DW_MAXRB * DW_STAGE_WARPS && w.H % 32 == 0)
+        w.nsplit = 2;
       w.NB = w.H / w.nsplit;
       w.first_net = (fzw || Ld.has_s) ? 0 : 1;
       w.units = (fzw ? 1 : Ld.has_s ? 2 : 1) * w.mtiles * w.nsplit;

@@ -27,6 +27,8 @@ CASES = {
     "c5_like_h512": (64, 16, 2, 512),
     # 20 transformed coordinates (a16 = 32) and 28 conditioner inputs (K0p = 32): the column limits of the TMEM-A weight-gradient kernel
     "h128_d40": (40, 8, 2, 128),
+    # 56 conditioner inputs and 32 transformed coordinates at hidden 256: 92 operand row-blocks per weight-gradient stage
+    "h256_d64_n24": (64, 24, 2, 256),
 }
 
 
@@ -121,7 +123,7 @@ def _check_grad(name, ochain, pc, x, th, B, per_dense=2e-4):
                 off += k
 
 
-@pytest.mark.parametrize("name", ["h128_d8", "h96_d6_n0", "c4_like_h256", "h128_d40"])
+@pytest.mark.parametrize("name", ["h128_d8", "h96_d6_n0", "c4_like_h256", "h128_d40", "h256_d64_n24"])
 @pytest.mark.parametrize("B", [5, 300, 2049])
 def test_wide_loss_grad(name, B):
     """Adjoint on tensor cores: stored activations, transposed-chain input gradients, K = samples weight-gradient GEMMs."""
