@@ -39,6 +39,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dwts_kernel(const __grid_con
   const int stage_fl = 2 * (brow[0] + brow[1] + brow[2]) * DW_KS;
   const int RB = (brow[0] + brow[1] + brow[2]) >> 3;
   const int NST = a.nstage;
+  // B staging groups: narrow nets have few row-blocks per stage, three warps cover them -- then two groups take stage
+  // pairs in turn (one group's loads fly while the other splits, stores and fences), as in tc_dw_kernel
+  const int BG = (RB <= DWTS_MAXB * 3 && NST >= 4) ? 2 : 1, BGW = BG == 2 ? 3 : DWTS_BW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NST * stage_fl);
   uint64_t* fullB = bars;        // [NST <= 4]
   uint64_t* emptyB = bars + 4;   // [NST]
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dwts_kernel(const __grid_con
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
-      mbar_init(fullB + i, DWTS_BW * 32u);
+      mbar_init(fullB + i, (uint32_t)BGW * 32u);
       mbar_init(emptyB + i, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -174,14 +177,15 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dwts_kernel(const __grid_con
     }
   } else if (warp < 15) {
     // ---- B stagers: global (fp32) -> hi/lo split -> shared operand layout, stage pairs behind one proxy fence ----
-    const int gw = warp - 8;
+    const int grp = (warp - 8) / BGW, gw = (warp - 8) % BGW;
+    const bool active = grp < BG;
     const float* ptr[DWTS_MAXB];
     int dst[DWTS_MAXB], lof[DWTS_MAXB], stride[DWTS_MAXB];
     uint32_t segmask = 0, biasmask = 0;
     const int lofs = (lane >> 3) * 32 + (lane & 7) * 4;
 #pragma unroll
     for (int i = 0; i < DWTS_MAXB; ++i) {
-      const int rb = gw + DWTS_BW * i;
+      const int rb = gw + BGW * i;
       const int sg = rb < (brow[0] >> 3) ? 0 : rb < ((brow[0] + brow[1]) >> 3) ? 1 : 2;
       const int rb0 = sg == 0 ? 0 : sg == 1 ? (brow[0] >> 3) : ((brow[0] + brow[1]) >> 3);
       const int r = (rb - rb0) * 8 + (lane & 7);
@@ -230,28 +234,29 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dwts_kernel(const __grid_con
       }
     };
     // nstages is a multiple of 8 and NST is even: a pair occupies ring slots (s % NST, s % NST + 1)
-    if (nstages > 0) {
-      load_stage(0, vA);
-      load_stage(1, vB);
+    const int s_first = 2 * grp, s_step = 2 * BG;
+    if (active && s_first < nstages) {
+      load_stage(s_first, vA);
+      load_stage(s_first + 1, vB);
     }
-    uint32_t slA = 0, prA = 0;
-    for (int s = 0; s < nstages; s += 2) {
+    uint32_t slA = (uint32_t)(s_first % NST), prA = 0;
+    for (int s = s_first; active && s < nstages; s += s_step) {
       put_stage(vA, slA, prA);
       put_stage(vB, slA + 1, prA);
       fence_async_smem();
       mbar_arrive(fullB + slA);
       mbar_arrive(fullB + slA + 1);
-      if (s + 2 < nstages) {
-        load_stage(s + 2, vA);
-        load_stage(s + 3, vB);
+      if (s + s_step < nstages) {
+        load_stage(s + s_step, vA);
+        load_stage(s + s_step + 1, vB);
       }
-      if (s + 4 < nstages) {  // the pair after next: pulled into L2 now, so that its loads above find it there
-        prefetch_stage(s + 4);
-        prefetch_stage(s + 5);
+      if (s + 2 * s_step < nstages) {  // the pair after next: pulled into L2 now, so that its loads above find it there
+        prefetch_stage(s + 2 * s_step);
+        prefetch_stage(s + 2 * s_step + 1);
       }
-      slA += 2;
-      if (slA >= (uint32_t)NST) {
-        slA = 0;
+      slA += (uint32_t)s_step;
+      while (slA >= (uint32_t)NST) {
+        slA -= (uint32_t)NST;
         prA ^= 1u;
       }
     }
@@ -261,8 +266,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) tc_dwts_kernel(const __grid_con
       float r = bacc[i];
       r += __shfl_xor_sync(0xffffffffu, r, 8);
       r += __shfl_xor_sync(0xffffffffu, r, 16);
-      if (((biasmask >> i) & 1u) && lane < 8 && nstages > 0) {
-        const int rb = gw + DWTS_BW * i;
+      if (active && ((biasmask >> i) & 1u) && lane < 8 && nstages > 0) {
+        const int rb = gw + BGW * i;
         const int row = (rb - ((brow[0] + brow[1]) >> 3)) * 8 + lane;
         const int bn = a.fused ? row / a.ablk : net, r2 = a.fused ? row % a.ablk : row;
         if (row < a16 && bn < 2 && r2 < a.a && a.p_b[bn][2] >= 0) atomicAdd(a.grad + a.p_b[bn][2] + r2, r);
